@@ -1,0 +1,7 @@
+"""Example simulations (definitions) -- the four sims named by the BASELINE configs."""
+from .sims import (  # noqa: F401
+    BattleAgent, TeamBattleSim,
+    MazeNavigationAgent, MazeNavigationSim,
+    MultiMazeNavigationAgent, MultiMazeNavigationSim,
+    PacmanAgent, WallAgent, FoodAgent, BaddieAgent, PacmanSim,
+)

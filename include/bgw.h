@@ -1,0 +1,259 @@
+/*
+ * bgw.h -- C-ABI of the B200 batched GridWorld engine (libbgw.so).
+ *
+ * The reference (gillette7/Abmarl 0.2.7, pure Python) has no FFI: its boundary for the hot path is the
+ * Python object protocol
+ *     SimulationManager.reset() / .step(action_dict)          abmarl/managers/simulation_manager.py:27-53
+ *     AllStepManager.reset / .step                            abmarl/managers/all_step_manager.py:37-95
+ *     TurnBasedManager.reset / .step                          abmarl/managers/turn_based_manager.py:22-94
+ *     AgentBasedSimulation.{reset,step,get_obs,get_reward,get_done,get_all_done}
+ *                                                             abmarl/sim/agent_based_simulation.py:238-294
+ * over ONE simulation.  This library is what a maintainer would bind (ctypes / cffi)
+ * to advance E independent copies of one compiled simulation in lockstep on one B200.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no torch types.  Every call returns 0 on success, non-zero on error;
+ *     bgw_last_error() returns a thread-local message.
+ *   - ALL large buffers are CALLER-OWNED DEVICE memory (e.g. torch CUDA tensors -> data_ptr()).
+ *     The library owns only the opaque handle and a few KB of constant tables.
+ *   - kernels are enqueued on the cudaStream_t passed as `stream` (void*, 0 = legacy default stream); no
+ *     internal threads, no host synchronisation inside bgw_reset / bgw_step.
+ *   - there is NO CPU fallback: without a CUDA device bgw_create fails.
+ *
+ * Index spaces
+ *   agent index a in [0, A)   : position in the reference's `sim.agents` dict (insertion order);
+ *   learner index l in [0, L) : rank of a among entities that are `abmarl.sim.Agent` instances
+ *                               (observing AND acting, agent_based_simulation.py:174-186);
+ *   cell index                : r * cols + c   (np.ravel_multi_index, state.py:135).
+ */
+#ifndef BGW_H_
+#define BGW_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BGW_ABI_VERSION 1
+#define BGW_MAX_ENCODING 63   /* encodings are bit positions in 64-bit overlap / attack rows */
+#define BGW_MAX_AGENTS 4096   /* Philox slot field (bgw_philox.h)                           */
+#define BGW_MAX_CELLS 65535   /* cell index is u16, 0xFFFF = none                           */
+#define BGW_NONE 0xFFFFu
+
+/* ---- per-agent class flags (which reference mixins the entity derives from) ------------------- */
+enum {
+    BGW_AG_OBSERVING = 1 << 0,  /* GridObservingAgent   agent.py:115-132 */
+    BGW_AG_MOVING = 1 << 1,     /* MovingAgent          agent.py:135-157 */
+    BGW_AG_ATTACKING = 1 << 2,  /* AttackingAgent       agent.py:199-288 */
+    BGW_AG_HEALTH = 1 << 3,     /* HealthAgent          agent.py:160-196 */
+    BGW_AG_ORIENT = 1 << 4,     /* OrientationAgent     agent.py:342-373 */
+    BGW_AG_LEARNER = 1 << 5,    /* isinstance(x, Agent) agent_based_simulation.py:174-186 */
+    BGW_AG_BLOCKING = 1 << 6    /* GridWorldAgent.blocking  agent.py:60-68 */
+};
+
+/* ---- per-agent role inside a sim program ----------------------------------------------------- */
+enum {
+    BGW_ROLE_NONE = 0,
+    BGW_ROLE_NAVIGATOR = 1, /* MazeNavigationSim.navigator / MultiMazeNavigationAgent */
+    BGW_ROLE_TARGET = 2,    /* maze target                                           */
+    BGW_ROLE_PACMAN = 3,    /* pacman.py:11                                          */
+    BGW_ROLE_FOOD = 4,      /* pacman.py:19                                          */
+    BGW_ROLE_BADDIE = 5,    /* pacman.py:24                                          */
+    BGW_ROLE_WALL = 6
+};
+
+/* ---- sim program: the user-written step()/get_* the engine reproduces ------------------------ */
+enum {
+    BGW_PROG_TEAM_BATTLE = 0, /* abmarl/examples/sim/team_battle_example.py:23-59 */
+    BGW_PROG_MAZE = 1,        /* abmarl/examples/sim/maze_navigation.py:14-42     */
+    BGW_PROG_MULTI_MAZE = 2,  /* abmarl/examples/sim/multi_maze_navigation.py:17-74 */
+    BGW_PROG_PACMAN = 3       /* abmarl/examples/sim/pacman.py:29-151             */
+};
+
+enum { BGW_MOVE_NONE = 0, BGW_MOVE_BOX = 1 /* MoveActor actor.py:55 */, BGW_MOVE_CROSS = 2 /* :117 */,
+       BGW_MOVE_DRIFT = 3 /* :197 */ };
+enum { BGW_ATTACK_NONE = 0, BGW_ATTACK_BINARY = 1 /* BinaryAttackActor actor.py:441 */ };
+enum {
+    BGW_OBS_POSITION_CENTERED = 0, /* PositionCenteredEncodingObserver (SingleGridObserver) observer.py:153 */
+    BGW_OBS_ABSOLUTE = 1,          /* AbsoluteEncodingObserver                              observer.py:55  */
+    BGW_OBS_STACKED = 2            /* StackedPositionCenteredEncodingObserver (MultiGridObserver) :253     */
+};
+enum {
+    BGW_DONE_ACTIVE = 1 << 0,           /* ActiveDone            done.py:39-56   */
+    BGW_DONE_ONE_TEAM = 1 << 1,         /* OneTeamRemainingDone  done.py:140-153 */
+    BGW_DONE_TARGET_AGENT = 1 << 2,     /* TargetAgentDone       done.py:59-99   */
+    BGW_DONE_TARGET_DESTROYED = 1 << 3  /* TargetDestroyedDone   done.py:102-137 */
+};
+enum { BGW_MANAGER_ALL_STEP = 0 /* all_step_manager.py */, BGW_MANAGER_TURN_BASED = 1 /* turn_based_manager.py */ };
+
+/* reward constant slots (float64; values live in the user's sim, e.g. team_battle_example.py:42-59) */
+enum {
+    BGW_RW_ATTACK_FAIL = 0, /* -0.1  team_battle_example.py:42 */
+    BGW_RW_KILL = 1,        /* +1    :47 / pacman 'kill'       */
+    BGW_RW_DIE = 2,         /* -1    :46 / pacman 'die'        */
+    BGW_RW_MOVE_FAIL = 3,   /* -0.1  :55 / pacman 'bad_move'   */
+    BGW_RW_ENTROPY = 4,     /* -0.01 :59 / pacman 'entropy'    */
+    BGW_RW_TARGET = 5,      /* +1    maze_navigation.py:33 / multi_maze_navigation.py:57 */
+    BGW_RW_EAT_FOOD = 6,    /* pacman 'eat_food' pacman.py:97  */
+    BGW_RW_COUNT = 8
+};
+
+/* ---- flags stored per agent in BgwState.flags -------------------------------------------------- */
+enum {
+    BGW_ST_ACTIVE = 1 << 0,        /* PrincipleAgent.active / HealthAgent: health > 0   agent.py:192-196 */
+    BGW_ST_IN_GRID = 1 << 1,       /* entity is present in its cell's dict              grid.py:107-140  */
+    BGW_ST_DONE_REPORTED = 1 << 2, /* member of SimulationManager.done_agents           all_step_manager.py:85-87 */
+    BGW_ST_ORIENT_SHIFT = 4        /* bits 4..6: orientation 1..4 (0 = none)            agent.py:344     */
+};
+
+/* per-learner output byte `done` */
+enum { BGW_OUT_DONE = 1 << 0, BGW_OUT_VALID = 1 << 1 /* this learner got (obs,reward,done) this call */ };
+/* per-env output byte `all_done` */
+enum {
+    BGW_ENV_ALL_DONE = 1 << 0,  /* dones['__all__']                                     all_step_manager.py:90-93 */
+    BGW_ENV_RESET = 1 << 1,     /* this call reset the env instead of stepping it (auto-reset): obs rows hold
+                                   the reset observations of every learner, reward/done rows are zero   */
+    BGW_ENV_TRUNCATED = 1 << 2, /* horizon reached (RLlib `horizon`, rllib_team_battle.py:89)           */
+    BGW_ENV_ERROR = 1 << 3      /* placement failed (state.py:147-149,161) -- see BgwState.error         */
+};
+
+/*
+ * Flat description of ONE simulation, compiled from a reference-style sim object (agents dict,
+ * grid.overlapping, actor.attack_mapping, chosen state / observer / done components, reward constants).
+ * All pointers are HOST pointers, read during bgw_create only.
+ */
+typedef struct BgwSpec {
+    int32_t abi_version;   /* BGW_ABI_VERSION */
+    int32_t rows, cols;    /* Grid(rows, cols)  grid.py:20 */
+    int32_t n_agents;      /* A */
+    int32_t n_envs;        /* E: envs on THIS device */
+    int32_t env_offset;    /* global index of env 0 on this device (Philox is keyed by the GLOBAL env
+                              index, so results do not depend on how envs are sharded over GPUs) */
+    int32_t program;       /* BGW_PROG_* */
+    int32_t move_actor;    /* BGW_MOVE_* */
+    int32_t attack_actor;  /* BGW_ATTACK_* */
+    int32_t observer;      /* BGW_OBS_* */
+    int32_t observe_self;  /* PositionCenteredEncodingObserver(observe_self=...) observer.py:164 */
+    int32_t done_mask;     /* BGW_DONE_* (Smart sims: all() over the set, smart.py:106-120) */
+    int32_t manager;       /* BGW_MANAGER_* */
+    int32_t ravel_actions; /* 1: RavelActionWrapper(MoveActor) wrapper.py:180 -- action byte 0 is the
+                              ravelled move  a = (dr+m)(2m+1) + (dc+m) */
+    int32_t no_overlap_at_reset; /* PositionState(no_overlap_at_reset=) state.py:29 */
+    int32_t stacked_attacks;     /* AttackActorBaseComponent(stacked_attacks=) actor.py:245 */
+    int32_t horizon;       /* 0 = none; else all_done|TRUNCATED once the episode has this many steps */
+    int32_t auto_reset;    /* 1: an env that reported __all__ is reset by the NEXT bgw_step call */
+    uint64_t seed;         /* Philox key */
+    double reward[BGW_RW_COUNT];
+
+    /* per-agent tables, length n_agents */
+    const int8_t *encoding;       /* GridWorldAgent.encoding (1..BGW_MAX_ENCODING)  agent.py:31-37 */
+    const uint8_t *klass;         /* BGW_AG_* */
+    const uint8_t *role;          /* BGW_ROLE_* */
+    const int16_t *init_row;      /* initial_position[0], -1 = random placement  state.py:107-114 */
+    const int16_t *init_col;
+    const double *init_health;    /* NaN = np.random.uniform(0,1)                state.py:637-641 */
+    const uint8_t *init_orient;   /* 0 = np.random.randint(1,5)                  state.py:672-675 */
+    const int16_t *view_range;    /* GridObservingAgent.view_range               agent.py:122 */
+    const int16_t *move_range;    /* MovingAgent.move_range                      agent.py:147 */
+    const int16_t *attack_range;  /* AttackingAgent.attack_range                 agent.py:213 */
+    const double *attack_strength;
+    const double *attack_accuracy;
+    const uint8_t *simultaneous_attacks;
+    const int16_t *target;        /* TargetAgentDone / TargetDestroyedDone mapping: agent -> target agent, -1 none */
+
+    /* per-encoding bit rows, length BGW_MAX_ENCODING+1; row e bit f set <=> f in map[e] */
+    const uint64_t *overlap;      /* Grid.overlapping, already symmetrised        grid.py:53-71 */
+    const uint64_t *attack_map;   /* AttackActorBaseComponent.attack_mapping      actor.py:272-288 */
+} BgwSpec;
+
+/*
+ * Mutable simulation state: structure-of-arrays in HBM, caller-owned (device pointers).
+ * [E][A] arrays are env-major so one CTA loads one env with coalesced accesses.
+ */
+typedef struct BgwState {
+    uint16_t *cell;      /* [E][A] r*cols+c; stays stale after death (actor.py:356-358)                */
+    uint16_t *next;      /* [E][A] next entity in the same cell's dict (arrival order, grid.py:125);
+                            BGW_NONE = tail.  Meaningful only while BGW_ST_IN_GRID.                     */
+    uint8_t *flags;      /* [E][A] BGW_ST_*                                                              */
+    double *health;      /* [E][A] float64 like the reference (agent.py:192-196)                        */
+    double *reward_acc;  /* [E][A] SmartGridWorldSimulation.rewards between reads (smart.py:91,101-104) */
+    uint32_t *episode;   /* [E]  number of resets - 1 (Philox key); initialise to 0xFFFFFFFF             */
+    uint32_t *step;      /* [E]  steps since the last reset (Philox key)                                */
+    uint8_t *env_flags;  /* [E]  BGW_ENV_* of the last call                                             */
+    int16_t *turn;       /* [E]  TurnBasedManager cursor: learner whose action is expected next         */
+    uint32_t *error;     /* [E]  0 ok; 1 fixed-position placement failed; 2 no cell available            */
+    uint16_t *layout;    /* [E][A] optional (NULL = unused): externally generated start cells that replace
+                            PositionState's placement at reset (BGW_NONE = leave the entity unplaced); used
+                            for MazePlacementState layouts generated host-side (state.py:385-619)          */
+    uint64_t *stats;     /* [BGW_STAT_COUNT] device-wide counters, see below                            */
+} BgwState;
+
+enum {
+    BGW_STAT_AGENT_STEPS = 0, /* learners that received (obs,reward,done) */
+    BGW_STAT_EPISODES = 1,    /* envs that reported __all__               */
+    BGW_STAT_KILLS = 2,       /* entities whose health reached 0 by attack */
+    BGW_STAT_ENV_STEPS = 3,
+    BGW_STAT_COUNT = 8
+};
+
+/* Derived sizes the caller needs to allocate buffers. */
+typedef struct BgwDims {
+    int32_t n_envs, n_agents, n_learners;
+    int32_t obs_h, obs_w, obs_c; /* logical observation shape per learner (obs_c = 1 unless STACKED) */
+    int32_t obs_stride;          /* bytes per learner in the int8 obs buffer = roundup(h*w*c, 16)     */
+    int32_t action_stride;       /* bytes per learner in the action buffer (4)                        */
+    int32_t threads_per_env, envs_per_cta, smem_bytes; /* launch geometry (informational)             */
+} BgwDims;
+
+typedef struct BgwEngine *bgw_handle;
+
+/* Compile the spec onto `device`; builds the line-of-sight LUT (utils.py:45-115 in IEEE float64). */
+int bgw_create(const BgwSpec *spec, int device, bgw_handle *out);
+int bgw_destroy(bgw_handle h);
+int bgw_dims(bgw_handle h, BgwDims *out);
+/* Attach the caller-owned state arrays (must stay alive while the handle is used). */
+int bgw_bind_state(bgw_handle h, const BgwState *state);
+
+/*
+ * AllStepManager.reset / TurnBasedManager.reset for the envs selected by env_mask ([E] u8 on device,
+ * NULL = all): PositionState.reset, HealthState.reset, OrientationState.reset (state.py:88-166,629-641,
+ * 666-675), rewards = 0 (smart.py:91), done_agents = non-learners (all_step_manager.py:41-44), then the
+ * first observations into obs[E][L][obs_stride] (rows of unselected envs are untouched).
+ */
+int bgw_reset(bgw_handle h, const uint8_t *env_mask, int8_t *obs, void *stream);
+
+/*
+ * One manager step for every env (all_step_manager.py:51-95 / turn_based_manager.py:34-94):
+ *   actions  [E][L][4] i8   byte0,1 = move (dr,dc | cross 0..4 | ravelled), byte2 = attack count, byte3 pad;
+ *                           rows of learners already reported done are ignored (the reference asserts
+ *                           they are absent, all_step_manager.py:59-61)
+ *   order    [E][L] i16     optional processing order of learners (randomize_action_input,
+ *                           all_step_manager.py:62-65); NULL = dict order
+ *   obs      [E][L][obs_stride] i8, reward [E][L] f32, done [E][L] u8 (BGW_OUT_*), all_done [E] u8 (BGW_ENV_*)
+ * Rows whose BGW_OUT_VALID bit is clear (and BGW_ENV_RESET is clear) are not written.
+ */
+int bgw_step(bgw_handle h, const int8_t *actions, const int16_t *order, int8_t *obs, float *reward,
+             uint8_t *done, uint8_t *all_done, void *stream);
+
+/* Synthetic random policy (policies/policy.py:81-92 `action_space.sample()`), keyed Philox site ACTION:
+ * fills actions[E][L][4] for the CURRENT step of every env.  Used by bench.py and the parity tests. */
+int bgw_sample_actions(bgw_handle h, int8_t *actions, void *stream);
+
+/* Host-callable Philox draw, identical to the device stream (used by the replay shim). */
+int bgw_rng_draw(uint64_t seed, uint32_t env, uint32_t episode, uint32_t step, uint32_t site,
+                 uint32_t slot, uint32_t k, uint32_t out[4]);
+
+/* Line-of-sight mask of utils.py:45-115 for one blocker offset: writes (2*range+1)^2 bytes (1 = visible). */
+int bgw_los_mask(int range, int r_diff, int c_diff, uint8_t *out);
+
+/* Number of kernels this handle has launched since creation (bench.py `gpu_launches`). */
+uint64_t bgw_launch_count(bgw_handle h);
+
+const char *bgw_last_error(void);
+int bgw_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BGW_H_ */

@@ -1,0 +1,195 @@
+"""Simulation definitions used by the parity tests and the golden generator.
+
+Every `build_*` function takes an `api` namespace and builds the sim from it.  `api` is either this
+package (`mirror_api()`) or the unmodified reference (`reference_api()`, build container only), so the
+SAME definition code produces the reference object the goldens were recorded from and the mirror object
+the tests compile -- the compiled specs must be identical (checked in tests/test_golden_oracle.py).
+"""
+import os
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LAYOUTS = os.path.join(HERE, 'golden', 'layouts')
+
+
+def mirror_api():
+    from abmarl_b200 import examples as ex, managers
+    from abmarl_b200.sim.gridworld import agent, actor, observer, state, done, wrapper
+    return types.SimpleNamespace(
+        name='mirror', ex=ex, agent=agent, actor=actor, observer=observer, state=state, done=done,
+        wrapper=wrapper, managers=managers, pacman=ex)
+
+
+def reference_api():
+    from oracle.refshim import load_reference
+    load_reference()
+    import abmarl.examples as ex
+    import abmarl.managers as managers
+    from abmarl.examples.sim import pacman
+    from abmarl.sim.gridworld import agent, actor, observer, state, done, wrapper
+    return types.SimpleNamespace(
+        name='reference', ex=ex, agent=agent, actor=actor, observer=observer, state=state, done=done,
+        wrapper=wrapper, managers=managers, pacman=pacman)
+
+
+# ---------------------------------------------------------------------------------------------------
+# team battle family (team_battle_example.py; examples/rllib_team_battle.py:9-43)
+# ---------------------------------------------------------------------------------------------------
+def _team_maps(n_teams):
+    overlap = {k: {k} for k in range(1, n_teams + 1)}
+    attack = {k: {j for j in range(1, n_teams + 1) if j != k} for k in range(1, n_teams + 1)}
+    return overlap, attack
+
+
+def build_tb_c2(api):
+    """BASELINE config 2: 4 teams on 8x8, 24 agents spawning on four corner cells, random health."""
+    positions = [np.array([1, 1]), np.array([1, 6]), np.array([6, 1]), np.array([6, 6])]
+    agents = {
+        f'agent{i}': api.ex.BattleAgent(id=f'agent{i}', encoding=i % 4 + 1, initial_position=positions[i % 4])
+        for i in range(24)
+    }
+    overlap, attack = _team_maps(4)
+    return api.ex.TeamBattleSim.build_sim(
+        8, 8, agents=agents, overlapping=overlap, attack_mapping=attack,
+        states={'PositionState', 'HealthState'}, observers={'PositionCenteredEncodingObserver'},
+        dones={'OneTeamRemainingDone'})
+
+
+def build_tb_c5(api, rows=64, cols=64, n_agents=256, view_range=5, initial_health=None):
+    """BASELINE config 5: synthetic team battle, random placement and health."""
+    agents = {}
+    for i in range(n_agents):
+        ag = api.ex.BattleAgent(id=f'agent{i}', encoding=i % 4 + 1, initial_health=initial_health)
+        ag.view_range = view_range
+        agents[ag.id] = ag
+    overlap, attack = _team_maps(4)
+    return api.ex.TeamBattleSim.build_sim(
+        rows, cols, agents=agents, overlapping=overlap, attack_mapping=attack,
+        states={'PositionState', 'HealthState'}, observers={'PositionCenteredEncodingObserver'},
+        dones={'OneTeamRemainingDone'})
+
+
+def build_tb_c5_small(api):
+    return build_tb_c5(api, rows=24, cols=24, n_agents=96, view_range=5)
+
+
+def build_tb_dense(api):
+    """Crowded 6x7 board, 3 teams, teams 1 and 2 may share cells (mixed-encoding cells => observer draws),
+    imperfect accuracy, strength < 1 (several hits to kill), heterogeneous ranges."""
+    agents = {}
+    for i in range(20):
+        ag = api.ex.BattleAgent(id=f'a{i}', encoding=i % 3 + 1, initial_health=1.0 if i % 2 else None)
+        ag.view_range = 2 + i % 3
+        ag.attack_range = 1 + i % 2
+        ag.move_range = 1 + (i % 5 == 0)
+        ag.attack_strength = 0.6 if i % 4 else 1
+        ag.attack_accuracy = 0.75 if i % 3 else 1
+        agents[ag.id] = ag
+    return api.ex.TeamBattleSim.build_sim(
+        6, 7, agents=agents, overlapping={1: {1, 2}, 2: {2}, 3: {3}},
+        attack_mapping={1: {2, 3}, 2: {1, 3}, 3: {1, 2}},
+        states={'PositionState', 'HealthState'}, observers={'PositionCenteredEncodingObserver'},
+        dones={'OneTeamRemainingDone'})
+
+
+def build_tb_blocking(api):
+    """Team battle among view- and attack-blocking pillars (encoding 5, never attackable), plus two
+    blocking fighters: exercises create_grid_and_mask in both the attack and the observation path."""
+    agents = {}
+    pillars = [(2, 2), (2, 7), (4, 4), (4, 5), (5, 4), (7, 2), (7, 7), (0, 5), (9, 4), (5, 9)]
+    for n, (r, c) in enumerate(pillars):
+        agents[f'pillar{n}'] = api.agent.GridWorldAgent(
+            id=f'pillar{n}', encoding=5, blocking=True, initial_position=np.array([r, c]))
+    for i in range(18):
+        ag = api.ex.BattleAgent(id=f'f{i}', encoding=i % 4 + 1, initial_health=1.0, blocking=(i in (3, 8)))
+        ag.view_range = 4
+        ag.attack_range = 2
+        agents[ag.id] = ag
+    overlap, attack = _team_maps(4)
+    return api.ex.TeamBattleSim.build_sim(
+        10, 10, agents=agents, overlapping=overlap, attack_mapping=attack,
+        states={'PositionState', 'HealthState'}, observers={'PositionCenteredEncodingObserver'},
+        dones={'OneTeamRemainingDone'})
+
+
+def build_tb_stacked(api):
+    """Stacked (per-encoding count) observer + observe-everything overlap."""
+    agents = {}
+    for i in range(14):
+        ag = api.ex.BattleAgent(id=f'a{i}', encoding=i % 3 + 1, initial_health=1.0)
+        ag.view_range = 2
+        agents[ag.id] = ag
+    return api.ex.TeamBattleSim.build_sim(
+        5, 6, agents=agents, overlapping={1: {1, 2, 3}, 2: {2, 3}, 3: {3}},
+        attack_mapping={1: {2}, 2: {3}, 3: {1}},
+        states={'PositionState', 'HealthState'}, observers={'StackedPositionCenteredEncodingObserver'},
+        dones={'OneTeamRemainingDone'})
+
+
+def build_tb_noself(api):
+    """observe_self=False (observer.py:238-246) with overlapping teams."""
+    agents = {}
+    for i in range(12):
+        ag = api.ex.BattleAgent(id=f'a{i}', encoding=i % 2 + 1, initial_health=1.0)
+        ag.view_range = 2
+        agents[ag.id] = ag
+    return api.ex.TeamBattleSim.build_sim(
+        5, 5, agents=agents, overlapping={1: {1, 2}, 2: {2}}, attack_mapping={1: {2}, 2: {1}},
+        observe_self=False,
+        states={'PositionState', 'HealthState'}, observers={'PositionCenteredEncodingObserver'},
+        dones={'OneTeamRemainingDone'})
+
+
+# ---------------------------------------------------------------------------------------------------
+# maze (maze_navigation.py; examples/rllib_maze_navigation.py:7-38)
+# ---------------------------------------------------------------------------------------------------
+def build_maze_c1(api):
+    """BASELINE config 1: maze.txt, one navigator (view 2), 65 view-blocking walls, one target."""
+    registry = {
+        'N': lambda n: api.ex.MazeNavigationAgent(id='navigator', encoding=1, view_range=2),
+        'T': lambda n: api.agent.GridWorldAgent(id='target', encoding=3),
+        'W': lambda n: api.agent.GridWorldAgent(id=f'wall{n}', encoding=2, blocking=True),
+    }
+    return api.ex.MazeNavigationSim.build_sim_from_file(
+        os.path.join(LAYOUTS, 'maze.txt'), registry, overlapping={1: {3}, 3: {1}},
+        states={'PositionState'}, observers={'PositionCenteredEncodingObserver'})
+
+
+# ---------------------------------------------------------------------------------------------------
+# pacman (pacman.py:29-151; examples/rllib_pacman.py with blocking walls)
+# ---------------------------------------------------------------------------------------------------
+def build_pacman_c3(api, view_range=20):
+    """BASELINE config 3: pacman.txt, multi-agent PacmanSim, view-blocking walls, absolute observer.
+    view_range 20 covers the 21x21 board exactly like the class default of 100."""
+    px = api.pacman
+
+    def ranged(agent):
+        agent.view_range = view_range
+        return agent
+
+    registry = {
+        'P': lambda n: ranged(px.PacmanAgent(id='pacman', encoding=1)),
+        'W': lambda n: px.WallAgent(id=f'wall_{n}', encoding=2, blocking=True),
+        'F': lambda n: px.FoodAgent(id=f'food_{n}', encoding=3),
+        'B': lambda n: ranged(px.BaddieAgent(id=f'baddie_{n}', encoding=4)),
+    }
+    return px.PacmanSim.build_sim_from_file(
+        os.path.join(LAYOUTS, 'pacman.txt'), registry,
+        states={'PositionState', 'OrientationState', 'HealthState'}, observers={'AbsoluteEncodingObserver'},
+        overlapping={1: {3, 4}, 4: {3, 4}},
+        reward_scheme={'bad_move': 0, 'entropy': -0.01, 'eat_food': 0.05, 'kill': 1, 'die': -1})
+
+
+SCENARIOS = {
+    # name: (builder, manager, steps recorded in the golden file)
+    'tb_c2': (build_tb_c2, 'all_step', 40),
+    'tb_c5_small': (build_tb_c5_small, 'all_step', 25),
+    'tb_dense': (build_tb_dense, 'all_step', 40),
+    'tb_blocking': (build_tb_blocking, 'all_step', 30),
+    'tb_stacked': (build_tb_stacked, 'all_step', 25),
+    'tb_noself': (build_tb_noself, 'all_step', 25),
+    'maze_c1': (build_maze_c1, 'all_step', 60),
+    'pacman_c3': (build_pacman_c3, 'all_step', 12),
+}
