@@ -11,7 +11,7 @@ BGW_MAX_ENCODING = 63
 BGW_MAX_AGENTS = 4096
 BGW_NONE = 0xFFFF
 BGW_RW_COUNT = 8
-BGW_STAT_COUNT = 8
+BGW_STAT_COUNT = 4
 
 # enums (include/bgw.h)
 AG_OBSERVING, AG_MOVING, AG_ATTACKING, AG_HEALTH, AG_ORIENT, AG_LEARNER, AG_BLOCKING = (1 << i for i in range(7))

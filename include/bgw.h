@@ -186,7 +186,8 @@ typedef struct BgwState {
     uint16_t *layout;    /* [E][A] optional (NULL = unused): externally generated start cells that replace
                             PositionState's placement at reset (BGW_NONE = leave the entity unplaced); used
                             for MazePlacementState layouts generated host-side (state.py:385-619)          */
-    uint64_t *stats;     /* [BGW_STAT_COUNT] device-wide counters, see below                            */
+    uint64_t *stats;     /* [E][BGW_STAT_COUNT] per-env running counters, see below (sum over E on demand;
+                            per-env rows avoid same-address atomics in the step kernel)                 */
 } BgwState;
 
 enum {
@@ -194,7 +195,7 @@ enum {
     BGW_STAT_EPISODES = 1,    /* envs that reported __all__               */
     BGW_STAT_KILLS = 2,       /* entities whose health reached 0 by attack */
     BGW_STAT_ENV_STEPS = 3,
-    BGW_STAT_COUNT = 8
+    BGW_STAT_COUNT = 4
 };
 
 /* Derived sizes the caller needs to allocate buffers. */

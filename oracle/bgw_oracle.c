@@ -417,7 +417,7 @@ static int process_attack(Ctx *c, int a, int attack, int *victims, int *nv, int 
         const int v = victims[t];
         if (!(c->flags[v] & BGW_ST_ACTIVE)) continue;
         set_health(c, v, c->health[v] - sp->attack_strength[a]);
-        if (!(c->flags[v] & BGW_ST_ACTIVE)) { grid_remove(c, v); c->st->stats[BGW_STAT_KILLS]++; }
+        if (!(c->flags[v] & BGW_ST_ACTIVE)) { grid_remove(c, v); c->st->stats[(size_t)c->env * BGW_STAT_COUNT + BGW_STAT_KILLS]++; }
     }
     return 1;
 }
@@ -743,7 +743,7 @@ static void emit(Ctx *c, int l, int8_t *obs_env, int stride, float *rew, double 
     if (rew) rew[l] = (float)r;
     if (rew64) rew64[l] = r;
     done[l] = (uint8_t)(BGW_OUT_VALID | (d ? BGW_OUT_DONE : 0));
-    c->st->stats[BGW_STAT_AGENT_STEPS]++;
+    c->st->stats[(size_t)c->env * BGW_STAT_COUNT + BGW_STAT_AGENT_STEPS]++;
 }
 
 int bgwo_step(const BgwSpec *sp, BgwState *st, const int8_t *actions, const int16_t *order, int8_t *obs,
@@ -772,7 +772,7 @@ int bgwo_step(const BgwSpec *sp, BgwState *st, const int8_t *actions, const int1
         }
         grid_build(&c);
         st->step[e] += 1;
-        st->stats[BGW_STAT_ENV_STEPS]++;
+        st->stats[(size_t)e * BGW_STAT_COUNT + BGW_STAT_ENV_STEPS]++;
         int env_done = 0;
 
         if (sp->manager == BGW_MANAGER_ALL_STEP) {              /* all_step_manager.py:51-95 */
@@ -826,7 +826,7 @@ int bgwo_step(const BgwSpec *sp, BgwState *st, const int8_t *actions, const int1
         uint8_t ef = 0;
         if (env_done) ef |= BGW_ENV_ALL_DONE;
         if (sp->horizon > 0 && (int)st->step[e] >= sp->horizon) ef |= BGW_ENV_ALL_DONE | BGW_ENV_TRUNCATED;
-        if (ef & BGW_ENV_ALL_DONE) st->stats[BGW_STAT_EPISODES]++;
+        if (ef & BGW_ENV_ALL_DONE) st->stats[(size_t)e * BGW_STAT_COUNT + BGW_STAT_EPISODES]++;
         st->env_flags[e] = ef;
         all_done[e] = ef;
     }

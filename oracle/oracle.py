@@ -46,7 +46,7 @@ def alloc_state(E, A):
     st['next'][:] = K.BGW_NONE
     st['episode'][:] = 0xFFFFFFFF
     st['turn'][:] = -1
-    st['stats'] = np.zeros(K.BGW_STAT_COUNT, dtype=np.uint64)
+    st['stats'] = np.zeros((E, K.BGW_STAT_COUNT), dtype=np.uint64)
     st['layout'] = None
     return st
 
