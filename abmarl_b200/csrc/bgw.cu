@@ -1,0 +1,375 @@
+/*
+ * bgw.cu -- host side of libbgw.so: the C-ABI declared in include/bgw.h.
+ *
+ * Plain C entry points over raw device pointers; kernels (bgw_dev.cuh) are enqueued on the caller's stream.
+ * The library owns the opaque handle and the compiled spec tables only; there is no CPU fallback and no
+ * dependency on the test oracle.
+ */
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "bgw_dev.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_OK(call)                                                                                  \
+    do {                                                                                               \
+        cudaError_t err__ = (call);                                                                    \
+        if (err__ != cudaSuccess) return fail(2, "%s failed: %s", #call, cudaGetErrorString(err__));   \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+int align16(int x) { return (x + 15) & ~15; }
+int pow2ceil(int x) { int p = 1; while (p < x) p <<= 1; return p; }
+
+}  // namespace
+
+struct BgwEngine {
+    int device = 0;
+    DevSpec ds{};
+    BgwDims dims{};
+    BgwState st{};
+    bool bound = false;
+    int threads = 0;
+    uint64_t launches = 0;
+    std::vector<void *> allocs;
+};
+
+namespace {
+
+template <typename T>
+int upload(BgwEngine *h, const T *src, size_t n, const T **dst)
+{
+    void *p = nullptr;
+    CUDA_OK(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+    h->allocs.push_back(p);
+    if (n) CUDA_OK(cudaMemcpy(p, src, n * sizeof(T), cudaMemcpyHostToDevice));
+    *dst = (const T *)p;
+    return 0;
+}
+
+/* host restatement of the LOS rays for bgw_los_mask (utils.py:45-115); same arithmetic as los_apply_dev:
+ * (a/b)*t in IEEE float64 (this file is compiled with -ffp-contract=off), strict comparisons. */
+void los_apply_host(uint8_t *mask, int R, int rd, int cd)
+{
+    const int n = 2 * R + 1;
+    if (rd == 0 && cd == 0) return;
+    if (cd != 0) {
+        double du, dl;
+        if (rd == 0) { du = dl = (cd > 0) ? (double)cd - 0.5 : (double)cd + 0.5; }
+        else if ((rd > 0) == (cd > 0)) { du = (double)cd - 0.5; dl = (double)cd + 0.5; }
+        else { du = (double)cd + 0.5; dl = (double)cd - 0.5; }
+        volatile double ku = ((double)rd + 0.5) / du, kl = ((double)rd - 0.5) / dl;
+        const int c0 = cd > 0 ? cd : -R, c1 = cd > 0 ? R : cd;
+        const int r0 = rd > 0 ? rd : -R, r1 = rd < 0 ? rd : R;
+        for (int c = c0; c <= c1; ++c) {
+            volatile double up = ku * (double)c, lo = kl * (double)c;
+            for (int r = r0; r <= r1; ++r) {
+                if (c == cd && r == rd) continue;
+                if (lo < (double)r && (double)r < up) mask[(r + R) * n + (c + R)] = 0;
+            }
+        }
+    } else {
+        const double d = rd > 0 ? (double)rd - 0.5 : (double)rd + 0.5;
+        volatile double kl = ((double)cd - 0.5) / d, kr = ((double)cd + 0.5) / d;
+        const int r0 = rd > 0 ? rd : -R, r1 = rd > 0 ? R : rd;
+        for (int r = r0; r <= r1; ++r) {
+            volatile double le = kl * (double)r, ri = kr * (double)r;
+            for (int c = -R; c <= R; ++c) {
+                if (c == cd && r == rd) continue;
+                if (le < (double)c && (double)c < ri) mask[(r + R) * n + (c + R)] = 0;
+            }
+        }
+    }
+}
+
+int first_role(const BgwSpec *sp, int role)
+{
+    for (int a = 0; a < sp->n_agents; ++a) if (sp->role[a] == role) return a;
+    return -1;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *bgw_last_error(void) { return g_err; }
+int bgw_abi_version(void) { return BGW_ABI_VERSION; }
+
+int bgw_create(const BgwSpec *sp, int device, bgw_handle *out)
+{
+    if (!sp || !out) return fail(1, "bgw_create: null argument");
+    *out = nullptr;
+    if (sp->abi_version != BGW_ABI_VERSION) return fail(1, "bgw_create: ABI version %d, library has %d", sp->abi_version, BGW_ABI_VERSION);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(2, "bgw_create: no CUDA device (this engine has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(1, "bgw_create: device %d out of range (%d devices)", device, ndev);
+    const int A = sp->n_agents, H = sp->rows, W = sp->cols, HW = H * W;
+    if (A < 1 || A > BGW_MAX_AGENTS) return fail(1, "bgw_create: n_agents %d not in 1..%d", A, BGW_MAX_AGENTS);
+    if (H < 1 || W < 1 || HW > BGW_MAX_CELLS) return fail(1, "bgw_create: grid %dx%d not supported (at most %d cells)", H, W, BGW_MAX_CELLS);
+    if (sp->n_envs < 1) return fail(1, "bgw_create: n_envs must be positive");
+
+    BgwEngine *h = new BgwEngine();
+    h->device = device;
+    DeviceGuard guard(device);
+    DevSpec &d = h->ds;
+    auto bail = [&](int rc) { bgw_destroy(h); return rc; };
+
+    d.H = H; d.W = W; d.HW = HW; d.A = A; d.E = sp->n_envs; d.env_offset = sp->env_offset;
+    d.program = sp->program; d.move_actor = sp->move_actor; d.attack_actor = sp->attack_actor;
+    d.observer = sp->observer; d.observe_self = sp->observe_self; d.done_mask = sp->done_mask;
+    d.manager = sp->manager; d.ravel = sp->ravel_actions; d.no_overlap = sp->no_overlap_at_reset;
+    d.stacked = sp->stacked_attacks; d.horizon = sp->horizon; d.auto_reset = sp->auto_reset;
+    d.seed = sp->seed;
+    memcpy(d.reward, sp->reward, sizeof(d.reward));
+
+    /* ---- per-entity tables ------------------------------------------------------------------ */
+    std::vector<int16_t> learner_of(A, -1), agent_of;
+    std::vector<uint16_t> blk, var, init_cell(A, BGW_NONE);
+    int max_enc = 0, rmax_obs = 0, rmax_att = 0;
+    for (int a = 0; a < A; ++a) {
+        const int e = sp->encoding[a];
+        if (e < 1 || e > BGW_MAX_ENCODING) return bail(fail(1, "bgw_create: entity %d has encoding %d, must be 1..%d", a, e, BGW_MAX_ENCODING));
+        max_enc = std::max(max_enc, e);
+        if (sp->klass[a] & BGW_AG_LEARNER) { learner_of[a] = (int16_t)agent_of.size(); agent_of.push_back((int16_t)a); }
+        if (sp->klass[a] & BGW_AG_BLOCKING) blk.push_back((uint16_t)a);
+        if (sp->init_row[a] < 0) var.push_back((uint16_t)a);
+        else {
+            if (sp->init_row[a] >= H || sp->init_col[a] < 0 || sp->init_col[a] >= W)
+                return bail(fail(1, "bgw_create: entity %d initial position off the grid", a));
+            init_cell[a] = (uint16_t)(sp->init_row[a] * W + sp->init_col[a]);
+        }
+        if ((sp->klass[a] & BGW_AG_LEARNER) && (sp->klass[a] & BGW_AG_OBSERVING)) {
+            int R = sp->view_range[a];
+            if (R < 0) return bail(fail(1, "bgw_create: negative view range"));
+            rmax_obs = std::max(rmax_obs, R);
+        }
+        if (sp->klass[a] & BGW_AG_ATTACKING) {
+            rmax_att = std::max(rmax_att, (int)sp->attack_range[a]);
+            if (sp->program == BGW_PROG_TEAM_BATTLE && sp->simultaneous_attacks[a] > 1)
+                return bail(fail(1, "bgw_create: TeamBattleSim.step is only defined for simultaneous_attacks == 1 (team_battle_example.py:41)"));
+        }
+    }
+    const int L = (int)agent_of.size();
+    if (L < 1) return bail(fail(1, "bgw_create: the simulation has no learning agent"));
+    d.L = L; d.max_enc = max_enc; d.n_blk = (int)blk.size(); d.n_var = (int)var.size();
+    if (sp->attack_actor != BGW_ATTACK_NONE && d.n_blk > 0 && (2 * rmax_att + 1) * (2 * rmax_att + 1) > 32 * BGW_ATT_MASK_WORDS)
+        return bail(fail(1, "bgw_create: attack_range %d with view-blocking entities exceeds the attacker's LOS mask (range <= 7)", rmax_att));
+    if (sp->observer == BGW_OBS_STACKED && A > 127) return bail(fail(1, "bgw_create: stacked observer counts are int8 (at most 127 entities)"));
+    if (sp->ravel_actions && sp->move_actor != BGW_MOVE_BOX) return bail(fail(1, "bgw_create: ravel_actions needs MoveActor"));
+
+    d.a_nav = first_role(sp, BGW_ROLE_NAVIGATOR); d.a_target = first_role(sp, BGW_ROLE_TARGET);
+    d.a_pacman = first_role(sp, BGW_ROLE_PACMAN); d.has_food = first_role(sp, BGW_ROLE_FOOD) >= 0;
+    if (sp->program == BGW_PROG_MAZE && (d.a_nav < 0 || d.a_target < 0 || learner_of[d.a_nav] < 0))
+        return bail(fail(1, "bgw_create: MazeNavigationSim needs a learning navigator and a target"));
+    if (sp->program == BGW_PROG_MULTI_MAZE && d.a_target < 0) return bail(fail(1, "bgw_create: MultiMazeNavigationSim needs a target"));
+    if (sp->program == BGW_PROG_PACMAN && (d.a_pacman < 0 || learner_of[d.a_pacman] < 0 || H <= 9 || W <= 20))
+        return bail(fail(1, "bgw_create: PacmanSim needs a learning pacman and the (9,0)<->(9,20) tunnel (pacman.py:87-92)"));
+    if (sp->program < BGW_PROG_TEAM_BATTLE || sp->program > BGW_PROG_PACMAN) return bail(fail(1, "bgw_create: unknown program %d", sp->program));
+
+    /* ---- observation geometry (same rule as the oracle's bgwo_dims) ------------------------------ */
+    BgwDims &dm = h->dims;
+    dm.n_envs = d.E; dm.n_agents = A; dm.n_learners = L;
+    dm.obs_c = 1;
+    if (sp->observer == BGW_OBS_ABSOLUTE) { dm.obs_h = H; dm.obs_w = W; }          /* observer.py:74 */
+    else dm.obs_h = dm.obs_w = 2 * rmax_obs + 1;                                    /* observer.py:170,266 */
+    if (sp->observer == BGW_OBS_STACKED) dm.obs_c = max_enc;                        /* observer.py:264 */
+    const long long ncell = (long long)dm.obs_h * dm.obs_w * dm.obs_c;
+    if (ncell > (1 << 24)) return bail(fail(1, "bgw_create: observation of %lld cells is too large", ncell));
+    dm.obs_stride = (int)((ncell + 15) / 16 * 16);
+    dm.action_stride = 4;
+    d.obs_h = dm.obs_h; d.obs_w = dm.obs_w; d.obs_c = dm.obs_c; d.obs_stride = dm.obs_stride; d.nchunks = dm.obs_stride / 16;
+
+    /* ---- reset template: place the fixed-position entities once (state.py:107-109,143-150) ------- */
+    d.hw_words = (HW + 31) / 32;
+    {
+        std::vector<uint16_t> cell(A, BGW_NONE), next(A, BGW_NONE), head(HW, BGW_NONE), tail(HW, BGW_NONE);
+        std::vector<uint8_t> flags(A, 0);
+        std::vector<uint32_t> avail((size_t)(max_enc + 1) * d.hw_words, 0);
+        for (int e = 0; e <= max_enc; ++e)
+            for (int i = 0; i < HW; ++i) avail[(size_t)e * d.hw_words + (i >> 5)] |= 1u << (i & 31);
+        int err = 0;
+        for (int a = 0; a < A; ++a) {
+            if (init_cell[a] == BGW_NONE) continue;
+            const int c = init_cell[a];
+            const uint64_t row = sp->overlap[sp->encoding[a]];
+            for (uint16_t o = head[c]; o != BGW_NONE; o = next[o])
+                if (!((row >> sp->encoding[o]) & 1)) { err = 1; break; }          /* assert at state.py:147-149 */
+            if (tail[c] != BGW_NONE) next[tail[c]] = (uint16_t)a; else head[c] = (uint16_t)a;
+            tail[c] = (uint16_t)a; cell[a] = (uint16_t)c; flags[a] = BGW_ST_IN_GRID;
+            for (int e = 1; e <= max_enc; ++e)                                       /* state.py:126-141 */
+                if (sp->no_overlap_at_reset || !((row >> e) & 1)) avail[(size_t)e * d.hw_words + (c >> 5)] &= ~(1u << (c & 31));
+        }
+        d.tpl_error = err;
+        int rc;
+        if ((rc = upload(h, cell.data(), A, &d.tpl_cell)) || (rc = upload(h, next.data(), A, &d.tpl_next)) ||
+            (rc = upload(h, flags.data(), A, &d.tpl_flags)) || (rc = upload(h, avail.data(), avail.size(), &d.tpl_avail)))
+            return bail(rc);
+    }
+    {
+        int rc;
+        std::vector<unsigned long long> ov(BGW_MAX_ENCODING + 1), am(BGW_MAX_ENCODING + 1);
+        for (int i = 0; i <= BGW_MAX_ENCODING; ++i) { ov[i] = sp->overlap[i]; am[i] = sp->attack_map[i]; }
+        if ((rc = upload(h, sp->encoding, A, &d.enc)) || (rc = upload(h, sp->klass, A, &d.klass)) ||
+            (rc = upload(h, sp->role, A, &d.role)) || (rc = upload(h, sp->init_orient, A, &d.init_orient)) ||
+            (rc = upload(h, sp->simultaneous_attacks, A, &d.simatt)) || (rc = upload(h, sp->view_range, A, &d.view_r)) ||
+            (rc = upload(h, sp->move_range, A, &d.move_r)) || (rc = upload(h, sp->attack_range, A, &d.attack_r)) ||
+            (rc = upload(h, sp->target, A, &d.target)) || (rc = upload(h, learner_of.data(), A, &d.learner_of)) ||
+            (rc = upload(h, agent_of.data(), L, &d.agent_of)) || (rc = upload(h, sp->init_health, A, &d.init_health)) ||
+            (rc = upload(h, sp->attack_strength, A, &d.strength)) || (rc = upload(h, sp->attack_accuracy, A, &d.accuracy)) ||
+            (rc = upload(h, ov.data(), ov.size(), &d.overlap)) || (rc = upload(h, am.data(), am.size(), &d.attack_map)) ||
+            (rc = upload(h, blk.data(), blk.size(), &d.blk_agents)) || (rc = upload(h, var.data(), var.size(), &d.var_agents)))
+            return bail(rc);
+    }
+
+    /* ---- launch geometry and the shared-memory carve-up ------------------------------------------ */
+    int T = A <= 32 ? 32 : A <= 64 ? 64 : A <= 128 ? 128 : 256;
+    if (const char *t = getenv("BGW_THREADS")) { const int v = atoi(t); if (v >= 32 && v <= 1024 && v % 32 == 0) T = v; }
+    h->threads = T;
+    d.parallel_actors = (sp->program == BGW_PROG_TEAM_BATTLE && (sp->move_actor == BGW_MOVE_BOX || sp->move_actor == BGW_MOVE_CROSS));
+    if (const char *t = getenv("BGW_SERIAL_ACTORS")) if (atoi(t)) d.parallel_actors = 0;
+    int slots = std::min(std::max(pow2ceil(HW), 32), 2048);
+    if (const char *t = getenv("BGW_SLOTS")) { const int v = atoi(t); if (v >= 32 && v <= 65536 && (v & (v - 1)) == 0) slots = v; }
+    d.slot_mask = slots - 1;
+    {
+        int reff = rmax_obs;
+        if (sp->observer == BGW_OBS_ABSOLUTE) reff = std::min(reff, std::max(H, W) - 1);
+        const long long nbits = (long long)(2 * reff + 1) * (2 * reff + 1);
+        d.mask_words = d.n_blk ? (int)((nbits + 31) / 32) : 0;
+        d.mask_batch = 0;
+        if (d.n_blk) {
+            if ((long long)d.mask_words * 4 > 96 * 1024) return bail(fail(1, "bgw_create: view range %d with view-blocking entities needs a %lld-bit LOS mask, too large for shared memory", reff, nbits));
+            d.mask_batch = std::max(1, std::min(L, 32 * 1024 / (d.mask_words * 4)));
+        }
+    }
+    int off = 0;
+    auto take = [&](int bytes) { const int o = off; off += align16(bytes); return o; };
+    d.o_head = take(HW * 2 + 2);
+    d.o_slot = take(slots * 4);
+    d.o_cell = take(A * 2); d.o_next = take(A * 2);
+    d.o_flags = take(A); d.o_enc = take(A); d.o_klass = take(A); d.o_tmp = take(A);
+    d.o_racc = take(A * 8);
+    d.o_act = take(L * 4);
+    d.o_ragent = take(L * 2); d.o_plist = take(L * 2); d.o_pstate = take(L);
+    d.o_avail = take((max_enc + 1) * d.hw_words * 4);
+    d.o_mask = take(d.mask_batch * d.mask_words * 4);
+    d.o_ctr = take(CTR_COUNT * 4);
+    d.smem_bytes = off;
+    if (off > 227 * 1024) return bail(fail(1, "bgw_create: one environment needs %d bytes of shared memory (limit 232448): grid or entity count too large", off));
+    cudaError_t ce;
+    if ((ce = cudaFuncSetAttribute(bgw_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, off)) != cudaSuccess ||
+        (ce = cudaFuncSetAttribute(bgw_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, off)) != cudaSuccess)
+        return bail(fail(2, "bgw_create: cudaFuncSetAttribute: %s", cudaGetErrorString(ce)));
+    dm.threads_per_env = T; dm.envs_per_cta = 1; dm.smem_bytes = off;
+    *out = h;
+    return 0;
+}
+
+int bgw_destroy(bgw_handle h)
+{
+    if (!h) return 0;
+    DeviceGuard guard(h->device);
+    for (void *p : h->allocs) cudaFree(p);
+    delete h;
+    return 0;
+}
+
+int bgw_dims(bgw_handle h, BgwDims *out)
+{
+    if (!h || !out) return fail(1, "bgw_dims: null argument");
+    *out = h->dims;
+    return 0;
+}
+
+int bgw_bind_state(bgw_handle h, const BgwState *state)
+{
+    if (!h || !state) return fail(1, "bgw_bind_state: null argument");
+    if (!state->cell || !state->next || !state->flags || !state->health || !state->reward_acc || !state->episode ||
+        !state->step || !state->env_flags || !state->turn || !state->error || !state->stats)
+        return fail(1, "bgw_bind_state: every array except `layout` is required");
+    h->st = *state;
+    h->bound = true;
+    return 0;
+}
+
+int bgw_reset(bgw_handle h, const uint8_t *env_mask, int8_t *obs, void *stream)
+{
+    if (!h) return fail(1, "bgw_reset: null handle");
+    if (!h->bound) return fail(1, "bgw_reset: call bgw_bind_state first");
+    DeviceGuard guard(h->device);
+    bgw_reset_kernel<<<h->ds.E, h->threads, h->ds.smem_bytes, (cudaStream_t)stream>>>(h->ds, h->st, env_mask, obs);
+    CUDA_OK(cudaGetLastError());
+    h->launches += 1;
+    return 0;
+}
+
+int bgw_step(bgw_handle h, const int8_t *actions, const int16_t *order, int8_t *obs, float *reward, uint8_t *done,
+             uint8_t *all_done, void *stream)
+{
+    if (!h) return fail(1, "bgw_step: null handle");
+    if (!h->bound) return fail(1, "bgw_step: call bgw_bind_state first");
+    if (!actions || !reward || !done || !all_done) return fail(1, "bgw_step: actions, reward, done and all_done are required");
+    DeviceGuard guard(h->device);
+    bgw_step_kernel<<<h->ds.E, h->threads, h->ds.smem_bytes, (cudaStream_t)stream>>>(
+        h->ds, h->st, (const uint32_t *)actions, order, obs, reward, done, all_done);
+    CUDA_OK(cudaGetLastError());
+    h->launches += 1;
+    return 0;
+}
+
+int bgw_sample_actions(bgw_handle h, int8_t *actions, void *stream)
+{
+    if (!h || !actions) return fail(1, "bgw_sample_actions: null argument");
+    if (!h->bound) return fail(1, "bgw_sample_actions: call bgw_bind_state first");
+    DeviceGuard guard(h->device);
+    const size_t n = (size_t)h->ds.E * h->ds.L;
+    bgw_sample_actions_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(h->ds, h->st, (uint32_t *)actions);
+    CUDA_OK(cudaGetLastError());
+    h->launches += 1;
+    return 0;
+}
+
+int bgw_rng_draw(uint64_t seed, uint32_t env, uint32_t episode, uint32_t step, uint32_t site, uint32_t slot, uint32_t k,
+                 uint32_t out[4])
+{
+    bgw_draw4(seed, env, episode, step, site, slot, k, out);
+    return 0;
+}
+
+int bgw_los_mask(int range, int r_diff, int c_diff, uint8_t *out)
+{
+    if (range < 0 || !out) return fail(1, "bgw_los_mask: bad argument");
+    const int n = 2 * range + 1;
+    memset(out, 1, (size_t)n * n);
+    if (r_diff < -range || r_diff > range || c_diff < -range || c_diff > range) return 0;   /* utils.py:49-50 */
+    los_apply_host(out, range, r_diff, c_diff);
+    return 0;
+}
+
+uint64_t bgw_launch_count(bgw_handle h) { return h ? h->launches : 0; }
+
+}  /* extern "C" */

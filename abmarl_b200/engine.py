@@ -1,0 +1,160 @@
+"""BatchedGridWorld: E independent copies of one compiled simulation advanced in lockstep on one B200.
+
+Thin host object over the C-ABI of include/bgw.h (libbgw.so, abmarl_b200/csrc): PyTorch provides the device
+memory and the CUDA stream, every buffer is handed to the library as a raw device pointer, and the kernels
+are enqueued on torch's current stream.  There is no CPU fallback: constructing the engine without the built
+extension or without a CUDA device raises.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from abmarl_b200 import _capi as K
+
+_STATE_FIELDS = (('cell', torch.int16, 'EA'), ('next', torch.int16, 'EA'), ('flags', torch.uint8, 'EA'),
+                 ('health', torch.float64, 'EA'), ('reward_acc', torch.float64, 'EA'),
+                 ('episode', torch.int32, 'E'), ('step', torch.int32, 'E'), ('env_flags', torch.uint8, 'E'),
+                 ('turn', torch.int16, 'E'), ('error', torch.int32, 'E'))
+_NP_VIEW = {'cell': np.uint16, 'next': np.uint16, 'episode': np.uint32, 'step': np.uint32, 'error': np.uint32}
+
+
+class BatchedGridWorld:
+    """reset() / step(actions) over device tensors.
+
+    actions  int8  [E, L, 4]   byte 0,1 = move (dr, dc | cross 0..4 | ravelled), byte 2 = attack
+    obs      int8  [E, L, obs_stride]   (see obs_view)
+    reward   f32   [E, L];  done uint8 [E, L] (OUT_VALID | OUT_DONE);  all_done uint8 [E] (ENV_* bits)
+    """
+
+    def __init__(self, spec, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("abmarl_b200 needs a CUDA device: the engine has no CPU fallback")
+        self.lib = K.load()
+        self.spec = spec
+        self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        self._c = spec.c_struct()
+        h = C.c_void_p()
+        K.check(self.lib.bgw_create(C.byref(self._c), self.device.index or 0, C.byref(h)), self.lib)
+        self._h = h
+        d = K.BgwDims()
+        K.check(self.lib.bgw_dims(h, C.byref(d)), self.lib)
+        self.dims = d
+        self.E, self.A, self.L = d.n_envs, d.n_agents, d.n_learners
+        dev = self.device
+        self.state = {}
+        for name, dt, shape in _STATE_FIELDS:
+            self.state[name] = torch.zeros((self.E, self.A) if shape == 'EA' else (self.E,), dtype=dt, device=dev)
+        self.state['cell'].fill_(-1)         # 0xFFFF
+        self.state['next'].fill_(-1)
+        self.state['episode'].fill_(-1)      # 0xFFFFFFFF: first reset makes it 0
+        self.state['turn'].fill_(-1)
+        self.state['stats'] = torch.zeros((self.E, K.BGW_STAT_COUNT), dtype=torch.int64, device=dev)
+        self.state['layout'] = None
+        self.obs = torch.zeros((self.E, self.L, d.obs_stride), dtype=torch.int8, device=dev)
+        self.reward = torch.zeros((self.E, self.L), dtype=torch.float32, device=dev)
+        self.done = torch.zeros((self.E, self.L), dtype=torch.uint8, device=dev)
+        self.all_done = torch.zeros((self.E,), dtype=torch.uint8, device=dev)
+        self.actions = torch.zeros((self.E, self.L, 4), dtype=torch.int8, device=dev)
+        self._bind()
+
+    # ---- plumbing -------------------------------------------------------------------------------
+    def _bind(self):
+        s = K.BgwState()
+        for name in ('cell', 'next', 'flags', 'health', 'reward_acc', 'episode', 'step', 'env_flags', 'turn',
+                     'error', 'layout', 'stats'):
+            t = self.state[name]
+            setattr(s, name, None if t is None else t.data_ptr())
+        K.check(self.lib.bgw_bind_state(self._h, C.byref(s)), self.lib)
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def close(self):
+        if getattr(self, '_h', None):
+            self.lib.bgw_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- the managers' interface ---------------------------------------------------------------
+    def set_layout(self, layout):
+        """[E, A] start cells generated host-side (0xFFFF = leave unplaced); None = PositionState placement."""
+        if layout is None:
+            self.state['layout'] = None
+        else:
+            lay = np.ascontiguousarray(layout, dtype=np.uint16).view(np.int16)
+            assert lay.shape == (self.E, self.A)
+            self.state['layout'] = torch.from_numpy(lay).to(self.device)
+        self._bind()
+
+    def reset(self, env_mask=None):
+        m = None
+        if env_mask is not None:
+            m = torch.as_tensor(env_mask, dtype=torch.uint8, device=self.device).contiguous()
+        K.check(self.lib.bgw_reset(self._h, None if m is None else m.data_ptr(), self.obs.data_ptr(), self._stream()),
+                self.lib)
+        return self.obs
+
+    def sample_actions(self, out=None):
+        out = self.actions if out is None else out
+        K.check(self.lib.bgw_sample_actions(self._h, out.data_ptr(), self._stream()), self.lib)
+        return out
+
+    def step(self, actions, order=None):
+        assert actions.dtype == torch.int8 and tuple(actions.shape) == (self.E, self.L, 4) and actions.is_cuda \
+            and actions.is_contiguous(), "actions must be a contiguous int8 CUDA tensor [E, L, 4]"
+        o = None
+        if order is not None:
+            o = torch.as_tensor(order, dtype=torch.int16, device=self.device).contiguous()
+            assert tuple(o.shape) == (self.E, self.L)
+        K.check(self.lib.bgw_step(self._h, actions.data_ptr(), None if o is None else o.data_ptr(),
+                                  self.obs.data_ptr(), self.reward.data_ptr(), self.done.data_ptr(),
+                                  self.all_done.data_ptr(), self._stream()), self.lib)
+        return self.obs, self.reward, self.done, self.all_done
+
+    # ---- views / introspection -------------------------------------------------------------------
+    def obs_view(self, obs=None):
+        """[E, L, h, w(, c)] logical view of the 16-byte padded int8 rows."""
+        obs = self.obs if obs is None else obs
+        d = self.dims
+        v = obs[..., :d.obs_h * d.obs_w * d.obs_c]
+        shape = tuple(obs.shape[:-1]) + ((d.obs_h, d.obs_w) if d.obs_c == 1 else (d.obs_h, d.obs_w, d.obs_c))
+        return v.reshape(shape)
+
+    def state_numpy(self):
+        """Host copy of the state in the oracle's numpy layout (tests)."""
+        out = {}
+        for name, t in self.state.items():
+            if t is None:
+                out[name] = None
+                continue
+            a = t.cpu().numpy()
+            if name in _NP_VIEW:
+                a = a.view(_NP_VIEW[name])
+            elif name == 'stats':
+                a = a.view(np.uint64)
+            out[name] = a
+        return out
+
+    def load_state(self, st):
+        """Overwrite the device state from numpy arrays in the oracle's layout (parity tests)."""
+        for name, t in self.state.items():
+            if t is None or name not in st or st[name] is None:
+                continue
+            a = np.ascontiguousarray(st[name])
+            if name in _NP_VIEW or name == 'stats':
+                a = a.view({2: np.int16, 4: np.int32, 8: np.int64}[a.dtype.itemsize])
+            t.copy_(torch.from_numpy(a).reshape(t.shape))
+
+    def stats(self):
+        """Summed episode statistics (agent_steps, episodes, kills, env_steps) of this device's envs."""
+        return self.state['stats'].sum(dim=0)
+
+    @property
+    def launches(self):
+        return int(self.lib.bgw_launch_count(self._h))

@@ -1,0 +1,130 @@
+"""AllStepManager / TurnBasedManager over E lockstep environments.
+
+The reference managers wrap ONE simulation and trade dicts keyed by agent id
+(abmarl/managers/simulation_manager.py:27-53, all_step_manager.py:37-95, turn_based_manager.py:22-94).  These
+wrap a simulation *definition* and drive E copies of it on the device: `reset()` and `step(actions)` trade
+dense tensors indexed [env, learner] (learner order = the order of `sim.agents`), and the manager rules --
+done agents stop acting and are never reported again, `__all__`, the turn cursor that is never rewound --
+are applied per env inside the step kernel (abmarl_b200/csrc/bgw_dev.cuh).  `as_dicts(env)` converts one
+env's last outputs into the reference's dict-of-dicts form.
+"""
+from abc import ABC
+
+import numpy as np
+import torch
+
+from abmarl_b200 import _capi as K
+from abmarl_b200.spec import compile_sim
+from abmarl_b200.engine import BatchedGridWorld
+
+
+class SimulationManager(ABC):
+    """simulation_manager.py:7-53 (batched)."""
+    _manager = None
+
+    def __init__(self, sim, n_envs=1, env_offset=0, seed=0, horizon=0, auto_reset=False, device=None,
+                 randomize_action_input=False, layouts=None):
+        assert not randomize_action_input or self._manager == 'all_step', \
+            "randomize_action_input is an AllStepManager option (all_step_manager.py:24-35)"
+        self.sim = sim
+        self.randomize_action_input = bool(randomize_action_input)
+        self.spec = compile_sim(sim, manager=self._manager, n_envs=n_envs, env_offset=env_offset, seed=seed,
+                                horizon=horizon, auto_reset=auto_reset)
+        self.engine = BatchedGridWorld(self.spec, device=device)
+        if layouts is not None:
+            self.engine.set_layout(layouts)
+        self.learner_ids = self.spec.learner_ids
+        self._order_gen = torch.Generator(device='cpu')
+        self._order_gen.manual_seed(int(seed) & 0x7FFFFFFF)
+
+    # -- tensors ---------------------------------------------------------------------------------
+    @property
+    def n_envs(self):
+        return self.engine.E
+
+    @property
+    def n_learners(self):
+        return self.engine.L
+
+    def reset(self, env_mask=None):
+        """-> obs int8 [E, L, h, w(, c)] (first observations; turn-based: only the row of the env's turn is fresh)."""
+        self.engine.reset(env_mask)
+        return self.engine.obs_view()
+
+    def step(self, actions, order=None):
+        """actions int8 [E, L, 4] on the device -> (obs, reward f32 [E, L], done uint8 [E, L], all_done uint8 [E]).
+
+        `done` carries OUT_VALID for the learners that received (obs, reward, done) this call and OUT_DONE for
+        those that are done; rows of learners already reported done are ignored on input (the reference
+        asserts they are absent, all_step_manager.py:59-61)."""
+        if order is None and self.randomize_action_input:       # all_step_manager.py:62-65
+            order = torch.stack([torch.randperm(self.engine.L, generator=self._order_gen)
+                                 for _ in range(self.engine.E)]).to(torch.int16)
+        _, reward, done, all_done = self.engine.step(actions, order)
+        return self.engine.obs_view(), reward, done, all_done
+
+    def sample_actions(self):
+        """A random action per learner from the keyed Philox stream (== action_space.sample() ranges)."""
+        return self.engine.sample_actions()
+
+    def encode_actions(self, action_dicts):
+        """[{agent_id: {'move': ..., 'attack': ...}}, ...] (one dict per env, reference format) -> int8 [E, L, 4]."""
+        sp = self.spec
+        act = np.zeros((self.engine.E, self.engine.L, 4), dtype=np.int8)
+        index = {aid: l for l, aid in enumerate(self.learner_ids)}
+        for e, d in enumerate(action_dicts):
+            for agent_id, a in d.items():
+                l = index[agent_id]
+                if 'move' in a:
+                    mv = a['move']
+                    if sp.move_actor == K.MOVE_BOX and not sp.ravel_actions:
+                        act[e, l, 0], act[e, l, 1] = int(mv[0]), int(mv[1])
+                    else:
+                        act[e, l, 0] = np.uint8(int(mv)).view(np.int8)
+                if 'attack' in a:
+                    act[e, l, 2] = int(a['attack'])
+        return torch.from_numpy(act).to(self.engine.device)
+
+    # -- reference-shaped view of one env --------------------------------------------------------
+    def as_dicts(self, env=0, after_reset=False):
+        """(obs, rewards, dones, infos) of env `env` as the reference's dicts (simulation_manager.py:38-53)."""
+        eng = self.engine
+        key = {K.OBS_POSITION_CENTERED: 'position_centered_encoding', K.OBS_ABSOLUTE: 'absolute_encoding',
+               K.OBS_STACKED: 'stacked_position_centered_encoding'}[self.spec.observer]
+        obs_all = eng.obs_view()[env].cpu().numpy().astype(np.int64)
+        done = eng.done[env].cpu().numpy()
+        reward = eng.reward[env].cpu().numpy()
+        flags = int(eng.all_done[env].item())
+        obs, rew, dn, info = {}, {}, {}, {}
+        for l, agent_id in enumerate(self.learner_ids):
+            if after_reset or (done[l] & K.OUT_VALID):
+                a = self.spec.learner_agents[l]
+                n = 2 * int(self.spec.view_range[a]) + 1
+                o = obs_all[l]
+                if self.spec.observer != K.OBS_ABSOLUTE and o.shape[0] != n:     # agent with a smaller view
+                    flat = o.reshape(-1)[:n * n * (o.shape[2] if o.ndim == 3 else 1)]
+                    o = flat.reshape((n, n) + o.shape[2:])
+                obs[agent_id] = {key: o}
+                if not after_reset:
+                    rew[agent_id] = float(reward[l])
+                    dn[agent_id] = bool(done[l] & K.OUT_DONE)
+                    info[agent_id] = {}
+        if after_reset:
+            return obs
+        dn['__all__'] = bool(flags & K.ENV_ALL_DONE)
+        return obs, rew, dn, info
+
+
+class AllStepManager(SimulationManager):
+    """all_step_manager.py:7-95: every not-done learner acts each step."""
+    _manager = 'all_step'
+
+
+class TurnBasedManager(SimulationManager):
+    """turn_based_manager.py:7-94: one learner per step, in `sim.agents` order; `actions[e, turn[e]]` is read."""
+    _manager = 'turn_based'
+
+    @property
+    def turn(self):
+        """int16 [E]: the learner whose action the next step() consumes."""
+        return self.engine.state['turn']

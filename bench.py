@@ -1,0 +1,296 @@
+#!/usr/bin/env python
+"""bench.py -- agent-steps/sec of the batched GridWorld step path (BASELINE.json metric).
+
+Workload (BASELINE.json configs[4], SURVEY.md section 8(d) "C5"): synthetic team battle, 64x64 grid, 256
+agents/env (4 teams), view range 5, move/attack range 1, random placement and random initial health,
+OneTeamRemainingDone, AllStepManager semantics, horizon 200 with auto-reset, random actions from the keyed
+Philox stream; 4096 envs per GPU (env batches shard across GPUs with no data-path collective -> weak scaling;
+NCCL only sums the episode statistics).
+
+One "step" = one manager step of every env on this GPU: the action-sampling kernel + the step kernel (actor
+resolution -> observation -> reward/done).  An agent-step = one learning agent receiving (obs, reward, done).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "agent-steps/sec (obs+reward+done) over batched envs"
+BYTES_PER_AGENT_STEP = 165     # action 4 + int8 obs 128 + reward 4 + done 1 + agent state r/w 28
+ENVS_PER_GPU = 4096
+WORKLOAD = "synthetic team battle 64x64, 256 agents/env, view 5, horizon 200 (BASELINE configs[4])"
+
+
+def build_spec(n_envs, env_offset, seed=0xB200):
+    from tests import scenarios
+    from abmarl_b200.spec import compile_sim
+    sim = scenarios.build_tb_c5(scenarios.mirror_api())
+    return compile_sim(sim, manager='all_step', n_envs=n_envs, env_offset=env_offset, seed=seed, horizon=200,
+                       auto_reset=True)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.proc = index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(',')])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace('.', '').isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace('.', '').isdigit()]
+        names = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')
+        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower().startswith('active')})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    except Exception:
+        return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's AllStepManager loop on the host cores
+# ---------------------------------------------------------------------------------------------------
+def cpu_rollout(n_envs, steps, threads, warmup=0):
+    """The C oracle (oracle/bgw_oracle.c: scalar restatement of the reference's per-agent loops) on `threads`
+    host threads, each advancing its own shard of envs.  Returns (agent_steps, seconds)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle.oracle import OracleEnv
+    from abmarl_b200 import _capi as K
+    shard = max(1, n_envs // threads)
+    envs = [OracleEnv(build_spec(shard, i * shard)) for i in range(threads)]
+    for o in envs:
+        o.reset()
+
+    def work(o, n):
+        before = int(o.state['stats'][:, K.STAT_AGENT_STEPS].sum())
+        for _ in range(n):
+            o.step(o.sample_actions())
+        return int(o.state['stats'][:, K.STAT_AGENT_STEPS].sum()) - before
+
+    with ThreadPoolExecutor(threads) as pool:        # ctypes releases the GIL inside the C calls
+        if warmup:
+            list(pool.map(lambda o: work(o, warmup), envs))
+        t0 = time.perf_counter()
+        n = sum(pool.map(lambda o: work(o, steps), envs))
+        dt = time.perf_counter() - t0
+    return n, dt, shard * threads
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cores = len(os.sched_getaffinity(0))
+    per_step_envs = cores * 8                      # bounded sample: 8 envs per host thread per step
+    n, dt, envs = cpu_rollout(per_step_envs, args.steps, cores, warmup=args.warmup)
+    value = n / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "agent-steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i8/f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "envs_per_step": envs},
+        "cpu_baseline": {"value": value, "unit": "agent-steps/s", "cores": cores, "kind": "port",
+                         "sample": f"oracle C port of the reference loop, {envs} envs x {args.steps} steps on {cores} host threads"},
+        "e2e": {"value": value, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from abmarl_b200 import _capi as K
+    from abmarl_b200.engine import BatchedGridWorld
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+
+    E = args.envs_per_gpu
+    eng = BatchedGridWorld(build_spec(E, rank * E), device=dev)
+    L = eng.L
+    stream = torch.cuda.current_stream(dev)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def agent_steps():
+        return int(eng.stats()[K.STAT_AGENT_STEPS].item())
+
+    # ---------------- device-resident rollout: `value` + roofline of the step kernel -----------------
+    eng.reset()
+    for _ in range(args.warmup):
+        eng.step(eng.sample_actions())
+    barrier()
+    n0, launches0 = agent_steps(), eng.launches
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t_beg, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_beg.record(stream)
+    for i in range(args.steps):
+        act = eng.sample_actions()
+        k_ev[i][0].record(stream)
+        eng.step(act)
+        k_ev[i][1].record(stream)
+    t_end.record(stream)
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    ms = t_beg.elapsed_time(t_end)
+    n_dev = agent_steps() - n0
+    launches = eng.launches - launches0
+    kernel_ms = sum(a.elapsed_time(b) for a, b in k_ev)
+
+    # ---------------- end to end through the public API with HOST buffers -----------------------------
+    e2e_steps = max(4, min(args.steps, args.e2e_steps))
+    rng = np.random.default_rng(1234 + rank)
+    pool = []
+    for _ in range(8):                                # pinned host action buffers (random policy, same ranges)
+        a = np.zeros((E, L, 4), dtype=np.int8)
+        a[..., 0:2] = rng.integers(-1, 2, size=(E, L, 2), dtype=np.int8)
+        a[..., 2] = rng.integers(0, 2, size=(E, L), dtype=np.int8)
+        pool.append(torch.from_numpy(a).pin_memory())
+    h_obs = torch.empty(eng.obs.shape, dtype=torch.int8).pin_memory()
+    h_rew = torch.empty(eng.reward.shape, dtype=torch.float32).pin_memory()
+    h_done = torch.empty(eng.done.shape, dtype=torch.uint8).pin_memory()
+    h_all = torch.empty(eng.all_done.shape, dtype=torch.uint8).pin_memory()
+    d_act = torch.empty((E, L, 4), dtype=torch.int8, device=dev)
+
+    def host_step(i):
+        d_act.copy_(pool[i % len(pool)], non_blocking=True)
+        obs, rew, done, alld = eng.step(d_act)
+        h_obs.copy_(obs, non_blocking=True)
+        h_rew.copy_(rew, non_blocking=True)
+        h_done.copy_(done, non_blocking=True)
+        h_all.copy_(alld, non_blocking=True)
+        stream.synchronize()                          # the caller holds the step's results on the host
+
+    for i in range(3):
+        host_step(i)
+    barrier()
+    n1 = agent_steps()
+    e_beg, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e_beg.record(stream)
+    for i in range(e2e_steps):
+        host_step(i)
+    e_end.record(stream)
+    barrier()
+    e2e_ms = e_beg.elapsed_time(e_end)
+    n_e2e = agent_steps() - n1
+    h2d = d_act.numel()
+    d2h = h_obs.numel() + h_rew.numel() * 4 + h_done.numel() + h_all.numel()
+
+    # ---------------- reduce over ranks: times = max, counts = sum (NCCL: episode statistics only) ----
+    t = torch.tensor([ms, e2e_ms, kernel_ms], dtype=torch.float64, device=dev)
+    c = torch.tensor([n_dev, n_e2e, launches], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+    ms, e2e_ms, kernel_ms_max = (float(x) for x in t.tolist())
+    n_dev_all, n_e2e_all, launches_all = (float(x) for x in c.tolist())
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        per_launch_ms = kernel_ms / args.steps                              # this rank's step kernel
+        algo_bytes = BYTES_PER_AGENT_STEP * n_dev / args.steps             # per launch, this rank
+        achieved = algo_bytes / (per_launch_ms * 1e-3) / 1e9
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, 'profiles', 'step_kernel_traffic.json')) as f:
+                traffic = json.load(f).get('dram_bytes_per_launch')
+        except Exception:
+            pass
+        line = {
+            "metric": METRIC, "value": n_dev_all / (ms * 1e-3), "unit": "agent-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "i8/f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "envs_per_gpu": E, "agents_per_env": L, "global_envs": E * world,
+                       "parallelism": f"env-sharded x{world}, no data-path collective",
+                       "l2": "working set per step (obs 134 MB + actions/state 10 MB per GPU) exceeds the 126 MB L2",
+                       "agent_steps_per_step": n_dev_all / args.steps},
+            "e2e": {"value": n_e2e_all / (e2e_ms * 1e-3), "unit": "agent-steps/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+            "gpu_launches": int(launches_all),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "bgw_step_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_agent_step": BYTES_PER_AGENT_STEP,
+                         "kernel_ms_per_launch": per_launch_ms, "kernel_share_of_step": kernel_ms / (ms if world == 1 else t_beg.elapsed_time(t_end))},
+        }
+        if world == 1 and not args.no_cpu:
+            cores = 1
+            n, dt, envs = cpu_rollout(32, 200, cores)
+            line["cpu_baseline"] = {"value": n / dt, "unit": "agent-steps/s", "cores": cores, "kind": "port",
+                                    "sample": f"oracle C port of the reference loop, {envs} envs x 200 steps (one full episode) of the same workload, 1 thread"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=400)
+    ap.add_argument('--warmup', type=int, default=20)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--envs-per-gpu', type=int, default=ENVS_PER_GPU)
+    ap.add_argument('--e2e-steps', type=int, default=40)
+    ap.add_argument('--no-cpu', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

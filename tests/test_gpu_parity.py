@@ -1,0 +1,164 @@
+"""GPU parity: the CUDA engine, called through the C-ABI (libbgw.so), against the CPU oracle on the same
+seeded inputs -- bit-exact observations, dones, __all__, positions, cell-list order, flags, float64 health,
+float32 rewards (both sides round the same float64 sum), episode statistics."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from abmarl_b200 import _capi as K
+from abmarl_b200.spec import compile_sim
+from tests import scenarios
+from tests.helpers import run_lockstep, assert_outputs_equal, assert_state_equal
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def _pair(spec):
+    from abmarl_b200.engine import BatchedGridWorld
+    from oracle.oracle import OracleEnv
+    return BatchedGridWorld(spec, device='cuda:0'), OracleEnv(spec)
+
+
+CASES = [
+    # scenario, envs, steps, horizon
+    ('tb_c2', 64, 120, 50),
+    ('tb_c5_small', 24, 90, 40),
+    ('tb_dense', 64, 120, 30),
+    ('tb_blocking', 48, 100, 40),
+    ('tb_stacked', 48, 80, 30),
+    ('tb_noself', 48, 80, 30),
+    ('maze_c1', 32, 150, 60),
+    ('pacman_c3', 6, 40, 25),
+]
+
+
+@pytest.mark.parametrize('name,n_envs,steps,horizon', CASES)
+def test_engine_matches_oracle(mirror, name, n_envs, steps, horizon):
+    builder, manager, _ = scenarios.SCENARIOS[name]
+    spec = compile_sim(builder(mirror), manager=manager, n_envs=n_envs, env_offset=7, seed=0xC0FFEE,
+                       horizon=horizon, auto_reset=True)
+    eng, ora = _pair(spec)
+    n = run_lockstep(eng, ora, steps, label=name)
+    assert n > 0
+    assert int(eng.stats()[K.STAT_AGENT_STEPS].item()) == n
+
+
+@pytest.mark.parametrize('name', ['tb_c2', 'tb_dense', 'tb_blocking'])
+def test_serial_and_reservation_actor_paths_agree(mirror, name, monkeypatch):
+    """The rank-order loop (one thread) and the reservation rounds must both equal the oracle."""
+    builder, manager, _ = scenarios.SCENARIOS[name]
+    spec = compile_sim(builder(mirror), manager=manager, n_envs=32, seed=11, horizon=40, auto_reset=True)
+    monkeypatch.setenv('BGW_SERIAL_ACTORS', '1')
+    eng, ora = _pair(spec)
+    run_lockstep(eng, ora, 60, label=name + '/serial')
+
+
+def test_aliased_reservation_slots(mirror, monkeypatch):
+    """Few reservation slots (many cells share one) only add rounds; results stay identical."""
+    spec = compile_sim(scenarios.build_tb_c5_small(mirror), n_envs=16, seed=5, horizon=30, auto_reset=True)
+    monkeypatch.setenv('BGW_SLOTS', '32')
+    eng, ora = _pair(spec)
+    run_lockstep(eng, ora, 45, label='tb_c5_small/slots32')
+
+
+def test_randomized_action_order(mirror):
+    """AllStepManager(randomize_action_input=True): a per-env processing order (all_step_manager.py:62-65)."""
+    spec = compile_sim(scenarios.build_tb_dense(mirror), n_envs=32, seed=3, horizon=30, auto_reset=True)
+    eng, ora = _pair(spec)
+    rng = np.random.default_rng(0)
+
+    def order(t):
+        return np.stack([rng.permutation(eng.L) for _ in range(eng.E)]).astype(np.int16)
+    run_lockstep(eng, ora, 60, order_fn=order, label='tb_dense/order')
+
+
+@pytest.mark.parametrize('name', list(scenarios.SCENARIOS))
+def test_engine_reproduces_reference_transcript(mirror, name):
+    """Replay the actions recorded from the UNMODIFIED reference (tests/golden/*.npz) through the engine."""
+    g = np.load(os.path.join(GOLDEN, name + '.npz'))
+    builder, manager, _ = scenarios.SCENARIOS[name]
+    spec = compile_sim(builder(mirror), manager=manager, n_envs=1, seed=int(g['seed']), auto_reset=False)
+    from abmarl_b200.engine import BatchedGridWorld
+    eng = BatchedGridWorld(spec, device='cuda:0')
+    for t in range(len(g['kind'])):
+        present = g['obs_present'][t]
+        if g['kind'][t] == 0:
+            eng.reset()
+        else:
+            act = torch.from_numpy(g['actions'][t][None].copy()).cuda()
+            eng.step(act)
+            np.testing.assert_array_equal(eng.done.cpu().numpy()[0], g['done'][t], err_msg=f'{name} call {t} done')
+            np.testing.assert_allclose(eng.reward.cpu().numpy()[0], g['reward'][t], rtol=0, atol=1e-6)
+            assert int(eng.all_done.cpu().numpy()[0] & K.ENV_ALL_DONE) == int(g['all_done'][t])
+        np.testing.assert_array_equal(eng.obs.cpu().numpy()[0][present], g['obs'][t][present], err_msg=f'{name} call {t} obs')
+        st = eng.state_numpy()
+        np.testing.assert_array_equal(st['flags'][0], g['flags'][t], err_msg=f'{name} call {t} flags')
+        np.testing.assert_array_equal(st['cell'][0], g['cell'][t], err_msg=f'{name} call {t} cell')
+        np.testing.assert_array_equal(st['health'][0], g['health'][t], err_msg=f'{name} call {t} health')
+        in_grid = (g['flags'][t] & K.ST_IN_GRID) != 0
+        np.testing.assert_array_equal(st['next'][0][in_grid], g['next'][t][in_grid], err_msg=f'{name} call {t} next')
+
+
+def test_rng_draw_and_los_mask_exports():
+    import ctypes as C
+    from abmarl_b200 import philox
+    from oracle.oracle import los_mask
+    lib = K.load()
+    out = (C.c_uint32 * 4)()
+    for key in [(0xB200, 0, 0, 0, 0, 0, 0), (2**63 + 5, 4095, 17, 199, 5, 255, 4000), (1, 2, 3, 4, 6, 7, 8)]:
+        assert lib.bgw_rng_draw(*key, C.byref(out)) == 0
+        assert tuple(out) == philox.draw4(*key)
+    for R in (1, 2, 5, 16):
+        n = 2 * R + 1
+        buf = np.empty((n, n), dtype=np.uint8)
+        for rd in range(-R, R + 1):
+            for cd in range(-R, R + 1):
+                assert lib.bgw_los_mask(R, rd, cd, buf.ctypes.data_as(C.c_void_p)) == 0
+                assert np.array_equal(buf, los_mask(R, rd, cd)), (R, rd, cd)
+
+
+def test_full_size_c5_properties(mirror):
+    """BASELINE config 5 at full size (64x64, 256 agents, view 5, 4096 envs): oracle parity on a slice of envs
+    plus size-independent invariants over the whole batch."""
+    E = 4096
+    spec = compile_sim(scenarios.build_tb_c5(mirror), n_envs=E, seed=0xB200, horizon=200, auto_reset=True)
+    from abmarl_b200.engine import BatchedGridWorld
+    from oracle.oracle import OracleEnv
+    eng = BatchedGridWorld(spec, device='cuda:0')
+    ora = OracleEnv(spec.with_envs(8, 0))                 # Philox is keyed by the global env index
+    eng.reset()
+    ora.reset()
+    total = 0
+    for t in range(30):
+        act = eng.sample_actions()
+        ora_act = ora.sample_actions()
+        assert np.array_equal(act[:8].cpu().numpy(), ora_act)
+        eng.step(act)
+        ora.step(ora_act)
+        assert np.array_equal(eng.obs[:8].cpu().numpy(), ora.obs), f'step {t}'
+        assert np.array_equal(eng.done[:8].cpu().numpy(), ora.done)
+        assert np.array_equal(eng.reward[:8].cpu().numpy(), ora.reward)
+        done = eng.done.cpu().numpy()
+        total += int(((done & K.OUT_VALID) != 0).sum())
+    st = eng.state_numpy()
+    flags, cell, health = st['flags'], st['cell'], st['health']
+    active, in_grid = (flags & K.ST_ACTIVE) != 0, (flags & K.ST_IN_GRID) != 0
+    assert np.array_equal(active, health > 0)                          # agent.py:192-196
+    assert np.array_equal(active, in_grid)                             # dead entities leave the grid (actor.py:357-358)
+    assert (cell < 64 * 64).all()
+    # cells hold one team only (overlapping = {k: {k}}): no two active agents of different encodings share a cell
+    enc = np.asarray(spec.encoding)
+    for e in range(0, E, 257):
+        cells = {}
+        for a in np.nonzero(in_grid[e])[0]:
+            assert cells.setdefault(int(cell[e, a]), int(enc[a])) == int(enc[a])
+    assert int(eng.stats()[K.STAT_AGENT_STEPS].item()) == total
+    obs = eng.obs_view().cpu().numpy()
+    valid = (eng.done.cpu().numpy() & K.OUT_VALID) != 0
+    assert obs.min() >= -1 and obs.max() <= 4                          # no blockers => never -2
+    own = obs[..., 5, 5][valid & (eng.done.cpu().numpy() & K.OUT_DONE == 0)]
+    assert (own >= 1).all()                                            # a live agent sees its own team on its cell
