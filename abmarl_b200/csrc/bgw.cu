@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "bgw_dev.cuh"
+#include "bgw_fast.cuh"
 
 namespace {
 
@@ -49,7 +50,9 @@ int pow2ceil(int x) { int p = 1; while (p < x) p <<= 1; return p; }
 
 struct BgwEngine {
     int device = 0;
-    DevSpec ds{};
+    DevSpec ds{}, dsf{};          /* general kernels / fast kernel (own slot table size) */
+    FastSpec fs{};
+    int threads_fast = 0;
     BgwDims dims{};
     BgwState st{};
     bool bound = false;
@@ -247,7 +250,8 @@ int bgw_create(const BgwSpec *sp, int device, bgw_handle *out)
     }
 
     /* ---- launch geometry and the shared-memory carve-up ------------------------------------------ */
-    int T = A <= 32 ? 32 : A <= 64 ? 64 : A <= 128 ? 128 : 256;
+    int T = A <= 32 ? 32 : A <= 64 ? 64 : 128;
+    if (A > 256 && !(sp->program == BGW_PROG_TEAM_BATTLE && sp->manager == BGW_MANAGER_ALL_STEP)) T = 256;
     if (const char *t = getenv("BGW_THREADS")) { const int v = atoi(t); if (v >= 32 && v <= 1024 && v % 32 == 0) T = v; }
     h->threads = T;
     d.parallel_actors = (sp->program == BGW_PROG_TEAM_BATTLE && (sp->move_actor == BGW_MOVE_BOX || sp->move_actor == BGW_MOVE_CROSS));
@@ -278,13 +282,90 @@ int bgw_create(const BgwSpec *sp, int device, bgw_handle *out)
     d.o_avail = take((max_enc + 1) * d.hw_words * 4);
     d.o_mask = take(d.mask_batch * d.mask_words * 4);
     d.o_ctr = take(CTR_COUNT * 4);
+    /* ---- specialised team-battle kernel (bgw_fast.cuh) when the sim qualifies: own launch geometry and its
+     *      own shared-memory carve-up ------------------------------------------------------------------- */
+    {
+        FastSpec &f = h->fs;
+        const int P = std::max(rmax_obs, rmax_att);
+        bool fast = sp->program == BGW_PROG_TEAM_BATTLE && sp->manager == BGW_MANAGER_ALL_STEP &&
+                    (sp->move_actor == BGW_MOVE_BOX || sp->move_actor == BGW_MOVE_CROSS) && d.n_blk == 0 &&
+                    sp->observer == BGW_OBS_POSITION_CENTERED && sp->attack_actor == BGW_ATTACK_BINARY &&
+                    (2 * rmax_att + 1) * (2 * rmax_att + 1) <= 32;
+        if (const char *t = getenv("BGW_GENERIC_KERNEL")) if (atoi(t)) fast = false;
+        int TF = A <= 32 ? 32 : 64;
+        if (const char *t = getenv("BGW_THREADS")) { const int v = atoi(t); if (v >= 32 && v <= 1024 && v % 32 == 0) TF = v; }
+        if (fast) {
+            f.P = P;
+            f.PL = P;
+            f.PW = (W + 2 * P + 3) / 4 * 4;
+            f.PH = H + 2 * P;
+            f.magic_w = (uint32_t)(((1ull << 32) + (uint64_t)W - 1) / (uint64_t)W);
+            int fslots = std::min(std::max(pow2ceil(HW), 32), 1024);
+            if (const char *t = getenv("BGW_SLOTS")) { const int v = atoi(t); if (v >= 32 && v <= 65536 && (v & (v - 1)) == 0) fslots = v; }
+            h->dsf = d;
+            h->dsf.slot_mask = fslots - 1;
+            const long long cbytes = (long long)f.PH * f.PW + 32;   /* + slack: the word gather reads past a row end */
+            int fo = 0;
+            auto ftake = [&](long long nbytes) { const int o = fo; fo += align16((int)nbytes); return o; };
+            f.o_enc = ftake(A); f.o_klass = ftake(A); f.o_tmp = ftake(A); f.o_lmask = ftake(A);
+            f.o_head = ftake(HW * 2 + 2);
+            f.o_cenc = ftake(cbytes);
+            f.o_rel = ftake(A * 2); f.o_ragent = ftake(L * 2); f.o_plist = ftake(L * 2);
+            f.o_ctr = ftake(CTR_COUNT * 4); f.o_wsum = ftake(72 * 4);
+            int bo = 0;
+            auto btake = [&](int nbytes) { const int o = bo; bo += align16(nbytes); return o; };
+            f.b_cell = btake(A * 2); f.b_next = btake(A * 2); f.b_flags = btake(A); f.b_act = btake(L * 4);
+            f.buf_bytes = bo;
+            f.o_buf = ftake(2 * bo);
+            /* scratch union */
+            int so = 0;
+            auto stake = [&](int nbytes) { const int o = so; so += align16(nbytes); return o; };
+            f.s_racc = stake(A * 8);
+            const int after_racc = so;
+            f.s_slot = stake(fslots * 4); f.s_rkmask = stake(L * 4); f.s_eff = stake(L * 2); f.s_pstate = stake(L);
+            f.s_killrank = stake(A * 2);
+            const int actor_bytes = so;
+            f.s_avail = after_racc;
+            const int reset_bytes = after_racc + align16((max_enc + 1) * d.hw_words * 4);
+            const int stage_bytes = (TF / 32) * 32 * BGW_STAGE_ROW;
+            f.scratch_bytes = std::max(actor_bytes, std::max(reset_bytes, stage_bytes));
+            f.o_scratch = ftake(f.scratch_bytes);
+            f.smem_bytes = fo;
+            f.async_ok = (A % 16 == 0) && (L % 4 == 0);
+            f.simd_ok = (A % 4 == 0);
+            f.uniform_view = -1;
+            bool first = true, uniform = true;
+            for (int a = 0; a < A; ++a)
+                if ((sp->klass[a] & BGW_AG_LEARNER) && (sp->klass[a] & BGW_AG_OBSERVING)) {
+                    if (first) { f.uniform_view = sp->view_range[a]; first = false; }
+                    else if (sp->view_range[a] != f.uniform_view) uniform = false;
+                }
+            if (!uniform) f.uniform_view = -1;
+            if (cbytes > 96 * 1024 || fo > 227 * 1024) fast = false;
+        }
+        f.enabled = fast;
+        h->threads_fast = TF;
+    }
     d.smem_bytes = off;
     if (off > 227 * 1024) return bail(fail(1, "bgw_create: one environment needs %d bytes of shared memory (limit 232448): grid or entity count too large", off));
     cudaError_t ce;
     if ((ce = cudaFuncSetAttribute(bgw_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, off)) != cudaSuccess ||
+        (h->fs.enabled && (ce = cudaFuncSetAttribute(bgw_step_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->fs.smem_bytes)) != cudaSuccess) ||
         (ce = cudaFuncSetAttribute(bgw_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, off)) != cudaSuccess)
         return bail(fail(2, "bgw_create: cudaFuncSetAttribute: %s", cudaGetErrorString(ce)));
-    dm.threads_per_env = T; dm.envs_per_cta = 1; dm.smem_bytes = off;
+    if (h->fs.enabled) {
+        int per_sm = 0, sms = 0;
+        if ((ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bgw_step_fast_kernel, h->threads_fast, h->fs.smem_bytes)) != cudaSuccess ||
+            (ce = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess)
+            return bail(fail(2, "bgw_create: occupancy query: %s", cudaGetErrorString(ce)));
+        h->fs.grid_ctas = std::max(1, std::min(d.E, per_sm * sms));
+        if (getenv("BGW_PROF_FILE")) {
+            void *pp = nullptr;
+            if (cudaMalloc(&pp, (size_t)h->fs.grid_ctas * 8 * 16 * sizeof(long long)) == cudaSuccess) { h->allocs.push_back(pp); cudaMemset(pp, 0, (size_t)h->fs.grid_ctas * 8 * 16 * sizeof(long long)); h->fs.prof = (long long *)pp; }
+        }
+        if (const char *t = getenv("BGW_GRID")) { const int v = atoi(t); if (v >= 1) h->fs.grid_ctas = std::min(d.E, v); }
+    }
+    dm.threads_per_env = h->fs.enabled ? h->threads_fast : T; dm.envs_per_cta = 1; dm.smem_bytes = h->fs.enabled ? h->fs.smem_bytes : off;
     *out = h;
     return 0;
 }
@@ -334,10 +415,21 @@ int bgw_step(bgw_handle h, const int8_t *actions, const int16_t *order, int8_t *
     if (!h->bound) return fail(1, "bgw_step: call bgw_bind_state first");
     if (!actions || !reward || !done || !all_done) return fail(1, "bgw_step: actions, reward, done and all_done are required");
     DeviceGuard guard(h->device);
-    bgw_step_kernel<<<h->ds.E, h->threads, h->ds.smem_bytes, (cudaStream_t)stream>>>(
-        h->ds, h->st, (const uint32_t *)actions, order, obs, reward, done, all_done);
+    if (h->fs.enabled)
+        bgw_step_fast_kernel<<<h->fs.grid_ctas, h->threads_fast, h->fs.smem_bytes, (cudaStream_t)stream>>>(
+            h->dsf, h->fs, h->st, (const uint32_t *)actions, order, obs, reward, done, all_done);
+    else
+        bgw_step_kernel<<<h->ds.E, h->threads, h->ds.smem_bytes, (cudaStream_t)stream>>>(
+            h->ds, h->st, (const uint32_t *)actions, order, obs, reward, done, all_done);
     CUDA_OK(cudaGetLastError());
     h->launches += 1;
+    if (h->fs.enabled && h->fs.prof) {                 /* debug only: dump the phase clocks of this launch */
+        const size_t n = (size_t)h->fs.grid_ctas * 8 * 16;
+        std::vector<long long> host(n);
+        cudaStreamSynchronize((cudaStream_t)stream);
+        cudaMemcpy(host.data(), h->fs.prof, n * sizeof(long long), cudaMemcpyDeviceToHost);
+        if (FILE *fp = fopen(getenv("BGW_PROF_FILE"), "wb")) { fwrite(host.data(), sizeof(long long), n, fp); fclose(fp); }
+    }
     return 0;
 }
 

@@ -33,7 +33,7 @@
 #define BGW_ATT_MASK_WORDS 8   /* thread-local LOS mask of an attacker: (2R+1)^2 <= 256 bits -> attack_range <= 7 */
 
 enum { CTR_KILLS = 0, CTR_ALLDONE, CTR_REMAINING, CTR_ENC_LO, CTR_ENC_HI, CTR_AND, CTR_NEMIT, CTR_ENVDONE,
-       CTR_ERR, CTR_TURN, CTR_COUNT = 16 };
+       CTR_ERR, CTR_TURN, CTR_MIXED, CTR_COUNT = 16 };
 
 struct DevSpec {
     int H, W, HW, A, L, E, env_offset;
@@ -152,6 +152,11 @@ __device__ __forceinline__ void set_health(Env &ev, int a, double v)
     __stcg(&ev.health[a], h);
     if (h > 0.0) ev.flags[a] |= BGW_ST_ACTIVE; else ev.flags[a] &= ~BGW_ST_ACTIVE;
 }
+
+/* Under AllStepManager every learner's reward accumulator is read (and zeroed) in the call that fills it
+ * (smart.py:101-104), so it is zero between calls and need not be staged -- except for entities that can be
+ * attacked but never report: non-learners with health (their accumulator keeps the 'die' reward forever). */
+__device__ __forceinline__ bool racc_persists(uint8_t klass) { return !(klass & BGW_AG_LEARNER) && (klass & BGW_AG_HEALTH); }
 
 /* rebuild the per-cell list heads from the persisted `next` pointers (all threads; ends synchronised) */
 __device__ void build_heads(const DevSpec &s, Env &ev, int tid, int T)
@@ -841,7 +846,7 @@ __device__ void store_env(const DevSpec &s, const BgwState &st, const Env &ev, b
         st.cell[off + a] = ev.cell[a];
         st.next[off + a] = ev.next[a];
         st.flags[off + a] = ev.flags[a];
-        if (with_racc) st.reward_acc[off + a] = ev.racc[a];
+        if (with_racc || racc_persists(ev.klass[a])) st.reward_acc[off + a] = ev.racc[a];
     }
 }
 
@@ -916,7 +921,7 @@ __global__ void bgw_step_kernel(const DevSpec s, const BgwState st, const uint32
     for (int a = tid; a < s.A; a += T) {
         ev.cell[a] = st.cell[off + a]; ev.next[a] = st.next[off + a]; ev.flags[a] = st.flags[off + a];
         ev.enc[a] = __ldg(&s.enc[a]); ev.klass[a] = __ldg(&s.klass[a]);
-        ev.racc[a] = turn_based ? st.reward_acc[off + a] : 0.0;     /* all-step: zero between calls (smart.py:101-104) */
+        ev.racc[a] = (turn_based || racc_persists(ev.klass[a])) ? st.reward_acc[off + a] : 0.0;
     }
     for (int l = tid; l < s.L; l += T) ev.act[l] = actions[(size_t)e * s.L + l];
     for (int i = tid; i <= s.slot_mask; i += T) ev.slot[i] = BGW_SLOT_FREE;

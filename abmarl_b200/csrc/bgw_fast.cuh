@@ -1,0 +1,758 @@
+/*
+ * bgw_fast.cuh -- the specialised step kernel for the headline path: TeamBattleSim under AllStepManager with
+ * MoveActor / CrossMoveActor, BinaryAttackActor, PositionCenteredEncodingObserver and no view-blocking entities
+ * (BASELINE configs 2 and 5).  Same semantics and same results as the general kernel in bgw_dev.cuh (the
+ * parity tests run both against the oracle); what changes is the amount of work per env:
+ *
+ *   - PERSISTENT CTAs: the grid is sized to the number of co-resident CTAs and each CTA loops over envs.  The
+ *     dense per-cell arrays (occupant list heads, reservation slots, encoding summary) are initialised once
+ *     per CTA and left clean by every env (each env removes exactly what it inserted), so an env costs
+ *     O(live entities), not O(cells);
+ *   - DOUBLE-BUFFERED STAGING: while env e is processed, the agent store of the CTA's next env (cell / next /
+ *     flags / health rows and the action row) streams HBM -> shared memory with cp.async (LDGSTS, 16-byte
+ *     chunks), so no phase waits on a dependent global load;
+ *   - only RELEVANT entities are touched (anything still in the grid, active, or not yet reported done); dead,
+ *     removed and reported entities never change again and are not stored back.  One warp compacts the relevant
+ *     entities and the acting learners (order preserving) with byte-parallel tests on the flag words and a
+ *     shuffle scan, so every later phase costs O(live agents);
+ *   - next to the per-cell occupant lists the env keeps `cenc`, a padded int8 summary of the grid
+ *     (border = -1 out of bounds, 0 empty, e = every occupant has encoding e, BGW_MIXED = mixed encodings).
+ *     The attack pre-pass, the move legality test and the observation gather read it instead of walking lists;
+ *   - only attackers that have a possible victim in their window enter the ordered reservation rounds, and they
+ *     reserve only their own cell and the cells that hold possible victims; attackers without one are settled
+ *     afterwards from the rank of whoever killed them (an attacker is charged for a failed attempt iff it
+ *     was still alive at its turn, team_battle_example.py:37-42);
+ *   - the observation window is gathered from `cenc` with aligned 32-bit loads + funnel shifts, one thread per
+ *     learner, assembled into the packed (2R+1)^2 row in registers (compile-time view range), transposed
+ *     through a per-warp shared-memory stage and written to HBM with coalesced 128-bit stores.  Envs that hold
+ *     a mixed cell (or observers that do not observe themselves, or other view ranges) take the per-cell path
+ *     with the keyed np.random.choice over the occupant list.
+ */
+#pragma once
+#include "bgw_dev.cuh"
+
+#define BGW_MIXED (-128)
+#define BGW_PROF_MARK(k) do { if (f.prof && tid == 0 && it_no < 8) f.prof[((size_t)blockIdx.x * 8 + it_no) * 16 + (k)] = clock64(); } while (0)
+#define BGW_STAGE_ROW 80        /* bytes per lane in the observation stage: 64 payload + 16 pad (conflict-free 128-bit) */
+
+struct FastSpec {
+    int enabled;
+    int P, PL, PW, PH;        /* padding (max range), left padding (16-byte aligned interior when W % 16 == 0),
+                                 padded width (multiple of 16) / height */
+    uint32_t magic_w;         /* ceil(2^32 / W): r = umulhi(cell, magic_w) for cell < 65536 */
+    int uniform_view;         /* view range shared by every observing learner, or -1 */
+    int grid_ctas;            /* persistent grid size */
+    int async_ok;             /* rows are 16-byte aligned: stage with cp.async */
+    int simd_ok;              /* A % 4 == 0: byte-parallel compaction */
+    int b_cell, b_next, b_flags, b_act, buf_bytes;   /* layout of one staging buffer */
+    /* shared-memory carve-up of the fast kernel.  `scratch` is a union: during the actor phases it holds
+     * racc | slot | rkmask | eff | pstate | killrank, during the observation phase the per-warp stage, and in
+     * the (general) reset path racc | avail. */
+    int o_enc, o_klass, o_tmp, o_lmask, o_head, o_cenc, o_rel, o_ragent, o_plist, o_ctr, o_wsum, o_buf, o_scratch;
+    int s_racc, s_slot, s_rkmask, s_eff, s_pstate, s_killrank, s_avail, scratch_bytes, smem_bytes;
+    long long *prof;          /* debug (BGW_PROF_FILE): clock64 at phase boundaries, [cta][8 envs][16 marks] */
+};
+
+struct FastEnv {
+    int8_t *cenc;
+    uint16_t *killrank, *eff, *rel;
+    uint32_t *rkmask, *act;
+    const uint32_t *lmask;
+    int *wsum;
+};
+
+__device__ __forceinline__ void cell_rc(const DevSpec &s, const FastSpec &f, int cell, int &r, int &c)
+{
+    r = (int)__umulhi((uint32_t)cell, f.magic_w);
+    c = cell - r * s.W;
+}
+
+__device__ __forceinline__ int pad_index(const DevSpec &s, const FastSpec &f, int cell)
+{
+    int r, c;
+    cell_rc(s, f, cell, r, c);
+    return (r + f.P) * f.PW + (c + f.PL);
+}
+
+/* summary of a cell from its occupant list */
+__device__ __forceinline__ int8_t cenc_of_list(const Env &ev, int cell)
+{
+    unsigned o = ev.head[cell];
+    if (o == BGW_NONE16) return 0;
+    const int8_t e = ev.enc[o];
+    for (o = ev.next[o]; o != BGW_NONE16; o = ev.next[o]) if (ev.enc[o] != e) return (int8_t)BGW_MIXED;
+    return e;
+}
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+/* stream env e's rows into one staging buffer */
+__device__ __forceinline__ void fast_issue_env(const DevSpec &s, const FastSpec &f, const BgwState &st, const uint32_t *actions,
+                                               int e, unsigned char *buf, int tid, int T)
+{
+    const size_t off = (size_t)e * s.A;
+    if (f.async_ok) {
+        const unsigned char *g;
+        g = (const unsigned char *)(st.cell + off);
+        for (int i = tid; i < s.A / 8; i += T) cp_async16(buf + f.b_cell + i * 16, g + i * 16);
+        g = (const unsigned char *)(st.next + off);
+        for (int i = tid; i < s.A / 8; i += T) cp_async16(buf + f.b_next + i * 16, g + i * 16);
+        g = (const unsigned char *)(st.flags + off);
+        for (int i = tid; i < s.A / 16; i += T) cp_async16(buf + f.b_flags + i * 16, g + i * 16);
+        g = (const unsigned char *)(actions + (size_t)e * s.L);
+        for (int i = tid; i < s.L / 4; i += T) cp_async16(buf + f.b_act + i * 16, g + i * 16);
+    } else {
+        uint16_t *c = (uint16_t *)(buf + f.b_cell), *n = (uint16_t *)(buf + f.b_next);
+        uint8_t *fl = buf + f.b_flags;
+        uint32_t *ac = (uint32_t *)(buf + f.b_act);
+        for (int a = tid; a < s.A; a += T) { c[a] = st.cell[off + a]; n[a] = st.next[off + a]; fl[a] = st.flags[off + a]; }
+        for (int l = tid; l < s.L; l += T) ac[l] = actions[(size_t)e * s.L + l];
+    }
+}
+
+/* BinaryAttackActor for one attacker with a candidate-cell bit mask (row-major window order, actor.py:489-496) */
+__device__ void fast_exec_attack(const DevSpec &s, const FastSpec &f, Env &ev, FastEnv &fe, int rank, int a, uint32_t mask)
+{
+    if (!(ev.flags[a] & BGW_ST_ACTIVE)) return;                   /* team_battle_example.py:37 */
+    const int R = __ldg(&s.attack_r[a]), n = 2 * R + 1;
+    const int own = ev.cell[a];
+    const unsigned long long row = __ldg(&s.attack_map[ev.enc[a]]);
+    const double acc = __ldg(&s.accuracy[a]);
+    int ncand = 0;
+    for (uint32_t m = mask; m; m &= m - 1) {
+        const int b = __ffs(m) - 1, wr = b / n, wc = b - wr * n;
+        for (unsigned o = ev.head[own + (wr - R) * s.W + (wc - R)]; o != BGW_NONE16; o = ev.next[o])
+            ncand += basic_criteria(s, ev, a, (int)o, row, acc) ? 1 : 0;
+    }
+    if (ncand == 0) { ev.racc[a] += s.reward[BGW_RW_ATTACK_FAIL]; return; }
+    int j = (int)bgw_index(dev_draw(s, ev, BGW_SITE_SUBSET, (uint32_t)a, 0), (uint32_t)ncand);
+    int v = -1, vcell = 0;
+    for (uint32_t m = mask; m && v < 0; m &= m - 1) {
+        const int b = __ffs(m) - 1, wr = b / n, wc = b - wr * n;
+        vcell = own + (wr - R) * s.W + (wc - R);
+        for (unsigned o = ev.head[vcell]; o != BGW_NONE16; o = ev.next[o])
+            if (basic_criteria(s, ev, a, (int)o, row, acc) && j-- == 0) { v = (int)o; break; }
+    }
+    /* actor.py:353-358; HealthAgent.health setter agent.py:192-196 (health stays in HBM, touched only on a hit) */
+    set_health(ev, v, __ldcg(&ev.health[v]) - __ldg(&s.strength[a]));
+    if (!(ev.flags[v] & BGW_ST_ACTIVE)) {
+        grid_unlink(ev, v);
+        fe.cenc[pad_index(s, f, vcell)] = cenc_of_list(ev, vcell);
+        fe.killrank[v] = (uint16_t)rank;
+        atomicAdd(&ev.ctr[CTR_KILLS], 1);
+        ev.racc[v] += s.reward[BGW_RW_DIE];                       /* team_battle_example.py:44-47 */
+        ev.racc[a] += s.reward[BGW_RW_KILL];
+    }
+}
+
+/* Ordered rounds over the effective attackers eff[0..n_eff) (all of them pending on entry).  Per round: every
+ * pending attacker atomicMin()s its rank into the slots of its own cell and of its candidate cells; after a
+ * barrier an attacker that holds all its slots executes and frees them (losers only read slots, so the check
+ * and the execution need no barrier between them); a second barrier separates the frees from the next round's
+ * reservations.  WARP = run by one warp with __syncwarp. */
+template <bool WARP>
+__device__ void fast_attack_rounds(const DevSpec &s, const FastSpec &f, Env &ev, FastEnv &fe, int n_eff, int tid, int T)
+{
+    const int stride = WARP ? 32 : T;
+    int pending = 1;
+    while (pending) {
+        for (int x = tid; x < n_eff; x += stride) {
+            const int i = fe.eff[x];
+            if (ev.pstate[i] != 1) continue;
+            const int a = ev.ragent[i], R = __ldg(&s.attack_r[a]), n = 2 * R + 1, own = ev.cell[a];
+            atomicMin(slot_of(s, ev, own), (uint32_t)i);
+            for (uint32_t m = fe.rkmask[i]; m; m &= m - 1) {
+                const int b = __ffs(m) - 1, wr = b / n, wc = b - wr * n;
+                atomicMin(slot_of(s, ev, own + (wr - R) * s.W + (wc - R)), (uint32_t)i);
+            }
+        }
+        if (WARP) __syncwarp(); else __syncthreads();
+        int lost = 0;
+        for (int x = tid; x < n_eff; x += stride) {
+            const int i = fe.eff[x];
+            if (ev.pstate[i] != 1) continue;
+            const int a = ev.ragent[i], R = __ldg(&s.attack_r[a]), n = 2 * R + 1, own = ev.cell[a];
+            const uint32_t mask = fe.rkmask[i];
+            bool win = *slot_of(s, ev, own) == (uint32_t)i;
+            for (uint32_t m = mask; m; m &= m - 1) {
+                const int b = __ffs(m) - 1, wr = b / n, wc = b - wr * n;
+                win &= *slot_of(s, ev, own + (wr - R) * s.W + (wc - R)) == (uint32_t)i;
+            }
+            if (!win) { lost = 1; continue; }
+            fast_exec_attack(s, f, ev, fe, i, a, mask);
+            *slot_of(s, ev, own) = BGW_SLOT_FREE;
+            for (uint32_t m = mask; m; m &= m - 1) {
+                const int b = __ffs(m) - 1, wr = b / n, wc = b - wr * n;
+                *slot_of(s, ev, own + (wr - R) * s.W + (wc - R)) = BGW_SLOT_FREE;
+            }
+            ev.pstate[i] = 0;
+        }
+        if (WARP) { pending = __any_sync(0xFFFFFFFFu, lost); __syncwarp(); } else pending = __syncthreads_or(lost);
+    }
+}
+
+/* one move: Grid.query through the summary, then remove / place (actor.py:99-114) */
+__device__ __forceinline__ void fast_exec_move(const DevSpec &s, const FastSpec &f, Env &ev, FastEnv &fe, int a, int to)
+{
+    const int from = ev.cell[a], pto = pad_index(s, f, to);
+    const int8_t summary = fe.cenc[pto], me = ev.enc[a];
+    bool ok;
+    if (summary == 0) ok = true;
+    else if (summary != (int8_t)BGW_MIXED) ok = (__ldg(&s.overlap[me]) >> summary) & 1ull;
+    else ok = grid_query(s, ev, a, to);
+    if (!ok) { ev.racc[a] += s.reward[BGW_RW_MOVE_FAIL]; return; }
+    grid_unlink(ev, a);
+    fe.cenc[pad_index(s, f, from)] = cenc_of_list(ev, from);
+    grid_append(ev, a, to);
+    const int8_t ns = summary == 0 ? me : (summary == me ? me : (int8_t)BGW_MIXED);
+    fe.cenc[pto] = ns;
+    if (ns == (int8_t)BGW_MIXED) ev.ctr[CTR_MIXED] = 1;
+}
+
+/* Ordered rounds over the pending movers (pstate == 1; targets in rkmask[], the attack masks are dead by
+ * then): each reserves its source and destination cell; same two-barrier round as the attack phase. */
+template <bool WARP>
+__device__ void fast_move_rounds(const DevSpec &s, const FastSpec &f, Env &ev, FastEnv &fe, int n_act, int pending, int tid, int T)
+{
+    const int stride = WARP ? 32 : T;
+    while (pending) {
+        for (int i = tid; i < n_act; i += stride) {
+            if (ev.pstate[i] != 1) continue;
+            atomicMin(slot_of(s, ev, ev.cell[ev.ragent[i]]), (uint32_t)i);
+            atomicMin(slot_of(s, ev, (int)fe.rkmask[i]), (uint32_t)i);
+        }
+        if (WARP) __syncwarp(); else __syncthreads();
+        int lost = 0;
+        for (int i = tid; i < n_act; i += stride) {
+            if (ev.pstate[i] != 1) continue;
+            const int a = ev.ragent[i], from = ev.cell[a], to = (int)fe.rkmask[i];
+            if (*slot_of(s, ev, from) != (uint32_t)i || *slot_of(s, ev, to) != (uint32_t)i) { lost = 1; continue; }
+            fast_exec_move(s, f, ev, fe, a, to);
+            *slot_of(s, ev, from) = BGW_SLOT_FREE;
+            *slot_of(s, ev, to) = BGW_SLOT_FREE;
+            ev.pstate[i] = 0;
+        }
+        if (WARP) { pending = __any_sync(0xFFFFFFFFu, lost); __syncwarp(); } else pending = __syncthreads_or(lost);
+    }
+}
+
+/* (re)initialise the dense per-cell arrays of this CTA: empty lists, clean head-detection marks, empty summary
+ * with a -1 border (the reservation slots live in the scratch union and are cleared per env) */
+__device__ void fast_init_dense(const DevSpec &s, const FastSpec &f, Env &ev, FastEnv &fe, int tid, int T)
+{
+    uint4 *h4 = (uint4 *)ev.head;
+    const uint4 ones = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+    for (int i = tid; i < (s.HW * 2 + 15) / 16; i += T) h4[i] = ones;
+    for (int a = tid; a < s.A; a += T) ev.tmp[a] = 0;
+    /* summary rows: word cw of an interior row has zeros where its 4 bytes fall inside the grid columns */
+    uint32_t *c32 = (uint32_t *)fe.cenc;
+    const int wpr = f.PW >> 2, lane = tid & 31, warp = tid >> 5, nwarp = T >> 5;
+    for (int cw = lane; cw < wpr; cw += 32) {
+        uint32_t inner = 0xFFFFFFFFu;
+#pragma unroll
+        for (int bb = 0; bb < 4; ++bb) {
+            const int cc = cw * 4 + bb;
+            if (cc >= f.PL && cc < f.PL + s.W) inner &= ~(0xFFu << (8 * bb));
+        }
+        for (int rr = warp; rr < f.PH; rr += nwarp)
+            c32[rr * wpr + cw] = (rr >= f.P && rr < f.P + s.H) ? inner : 0xFFFFFFFFu;
+    }
+    if (tid < 8) c32[f.PH * wpr + tid] = 0xFFFFFFFFu;           /* slack words read by the row gather */
+    __syncthreads();
+}
+
+/* the general per-cell observation chunk on top of the summary: used when the env holds a mixed cell, an
+ * observer does not observe itself, or the compile-time gather does not apply */
+__device__ void fast_obs_chunk_slow(const DevSpec &s, const FastSpec &f, const Env &ev, const FastEnv &fe, int a, int ch,
+                                    uint32_t w[4])
+{
+    w[0] = w[1] = w[2] = w[3] = 0;
+    if (!(ev.klass[a] & BGW_AG_OBSERVING)) return;
+    const int R = __ldg(&s.view_r[a]), n = 2 * R + 1, valid = n * n, k0 = ch * 16;
+    int r0, c0;
+    cell_rc(s, f, ev.cell[a], r0, c0);
+    const int8_t *win = fe.cenc + (r0 + f.P - R) * f.PW + (c0 + f.PL - R);
+    int wr = k0 / n, wc = k0 - wr * n;
+    for (int t = 0; t < 16 && k0 + t < valid; ++t) {
+        int v = win[wr * f.PW + wc];
+        const bool centre = (wr == R && wc == R);
+        if (v == BGW_MIXED || (centre && !s.observe_self && v > 0))
+            v = choose_encoding(s, ev, a, (r0 - R + wr) * s.W + (c0 - R + wc), s.observe_self ? -1 : a);
+        w[t >> 2] |= (uint32_t)(uint8_t)(int8_t)v << ((t & 3) * 8);
+        if (++wc == n) { wc = 0; ++wr; }
+    }
+}
+
+/* Observation rows of the acting learners, view range R known at compile time.  One thread gathers one
+ * learner's window: per window row LW aligned words, funnel-shifted to the row's first byte, then appended at
+ * byte n*i of the packed output (all shifts are compile-time after unrolling).  The packed row is produced in
+ * groups of 64 bytes, staged in shared memory (one BGW_STAGE_ROW per lane) and copied out by the warp as
+ * 128-bit stores, 4 lanes per learner. */
+template <int R>
+__device__ void fast_obs_rows(const DevSpec &s, const FastSpec &f, const Env &ev, const FastEnv &fe, int n_act, int8_t *obs_env,
+                              unsigned char *stage_all, int tid, int T)
+{
+    constexpr int n = 2 * R + 1, NB = n * n;
+    constexpr int RW = (n + 3) / 4;            /* words of an aligned row */
+    constexpr int LW = (n + 6) / 4;            /* words to load: alignment shift (<= 3 bytes) + n bytes */
+    constexpr int NG = (NB + 63) / 64;         /* 64-byte groups of the output row */
+    const int lane = tid & 31, warp = tid >> 5, nwarp = T >> 5;
+    unsigned char *stage = stage_all + (size_t)warp * 32 * BGW_STAGE_ROW;
+    const int pw4 = f.PW >> 2;
+    for (int base = warp * 32; base < n_act; base += nwarp * 32) {
+        const int li = base + lane;
+        const bool have = li < n_act;
+        const int a = have ? ev.ragent[li] : 0;
+        const bool observing = have && (ev.klass[a] & BGW_AG_OBSERVING);
+        const int o = pad_index(s, f, ev.cell[a]) - R * f.PW - R;
+        const uint32_t *wp = reinterpret_cast<const uint32_t *>(fe.cenc + (o & ~3));
+        const int sh = (o & 3) * 8;
+        const int cnt = min(32, n_act - base);
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+            uint32_t out[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) out[j] = 0;
+            if (observing) {
+#pragma unroll
+                for (int i = 0; i < n; ++i) {
+                    const int d = n * i;                              /* first output byte of window row i */
+                    if (d + n <= 64 * g || d >= 64 * (g + 1)) continue;   /* row does not touch this group */
+                    const uint32_t *rp = wp + i * pw4;
+                    uint32_t x[LW + 1], y[RW];
+#pragma unroll
+                    for (int j = 0; j < LW; ++j) x[j] = rp[j];
+                    x[LW] = 0;
+#pragma unroll
+                    for (int j = 0; j < RW; ++j) y[j] = __funnelshift_r(x[j], x[j + 1], sh);
+                    constexpr int vb = n - 4 * (RW - 1);
+                    if (vb < 4) y[RW - 1] &= (1u << (8 * (vb & 3))) - 1u;
+                    const int q = (d >> 2) - 16 * g, s8 = (d & 3) * 8;
+#pragma unroll
+                    for (int j = 0; j < RW; ++j) {
+                        if (q + j >= 0 && q + j < 16) out[q + j] |= y[j] << s8;
+                        if (s8 != 0 && q + j + 1 >= 0 && q + j + 1 < 16) out[q + j + 1] |= y[j] >> (32 - s8);
+                    }
+                }
+            }
+            uint4 *sp4 = reinterpret_cast<uint4 *>(stage + lane * BGW_STAGE_ROW);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) sp4[j] = make_uint4(out[4 * j], out[4 * j + 1], out[4 * j + 2], out[4 * j + 3]);
+            __syncwarp();
+            constexpr int gch = 4;                                       /* 16-byte chunks per group */
+            const int nchg = min(4, s.nchunks - 4 * g);                  /* 16-byte chunks of this group that exist */
+            for (int qq = lane; qq < cnt * gch; qq += 32) {
+                const int ll = qq >> 2, ch = qq & 3;
+                if (ch < nchg) {
+                    const uint4 v = *reinterpret_cast<const uint4 *>(stage + ll * BGW_STAGE_ROW + ch * 16);
+                    const int l = ev.plist[base + ll];
+                    *reinterpret_cast<uint4 *>(obs_env + (size_t)l * s.obs_stride + (4 * g + ch) * 16) = v;
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+__global__ void bgw_step_fast_kernel(const DevSpec s, const FastSpec f, const BgwState st, const uint32_t *actions,
+                                     const int16_t *order, int8_t *obs, float *reward, uint8_t *done, uint8_t *all_done)
+{
+    const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = T >> 5;
+    unsigned char *scratch = bgw_smem + f.o_scratch;
+    Env ev;
+    ev.enc = (int8_t *)(bgw_smem + f.o_enc);
+    ev.klass = bgw_smem + f.o_klass;
+    ev.tmp = bgw_smem + f.o_tmp;
+    ev.head = (uint16_t *)(bgw_smem + f.o_head);
+    ev.ragent = (uint16_t *)(bgw_smem + f.o_ragent);
+    ev.plist = (uint16_t *)(bgw_smem + f.o_plist);
+    ev.ctr = (int *)(bgw_smem + f.o_ctr);
+    ev.racc = (double *)(scratch + f.s_racc);
+    ev.slot = (uint32_t *)(scratch + f.s_slot);
+    ev.pstate = scratch + f.s_pstate;
+    ev.avail = (uint32_t *)(scratch + f.s_avail);
+    ev.mask = nullptr; ev.act = nullptr;
+    FastEnv fe;
+    fe.cenc = (int8_t *)(bgw_smem + f.o_cenc);
+    fe.rel = (uint16_t *)(bgw_smem + f.o_rel);
+    fe.lmask = (const uint32_t *)(bgw_smem + f.o_lmask);
+    fe.wsum = (int *)(bgw_smem + f.o_wsum);
+    fe.rkmask = (uint32_t *)(scratch + f.s_rkmask);
+    fe.eff = (uint16_t *)(scratch + f.s_eff);
+    fe.killrank = (uint16_t *)(scratch + f.s_killrank);
+    const double *rw = s.reward;
+    const int nch = s.nchunks;
+
+    /* ---- once per CTA: spec tables, learner byte masks, clean dense arrays ------------------------- */
+    if ((s.A & 3) == 0) {
+        const uint32_t *e32 = (const uint32_t *)s.enc, *k32 = (const uint32_t *)s.klass;
+        for (int w = tid; w < (s.A >> 2); w += T) {
+            const uint32_t k = __ldg(&k32[w]);
+            ((uint32_t *)ev.enc)[w] = __ldg(&e32[w]);
+            ((uint32_t *)ev.klass)[w] = k;
+            ((uint32_t *)(bgw_smem + f.o_lmask))[w] = __vcmpne4(k & (0x01010101u * BGW_AG_LEARNER), 0u);
+        }
+    } else {
+        for (int a = tid; a < s.A; a += T) {
+            const uint8_t k = __ldg(&s.klass[a]);
+            ev.enc[a] = __ldg(&s.enc[a]); ev.klass[a] = k;
+            (bgw_smem + f.o_lmask)[a] = (k & BGW_AG_LEARNER) ? 0xFF : 0;
+        }
+    }
+    fast_init_dense(s, f, ev, fe, tid, T);
+
+    int e = blockIdx.x, b = 0;
+    uint8_t ef_cur = 0, ef_nxt = 0;
+    uint32_t step_cur = 0, step_nxt = 0, epi_cur = 0, epi_nxt = 0;
+    if (e < s.E) {
+        fast_issue_env(s, f, st, actions, e, bgw_smem + f.o_buf, tid, T);
+        ef_cur = st.env_flags[e]; step_cur = st.step[e]; epi_cur = st.episode[e];
+    }
+    cp_async_commit();
+
+    int it_no = -1;
+    for (; e < s.E; e += gridDim.x) {
+        ++it_no;
+        BGW_PROF_MARK(0);
+        const int en = e + gridDim.x;
+        if (en < s.E) {
+            fast_issue_env(s, f, st, actions, en, bgw_smem + f.o_buf + (b ^ 1) * f.buf_bytes, tid, T);
+            ef_nxt = st.env_flags[en]; step_nxt = st.step[en]; epi_nxt = st.episode[en];
+        }
+        cp_async_commit();
+
+        unsigned char *buf = bgw_smem + f.o_buf + b * f.buf_bytes;
+        ev.cell = (uint16_t *)(buf + f.b_cell);
+        ev.next = (uint16_t *)(buf + f.b_next);
+        ev.flags = buf + f.b_flags;
+        fe.act = (uint32_t *)(buf + f.b_act);
+        ev.health = st.health + (size_t)e * s.A;
+        ev.e = e; ev.genv = (uint32_t)(s.env_offset + e);
+        int8_t *obs_env = obs ? obs + (size_t)e * s.L * s.obs_stride : nullptr;
+        float *rew = reward + (size_t)e * s.L;
+        uint8_t *dn = done + (size_t)e * s.L;
+        const size_t off = (size_t)e * s.A;
+        const uint8_t ef0 = ef_cur;
+        ev.episode = epi_cur;
+        ev.step = step_cur + 1u;
+        b ^= 1; ef_cur = ef_nxt; step_cur = step_nxt; epi_cur = epi_nxt;
+
+        /* rows of learners that receive nothing this call read as zero; free slots; zero counters */
+        if ((s.L & 15) == 0) {
+            uint4 *d4 = (uint4 *)dn, *r4 = (uint4 *)rew;
+            const uint4 z = make_uint4(0, 0, 0, 0);
+            for (int i = tid; i < s.L / 16; i += T) d4[i] = z;
+            for (int i = tid; i < s.L / 4; i += T) r4[i] = z;
+        } else {
+            for (int l = tid; l < s.L; l += T) { dn[l] = 0; rew[l] = 0.f; }
+        }
+        {
+            uint4 *s4 = (uint4 *)ev.slot;
+            const uint4 ones = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+            for (int i = tid; i < (s.slot_mask + 1) / 4; i += T) s4[i] = ones;
+        }
+        if (tid < CTR_COUNT) ev.ctr[tid] = 0;
+        cp_async_wait<1>();
+        __syncthreads();
+        BGW_PROF_MARK(1);
+
+        if (ef0 & BGW_ENV_ALL_DONE) {
+            if (s.auto_reset) {
+                /* general reset path on this env's (otherwise unused) staging buffer; leaves lists in `head` */
+                Env evr = ev;
+                evr.health = st.health + (size_t)e * s.A;
+                env_reset(s, st, evr, obs_env, tid, T);
+                if (tid == 0) {
+                    const uint8_t fl = (uint8_t)((evr.ctr[CTR_ERR] ? BGW_ENV_ERROR : 0) | BGW_ENV_RESET);
+                    st.env_flags[e] = fl; all_done[e] = fl;
+                }
+                __syncthreads();
+                fast_init_dense(s, f, ev, fe, tid, T);
+            } else if (tid == 0) all_done[e] = ef0;
+            __syncthreads();
+            continue;
+        }
+        BGW_PROF_MARK(2);
+
+        /* ---- relevant entities and acting learners, both compacted in entity order ------------------ */
+        int n_rel = 0, n_act = 0;
+        if (f.simd_ok) {
+            if (warp == 0) {
+                const uint32_t *fw = (const uint32_t *)ev.flags;
+                const int nwords = s.A >> 2, wpl = (nwords + 31) >> 5;
+                int cnt = 0;
+                for (int j = 0; j < wpl; ++j) {
+                    const int w = lane * wpl + j;
+                    if (w < nwords) {
+                        const uint32_t x = fw[w];
+                        const uint32_t rel = ~__vcmpeq4(x & 0x07070707u, 0x04040404u);      /* not (dead, removed, reported) */
+                        const uint32_t act = fe.lmask[w] & __vcmpeq4(x & 0x04040404u, 0u);   /* learner, not reported */
+                        cnt += (__popc(rel) >> 3) + ((__popc(act) >> 3) << 16);
+                    }
+                }
+                int incl = cnt;
+#pragma unroll
+                for (int dd = 1; dd < 32; dd <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, incl, dd); if (lane >= dd) incl += t; }
+                int pr = (incl - cnt) & 0xFFFF, pa = (incl - cnt) >> 16;
+                for (int j = 0; j < wpl; ++j) {
+                    const int w = lane * wpl + j;
+                    if (w < nwords) {
+                        const uint32_t x = fw[w];
+                        const uint32_t rel = ~__vcmpeq4(x & 0x07070707u, 0x04040404u);
+                        const uint32_t act = fe.lmask[w] & __vcmpeq4(x & 0x04040404u, 0u);
+#pragma unroll
+                        for (int bb = 0; bb < 4; ++bb) {
+                            const int a = 4 * w + bb;
+                            if ((rel >> (8 * bb)) & 1u) fe.rel[pr++] = (uint16_t)a;
+                            if ((act >> (8 * bb)) & 1u) ev.ragent[pa++] = (uint16_t)a;
+                        }
+                    }
+                }
+                if (lane == 31) { fe.wsum[0] = incl & 0xFFFF; fe.wsum[1] = incl >> 16; }
+            }
+            __syncthreads();
+            n_rel = fe.wsum[0]; n_act = fe.wsum[1];
+        } else {
+            for (int a0 = 0; a0 < s.A; a0 += T) {
+                const int a = a0 + tid;
+                bool rel = false, acting = false;
+                if (a < s.A) {
+                    const uint8_t fl = ev.flags[a];
+                    rel = (fl & (BGW_ST_ACTIVE | BGW_ST_IN_GRID)) || !(fl & BGW_ST_DONE_REPORTED);
+                    acting = (ev.klass[a] & BGW_AG_LEARNER) && !(fl & BGW_ST_DONE_REPORTED);
+                }
+                const unsigned br = __ballot_sync(0xFFFFFFFFu, rel), ba = __ballot_sync(0xFFFFFFFFu, acting);
+                if (lane == 0) { fe.wsum[2 + warp] = __popc(br); fe.wsum[34 + warp] = __popc(ba); }
+                __syncthreads();
+                int before_r = n_rel, before_a = n_act;
+                for (int w = 0; w < nwarp; ++w) {
+                    const int cr = fe.wsum[2 + w], ca = fe.wsum[34 + w];
+                    if (w < warp) { before_r += cr; before_a += ca; }
+                    n_rel += cr; n_act += ca;
+                }
+                const unsigned lt = (1u << lane) - 1u;
+                if (rel) fe.rel[before_r + __popc(br & lt)] = (uint16_t)a;
+                if (acting) ev.ragent[before_a + __popc(ba & lt)] = (uint16_t)a;
+                __syncthreads();
+            }
+        }
+        if (order) {                                               /* all_step_manager.py:62-65: caller-given order */
+            n_act = 0;
+            for (int i0 = 0; i0 < s.L; i0 += T) {
+                const int i = i0 + tid;
+                int a = 0;
+                bool acting = false;
+                if (i < s.L) {
+                    a = __ldg(&s.agent_of[order[(size_t)e * s.L + i]]);
+                    acting = !(ev.flags[a] & BGW_ST_DONE_REPORTED);
+                }
+                __syncthreads();                                    /* wsum / ragent of the previous pass are consumed */
+                const unsigned ba = __ballot_sync(0xFFFFFFFFu, acting);
+                if (lane == 0) fe.wsum[2 + warp] = __popc(ba);
+                __syncthreads();
+                int before = n_act;
+                for (int w = 0; w < nwarp; ++w) { const int c = fe.wsum[2 + w]; if (w < warp) before += c; n_act += c; }
+                if (acting) ev.ragent[before + __popc(ba & ((1u << lane) - 1u))] = (uint16_t)a;
+            }
+            __syncthreads();
+        }
+        BGW_PROF_MARK(3);
+
+        /* ---- occupant lists and summary from the relevant entities --------------------------------- */
+        for (int x = tid; x < n_rel; x += T) {
+            const int a = fe.rel[x];
+            ev.racc[a] = racc_persists(ev.klass[a]) ? st.reward_acc[off + a] : 0.0;
+            fe.killrank[a] = BGW_NONE16;
+            if (ev.flags[a] & BGW_ST_IN_GRID) {
+                if (ev.next[a] != BGW_NONE16) ev.tmp[ev.next[a]] = 1;
+                fe.cenc[pad_index(s, f, ev.cell[a])] = ev.enc[a];
+            }
+        }
+        __syncthreads();
+        for (int x = tid; x < n_rel; x += T) {
+            const int a = fe.rel[x];
+            if (ev.flags[a] & BGW_ST_IN_GRID) {
+                if (!ev.tmp[a]) ev.head[ev.cell[a]] = (uint16_t)a;
+                ev.tmp[a] = 0;
+                const int p = pad_index(s, f, ev.cell[a]);
+                if (fe.cenc[p] != ev.enc[a]) { fe.cenc[p] = (int8_t)BGW_MIXED; ev.ctr[CTR_MIXED] = 1; }
+            }
+        }
+        __syncthreads();
+        BGW_PROF_MARK(4);
+
+        /* ---- attack phase team_battle_example.py:35-47 ---------------------------------------------- */
+        for (int i = tid; i < n_act; i += T) {
+            const int a = ev.ragent[i], l = __ldg(&s.learner_of[a]);
+            ev.plist[i] = (uint16_t)l;
+            uint8_t p = 0;
+            if ((ev.flags[a] & BGW_ST_ACTIVE) && (ev.klass[a] & BGW_AG_ATTACKING) && (int8_t)((fe.act[l] >> 16) & 0xFF) != 0) {
+                /* candidate cells: the summary says an attackable encoding (or a mix) is present */
+                const int R = __ldg(&s.attack_r[a]), n = 2 * R + 1;
+                const unsigned long long row = __ldg(&s.attack_map[ev.enc[a]]);
+                const int8_t *w = fe.cenc + pad_index(s, f, ev.cell[a]) - R * f.PW - R;
+                uint32_t mask = 0;
+                if (R == 1) {
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) {
+                        const int v = w[(k / 3) * f.PW + (k % 3)];
+                        if (v > 0 ? (int)((row >> v) & 1ull) : (v == BGW_MIXED)) mask |= 1u << k;
+                    }
+                } else {
+                    for (int wr = 0; wr < n; ++wr)
+                        for (int wc = 0; wc < n; ++wc) {
+                            const int v = w[wr * f.PW + wc];
+                            if (v > 0 ? (int)((row >> v) & 1ull) : (v == BGW_MIXED)) mask |= 1u << (wr * n + wc);
+                        }
+                }
+                fe.rkmask[i] = mask;
+                if (mask) { p = 1; fe.eff[atomicAdd(&ev.ctr[CTR_NEMIT], 1)] = (uint16_t)i; }
+                else p = 3;                                         /* no possible victim: settled after the rounds */
+            }
+            ev.pstate[i] = p;
+        }
+        __syncthreads();
+        BGW_PROF_MARK(5);
+        {
+            const int n_eff = ev.ctr[CTR_NEMIT];
+            if (n_eff > 32) fast_attack_rounds<false>(s, f, ev, fe, n_eff, tid, T);
+            else if (n_eff > 0 && warp == 0) fast_attack_rounds<true>(s, f, ev, fe, n_eff, tid, T);
+            if (n_eff > 0 && n_eff <= 32) __syncthreads();
+        }
+        BGW_PROF_MARK(6);
+
+        /* ---- settle attackers without candidates; classify the moves :50-55 --------------------------- */
+        int pend = 0;
+        for (int i = tid; i < n_act; i += T) {
+            const int a = ev.ragent[i];
+            const bool active = ev.flags[a] & BGW_ST_ACTIVE;
+            if (ev.pstate[i] == 3) {
+                const unsigned kr = fe.killrank[a];
+                if (active || (kr != BGW_NONE16 && kr > (unsigned)i)) ev.racc[a] += rw[BGW_RW_ATTACK_FAIL];   /* :41-42 */
+            }
+            uint8_t p = 0;
+            if (active) {
+                bool ok = false;
+                if (ev.klass[a] & BGW_AG_MOVING) {
+                    int dr, dc, r0, c0;
+                    decode_move(s, a, fe.act[ev.plist[i]], dr, dc);
+                    cell_rc(s, f, ev.cell[a], r0, c0);
+                    const int r = r0 + dr, c = c0 + dc;
+                    if (r >= 0 && r < s.H && c >= 0 && c < s.W) {
+                        if (dr == 0 && dc == 0) ok = true;
+                        else { p = 1; fe.rkmask[i] = (uint32_t)(r * s.W + c); }
+                    }
+                }
+                if (!p && !ok) ev.racc[a] += rw[BGW_RW_MOVE_FAIL];
+            }
+            ev.pstate[i] = p;
+            pend |= p;
+        }
+        pend = __syncthreads_or(pend);
+        BGW_PROF_MARK(7);
+        if (n_act > 32) fast_move_rounds<false>(s, f, ev, fe, n_act, pend, tid, T);
+        else {
+            if (warp == 0) fast_move_rounds<true>(s, f, ev, fe, n_act, pend, tid, T);
+            __syncthreads();
+        }
+        BGW_PROF_MARK(8);
+
+        /* ---- entropy :58-59, rewards / dones of the acting learners (all_step_manager.py:68-87) -------- */
+        for (int i = tid; i < n_act; i += T) {
+            const int a = ev.ragent[i], l = ev.plist[i];
+            const double r = ev.racc[a] + rw[BGW_RW_ENTROPY];
+            const bool dd = prog_done(s, ev, a);
+            rew[l] = (float)r;
+            dn[l] = (uint8_t)(BGW_OUT_VALID | (dd ? BGW_OUT_DONE : 0));
+            if (dd) ev.flags[a] |= BGW_ST_DONE_REPORTED; else atomicAdd(&ev.ctr[CTR_REMAINING], 1);
+        }
+        /* racc of entities whose accumulator persists (non-learners with health) goes back before the scratch is reused */
+        for (int x = tid; x < n_rel; x += T) {
+            const int a = fe.rel[x];
+            if (racc_persists(ev.klass[a])) st.reward_acc[off + a] = ev.racc[a];
+        }
+        __syncthreads();                                            /* the scratch union becomes the observation stage */
+        BGW_PROF_MARK(9);
+
+        /* ---- observations ------------------------------------------------------------------------------ */
+        if (obs_env) {
+            const bool direct = s.observe_self && !ev.ctr[CTR_MIXED];
+            const int R = direct ? f.uniform_view : -1;
+            switch (R) {
+            case 1: fast_obs_rows<1>(s, f, ev, fe, n_act, obs_env, scratch, tid, T); break;
+            case 2: fast_obs_rows<2>(s, f, ev, fe, n_act, obs_env, scratch, tid, T); break;
+            case 3: fast_obs_rows<3>(s, f, ev, fe, n_act, obs_env, scratch, tid, T); break;
+            case 4: fast_obs_rows<4>(s, f, ev, fe, n_act, obs_env, scratch, tid, T); break;
+            case 5: fast_obs_rows<5>(s, f, ev, fe, n_act, obs_env, scratch, tid, T); break;
+            default: {
+                const int items = n_act * nch;
+                for (int it = tid; it < items; it += T) {
+                    const int li = it / nch, ch = it - li * nch;
+                    const int l = ev.plist[li], a = ev.ragent[li];
+                    uint32_t w[4];
+                    fast_obs_chunk_slow(s, f, ev, fe, a, ch, w);
+                    *reinterpret_cast<uint4 *>(obs_env + (size_t)l * s.obs_stride + ch * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+            }
+            }
+        }
+        __syncthreads();
+        BGW_PROF_MARK(10);
+
+        /* ---- store the relevant entities, get_all_done (done.py:49-56,147-153), clean the dense arrays ---- */
+        {
+            uint32_t lo = 0, hi = 0;
+            int ok = 1;
+            for (int x = tid; x < n_rel; x += T) {
+                const int a = fe.rel[x];
+                const uint8_t fl = ev.flags[a];
+                st.cell[off + a] = ev.cell[a]; st.next[off + a] = ev.next[a]; st.flags[off + a] = fl;
+                if (fl & BGW_ST_ACTIVE) { const int en2 = ev.enc[a]; if (en2 < 32) lo |= 1u << en2; else hi |= 1u << (en2 - 32); }
+                if (s.done_mask & (BGW_DONE_TARGET_AGENT | BGW_DONE_TARGET_DESTROYED)) {
+                    const int t = __ldg(&s.target[a]);
+                    if ((s.done_mask & BGW_DONE_TARGET_AGENT) && t >= 0 && !same_position(ev, a, t)) ok = 0;
+                    if ((s.done_mask & BGW_DONE_TARGET_DESTROYED) && t >= 0 && (ev.flags[t] & BGW_ST_ACTIVE)) ok = 0;
+                }
+                if (fl & BGW_ST_IN_GRID) {
+                    ev.head[ev.cell[a]] = BGW_NONE16;
+                    fe.cenc[pad_index(s, f, ev.cell[a])] = 0;
+                }
+            }
+            lo = __reduce_or_sync(0xFFFFFFFFu, lo);
+            hi = __reduce_or_sync(0xFFFFFFFFu, hi);
+            ok = __all_sync(0xFFFFFFFFu, ok);
+            if (lane == 0) {
+                if (lo) atomicOr((unsigned *)&ev.ctr[CTR_ENC_LO], lo);
+                if (hi) atomicOr((unsigned *)&ev.ctr[CTR_ENC_HI], hi);
+                if (!ok) atomicOr((unsigned *)&ev.ctr[CTR_AND], 1u);   /* here: 1 = some target condition unmet */
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned long long encs = ((unsigned long long)(unsigned)ev.ctr[CTR_ENC_HI] << 32) | (unsigned)ev.ctr[CTR_ENC_LO];
+            int d = !ev.ctr[CTR_AND];
+            if (s.done_mask & BGW_DONE_ACTIVE) d &= (encs == 0);
+            if (s.done_mask & BGW_DONE_ONE_TEAM) d &= ((encs & (encs - 1)) == 0);
+            uint8_t ef = 0;
+            if (d || ev.ctr[CTR_REMAINING] == 0) ef |= BGW_ENV_ALL_DONE;            /* all_step_manager.py:90-93 */
+            if (s.horizon > 0 && (int)ev.step >= s.horizon) ef |= BGW_ENV_ALL_DONE | BGW_ENV_TRUNCATED;
+            st.step[e] = ev.step;
+            st.env_flags[e] = ef;
+            all_done[e] = ef;
+            unsigned long long *sr = (unsigned long long *)st.stats + (size_t)e * BGW_STAT_COUNT;
+            sr[BGW_STAT_AGENT_STEPS] += (unsigned long long)n_act;
+            sr[BGW_STAT_ENV_STEPS] += 1ull;
+            if (ev.ctr[CTR_KILLS]) sr[BGW_STAT_KILLS] += (unsigned long long)ev.ctr[CTR_KILLS];
+            if (ef & BGW_ENV_ALL_DONE) sr[BGW_STAT_EPISODES] += 1ull;
+        }
+        __syncthreads();                                            /* ctr, scratch and the staging buffer are rewritten next */
+        BGW_PROF_MARK(11);
+    }
+    cp_async_wait<0>();
+}

@@ -188,7 +188,11 @@ def run_ours(args):
     ms = t_beg.elapsed_time(t_end)
     n_dev = agent_steps() - n0
     launches = eng.launches - launches0
-    kernel_ms = sum(a.elapsed_time(b) for a, b in k_ev)
+    per_step_ms = [a.elapsed_time(b) for a, b in k_ev]
+    kernel_ms = sum(per_step_ms)
+    if args.dump_steps and rank == 0:
+        with open(args.dump_steps, 'w') as fh:
+            json.dump(per_step_ms, fh)
 
     # ---------------- end to end through the public API with HOST buffers -----------------------------
     e2e_steps = max(4, min(args.steps, args.e2e_steps))
@@ -285,6 +289,7 @@ def main():
     ap.add_argument('--envs-per-gpu', type=int, default=ENVS_PER_GPU)
     ap.add_argument('--e2e-steps', type=int, default=40)
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--dump-steps', default=None, help='write the per-step kernel times (ms) to this JSON file')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

@@ -1,0 +1,61 @@
+#!/usr/bin/env python
+"""Group an `ncu --page source --csv --print-source cuda,sass` dump of bgw_step_fast_kernel by kernel phase
+(line ranges of abmarl_b200/csrc/bgw_fast.cuh found from its section comments).
+
+    python profiles/ncu_phases.py src.csv [n_envs]
+"""
+import csv
+import re
+import sys
+
+MARKS = [('exec_attack', r'__device__ void fast_exec_attack'), ('attack rounds', r'__device__ void fast_attack_rounds'),
+         ('exec_move', r'void fast_exec_move'), ('move rounds', r'__device__ void fast_move_rounds'),
+         ('init_dense', r'__device__ void fast_init_dense'), ('obs slow', r'__device__ void fast_obs_chunk_slow'),
+         ('kernel prologue', r'__global__ void bgw_step_fast_kernel'), ('per-CTA setup', r'once per CTA'),
+         ('env prologue', r'for \(int e = blockIdx.x'), ('relevant+acting compaction', r'relevant entities and acting'),
+         ('order compaction', r'if \(order\) \{'), ('lists+summary', r'occupant lists and summary'),
+         ('attack pre-pass', r'attack phase team'), ('settle+classify', r'settle attackers'),
+         ('emit reward/done', r'entropy :58'), ('obs gather', r'observations: byte gather'),
+         ('store+all_done+clean', r'store the relevant')]
+
+
+def main(path, n_envs=4096, src='abmarl_b200/csrc/bgw_fast.cuh'):
+    lines = open(src).read().split('\n')
+    starts = []
+    for name, pat in MARKS:
+        for i, l in enumerate(lines, 1):
+            if re.search(pat, l):
+                starts.append((i, name))
+                break
+    starts.sort()
+    rows = list(csv.reader(open(path)))
+    hdr, fname, agg = None, '', {}
+    for r in rows:
+        if r and r[0] == 'File Path':
+            fname = r[1].split('/')[-1]
+            continue
+        if r and r[0] == 'Line No':
+            hdr = r
+            continue
+        if hdr is None or len(r) < len(hdr) or r[2] != '-':
+            continue
+        inst, samp = int(r[hdr.index('Instructions Executed')]), int(r[hdr.index('# Samples')])
+        if fname == 'bgw_fast.cuh':
+            ln = int(r[0])
+            name = 'helpers (cell_rc/pad_index/cenc_of_list)'
+            for s, n in starts:
+                if ln >= s:
+                    name = n
+        else:
+            name = fname
+        a = agg.setdefault(name, [0, 0])
+        a[0] += inst
+        a[1] += samp
+    ti, ts = sum(v[0] for v in agg.values()), sum(v[1] for v in agg.values())
+    print(f"total warp-instructions {ti} ({ti / n_envs:.0f}/env), samples {ts}")
+    for name, (i, s) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
+        print(f"{name:42s} inst {100 * i / ti:5.1f}% ({i / n_envs:7.0f}/env)   samples {100 * s / ts:5.1f}%")
+
+
+if __name__ == '__main__':
+    main(sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 4096)

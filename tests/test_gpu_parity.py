@@ -47,12 +47,32 @@ def test_engine_matches_oracle(mirror, name, n_envs, steps, horizon):
     assert int(eng.stats()[K.STAT_AGENT_STEPS].item()) == n
 
 
+@pytest.mark.parametrize('name', ['tb_c2', 'tb_c5_small', 'tb_dense', 'tb_noself'])
+def test_general_kernel_on_fast_path_scenarios(mirror, name, monkeypatch):
+    """Scenarios that qualify for the specialised team-battle kernel must give the same results through the
+    general kernel (BGW_GENERIC_KERNEL=1), i.e. both equal the oracle."""
+    builder, manager, _ = scenarios.SCENARIOS[name]
+    spec = compile_sim(builder(mirror), manager=manager, n_envs=32, seed=21, horizon=40, auto_reset=True)
+    monkeypatch.setenv('BGW_GENERIC_KERNEL', '1')
+    eng, ora = _pair(spec)
+    run_lockstep(eng, ora, 60, label=name + '/general')
+
+
+@pytest.mark.parametrize('threads', ['64', '128', '512'])
+def test_thread_count_does_not_change_results(mirror, threads, monkeypatch):
+    spec = compile_sim(scenarios.build_tb_c5_small(mirror), n_envs=16, seed=9, horizon=30, auto_reset=True)
+    monkeypatch.setenv('BGW_THREADS', threads)
+    eng, ora = _pair(spec)
+    run_lockstep(eng, ora, 45, label='tb_c5_small/T' + threads)
+
+
 @pytest.mark.parametrize('name', ['tb_c2', 'tb_dense', 'tb_blocking'])
 def test_serial_and_reservation_actor_paths_agree(mirror, name, monkeypatch):
     """The rank-order loop (one thread) and the reservation rounds must both equal the oracle."""
     builder, manager, _ = scenarios.SCENARIOS[name]
     spec = compile_sim(builder(mirror), manager=manager, n_envs=32, seed=11, horizon=40, auto_reset=True)
     monkeypatch.setenv('BGW_SERIAL_ACTORS', '1')
+    monkeypatch.setenv('BGW_GENERIC_KERNEL', '1')
     eng, ora = _pair(spec)
     run_lockstep(eng, ora, 60, label=name + '/serial')
 
