@@ -157,7 +157,38 @@ def record(name, builder, manager, n_steps):
           f"{int(out['done'].astype(bool).sum())} agent-steps -> {os.path.getsize(path) / 1024:.0f} KiB   oracle == reference")
 
 
+def record_los(R=16):
+    """create_grid_and_mask (utils.py:5-117) of the unmodified reference for every blocker offset at range R."""
+    scenarios.reference_api()
+    from abmarl.sim.gridworld.utils import create_grid_and_mask
+    from abmarl.sim.gridworld.grid import Grid
+    from abmarl.sim.gridworld.agent import GridObservingAgent, GridWorldAgent
+    from oracle.oracle import los_mask
+    n = 2 * R + 1
+    out = np.zeros((n, n, n * n), dtype=np.uint8)
+    for rd in range(-R, R + 1):
+        for cd in range(-R, R + 1):
+            grid = Grid(n, n, overlapping={1: {2}})
+            viewer = GridObservingAgent(id='o', encoding=1, view_range=R, initial_position=np.array([R, R]))
+            blocker = GridWorldAgent(id='b', encoding=2, blocking=True, initial_position=np.array([R + rd, R + cd]))
+            agents = {'o': viewer, 'b': blocker}
+            grid.reset()
+            for a in agents.values():
+                a.active = True
+                assert grid.place(a, a.initial_position)
+            _, mask = create_grid_and_mask(viewer, grid, R, agents)
+            out[rd + R, cd + R] = mask.astype(np.uint8).ravel()
+            if not np.array_equal(los_mask(R, rd, cd).ravel(), out[rd + R, cd + R]):
+                raise SystemExit(f"oracle LOS mask != reference at blocker offset {(rd, cd)}")
+    path = os.path.join(OUT, f'los_r{R}.npz')
+    np.savez_compressed(path, range=np.int64(R), packed=np.packbits(out, axis=-1))
+    print(f"los_r{R}: {n * n} blocker offsets -> {os.path.getsize(path) / 1024:.0f} KiB   oracle == reference")
+
+
 if __name__ == '__main__':
+    if sys.argv[1:] == ['los']:
+        record_los()
+        sys.exit(0)
     names = sys.argv[1:] or list(scenarios.SCENARIOS)
     for n in names:
         b, m, steps = scenarios.SCENARIOS[n]

@@ -1,0 +1,99 @@
+"""Host-side mirror of the reference's component API: same names (plus the pre-0.2.6 aliases), same spaces and
+null actions, same validation, and the builders compile to the flat spec (no GPU needed)."""
+import numpy as np
+import pytest
+
+from abmarl_b200 import _capi as K
+from abmarl_b200.spaces import Box, Discrete
+from abmarl_b200.spec import compile_sim
+from abmarl_b200.sim.gridworld import actor, agent, observer, state, done, wrapper
+from abmarl_b200.sim.gridworld.grid import Grid
+from abmarl_b200 import examples as ex
+from tests import scenarios
+
+
+def test_old_and_new_component_names():
+    assert observer.SingleGridObserver is observer.PositionCenteredEncodingObserver
+    assert observer.MultiGridObserver is observer.StackedPositionCenteredEncodingObserver
+    assert actor.AttackActor is actor.BinaryAttackActor
+    for name in ('ActiveDone', 'TargetAgentDone', 'OneTeamRemainingDone'):
+        assert hasattr(done, name)
+    for name in ('PositionState', 'HealthState', 'OrientationState', 'MazePlacementState'):
+        assert hasattr(state, name)
+
+
+def test_grid_overlapping_is_symmetrised():                    # test_grid.py:30-32
+    g = Grid(3, 3, overlapping={1: {2}, 3: {1}})
+    assert g.overlapping == {1: {2, 3}, 2: {1}, 3: {1}}
+    with pytest.raises(AssertionError):
+        Grid(0, 3)
+    with pytest.raises(AssertionError):
+        Grid(3, 3, overlapping={1: [2]})
+
+
+def test_agent_validation():                                   # test_agent.py
+    with pytest.raises(AssertionError):
+        agent.GridWorldAgent(id='a', encoding=0)
+    with pytest.raises(AssertionError):
+        agent.GridWorldAgent(id='a', encoding=-2)
+    a = agent.HealthAgent(id='a', encoding=1, initial_health=0.5)
+    assert a.initial_health == 0.5
+    with pytest.raises(AssertionError):
+        agent.MovingAgent(id='m', encoding=1, move_range=-1)
+
+
+def test_actor_spaces_and_ravel_wrapper():                     # test_actor.py:36-48, test_wrapper.py:66-144
+    agents = {f'agent{i}': agent.MovingAgent(id=f'agent{i}', encoding=1, move_range=i + 1,
+                                             initial_position=np.array([i, i])) for i in range(3)}
+    grid = Grid(8, 8)
+    mv = actor.MoveActor(agents=agents, grid=grid)
+    assert agents['agent0'].action_space['move'] == Box(-1, 1, (2,), int)
+    assert agents['agent2'].action_space['move'] == Box(-3, 3, (2,), int)
+    rv = wrapper.RavelActionWrapper(mv)
+    assert [agents[f'agent{i}'].action_space['move'] for i in range(3)] == [Discrete(9), Discrete(25), Discrete(49)]
+    assert [agents[f'agent{i}'].null_action['move'] for i in range(3)] == [4, 12, 24]
+    assert list(rv.unwrap_point(rv.from_space['agent0'], 7)) == [1, 0]
+    assert list(rv.unwrap_point(rv.from_space['agent1'], 3)) == [-2, 1]
+    assert list(rv.unwrap_point(rv.from_space['agent2'], 34)) == [1, 3]
+    assert rv.wrap_point(rv.from_space['agent2'], np.array([1, 3])) == 34
+
+
+def test_attack_actor_validation():                            # test_actor.py:503-528
+    agents = {'a': agent.AttackingAgent(id='a', encoding=1, attack_range=1, attack_strength=1, attack_accuracy=1,
+                                        initial_position=np.array([0, 0]))}
+    grid = Grid(3, 3)
+    for bad in ([1, 2, 3], {'1': {3}}, {1: 3}, {1: {'2'}}):
+        with pytest.raises(AssertionError):
+            actor.BinaryAttackActor(agents=agents, grid=grid, attack_mapping=bad)
+    actor.BinaryAttackActor(agents=agents, grid=grid, attack_mapping={1: {1}})
+    assert agents['a'].action_space['attack'] == Discrete(2) and agents['a'].null_action['attack'] == 0
+
+
+def test_build_sim_from_file_counts_registered_characters(mirror):   # base.py:178-191
+    sim = scenarios.build_maze_c1(mirror)
+    assert list(sim.agents)[0].startswith('wall') and 'navigator' in sim.agents and 'target' in sim.agents
+    spec = compile_sim(sim)
+    assert (spec.rows, spec.cols, spec.n_agents, spec.n_learners) == (8, 18, 67, 1)
+    assert spec.program == K.PROG_MAZE and spec.role[spec.agent_ids.index('navigator')] == K.ROLE_NAVIGATOR
+    blocking = [(spec.klass[i] & K.AG_BLOCKING) != 0 for i in range(spec.n_agents)]
+    assert sum(blocking) == 65
+
+
+def test_team_battle_spec_tables(mirror):
+    spec = compile_sim(scenarios.build_tb_c2(mirror), n_envs=16, seed=5, horizon=200, auto_reset=True)
+    assert (spec.rows, spec.cols, spec.n_agents, spec.n_learners, spec.max_encoding) == (8, 8, 24, 24, 4)
+    assert spec.obs_shape() == (7, 7, 1, 64)
+    assert spec.done_mask == K.DONE_ONE_TEAM and spec.attack_actor == K.ATTACK_BINARY and spec.move_actor == K.MOVE_BOX
+    assert int(spec.overlap[1]) == 1 << 1 and int(spec.attack_map[1]) == (1 << 2) | (1 << 3) | (1 << 4)
+    np.testing.assert_allclose(spec.reward[:5], [-0.1, 1.0, -1.0, -0.1, -0.01])
+    assert np.isnan(spec.init_health).all()                     # rllib_team_battle.py leaves initial_health unset
+
+
+def test_team_battle_rejects_simultaneous_attacks(mirror):     # ValueError in the reference
+    agents = {'a0': ex.BattleAgent(id='a0', encoding=1), 'a1': ex.BattleAgent(id='a1', encoding=2)}
+    agents['a0'].simultaneous_attacks = 2
+    sim = ex.TeamBattleSim.build_sim(4, 4, agents=agents, overlapping={1: {1}}, attack_mapping={1: {2}, 2: {1}},
+                                     states={'PositionState', 'HealthState'},
+                                     observers={'PositionCenteredEncodingObserver'}, dones={'ActiveDone'})
+    with pytest.raises(AssertionError):
+        compile_sim(sim)
