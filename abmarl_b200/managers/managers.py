@@ -31,8 +31,12 @@ class SimulationManager(ABC):
         self.spec = compile_sim(sim, manager=self._manager, n_envs=n_envs, env_offset=env_offset, seed=seed,
                                 horizon=horizon, auto_reset=auto_reset)
         self.engine = BatchedGridWorld(self.spec, device=device)
+        self._feeder = None
         if layouts is not None:
             self.engine.set_layout(layouts)
+        elif self.spec.layout_generator is not None:        # e.g. MazePlacementState: per-episode host-side layouts
+            from abmarl_b200.layouts import LayoutFeeder
+            self._feeder = LayoutFeeder(self.spec)
         self.learner_ids = self.spec.learner_ids
         self._order_gen = torch.Generator(device='cpu')
         self._order_gen.manual_seed(int(seed) & 0x7FFFFFFF)
@@ -48,6 +52,10 @@ class SimulationManager(ABC):
 
     def reset(self, env_mask=None):
         """-> obs int8 [E, L, h, w(, c)] (first observations; turn-based: only the row of the env's turn is fresh)."""
+        if self._feeder is not None:
+            episode = self.engine.state['episode'].cpu().numpy().view(np.uint32)
+            mask = None if env_mask is None else np.asarray(torch.as_tensor(env_mask).cpu())
+            self.engine.set_layout(self._feeder.prime(episode, mask))
         self.engine.reset(env_mask)
         return self.engine.obs_view()
 
@@ -61,6 +69,9 @@ class SimulationManager(ABC):
             order = torch.stack([torch.randperm(self.engine.L, generator=self._order_gen)
                                  for _ in range(self.engine.E)]).to(torch.int16)
         _, reward, done, all_done = self.engine.step(actions, order)
+        if self._feeder is not None and self.spec.auto_reset:
+            if self._feeder.after_step(all_done.cpu().numpy(), self.engine.state['episode'].cpu().numpy().view(np.uint32)):
+                self.engine.set_layout(self._feeder.rows)
         return self.engine.obs_view(), reward, done, all_done
 
     def sample_actions(self):

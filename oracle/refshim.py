@@ -41,6 +41,7 @@ class PhiloxReplay:
         self.sim, self.seed, self.env = sim, int(seed), int(env)
         self.index = {agent_id: i for i, agent_id in enumerate(sim.agents)}
         self.episode, self.step = -1, 0
+        self.maze_k, self.maze_episode = 0, None                  # position in the episode's maze draw sequence
         self.log = []                       # (site, slot, k) of every replayed draw, for debugging
 
     # -- keyed draw -------------------------------------------------------------------------------
@@ -103,6 +104,22 @@ class PhiloxReplay:
         if name == 'reset' and 'agent' in loc:               # OrientationState.reset state.py:675
             x = self._x(K.SITE_ORIENT, self.index[loc['agent'].id])
             return low + philox.index(x, high - low)
+        if name in ('_build_available_positions', 'generate_maze'):   # state.py:534, utils.py:193,198
+            if self.maze_episode != self.episode:
+                self.maze_episode, self.maze_k = self.episode, 0
+            saved_step, self.step = self.step, 0              # maze draws are keyed by (episode, k) only
+
+            def one(lo, hi):
+                x = self._x(K.SITE_MAZE, 0, self.maze_k)
+                self.maze_k += 1
+                return int(lo) + philox.index(x, int(hi) - int(lo))
+            try:
+                if np.ndim(high) == 0:
+                    return one(low, high)
+                lows = np.broadcast_to(low, np.shape(high))
+                return np.array([one(lo, hi) for lo, hi in zip(lows, high)])
+            finally:
+                self.step = saved_step
         raise RuntimeError(f"unexpected np.random.randint call site: {name}")
 
     def __enter__(self):

@@ -23,18 +23,20 @@ from abmarl_b200 import _capi as K                      # noqa: E402
 from abmarl_b200.spec import compile_sim, CompiledSpec  # noqa: E402
 from oracle.oracle import OracleEnv                     # noqa: E402
 from oracle.refshim import PhiloxReplay, extract_state  # noqa: E402
+from abmarl_b200.layouts import layouts_for             # noqa: E402
 from tests import scenarios                             # noqa: E402
 
 SEED = 0xB200
 OUT = os.path.dirname(os.path.abspath(__file__))
 
 
-def action_dict(spec, sim, done_agents, act):
-    """bytes [L,4] -> the reference's {agent_id: {'move': ..., 'attack': ...}} for learners not yet done."""
+def action_dict(spec, sim, done_agents, act, only=None):
+    """bytes [L,4] -> the reference's {agent_id: {'move': ..., 'attack': ...}} for learners not yet done
+    (`only` = the learner whose turn it is under TurnBasedManager)."""
     out = {}
     for l, a in enumerate(spec.learner_agents):
         agent_id = spec.agent_ids[a]
-        if agent_id in done_agents:
+        if agent_id in done_agents or (only is not None and l != only):
             continue
         agent = sim.agents[agent_id]
         d = {}
@@ -74,8 +76,7 @@ def check(name, what, t, got, want):
 def record(name, builder, manager, n_steps):
     api = scenarios.reference_api()
     sim = builder(api)
-    assert manager == 'all_step'
-    mgr = api.managers.AllStepManager(sim)
+    mgr = {'all_step': api.managers.AllStepManager, 'turn_based': api.managers.TurnBasedManager}[manager](sim)
     spec = compile_sim(sim, manager=manager, n_envs=1, seed=SEED, auto_reset=False)
     ora = OracleEnv(spec)
     L, stride = spec.n_learners, ora.dims.obs_stride
@@ -112,6 +113,8 @@ def record(name, builder, manager, n_steps):
             if need_reset:
                 rp.episode += 1
                 rp.step = 0
+                if spec.layout_generator:
+                    ora.set_layout(layouts_for(spec, [0], [rp.episode]))
                 ref_obs = mgr.reset()
                 ora.reset()
                 rows, present = ref_obs_rows(spec, ref_obs, stride)
@@ -122,7 +125,8 @@ def record(name, builder, manager, n_steps):
                 continue
             act = ora.sample_actions()[0]
             rp.step += 1
-            ref_obs, ref_rew, ref_done, _ = mgr.step(action_dict(spec, sim, mgr.done_agents, act))
+            only = int(ora.state['turn'][0]) if manager == 'turn_based' else None
+            ref_obs, ref_rew, ref_done, _ = mgr.step(action_dict(spec, sim, mgr.done_agents, act, only))
             ora.step(act[None])
             rows, present = ref_obs_rows(spec, ref_obs, stride)
             reward = np.zeros(L)

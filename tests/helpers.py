@@ -34,6 +34,13 @@ def assert_outputs_equal(eng, ora, where, rewards_exact=True):
 
 def run_lockstep(eng, ora, steps, order_fn=None, check_every=1, label=''):
     """Reset both, then drive both with the keyed random policy for `steps` calls, comparing everything."""
+    feeder = None
+    if eng.spec.layout_generator is not None:                  # per-episode host-side layouts (MazePlacementState)
+        from abmarl_b200.layouts import LayoutFeeder
+        feeder = LayoutFeeder(eng.spec)
+        rows = feeder.prime(ora.state['episode'])
+        eng.set_layout(rows)
+        ora.set_layout(rows)
     eng.reset()
     ora.reset()
     assert np.array_equal(eng.obs.cpu().numpy(), ora.obs), f"{label}: reset observations differ"
@@ -46,6 +53,9 @@ def run_lockstep(eng, ora, steps, order_fn=None, check_every=1, label=''):
         order = None if order_fn is None else order_fn(t)
         eng.step(act_e, order)
         ora.step(act_o, order)
+        if feeder is not None and feeder.after_step(ora.all_done, ora.state['episode']):
+            eng.set_layout(feeder.rows)
+            ora.set_layout(feeder.rows)
         if t % check_every == 0 or t == steps - 1:
             assert_outputs_equal(eng, ora, f"{label} step {t}")
             assert_state_equal(eng.state_numpy(), ora.state, f"{label} step {t}")

@@ -182,6 +182,56 @@ def build_pacman_c3(api, view_range=20):
         reward_scheme={'bad_move': 0, 'entropy': -0.01, 'eat_food': 0.05, 'kill': 1, 'die': -1})
 
 
+# ---------------------------------------------------------------------------------------------------
+# multi maze (multi_maze_navigation.py; examples/rllib_multi_maze_navigation.py:7-41)
+# ---------------------------------------------------------------------------------------------------
+def build_mm_c4(api, ravel=True):
+    """BASELINE config 4: 10x10 maze rebuilt every episode around the target (MazePlacementState), 20 clustered
+    barriers, 5 scattered navigators with view 5; RavelActionWrapper on the move actor."""
+    agents = {'target': api.agent.GridWorldAgent(id='target', encoding=1)}
+    agents.update({f'barrier{i}': api.agent.GridWorldAgent(id=f'barrier{i}', encoding=2) for i in range(20)})
+    agents.update({f'navigator{i}': api.ex.MultiMazeNavigationAgent(id=f'navigator{i}', encoding=3, view_range=5)
+                   for i in range(5)})
+    sim = api.ex.MultiMazeNavigationSim.build_sim(
+        10, 10, agents=agents, overlapping={1: {3}, 3: {3}}, target_agent=agents['target'],
+        barrier_encodings={2}, free_encodings={1, 3}, cluster_barriers=True, scatter_free_agents=True,
+        no_overlap_at_reset=True)
+    if ravel:
+        sim.move_actor = api.wrapper.RavelActionWrapper(sim.move_actor)
+    return sim
+
+
+def build_mm_random(api):
+    """Multi maze with randomly placed barriers and navigators (no clustering / scattering), move range 2, and a
+    fixed target: exercises the PLACE draws of MazePlacementState and the ravel decode for a 5x5 action box."""
+    agents = {'target': api.agent.GridWorldAgent(id='target', encoding=1, initial_position=np.array([4, 3]))}
+    agents.update({f'barrier{i}': api.agent.GridWorldAgent(id=f'barrier{i}', encoding=2) for i in range(12)})
+    for i in range(4):
+        nav = api.ex.MultiMazeNavigationAgent(id=f'navigator{i}', encoding=3, view_range=3)
+        nav.move_range = 2
+        agents[nav.id] = nav
+    sim = api.ex.MultiMazeNavigationSim.build_sim(
+        8, 9, agents=agents, overlapping={1: {3}, 3: {3}}, target_agent=agents['target'],
+        barrier_encodings={2}, free_encodings={1, 3})
+    sim.move_actor = api.wrapper.RavelActionWrapper(api.actor.MoveActor(agents=sim.agents, grid=sim.grid))
+    return sim
+
+
+def build_mm_tiny(api):
+    """A 4x5 multi maze: navigators reach the target within a few turns, so a short transcript covers several
+    episodes -- done agents leaving the turn cycle, the 'just finished + next agent' double report and the
+    cycle that is not rewound by reset (turn_based_manager.py:17-20,53-92)."""
+    agents = {'target': api.agent.GridWorldAgent(id='target', encoding=1)}
+    agents.update({f'barrier{i}': api.agent.GridWorldAgent(id=f'barrier{i}', encoding=2) for i in range(3)})
+    agents.update({f'navigator{i}': api.ex.MultiMazeNavigationAgent(id=f'navigator{i}', encoding=3, view_range=2)
+                   for i in range(3)})
+    sim = api.ex.MultiMazeNavigationSim.build_sim(
+        4, 5, agents=agents, overlapping={1: {3}, 3: {3}}, target_agent=agents['target'],
+        barrier_encodings={2}, free_encodings={1, 3}, cluster_barriers=True, scatter_free_agents=False)
+    sim.move_actor = api.wrapper.RavelActionWrapper(sim.move_actor)
+    return sim
+
+
 SCENARIOS = {
     # name: (builder, manager, steps recorded in the golden file)
     'tb_c2': (build_tb_c2, 'all_step', 40),
@@ -192,4 +242,9 @@ SCENARIOS = {
     'tb_noself': (build_tb_noself, 'all_step', 25),
     'maze_c1': (build_maze_c1, 'all_step', 60),
     'pacman_c3': (build_pacman_c3, 'all_step', 12),
+    'mm_c4': (build_mm_c4, 'turn_based', 120),
+    'mm_random': (build_mm_random, 'turn_based', 90),
+    'mm_allstep': (build_mm_c4, 'all_step', 60),
+    'mm_tiny': (build_mm_tiny, 'turn_based', 400),
+    'mm_tiny_allstep': (build_mm_tiny, 'all_step', 200),
 }

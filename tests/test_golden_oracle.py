@@ -34,10 +34,14 @@ def test_oracle_reproduces_reference_transcript(mirror, name):
     builder, manager, _ = scenarios.SCENARIOS[name]
     spec = compile_sim(builder(mirror), manager=manager, n_envs=1, seed=int(g['seed']), auto_reset=False)
     ora = OracleEnv(spec)
-    n_valid = 0
+    n_valid, episode = 0, -1
     for t in range(len(g['kind'])):
         present = g['obs_present'][t]
         if g['kind'][t] == 0:
+            episode += 1
+            if spec.layout_generator is not None:
+                from abmarl_b200.layouts import layouts_for
+                ora.set_layout(layouts_for(spec, [0], [episode]))
             ora.reset()
         else:
             ora.step(g['actions'][t][None])

@@ -33,6 +33,11 @@ CASES = [
     ('tb_noself', 48, 80, 30),
     ('maze_c1', 32, 150, 60),
     ('pacman_c3', 6, 40, 25),
+    ('mm_c4', 12, 150, 60),
+    ('mm_random', 12, 120, 50),
+    ('mm_allstep', 12, 100, 40),
+    ('mm_tiny', 16, 300, 0),
+    ('mm_tiny_allstep', 16, 200, 0),
 ]
 
 
@@ -104,9 +109,14 @@ def test_engine_reproduces_reference_transcript(mirror, name):
     spec = compile_sim(builder(mirror), manager=manager, n_envs=1, seed=int(g['seed']), auto_reset=False)
     from abmarl_b200.engine import BatchedGridWorld
     eng = BatchedGridWorld(spec, device='cuda:0')
+    episode = -1
     for t in range(len(g['kind'])):
         present = g['obs_present'][t]
         if g['kind'][t] == 0:
+            episode += 1
+            if spec.layout_generator is not None:
+                from abmarl_b200.layouts import layouts_for
+                eng.set_layout(layouts_for(spec, [0], [episode]))
             eng.reset()
         else:
             act = torch.from_numpy(g['actions'][t][None].copy()).cuda()
