@@ -445,6 +445,21 @@ int bgw_sample_actions(bgw_handle h, int8_t *actions, void *stream)
     return 0;
 }
 
+int bgw_gather_valid(bgw_handle h, const int8_t *obs, const float *reward, const uint8_t *done, const uint8_t *all_done,
+                     int32_t *count, int32_t *index, int8_t *obs_c, float *reward_c, uint8_t *done_c, void *stream)
+{
+    if (!h || !obs || !reward || !done || !all_done || !count || !index || !obs_c || !reward_c || !done_c)
+        return fail(1, "bgw_gather_valid: null argument");
+    DeviceGuard guard(h->device);
+    CUDA_OK(cudaMemsetAsync(count, 0, sizeof(int32_t), (cudaStream_t)stream));
+    const int L = h->ds.L;
+    bgw_gather_kernel<<<h->ds.E, 128, 16 + align16(L * 2), (cudaStream_t)stream>>>(
+        L, h->ds.obs_stride, obs, reward, done, all_done, count, index, obs_c, reward_c, done_c);
+    CUDA_OK(cudaGetLastError());
+    h->launches += 1;
+    return 0;
+}
+
 int bgw_rng_draw(uint64_t seed, uint32_t env, uint32_t episode, uint32_t step, uint32_t site, uint32_t slot, uint32_t k,
                  uint32_t out[4])
 {

@@ -1055,3 +1055,38 @@ __global__ void bgw_sample_actions_kernel(const DevSpec s, const BgwState st, ui
         o |= (bgw_index(x[2], (uint32_t)__ldg(&s.simatt[a]) + 1) & 0xFF) << 16;   /* Discrete(n+1) actor.py:452 */
     actions[i] = o;
 }
+
+/* bgw_gather_valid: one CTA per env; rows are claimed with one global atomicAdd per env and copied as 16-byte chunks */
+__global__ void bgw_gather_kernel(int L, int obs_stride, const int8_t *obs, const float *reward, const uint8_t *done,
+                                  const uint8_t *all_done, int *count, int *index, int8_t *obs_c, float *reward_c,
+                                  uint8_t *done_c)
+{
+    extern __shared__ __align__(16) unsigned char gsm[];
+    int *sc = (int *)gsm;                 /* [0] rows of this env, [1] base in the compacted buffers */
+    uint16_t *list = (uint16_t *)(gsm + 16);
+    const int e = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
+    const bool whole = all_done[e] & BGW_ENV_RESET;
+    const uint8_t *dn = done + (size_t)e * L;
+    if (tid == 0) sc[0] = 0;
+    __syncthreads();
+    for (int l = tid; l < L; l += T)
+        if (whole || (dn[l] & BGW_OUT_VALID)) list[atomicAdd(&sc[0], 1)] = (uint16_t)l;
+    __syncthreads();
+    const int n = sc[0];
+    if (n == 0) return;
+    if (tid == 0) sc[1] = atomicAdd(count, n);
+    __syncthreads();
+    const int base = sc[1], nch = obs_stride >> 4;
+    for (int i = tid; i < n; i += T) {
+        const int l = list[i];
+        index[base + i] = e * L + l;
+        reward_c[base + i] = reward[(size_t)e * L + l];
+        done_c[base + i] = dn[l];
+    }
+    const uint4 *src = (const uint4 *)(obs + (size_t)e * L * obs_stride);
+    uint4 *dst = (uint4 *)(obs_c + (size_t)base * obs_stride);
+    for (int it = tid; it < n * nch; it += T) {
+        const int i = it / nch, ch = it - i * nch;
+        dst[(size_t)i * nch + ch] = src[(size_t)list[i] * nch + ch];
+    }
+}

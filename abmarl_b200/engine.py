@@ -117,6 +117,45 @@ class BatchedGridWorld:
                                   self.all_done.data_ptr(), self._stream()), self.lib)
         return self.obs, self.reward, self.done, self.all_done
 
+    # ---- host-facing step: HOST buffers in, only the rows the reference's manager would return out ---------
+    def _host_buffers(self):
+        if getattr(self, '_hb', None) is None:
+            E, L, dev = self.E, self.L, self.device
+            n = E * L
+            self._hb = dict(
+                count=torch.zeros(1, dtype=torch.int32, device=dev), index=torch.empty(n, dtype=torch.int32, device=dev),
+                obs=torch.empty((n, self.dims.obs_stride), dtype=torch.int8, device=dev),
+                reward=torch.empty(n, dtype=torch.float32, device=dev), done=torch.empty(n, dtype=torch.uint8, device=dev),
+                h_count=torch.zeros(1, dtype=torch.int32).pin_memory(), h_index=torch.empty(n, dtype=torch.int32).pin_memory(),
+                h_obs=torch.empty((n, self.dims.obs_stride), dtype=torch.int8).pin_memory(),
+                h_reward=torch.empty(n, dtype=torch.float32).pin_memory(), h_done=torch.empty(n, dtype=torch.uint8).pin_memory(),
+                h_all=torch.empty(E, dtype=torch.uint8).pin_memory(), d_act=torch.empty((E, L, 4), dtype=torch.int8, device=dev))
+        return self._hb
+
+    def step_host(self, actions_host, order=None):
+        """One manager step for a HOST caller: `actions_host` int8 [E, L, 4] (pinned for speed) is copied to the
+        device, the batch is stepped, and the rows of the learners that received (obs, reward, done) -- plus all
+        rows of envs that were auto-reset -- are compacted on the device and copied back.  Returns
+        (n, index[:n], obs[:n], reward[:n], done[:n], all_done[E]) as pinned host tensors; index = env * L + learner.
+        Bytes over PCIe per call: 4*E*L in, n*(obs_stride + 9) + E + 4 out."""
+        hb = self._host_buffers()
+        stream = torch.cuda.current_stream(self.device)
+        hb['d_act'].copy_(actions_host, non_blocking=True)
+        self.step(hb['d_act'], order)
+        p = lambda t: t.data_ptr()
+        K.check(self.lib.bgw_gather_valid(self._h, p(self.obs), p(self.reward), p(self.done), p(self.all_done),
+                                          p(hb['count']), p(hb['index']), p(hb['obs']), p(hb['reward']), p(hb['done']),
+                                          self._stream()), self.lib)
+        hb['h_count'].copy_(hb['count'], non_blocking=True)
+        hb['h_all'].copy_(self.all_done, non_blocking=True)
+        stream.synchronize()
+        n = int(hb['h_count'][0])
+        for k in ('index', 'obs', 'reward', 'done'):
+            hb['h_' + k][:n].copy_(hb[k][:n], non_blocking=True)
+        stream.synchronize()
+        self.last_d2h_bytes = n * (self.dims.obs_stride + 9) + self.E + 4
+        return n, hb['h_index'][:n], hb['h_obs'][:n], hb['h_reward'][:n], hb['h_done'][:n], hb['h_all']
+
     # ---- views / introspection -------------------------------------------------------------------
     def obs_view(self, obs=None):
         """[E, L, h, w(, c)] logical view of the 16-byte padded int8 rows."""

@@ -237,6 +237,19 @@ int bgw_reset(bgw_handle h, const uint8_t *env_mask, int8_t *obs, void *stream);
 int bgw_step(bgw_handle h, const int8_t *actions, const int16_t *order, int8_t *obs, float *reward,
              uint8_t *done, uint8_t *all_done, void *stream);
 
+/*
+ * Compact the outputs of the last bgw_step for a host consumer.  The reference's managers return dicts that hold
+ * only the agents that received something (all_step_manager.py:68-83, turn_based_manager.py:49-92); the dense
+ * [E][L] outputs of bgw_step keep a row for every learner.  bgw_gather_valid copies the rows whose BGW_OUT_VALID
+ * bit is set -- and every row of an env that was reset by this call (BGW_ENV_RESET: first observations) -- into
+ * contiguous buffers, so that only those bytes have to cross PCIe:
+ *   count    [1] i32 device      number of compacted rows n
+ *   index    [E*L] i32           index[i] = e * L + l of compacted row i (grouped by env, env order unspecified)
+ *   obs_c    [E*L][obs_stride] i8, reward_c [E*L] f32, done_c [E*L] u8    rows 0..n-1 are written
+ */
+int bgw_gather_valid(bgw_handle h, const int8_t *obs, const float *reward, const uint8_t *done, const uint8_t *all_done,
+                     int32_t *count, int32_t *index, int8_t *obs_c, float *reward_c, uint8_t *done_c, void *stream);
+
 /* Synthetic random policy (policies/policy.py:81-92 `action_space.sample()`), keyed Philox site ACTION:
  * fills actions[E][L][4] for the CURRENT step of every env.  Used by bench.py and the parity tests. */
 int bgw_sample_actions(bgw_handle h, int8_t *actions, void *stream);

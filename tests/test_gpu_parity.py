@@ -192,3 +192,27 @@ def test_full_size_c5_properties(mirror):
     assert obs.min() >= -1 and obs.max() <= 4                          # no blockers => never -2
     own = obs[..., 5, 5][valid & (eng.done.cpu().numpy() & K.OUT_DONE == 0)]
     assert (own >= 1).all()                                            # a live agent sees its own team on its cell
+
+
+def test_step_host_returns_exactly_the_valid_rows(mirror):
+    """bgw_gather_valid / BatchedGridWorld.step_host: the compacted host buffers hold the rows with BGW_OUT_VALID
+    (and every row of an env that was auto-reset), identical to the dense device outputs."""
+    spec = compile_sim(scenarios.build_tb_dense(mirror), n_envs=48, seed=13, horizon=12, auto_reset=True)
+    from abmarl_b200.engine import BatchedGridWorld
+    eng = BatchedGridWorld(spec, device='cuda:0')
+    eng.reset()
+    seen_reset = False
+    for t in range(40):
+        act = eng.sample_actions().cpu().pin_memory()
+        n, index, obs_c, rew_c, done_c, all_done = eng.step_host(act)
+        dense_obs, dense_rew = eng.obs.cpu().numpy().reshape(-1, eng.dims.obs_stride), eng.reward.cpu().numpy().ravel()
+        dense_done, flags = eng.done.cpu().numpy().ravel(), eng.all_done.cpu().numpy()
+        want = ((dense_done & K.OUT_VALID) != 0).reshape(eng.E, eng.L) | ((flags & K.ENV_RESET) != 0)[:, None]
+        idx = index.numpy()
+        assert n == int(want.sum()) and sorted(idx.tolist()) == np.flatnonzero(want.ravel()).tolist()
+        np.testing.assert_array_equal(obs_c.numpy(), dense_obs[idx])
+        np.testing.assert_array_equal(rew_c.numpy(), dense_rew[idx])
+        np.testing.assert_array_equal(done_c.numpy(), dense_done[idx])
+        np.testing.assert_array_equal(all_done.numpy(), flags)
+        seen_reset |= bool((flags & K.ENV_RESET).any())
+    assert seen_reset
