@@ -292,8 +292,8 @@ int bgw_create(const BgwSpec *sp, int device, bgw_handle *out)
                     sp->observer == BGW_OBS_POSITION_CENTERED && sp->attack_actor == BGW_ATTACK_BINARY &&
                     (2 * rmax_att + 1) * (2 * rmax_att + 1) <= 32;
         if (const char *t = getenv("BGW_GENERIC_KERNEL")) if (atoi(t)) fast = false;
-        int TF = A <= 32 ? 32 : 64;
-        if (const char *t = getenv("BGW_THREADS")) { const int v = atoi(t); if (v >= 32 && v <= 1024 && v % 32 == 0) TF = v; }
+        int TF = A <= 32 ? 32 : A <= 64 ? 64 : 128;
+        if (const char *t = getenv("BGW_THREADS")) { const int v = atoi(t); if (v >= 32 && v <= 1024 && v % 32 == 0) TF = std::min(v, 128); }   /* __launch_bounds__(128, 7) */
         if (fast) {
             f.P = P;
             f.PL = P;
@@ -308,7 +308,6 @@ int bgw_create(const BgwSpec *sp, int device, bgw_handle *out)
             int fo = 0;
             auto ftake = [&](long long nbytes) { const int o = fo; fo += align16((int)nbytes); return o; };
             f.o_enc = ftake(A); f.o_klass = ftake(A); f.o_tmp = ftake(A); f.o_lmask = ftake(A);
-            f.o_head = ftake(HW * 2 + 2);
             f.o_cenc = ftake(cbytes);
             f.o_rel = ftake(A * 2); f.o_ragent = ftake(L * 2); f.o_plist = ftake(L * 2);
             f.o_ctr = ftake(CTR_COUNT * 4); f.o_wsum = ftake(72 * 4);
@@ -328,7 +327,11 @@ int bgw_create(const BgwSpec *sp, int device, bgw_handle *out)
             f.s_avail = after_racc;
             const int reset_bytes = after_racc + align16((max_enc + 1) * d.hw_words * 4);
             const int stage_bytes = (TF / 32) * 32 * BGW_STAGE_ROW;
-            f.scratch_bytes = std::max(actor_bytes, std::max(reset_bytes, stage_bytes));
+            /* the observation stage spans `head` + scratch (the occupant lists are dead once the row gather
+             * starts; `head` is refilled with NONE afterwards), so head and scratch are laid out back to back */
+            const int head_bytes = align16(HW * 2 + 2);
+            f.scratch_bytes = std::max(std::max(actor_bytes, reset_bytes), std::max(16, stage_bytes - head_bytes));
+            f.o_head = ftake(head_bytes);
             f.o_scratch = ftake(f.scratch_bytes);
             f.smem_bytes = fo;
             f.async_ok = (A % 16 == 0) && (L % 4 == 0);
@@ -363,6 +366,7 @@ int bgw_create(const BgwSpec *sp, int device, bgw_handle *out)
             void *pp = nullptr;
             if (cudaMalloc(&pp, (size_t)h->fs.grid_ctas * 8 * 16 * sizeof(long long)) == cudaSuccess) { h->allocs.push_back(pp); cudaMemset(pp, 0, (size_t)h->fs.grid_ctas * 8 * 16 * sizeof(long long)); h->fs.prof = (long long *)pp; }
         }
+        if (getenv("BGW_VERBOSE")) fprintf(stderr, "[bgw] fast kernel: T=%d smem=%d B/CTA, %d CTAs/SM x %d SMs, grid=%d, slots=%d\n", h->threads_fast, h->fs.smem_bytes, per_sm, sms, h->fs.grid_ctas, h->dsf.slot_mask + 1);
         if (const char *t = getenv("BGW_GRID")) { const int v = atoi(t); if (v >= 1) h->fs.grid_ctas = std::min(d.E, v); }
     }
     dm.threads_per_env = h->fs.enabled ? h->threads_fast : T; dm.envs_per_cta = 1; dm.smem_bytes = h->fs.enabled ? h->fs.smem_bytes : off;

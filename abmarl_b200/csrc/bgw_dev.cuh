@@ -777,29 +777,48 @@ __device__ void sim_reset(const DevSpec &s, const BgwState &st, Env &ev, int tid
         if (tid == 0) ev.ctr[CTR_ERR] = s.tpl_error;
         __syncthreads();
         build_heads(s, ev, tid, T);
+        /* the placement draws are keyed by the entity, not by the state: all threads precompute them (into the
+         * reward accumulators' storage, zeroed again below) so the serial chain holds no Philox rounds */
+        uint32_t *xs = reinterpret_cast<uint32_t *>(ev.racc);
+        for (int vi = tid; vi < s.n_var; vi += T) xs[vi] = dev_draw(s, ev, BGW_SITE_PLACE, (uint32_t)__ldg(&s.var_agents[vi]), 0);
+        __syncthreads();
         if (tid < 32 && s.n_var > 0) {
             /* variable-position entities in dict order (state.py:112-114,152-166): uniform choice over the
              * ascending list of cells still available to the entity's encoding == select the k-th set bit */
             const int lane = tid, per = (s.hw_words + 31) / 32;
+            const int w0 = lane * per, w1 = min(s.hw_words, (lane + 1) * per);
             int err = ev.ctr[CTR_ERR];
+            int a_next = __ldg(&s.var_agents[0]);
             for (int vi = 0; vi < s.n_var; ++vi) {
-                const int a = __ldg(&s.var_agents[vi]), en = ev.enc[a];
+                const int a = a_next, en = ev.enc[a];
+                if (vi + 1 < s.n_var) a_next = __ldg(&s.var_agents[vi + 1]);
+                const uint32_t x = xs[vi];
                 uint32_t *av = ev.avail + (size_t)en * s.hw_words;
                 int cnt = 0;
-                for (int w = lane * per; w < min(s.hw_words, (lane + 1) * per); ++w) cnt += __popc(av[w]);
+                for (int w = w0; w < w1; ++w) cnt += __popc(av[w]);
                 int incl = cnt;
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += t; }
                 const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
                 if (total == 0) { if (!err) err = 2; continue; }          /* RuntimeError state.py:161 */
-                const int k = (int)bgw_index(dev_draw(s, ev, BGW_SITE_PLACE, (uint32_t)a, 0), (uint32_t)total);
+                const int k = (int)bgw_index(x, (uint32_t)total);
                 const int excl = incl - cnt;
                 int cell = -1;
                 if (k >= excl && k < incl) {
                     int rem = k - excl;
-                    for (int w = lane * per; w < min(s.hw_words, (lane + 1) * per); ++w) {
-                        const int pc = __popc(av[w]);
-                        if (rem < pc) { cell = w * 32 + (int)__fns(av[w], 0, rem + 1); break; }
+                    for (int w = w0; w < w1; ++w) {
+                        uint32_t bits = av[w];
+                        const int pc = __popc(bits);
+                        if (rem < pc) {                                    /* rem-th set bit of this word */
+                            int pos = 0, t;
+                            t = __popc(bits & 0xFFFFu); if (rem >= t) { rem -= t; pos += 16; bits >>= 16; }
+                            t = __popc(bits & 0xFFu);   if (rem >= t) { rem -= t; pos += 8;  bits >>= 8; }
+                            t = __popc(bits & 0xFu);    if (rem >= t) { rem -= t; pos += 4;  bits >>= 4; }
+                            t = __popc(bits & 0x3u);    if (rem >= t) { rem -= t; pos += 2;  bits >>= 2; }
+                            if (rem >= (int)(bits & 1u)) pos += 1;
+                            cell = w * 32 + pos;
+                            break;
+                        }
                         rem -= pc;
                     }
                 }
@@ -817,6 +836,7 @@ __device__ void sim_reset(const DevSpec &s, const BgwState &st, Env &ev, int tid
         __syncthreads();
     }
     for (int a = tid; a < s.A; a += T) {
+        ev.racc[a] = 0.0;                                             /* rewards = 0 (smart.py:91); also clears the draw scratch */
         uint8_t f = ev.flags[a] | BGW_ST_ACTIVE;                      /* PrincipleAgent.active = True */
         double h = 0.0;
         if (ev.klass[a] & BGW_AG_HEALTH) {                            /* HealthState.reset state.py:635-641 */

@@ -360,7 +360,7 @@ __device__ void fast_obs_rows(const DevSpec &s, const FastSpec &f, const Env &ev
     }
 }
 
-__global__ void bgw_step_fast_kernel(const DevSpec s, const FastSpec f, const BgwState st, const uint32_t *actions,
+__global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s, const FastSpec f, const BgwState st, const uint32_t *actions,
                                      const int16_t *order, int8_t *obs, float *reward, uint8_t *done, uint8_t *all_done)
 {
     const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = T >> 5;
@@ -462,21 +462,27 @@ __global__ void bgw_step_fast_kernel(const DevSpec s, const FastSpec f, const Bg
         __syncthreads();
         BGW_PROF_MARK(1);
 
+        bool fresh = false;                                         /* this call resets the env instead of stepping it */
         if (ef0 & BGW_ENV_ALL_DONE) {
-            if (s.auto_reset) {
-                /* general reset path on this env's (otherwise unused) staging buffer; leaves lists in `head` */
-                Env evr = ev;
-                evr.health = st.health + (size_t)e * s.A;
-                env_reset(s, st, evr, obs_env, tid, T);
-                if (tid == 0) {
-                    const uint8_t fl = (uint8_t)((evr.ctr[CTR_ERR] ? BGW_ENV_ERROR : 0) | BGW_ENV_RESET);
-                    st.env_flags[e] = fl; all_done[e] = fl;
-                }
+            if (!s.auto_reset) {
+                if (tid == 0) all_done[e] = ef0;
                 __syncthreads();
-                fast_init_dense(s, f, ev, fe, tid, T);
-            } else if (tid == 0) all_done[e] = ef0;
+                continue;
+            }
+            /* sim.reset() on this env's staging buffer (general code: placement, health, orientation), state to
+             * HBM, then the first observations through the same summary + row-gather path as a step */
+            sim_reset(s, st, ev, tid, T);
+            store_env(s, st, ev, true, tid, T);
+            if (tid == 0) {
+                const uint8_t fl = (uint8_t)((ev.ctr[CTR_ERR] ? BGW_ENV_ERROR : 0) | BGW_ENV_RESET);
+                st.error[e] = (uint32_t)ev.ctr[CTR_ERR];
+                st.env_flags[e] = fl; all_done[e] = fl;
+            }
             __syncthreads();
-            continue;
+            fast_init_dense(s, f, ev, fe, tid, T);                  /* sim_reset left its lists in `head` */
+            if (tid < CTR_COUNT) ev.ctr[tid] = 0;
+            __syncthreads();
+            fresh = true;
         }
         BGW_PROF_MARK(2);
 
@@ -567,7 +573,7 @@ __global__ void bgw_step_fast_kernel(const DevSpec s, const FastSpec f, const Bg
         /* ---- occupant lists and summary from the relevant entities --------------------------------- */
         for (int x = tid; x < n_rel; x += T) {
             const int a = fe.rel[x];
-            ev.racc[a] = racc_persists(ev.klass[a]) ? st.reward_acc[off + a] : 0.0;
+            ev.racc[a] = (!fresh && racc_persists(ev.klass[a])) ? st.reward_acc[off + a] : 0.0;
             fe.killrank[a] = BGW_NONE16;
             if (ev.flags[a] & BGW_ST_IN_GRID) {
                 if (ev.next[a] != BGW_NONE16) ev.tmp[ev.next[a]] = 1;
@@ -587,109 +593,115 @@ __global__ void bgw_step_fast_kernel(const DevSpec s, const FastSpec f, const Bg
         __syncthreads();
         BGW_PROF_MARK(4);
 
-        /* ---- attack phase team_battle_example.py:35-47 ---------------------------------------------- */
-        for (int i = tid; i < n_act; i += T) {
-            const int a = ev.ragent[i], l = __ldg(&s.learner_of[a]);
-            ev.plist[i] = (uint16_t)l;
-            uint8_t p = 0;
-            if ((ev.flags[a] & BGW_ST_ACTIVE) && (ev.klass[a] & BGW_AG_ATTACKING) && (int8_t)((fe.act[l] >> 16) & 0xFF) != 0) {
-                /* candidate cells: the summary says an attackable encoding (or a mix) is present */
-                const int R = __ldg(&s.attack_r[a]), n = 2 * R + 1;
-                const unsigned long long row = __ldg(&s.attack_map[ev.enc[a]]);
-                const int8_t *w = fe.cenc + pad_index(s, f, ev.cell[a]) - R * f.PW - R;
-                uint32_t mask = 0;
-                if (R == 1) {
-#pragma unroll
-                    for (int k = 0; k < 9; ++k) {
-                        const int v = w[(k / 3) * f.PW + (k % 3)];
-                        if (v > 0 ? (int)((row >> v) & 1ull) : (v == BGW_MIXED)) mask |= 1u << k;
-                    }
-                } else {
-                    for (int wr = 0; wr < n; ++wr)
-                        for (int wc = 0; wc < n; ++wc) {
-                            const int v = w[wr * f.PW + wc];
-                            if (v > 0 ? (int)((row >> v) & 1ull) : (v == BGW_MIXED)) mask |= 1u << (wr * n + wc);
+        if (fresh) {
+            for (int i = tid; i < n_act; i += T) ev.plist[i] = (uint16_t)__ldg(&s.learner_of[ev.ragent[i]]);
+        } else {
+            /* ---- attack phase team_battle_example.py:35-47 ---------------------------------------------- */
+            for (int i = tid; i < n_act; i += T) {
+                const int a = ev.ragent[i], l = __ldg(&s.learner_of[a]);
+                ev.plist[i] = (uint16_t)l;
+                uint8_t p = 0;
+                if ((ev.flags[a] & BGW_ST_ACTIVE) && (ev.klass[a] & BGW_AG_ATTACKING) && (int8_t)((fe.act[l] >> 16) & 0xFF) != 0) {
+                    /* candidate cells: the summary says an attackable encoding (or a mix) is present */
+                    const int R = __ldg(&s.attack_r[a]), n = 2 * R + 1;
+                    const unsigned long long row = __ldg(&s.attack_map[ev.enc[a]]);
+                    const int8_t *w = fe.cenc + pad_index(s, f, ev.cell[a]) - R * f.PW - R;
+                    uint32_t mask = 0;
+                    if (R == 1) {
+    #pragma unroll
+                        for (int k = 0; k < 9; ++k) {
+                            const int v = w[(k / 3) * f.PW + (k % 3)];
+                            if (v > 0 ? (int)((row >> v) & 1ull) : (v == BGW_MIXED)) mask |= 1u << k;
                         }
-                }
-                fe.rkmask[i] = mask;
-                if (mask) { p = 1; fe.eff[atomicAdd(&ev.ctr[CTR_NEMIT], 1)] = (uint16_t)i; }
-                else p = 3;                                         /* no possible victim: settled after the rounds */
-            }
-            ev.pstate[i] = p;
-        }
-        __syncthreads();
-        BGW_PROF_MARK(5);
-        {
-            const int n_eff = ev.ctr[CTR_NEMIT];
-            if (n_eff > 32) fast_attack_rounds<false>(s, f, ev, fe, n_eff, tid, T);
-            else if (n_eff > 0 && warp == 0) fast_attack_rounds<true>(s, f, ev, fe, n_eff, tid, T);
-            if (n_eff > 0 && n_eff <= 32) __syncthreads();
-        }
-        BGW_PROF_MARK(6);
-
-        /* ---- settle attackers without candidates; classify the moves :50-55 --------------------------- */
-        int pend = 0;
-        for (int i = tid; i < n_act; i += T) {
-            const int a = ev.ragent[i];
-            const bool active = ev.flags[a] & BGW_ST_ACTIVE;
-            if (ev.pstate[i] == 3) {
-                const unsigned kr = fe.killrank[a];
-                if (active || (kr != BGW_NONE16 && kr > (unsigned)i)) ev.racc[a] += rw[BGW_RW_ATTACK_FAIL];   /* :41-42 */
-            }
-            uint8_t p = 0;
-            if (active) {
-                bool ok = false;
-                if (ev.klass[a] & BGW_AG_MOVING) {
-                    int dr, dc, r0, c0;
-                    decode_move(s, a, fe.act[ev.plist[i]], dr, dc);
-                    cell_rc(s, f, ev.cell[a], r0, c0);
-                    const int r = r0 + dr, c = c0 + dc;
-                    if (r >= 0 && r < s.H && c >= 0 && c < s.W) {
-                        if (dr == 0 && dc == 0) ok = true;
-                        else { p = 1; fe.rkmask[i] = (uint32_t)(r * s.W + c); }
+                    } else {
+                        for (int wr = 0; wr < n; ++wr)
+                            for (int wc = 0; wc < n; ++wc) {
+                                const int v = w[wr * f.PW + wc];
+                                if (v > 0 ? (int)((row >> v) & 1ull) : (v == BGW_MIXED)) mask |= 1u << (wr * n + wc);
+                            }
                     }
+                    fe.rkmask[i] = mask;
+                    if (mask) { p = 1; fe.eff[atomicAdd(&ev.ctr[CTR_NEMIT], 1)] = (uint16_t)i; }
+                    else p = 3;                                         /* no possible victim: settled after the rounds */
                 }
-                if (!p && !ok) ev.racc[a] += rw[BGW_RW_MOVE_FAIL];
+                ev.pstate[i] = p;
             }
-            ev.pstate[i] = p;
-            pend |= p;
-        }
-        pend = __syncthreads_or(pend);
-        BGW_PROF_MARK(7);
-        if (n_act > 32) fast_move_rounds<false>(s, f, ev, fe, n_act, pend, tid, T);
-        else {
-            if (warp == 0) fast_move_rounds<true>(s, f, ev, fe, n_act, pend, tid, T);
             __syncthreads();
-        }
-        BGW_PROF_MARK(8);
+            BGW_PROF_MARK(5);
+            {
+                const int n_eff = ev.ctr[CTR_NEMIT];
+                if (n_eff > 32) fast_attack_rounds<false>(s, f, ev, fe, n_eff, tid, T);
+                else if (n_eff > 0 && warp == 0) fast_attack_rounds<true>(s, f, ev, fe, n_eff, tid, T);
+                if (n_eff > 0 && n_eff <= 32) __syncthreads();
+            }
+            BGW_PROF_MARK(6);
 
-        /* ---- entropy :58-59, rewards / dones of the acting learners (all_step_manager.py:68-87) -------- */
-        for (int i = tid; i < n_act; i += T) {
-            const int a = ev.ragent[i], l = ev.plist[i];
-            const double r = ev.racc[a] + rw[BGW_RW_ENTROPY];
-            const bool dd = prog_done(s, ev, a);
-            rew[l] = (float)r;
-            dn[l] = (uint8_t)(BGW_OUT_VALID | (dd ? BGW_OUT_DONE : 0));
-            if (dd) ev.flags[a] |= BGW_ST_DONE_REPORTED; else atomicAdd(&ev.ctr[CTR_REMAINING], 1);
+            /* ---- settle attackers without candidates; classify the moves :50-55 --------------------------- */
+            int pend = 0;
+            for (int i = tid; i < n_act; i += T) {
+                const int a = ev.ragent[i];
+                const bool active = ev.flags[a] & BGW_ST_ACTIVE;
+                if (ev.pstate[i] == 3) {
+                    const unsigned kr = fe.killrank[a];
+                    if (active || (kr != BGW_NONE16 && kr > (unsigned)i)) ev.racc[a] += rw[BGW_RW_ATTACK_FAIL];   /* :41-42 */
+                }
+                uint8_t p = 0;
+                if (active) {
+                    bool ok = false;
+                    if (ev.klass[a] & BGW_AG_MOVING) {
+                        int dr, dc, r0, c0;
+                        decode_move(s, a, fe.act[ev.plist[i]], dr, dc);
+                        cell_rc(s, f, ev.cell[a], r0, c0);
+                        const int r = r0 + dr, c = c0 + dc;
+                        if (r >= 0 && r < s.H && c >= 0 && c < s.W) {
+                            if (dr == 0 && dc == 0) ok = true;
+                            else { p = 1; fe.rkmask[i] = (uint32_t)(r * s.W + c); }
+                        }
+                    }
+                    if (!p && !ok) ev.racc[a] += rw[BGW_RW_MOVE_FAIL];
+                }
+                ev.pstate[i] = p;
+                pend |= p;
+            }
+            pend = __syncthreads_or(pend);
+            BGW_PROF_MARK(7);
+            if (n_act > 32) fast_move_rounds<false>(s, f, ev, fe, n_act, pend, tid, T);
+            else {
+                if (warp == 0) fast_move_rounds<true>(s, f, ev, fe, n_act, pend, tid, T);
+                __syncthreads();
+            }
+            BGW_PROF_MARK(8);
+
+            /* ---- entropy :58-59, rewards / dones of the acting learners (all_step_manager.py:68-87) -------- */
+            for (int i = tid; i < n_act; i += T) {
+                const int a = ev.ragent[i], l = ev.plist[i];
+                const double r = ev.racc[a] + rw[BGW_RW_ENTROPY];
+                const bool dd = prog_done(s, ev, a);
+                rew[l] = (float)r;
+                dn[l] = (uint8_t)(BGW_OUT_VALID | (dd ? BGW_OUT_DONE : 0));
+                if (dd) ev.flags[a] |= BGW_ST_DONE_REPORTED; else atomicAdd(&ev.ctr[CTR_REMAINING], 1);
+            }
         }
         /* racc of entities whose accumulator persists (non-learners with health) goes back before the scratch is reused */
-        for (int x = tid; x < n_rel; x += T) {
-            const int a = fe.rel[x];
-            if (racc_persists(ev.klass[a])) st.reward_acc[off + a] = ev.racc[a];
-        }
+        if (!fresh)
+            for (int x = tid; x < n_rel; x += T) {
+                const int a = fe.rel[x];
+                if (racc_persists(ev.klass[a])) st.reward_acc[off + a] = ev.racc[a];
+            }
         __syncthreads();                                            /* the scratch union becomes the observation stage */
         BGW_PROF_MARK(9);
 
         /* ---- observations ------------------------------------------------------------------------------ */
+        bool staged = false;                                        /* the row gather staged through `head` + scratch */
         if (obs_env) {
             const bool direct = s.observe_self && !ev.ctr[CTR_MIXED];
             const int R = direct ? f.uniform_view : -1;
             switch (R) {
-            case 1: fast_obs_rows<1>(s, f, ev, fe, n_act, obs_env, scratch, tid, T); break;
-            case 2: fast_obs_rows<2>(s, f, ev, fe, n_act, obs_env, scratch, tid, T); break;
-            case 3: fast_obs_rows<3>(s, f, ev, fe, n_act, obs_env, scratch, tid, T); break;
-            case 4: fast_obs_rows<4>(s, f, ev, fe, n_act, obs_env, scratch, tid, T); break;
-            case 5: fast_obs_rows<5>(s, f, ev, fe, n_act, obs_env, scratch, tid, T); break;
+            case 1: fast_obs_rows<1>(s, f, ev, fe, n_act, obs_env, (unsigned char *)ev.head, tid, T); staged = true; break;
+            case 2: fast_obs_rows<2>(s, f, ev, fe, n_act, obs_env, (unsigned char *)ev.head, tid, T); staged = true; break;
+            case 3: fast_obs_rows<3>(s, f, ev, fe, n_act, obs_env, (unsigned char *)ev.head, tid, T); staged = true; break;
+            case 4: fast_obs_rows<4>(s, f, ev, fe, n_act, obs_env, (unsigned char *)ev.head, tid, T); staged = true; break;
+            case 5: fast_obs_rows<5>(s, f, ev, fe, n_act, obs_env, (unsigned char *)ev.head, tid, T); staged = true; break;
             default: {
                 const int items = n_act * nch;
                 for (int it = tid; it < items; it += T) {
@@ -706,13 +718,18 @@ __global__ void bgw_step_fast_kernel(const DevSpec s, const FastSpec f, const Bg
         BGW_PROF_MARK(10);
 
         /* ---- store the relevant entities, get_all_done (done.py:49-56,147-153), clean the dense arrays ---- */
+        if (staged) {                                               /* `head` held the observation stage: empty lists again */
+            uint4 *h4 = (uint4 *)ev.head;
+            const uint4 ones = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+            for (int i = tid; i < (s.HW * 2 + 15) / 16; i += T) h4[i] = ones;
+        }
         {
             uint32_t lo = 0, hi = 0;
             int ok = 1;
             for (int x = tid; x < n_rel; x += T) {
                 const int a = fe.rel[x];
                 const uint8_t fl = ev.flags[a];
-                st.cell[off + a] = ev.cell[a]; st.next[off + a] = ev.next[a]; st.flags[off + a] = fl;
+                if (!fresh) { st.cell[off + a] = ev.cell[a]; st.next[off + a] = ev.next[a]; st.flags[off + a] = fl; }
                 if (fl & BGW_ST_ACTIVE) { const int en2 = ev.enc[a]; if (en2 < 32) lo |= 1u << en2; else hi |= 1u << (en2 - 32); }
                 if (s.done_mask & (BGW_DONE_TARGET_AGENT | BGW_DONE_TARGET_DESTROYED)) {
                     const int t = __ldg(&s.target[a]);
@@ -720,7 +737,7 @@ __global__ void bgw_step_fast_kernel(const DevSpec s, const FastSpec f, const Bg
                     if ((s.done_mask & BGW_DONE_TARGET_DESTROYED) && t >= 0 && (ev.flags[t] & BGW_ST_ACTIVE)) ok = 0;
                 }
                 if (fl & BGW_ST_IN_GRID) {
-                    ev.head[ev.cell[a]] = BGW_NONE16;
+                    if (!staged) ev.head[ev.cell[a]] = BGW_NONE16;
                     fe.cenc[pad_index(s, f, ev.cell[a])] = 0;
                 }
             }
@@ -734,7 +751,7 @@ __global__ void bgw_step_fast_kernel(const DevSpec s, const FastSpec f, const Bg
             }
         }
         __syncthreads();
-        if (tid == 0) {
+        if (tid == 0 && !fresh) {
             const unsigned long long encs = ((unsigned long long)(unsigned)ev.ctr[CTR_ENC_HI] << 32) | (unsigned)ev.ctr[CTR_ENC_LO];
             int d = !ev.ctr[CTR_AND];
             if (s.done_mask & BGW_DONE_ACTIVE) d &= (encs == 0);

@@ -63,7 +63,7 @@ def test_general_kernel_on_fast_path_scenarios(mirror, name, monkeypatch):
     run_lockstep(eng, ora, 60, label=name + '/general')
 
 
-@pytest.mark.parametrize('threads', ['64', '128', '512'])
+@pytest.mark.parametrize('threads', ['32', '64', '256'])
 def test_thread_count_does_not_change_results(mirror, threads, monkeypatch):
     spec = compile_sim(scenarios.build_tb_c5_small(mirror), n_envs=16, seed=9, horizon=30, auto_reset=True)
     monkeypatch.setenv('BGW_THREADS', threads)
