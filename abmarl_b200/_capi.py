@@ -60,7 +60,7 @@ class BgwDims(C.Structure):
 
 
 EXPORTS = ('bgw_create', 'bgw_destroy', 'bgw_dims', 'bgw_bind_state', 'bgw_reset', 'bgw_step',
-           'bgw_sample_actions', 'bgw_gather_valid', 'bgw_rng_draw', 'bgw_los_mask', 'bgw_launch_count', 'bgw_last_error',
+           'bgw_sample_actions', 'bgw_step_sampled', 'bgw_gather_valid', 'bgw_rng_draw', 'bgw_los_mask', 'bgw_launch_count', 'bgw_last_error',
            'bgw_abi_version')
 
 _LIB = None
@@ -89,6 +89,8 @@ def load():
     lib.bgw_reset.argtypes = [h, _p, _p, _p]
     lib.bgw_step.argtypes = [h, _p, _p, _p, _p, _p, _p, _p]
     lib.bgw_sample_actions.argtypes = [h, _p, _p]
+    lib.bgw_step_sampled.argtypes = [h, _p, _p, _p, _p, _p, _p, _p]
+    lib.bgw_step_sampled.restype = C.c_int
     lib.bgw_gather_valid.argtypes = [h] + [_p] * 10
     lib.bgw_gather_valid.restype = C.c_int
     lib.bgw_rng_draw.argtypes = [C.c_uint64] + [C.c_uint32] * 6 + [C.POINTER(C.c_uint32 * 4)]

@@ -333,6 +333,7 @@ int bgw_create(const BgwSpec *sp, int device, bgw_handle *out)
             f.scratch_bytes = std::max(std::max(actor_bytes, reset_bytes), std::max(16, stage_bytes - head_bytes));
             f.o_head = ftake(head_bytes);
             f.o_scratch = ftake(f.scratch_bytes);
+            f.stage_hits_slots = (stage_bytes - head_bytes > f.s_slot) ? 1 : 0;   /* stage spills past racc */
             f.smem_bytes = fo;
             f.async_ok = (A % 16 == 0) && (L % 4 == 0);
             f.simd_ok = (A % 4 == 0);
@@ -412,19 +413,24 @@ int bgw_reset(bgw_handle h, const uint8_t *env_mask, int8_t *obs, void *stream)
     return 0;
 }
 
-int bgw_step(bgw_handle h, const int8_t *actions, const int16_t *order, int8_t *obs, float *reward, uint8_t *done,
-             uint8_t *all_done, void *stream)
+static int step_impl(bgw_handle h, const int8_t *actions, int8_t *sampled, const int16_t *order, int8_t *obs, float *reward,
+                     uint8_t *done, uint8_t *all_done, void *stream)
 {
-    if (!h) return fail(1, "bgw_step: null handle");
-    if (!h->bound) return fail(1, "bgw_step: call bgw_bind_state first");
-    if (!actions || !reward || !done || !all_done) return fail(1, "bgw_step: actions, reward, done and all_done are required");
     DeviceGuard guard(h->device);
-    if (h->fs.enabled)
+    if (h->fs.enabled) {
         bgw_step_fast_kernel<<<h->fs.grid_ctas, h->threads_fast, h->fs.smem_bytes, (cudaStream_t)stream>>>(
-            h->dsf, h->fs, h->st, (const uint32_t *)actions, order, obs, reward, done, all_done);
-    else
+            h->dsf, h->fs, h->st, (const uint32_t *)actions, (uint32_t *)sampled, order, obs, reward, done, all_done);
+    } else {
+        if (sampled) {                                 /* general kernel: sample, then step (two launches) */
+            const size_t n = (size_t)h->ds.E * h->ds.L;
+            bgw_sample_actions_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(h->ds, h->st, (uint32_t *)sampled);
+            CUDA_OK(cudaGetLastError());
+            h->launches += 1;
+            actions = sampled;
+        }
         bgw_step_kernel<<<h->ds.E, h->threads, h->ds.smem_bytes, (cudaStream_t)stream>>>(
             h->ds, h->st, (const uint32_t *)actions, order, obs, reward, done, all_done);
+    }
     CUDA_OK(cudaGetLastError());
     h->launches += 1;
     if (h->fs.enabled && h->fs.prof) {                 /* debug only: dump the phase clocks of this launch */
@@ -435,6 +441,24 @@ int bgw_step(bgw_handle h, const int8_t *actions, const int16_t *order, int8_t *
         if (FILE *fp = fopen(getenv("BGW_PROF_FILE"), "wb")) { fwrite(host.data(), sizeof(long long), n, fp); fclose(fp); }
     }
     return 0;
+}
+
+int bgw_step(bgw_handle h, const int8_t *actions, const int16_t *order, int8_t *obs, float *reward, uint8_t *done,
+             uint8_t *all_done, void *stream)
+{
+    if (!h) return fail(1, "bgw_step: null handle");
+    if (!h->bound) return fail(1, "bgw_step: call bgw_bind_state first");
+    if (!actions || !reward || !done || !all_done) return fail(1, "bgw_step: actions, reward, done and all_done are required");
+    return step_impl(h, actions, nullptr, order, obs, reward, done, all_done, stream);
+}
+
+int bgw_step_sampled(bgw_handle h, int8_t *actions_out, const int16_t *order, int8_t *obs, float *reward, uint8_t *done,
+                     uint8_t *all_done, void *stream)
+{
+    if (!h) return fail(1, "bgw_step_sampled: null handle");
+    if (!h->bound) return fail(1, "bgw_step_sampled: call bgw_bind_state first");
+    if (!actions_out || !reward || !done || !all_done) return fail(1, "bgw_step_sampled: actions_out, reward, done and all_done are required");
+    return step_impl(h, nullptr, actions_out, order, obs, reward, done, all_done, stream);
 }
 
 int bgw_sample_actions(bgw_handle h, int8_t *actions, void *stream)

@@ -1051,16 +1051,13 @@ __global__ void bgw_step_kernel(const DevSpec s, const BgwState st, const uint32
 }
 
 /* RandomPolicy.compute_action = action_space.sample() (policies/policy.py:81-92) on the keyed stream: one
- * Philox block per (env, step, agent); words 0,1 -> move, word 2 -> attack.  One thread per (env, learner). */
-__global__ void bgw_sample_actions_kernel(const DevSpec s, const BgwState st, uint32_t *actions)
+ * Philox block per (env, step, agent); words 0,1 -> move, word 2 -> attack. */
+__device__ __forceinline__ uint32_t sample_action_word(const DevSpec &s, int a, int klass, uint32_t genv, uint32_t episode,
+                                                       uint32_t step)
 {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (size_t)s.E * s.L) return;
-    const int e = (int)(i / s.L), l = (int)(i % s.L), a = __ldg(&s.agent_of[l]);
     uint32_t x[4];
-    bgw_draw4(s.seed, (uint32_t)(s.env_offset + e), st.episode[e], st.step[e], BGW_SITE_ACTION, (uint32_t)a, 0, x);
+    bgw_draw4(s.seed, genv, episode, step, BGW_SITE_ACTION, (uint32_t)a, 0, x);
     uint32_t o = 0;
-    const int klass = __ldg(&s.klass[a]);
     if (klass & BGW_AG_MOVING) {
         if (s.move_actor == BGW_MOVE_BOX) {                          /* Box(-m, m, (2,), int) actor.py:63-65 */
             const int m = __ldg(&s.move_r[a]), w = 2 * m + 1;
@@ -1073,7 +1070,16 @@ __global__ void bgw_sample_actions_kernel(const DevSpec s, const BgwState st, ui
     }
     if ((klass & BGW_AG_ATTACKING) && s.attack_actor != BGW_ATTACK_NONE)
         o |= (bgw_index(x[2], (uint32_t)__ldg(&s.simatt[a]) + 1) & 0xFF) << 16;   /* Discrete(n+1) actor.py:452 */
-    actions[i] = o;
+    return o;
+}
+
+/* one thread per (env, learner) */
+__global__ void bgw_sample_actions_kernel(const DevSpec s, const BgwState st, uint32_t *actions)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)s.E * s.L) return;
+    const int e = (int)(i / s.L), l = (int)(i % s.L), a = __ldg(&s.agent_of[l]);
+    actions[i] = sample_action_word(s, a, __ldg(&s.klass[a]), (uint32_t)(s.env_offset + e), st.episode[e], st.step[e]);
 }
 
 /* bgw_gather_valid: one CTA per env; rows are claimed with one global atomicAdd per env and copied as 16-byte chunks */

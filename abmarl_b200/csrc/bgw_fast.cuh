@@ -32,7 +32,11 @@
 #include "bgw_dev.cuh"
 
 #define BGW_MIXED (-128)
+#ifdef BGW_PROFILE   /* debug build (BGW_PROFILE=1 python -m abmarl_b200.csrc.build): clock64 at the phase boundaries */
 #define BGW_PROF_MARK(k) do { if (f.prof && tid == 0 && it_no < 8) f.prof[((size_t)blockIdx.x * 8 + it_no) * 16 + (k)] = clock64(); } while (0)
+#else
+#define BGW_PROF_MARK(k) do { } while (0)
+#endif
 #define BGW_STAGE_ROW 80        /* bytes per lane in the observation stage: 64 payload + 16 pad (conflict-free 128-bit) */
 
 struct FastSpec {
@@ -44,6 +48,7 @@ struct FastSpec {
     int grid_ctas;            /* persistent grid size */
     int async_ok;             /* rows are 16-byte aligned: stage with cp.async */
     int simd_ok;              /* A % 4 == 0: byte-parallel compaction */
+    int stage_hits_slots;     /* the observation stage overlaps the reservation slots: refill them after it */
     int b_cell, b_next, b_flags, b_act, buf_bytes;   /* layout of one staging buffer */
     /* shared-memory carve-up of the fast kernel.  `scratch` is a union: during the actor phases it holds
      * racc | slot | rkmask | eff | pstate | killrank, during the observation phase the per-warp stage, and in
@@ -105,14 +110,16 @@ __device__ __forceinline__ void fast_issue_env(const DevSpec &s, const FastSpec 
         for (int i = tid; i < s.A / 8; i += T) cp_async16(buf + f.b_next + i * 16, g + i * 16);
         g = (const unsigned char *)(st.flags + off);
         for (int i = tid; i < s.A / 16; i += T) cp_async16(buf + f.b_flags + i * 16, g + i * 16);
-        g = (const unsigned char *)(actions + (size_t)e * s.L);
-        for (int i = tid; i < s.L / 4; i += T) cp_async16(buf + f.b_act + i * 16, g + i * 16);
+        if (actions) {
+            g = (const unsigned char *)(actions + (size_t)e * s.L);
+            for (int i = tid; i < s.L / 4; i += T) cp_async16(buf + f.b_act + i * 16, g + i * 16);
+        }
     } else {
         uint16_t *c = (uint16_t *)(buf + f.b_cell), *n = (uint16_t *)(buf + f.b_next);
         uint8_t *fl = buf + f.b_flags;
         uint32_t *ac = (uint32_t *)(buf + f.b_act);
         for (int a = tid; a < s.A; a += T) { c[a] = st.cell[off + a]; n[a] = st.next[off + a]; fl[a] = st.flags[off + a]; }
-        for (int l = tid; l < s.L; l += T) ac[l] = actions[(size_t)e * s.L + l];
+        if (actions) for (int l = tid; l < s.L; l += T) ac[l] = actions[(size_t)e * s.L + l];
     }
 }
 
@@ -242,14 +249,19 @@ __device__ void fast_move_rounds(const DevSpec &s, const FastSpec &f, Env &ev, F
     }
 }
 
-/* (re)initialise the dense per-cell arrays of this CTA: empty lists, clean head-detection marks, empty summary
- * with a -1 border (the reservation slots live in the scratch union and are cleared per env) */
+/* (re)initialise the dense per-cell arrays of this CTA: empty lists, clean head-detection marks, free
+ * reservation slots, empty summary with a -1 border */
 __device__ void fast_init_dense(const DevSpec &s, const FastSpec &f, Env &ev, FastEnv &fe, int tid, int T)
 {
     uint4 *h4 = (uint4 *)ev.head;
     const uint4 ones = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
     for (int i = tid; i < (s.HW * 2 + 15) / 16; i += T) h4[i] = ones;
     for (int a = tid; a < s.A; a += T) ev.tmp[a] = 0;
+    {   /* reservation slots: every round frees what it reserved, so they only need filling here (and after a
+         * reset, whose availability maps share the scratch union) */
+        uint4 *s4 = (uint4 *)ev.slot;
+        for (int i = tid; i < (s.slot_mask + 1) / 4; i += T) s4[i] = ones;
+    }
     /* summary rows: word cw of an interior row has zeros where its 4 bytes fall inside the grid columns */
     uint32_t *c32 = (uint32_t *)fe.cenc;
     const int wpr = f.PW >> 2, lane = tid & 31, warp = tid >> 5, nwarp = T >> 5;
@@ -361,7 +373,8 @@ __device__ void fast_obs_rows(const DevSpec &s, const FastSpec &f, const Env &ev
 }
 
 __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s, const FastSpec f, const BgwState st, const uint32_t *actions,
-                                     const int16_t *order, int8_t *obs, float *reward, uint8_t *done, uint8_t *all_done)
+                                     uint32_t *sampled, const int16_t *order, int8_t *obs, float *reward, uint8_t *done,
+                                     uint8_t *all_done)
 {
     const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = T >> 5;
     unsigned char *scratch = bgw_smem + f.o_scratch;
@@ -443,7 +456,7 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s, 
         ev.step = step_cur + 1u;
         b ^= 1; ef_cur = ef_nxt; step_cur = step_nxt; epi_cur = epi_nxt;
 
-        /* rows of learners that receive nothing this call read as zero; free slots; zero counters */
+        /* rows of learners that receive nothing this call read as zero; zero counters */
         if ((s.L & 15) == 0) {
             uint4 *d4 = (uint4 *)dn, *r4 = (uint4 *)rew;
             const uint4 z = make_uint4(0, 0, 0, 0);
@@ -451,11 +464,6 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s, 
             for (int i = tid; i < s.L / 4; i += T) r4[i] = z;
         } else {
             for (int l = tid; l < s.L; l += T) { dn[l] = 0; rew[l] = 0.f; }
-        }
-        {
-            uint4 *s4 = (uint4 *)ev.slot;
-            const uint4 ones = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
-            for (int i = tid; i < (s.slot_mask + 1) / 4; i += T) s4[i] = ones;
         }
         if (tid < CTR_COUNT) ev.ctr[tid] = 0;
         cp_async_wait<1>();
@@ -600,6 +608,11 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s, 
             for (int i = tid; i < n_act; i += T) {
                 const int a = ev.ragent[i], l = __ldg(&s.learner_of[a]);
                 ev.plist[i] = (uint16_t)l;
+                if (sampled) {                                   /* bgw_step_sampled: the keyed random policy, fused */
+                    const uint32_t w = sample_action_word(s, a, ev.klass[a], ev.genv, ev.episode, ev.step - 1u);
+                    fe.act[l] = w;
+                    sampled[(size_t)e * s.L + l] = w;
+                }
                 uint8_t p = 0;
                 if ((ev.flags[a] & BGW_ST_ACTIVE) && (ev.klass[a] & BGW_AG_ATTACKING) && (int8_t)((fe.act[l] >> 16) & 0xFF) != 0) {
                     /* candidate cells: the summary says an attackable encoding (or a mix) is present */
@@ -722,6 +735,10 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s, 
             uint4 *h4 = (uint4 *)ev.head;
             const uint4 ones = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
             for (int i = tid; i < (s.HW * 2 + 15) / 16; i += T) h4[i] = ones;
+            if (f.stage_hits_slots) {
+                uint4 *s4 = (uint4 *)ev.slot;
+                for (int i = tid; i < (s.slot_mask + 1) / 4; i += T) s4[i] = ones;
+            }
         }
         {
             uint32_t lo = 0, hi = 0;

@@ -25,6 +25,8 @@ def build(force=False, verbose=False):
     cmd = [NVCC, '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
            '-shared', '-Xcompiler', '-fPIC,-ffp-contract=off,-fno-fast-math', '--fmad=false',
            '-I', os.path.join(ROOT, 'include'), '-o', OUT, SRC, '-lcudart']
+    if os.environ.get('BGW_PROFILE'):
+        cmd.insert(1, '-DBGW_PROFILE')
     if verbose:
         cmd.insert(1, '-Xptxas=-v')
         print(' '.join(cmd))

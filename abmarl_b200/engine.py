@@ -117,6 +117,17 @@ class BatchedGridWorld:
                                   self.all_done.data_ptr(), self._stream()), self.lib)
         return self.obs, self.reward, self.done, self.all_done
 
+    def step_sampled(self, order=None):
+        """sample_actions() + step() in one call (one launch on the specialised kernel): the keyed random policy
+        acts for every learner that may act; the sampled actions land in self.actions."""
+        o = None
+        if order is not None:
+            o = torch.as_tensor(order, dtype=torch.int16, device=self.device).contiguous()
+        K.check(self.lib.bgw_step_sampled(self._h, self.actions.data_ptr(), None if o is None else o.data_ptr(),
+                                          self.obs.data_ptr(), self.reward.data_ptr(), self.done.data_ptr(),
+                                          self.all_done.data_ptr(), self._stream()), self.lib)
+        return self.obs, self.reward, self.done, self.all_done
+
     # ---- host-facing step: HOST buffers in, only the rows the reference's manager would return out ---------
     def _host_buffers(self):
         if getattr(self, '_hb', None) is None:

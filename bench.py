@@ -7,8 +7,8 @@ OneTeamRemainingDone, AllStepManager semantics, horizon 200 with auto-reset, ran
 Philox stream; 4096 envs per GPU (env batches shard across GPUs with no data-path collective -> weak scaling;
 NCCL only sums the episode statistics).
 
-One "step" = one manager step of every env on this GPU: the action-sampling kernel + the step kernel (actor
-resolution -> observation -> reward/done).  An agent-step = one learning agent receiving (obs, reward, done).
+One "step" = one manager step of every env on this GPU through bgw_step_sampled: the keyed random policy draws
+every acting learner's action inside the step kernel (actor resolution -> observation -> reward/done).  An agent-step = one learning agent receiving (obs, reward, done).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
@@ -166,7 +166,7 @@ def run_ours(args):
     # ---------------- device-resident rollout: `value` + roofline of the step kernel -----------------
     eng.reset()
     for _ in range(args.warmup):
-        eng.step(eng.sample_actions())
+        eng.step_sampled()
     barrier()
     n0, launches0 = agent_steps(), eng.launches
     sampler = ClockSampler(local) if rank == 0 else None
@@ -178,9 +178,8 @@ def run_ours(args):
     barrier()
     t_beg.record(stream)
     for i in range(args.steps):
-        act = eng.sample_actions()
         k_ev[i][0].record(stream)
-        eng.step(act)
+        eng.step_sampled()                            # keyed random policy + manager step, one launch
         k_ev[i][1].record(stream)
     t_end.record(stream)
     barrier()

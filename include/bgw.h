@@ -237,6 +237,12 @@ int bgw_reset(bgw_handle h, const uint8_t *env_mask, int8_t *obs, void *stream);
 int bgw_step(bgw_handle h, const int8_t *actions, const int16_t *order, int8_t *obs, float *reward,
              uint8_t *done, uint8_t *all_done, void *stream);
 
+/* bgw_sample_actions + bgw_step in one call: every acting learner draws its action from the keyed random policy
+ * and the batch is stepped with them.  actions_out[E][L][4] receives the sampled actions of the learners that acted
+ * (rows of learners already reported done are not written).  Same results as the two calls made separately. */
+int bgw_step_sampled(bgw_handle h, int8_t *actions_out, const int16_t *order, int8_t *obs, float *reward,
+                     uint8_t *done, uint8_t *all_done, void *stream);
+
 /*
  * Compact the outputs of the last bgw_step for a host consumer.  The reference's managers return dicts that hold
  * only the agents that received something (all_step_manager.py:68-83, turn_based_manager.py:49-92); the dense

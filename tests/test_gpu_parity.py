@@ -216,3 +216,24 @@ def test_step_host_returns_exactly_the_valid_rows(mirror):
         np.testing.assert_array_equal(all_done.numpy(), flags)
         seen_reset |= bool((flags & K.ENV_RESET).any())
     assert seen_reset
+
+
+@pytest.mark.parametrize('name', ['tb_c2', 'tb_c5_small', 'tb_blocking', 'maze_c1'])
+def test_step_sampled_equals_sample_then_step(mirror, name):
+    """bgw_step_sampled (fused on the specialised kernel, two launches on the general one) against the oracle's
+    sample_actions + step."""
+    builder, manager, _ = scenarios.SCENARIOS[name]
+    spec = compile_sim(builder(mirror), manager=manager, n_envs=24, env_offset=3, seed=31, horizon=25, auto_reset=True)
+    eng, ora = _pair(spec)
+    eng.reset()
+    ora.reset()
+    for t in range(60):
+        act = ora.sample_actions()
+        before = ora.state['flags'].copy()
+        was_done = (ora.state['env_flags'] & K.ENV_ALL_DONE) != 0
+        ora.step(act)
+        eng.step_sampled()
+        assert_outputs_equal(eng, ora, f'{name} step {t}')
+        assert_state_equal(eng.state_numpy(), ora.state, f'{name} step {t}')
+        acting = np.stack([(before[:, a] & K.ST_DONE_REPORTED) == 0 for a in spec.learner_agents], axis=1) & ~was_done[:, None]
+        np.testing.assert_array_equal(eng.actions.cpu().numpy()[acting], act[acting])
