@@ -260,7 +260,7 @@ def run_ours(args):
                     "api": "BatchedGridWorld.step_host: pinned host actions in, valid rows compacted on the device and copied out"},
             "gpu_launches": int(launches_all),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "bgw_step_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "bgw_step_fast_kernel (bgw_step_sampled)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_agent_step": BYTES_PER_AGENT_STEP,
                          "kernel_ms_per_launch": per_launch_ms, "kernel_share_of_step": kernel_ms / (ms if world == 1 else t_beg.elapsed_time(t_end))},
