@@ -53,6 +53,7 @@ struct BgwEngine {
     DevSpec ds{}, dsf{};          /* general kernels / fast kernel (own slot table size) */
     FastSpec fs{};
     int threads_fast = 0;
+    bool fast_static = false;     /* compile-time shapes of the headline workload apply (FastStaticC5) */
     BgwDims dims{};
     BgwState st{};
     bool bound = false;
@@ -349,17 +350,28 @@ int bgw_create(const BgwSpec *sp, int device, bgw_handle *out)
         }
         f.enabled = fast;
         h->threads_fast = TF;
+        if (fast) {
+            typedef FastStaticC5 C;
+            const DevSpec &q = h->dsf;
+            h->fast_static = q.A == C::A && q.L == C::L && q.H == C::H && q.W == C::W && q.obs_stride == C::obs_stride &&
+                             q.obs_h == C::obs_h && q.obs_c == 1 && q.move_actor == C::move_actor && q.ravel == C::ravel &&
+                             q.observe_self == C::observe_self && q.done_mask == C::done_mask && q.max_enc == C::max_enc &&
+                             f.P == C::P && f.PL == C::PL && f.PW == C::PW && f.PH == C::PH && f.uniform_view == C::view &&
+                             f.simd_ok == C::simd_ok && f.async_ok == C::async_ok;
+            if (const char *t = getenv("BGW_DYNAMIC_SHAPES")) if (atoi(t)) h->fast_static = false;
+        }
     }
     d.smem_bytes = off;
     if (off > 227 * 1024) return bail(fail(1, "bgw_create: one environment needs %d bytes of shared memory (limit 232448): grid or entity count too large", off));
     cudaError_t ce;
     if ((ce = cudaFuncSetAttribute(bgw_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, off)) != cudaSuccess ||
-        (h->fs.enabled && (ce = cudaFuncSetAttribute(bgw_step_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->fs.smem_bytes)) != cudaSuccess) ||
+        (h->fs.enabled && (ce = cudaFuncSetAttribute(bgw_step_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->fs.smem_bytes)) != cudaSuccess) ||
+        (h->fs.enabled && (ce = cudaFuncSetAttribute(bgw_step_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->fs.smem_bytes)) != cudaSuccess) ||
         (ce = cudaFuncSetAttribute(bgw_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, off)) != cudaSuccess)
         return bail(fail(2, "bgw_create: cudaFuncSetAttribute: %s", cudaGetErrorString(ce)));
     if (h->fs.enabled) {
         int per_sm = 0, sms = 0;
-        if ((ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bgw_step_fast_kernel, h->threads_fast, h->fs.smem_bytes)) != cudaSuccess ||
+        if ((ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bgw_step_fast_kernel<false>, h->threads_fast, h->fs.smem_bytes)) != cudaSuccess ||
             (ce = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess)
             return bail(fail(2, "bgw_create: occupancy query: %s", cudaGetErrorString(ce)));
         h->fs.grid_ctas = std::max(1, std::min(d.E, per_sm * sms));
@@ -418,8 +430,12 @@ static int step_impl(bgw_handle h, const int8_t *actions, int8_t *sampled, const
 {
     DeviceGuard guard(h->device);
     if (h->fs.enabled) {
-        bgw_step_fast_kernel<<<h->fs.grid_ctas, h->threads_fast, h->fs.smem_bytes, (cudaStream_t)stream>>>(
-            h->dsf, h->fs, h->st, (const uint32_t *)actions, (uint32_t *)sampled, order, obs, reward, done, all_done);
+        if (h->fast_static)
+            bgw_step_fast_kernel<true><<<h->fs.grid_ctas, h->threads_fast, h->fs.smem_bytes, (cudaStream_t)stream>>>(
+                h->dsf, h->fs, h->st, (const uint32_t *)actions, (uint32_t *)sampled, order, obs, reward, done, all_done);
+        else
+            bgw_step_fast_kernel<false><<<h->fs.grid_ctas, h->threads_fast, h->fs.smem_bytes, (cudaStream_t)stream>>>(
+                h->dsf, h->fs, h->st, (const uint32_t *)actions, (uint32_t *)sampled, order, obs, reward, done, all_done);
     } else {
         if (sampled) {                                 /* general kernel: sample, then step (two launches) */
             const size_t n = (size_t)h->ds.E * h->ds.L;

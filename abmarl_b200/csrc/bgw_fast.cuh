@@ -372,10 +372,32 @@ __device__ void fast_obs_rows(const DevSpec &s, const FastSpec &f, const Env &ev
     }
 }
 
-__global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s, const FastSpec f, const BgwState st, const uint32_t *actions,
+/* Compile-time shape of the headline workload (BASELINE configs[4]: 64x64 grid, 256 agents that are all learners,
+ * view 5, MoveActor, observe_self, OneTeamRemainingDone).  bgw_create selects the <true> instantiation when the
+ * compiled spec matches it exactly; every other sim runs the <false> instantiation with run-time shapes.  The
+ * code is the same: the constants below only let the compiler fold divisions, strides and trip counts. */
+struct FastStaticC5 {
+    static constexpr int A = 256, L = 256, H = 64, W = 64, P = 5, PL = 5, PW = 76, PH = 74, obs_stride = 128, nchunks = 8,
+                         obs_h = 11, view = 5, move_actor = BGW_MOVE_BOX, ravel = 0, observe_self = 1, done_mask = BGW_DONE_ONE_TEAM,
+                         max_enc = 4, simd_ok = 1, async_ok = 1;
+};
+
+template <bool STATIC>
+__global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_in, const FastSpec f_in, const BgwState st, const uint32_t *actions,
                                      uint32_t *sampled, const int16_t *order, int8_t *obs, float *reward, uint8_t *done,
                                      uint8_t *all_done)
 {
+    DevSpec s = s_in;
+    FastSpec f = f_in;
+    if (STATIC) {
+        typedef FastStaticC5 C;
+        s.A = C::A; s.L = C::L; s.H = C::H; s.W = C::W; s.HW = C::H * C::W; s.obs_stride = C::obs_stride; s.nchunks = C::nchunks;
+        s.obs_h = s.obs_w = C::obs_h; s.obs_c = 1; s.move_actor = C::move_actor; s.ravel = C::ravel; s.observe_self = C::observe_self;
+        s.done_mask = C::done_mask; s.max_enc = C::max_enc; s.n_blk = 0; s.program = BGW_PROG_TEAM_BATTLE;
+        s.manager = BGW_MANAGER_ALL_STEP; s.attack_actor = BGW_ATTACK_BINARY; s.hw_words = (C::H * C::W + 31) / 32;
+        f.P = C::P; f.PL = C::PL; f.PW = C::PW; f.PH = C::PH; f.uniform_view = C::view; f.simd_ok = C::simd_ok; f.async_ok = C::async_ok;
+        f.magic_w = (uint32_t)(((1ull << 32) + C::W - 1) / C::W);
+    }
     const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = T >> 5;
     unsigned char *scratch = bgw_smem + f.o_scratch;
     Env ev;

@@ -237,3 +237,13 @@ def test_step_sampled_equals_sample_then_step(mirror, name):
         assert_state_equal(eng.state_numpy(), ora.state, f'{name} step {t}')
         acting = np.stack([(before[:, a] & K.ST_DONE_REPORTED) == 0 for a in spec.learner_agents], axis=1) & ~was_done[:, None]
         np.testing.assert_array_equal(eng.actions.cpu().numpy()[acting], act[acting])
+
+
+@pytest.mark.parametrize('dynamic', ['0', '1'])
+def test_c5_shape_static_and_dynamic_instantiations(mirror, dynamic, monkeypatch):
+    """BASELINE config 5's exact shape selects the compile-time-shape instantiation of the specialised kernel;
+    BGW_DYNAMIC_SHAPES=1 forces the run-time-shape one.  Both against the oracle over a full episode + reset."""
+    monkeypatch.setenv('BGW_DYNAMIC_SHAPES', dynamic)
+    spec = compile_sim(scenarios.build_tb_c5(mirror), n_envs=6, env_offset=11, seed=0xB200, horizon=40, auto_reset=True)
+    eng, ora = _pair(spec)
+    run_lockstep(eng, ora, 90, label='tb_c5/dynamic=' + dynamic)
