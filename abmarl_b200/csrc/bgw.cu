@@ -305,37 +305,10 @@ int bgw_create(const BgwSpec *sp, int device, bgw_handle *out)
             if (const char *t = getenv("BGW_SLOTS")) { const int v = atoi(t); if (v >= 32 && v <= 65536 && (v & (v - 1)) == 0) fslots = v; }
             h->dsf = d;
             h->dsf.slot_mask = fslots - 1;
-            const long long cbytes = (long long)f.PH * f.PW + 32;   /* + slack: the word gather reads past a row end */
-            int fo = 0;
-            auto ftake = [&](long long nbytes) { const int o = fo; fo += align16((int)nbytes); return o; };
-            f.o_enc = ftake(A); f.o_klass = ftake(A); f.o_tmp = ftake(A); f.o_lmask = ftake(A);
-            f.o_cenc = ftake(cbytes);
-            f.o_rel = ftake(A * 2); f.o_ragent = ftake(L * 2); f.o_plist = ftake(L * 2);
-            f.o_ctr = ftake(CTR_COUNT * 4); f.o_wsum = ftake(72 * 4);
-            int bo = 0;
-            auto btake = [&](int nbytes) { const int o = bo; bo += align16(nbytes); return o; };
-            f.b_cell = btake(A * 2); f.b_next = btake(A * 2); f.b_flags = btake(A); f.b_act = btake(L * 4);
-            f.buf_bytes = bo;
-            f.o_buf = ftake(2 * bo);
-            /* scratch union */
-            int so = 0;
-            auto stake = [&](int nbytes) { const int o = so; so += align16(nbytes); return o; };
-            f.s_racc = stake(A * 8);
-            const int after_racc = so;
-            f.s_slot = stake(fslots * 4); f.s_rkmask = stake(L * 4); f.s_eff = stake(L * 2); f.s_pstate = stake(L);
-            f.s_killrank = stake(A * 2);
-            const int actor_bytes = so;
-            f.s_avail = after_racc;
-            const int reset_bytes = after_racc + align16((max_enc + 1) * d.hw_words * 4);
-            const int stage_bytes = (TF / 32) * 32 * BGW_STAGE_ROW;
-            /* the observation stage spans `head` + scratch (the occupant lists are dead once the row gather
-             * starts; `head` is refilled with NONE afterwards), so head and scratch are laid out back to back */
-            const int head_bytes = align16(HW * 2 + 2);
-            f.scratch_bytes = std::max(std::max(actor_bytes, reset_bytes), std::max(16, stage_bytes - head_bytes));
-            f.o_head = ftake(head_bytes);
-            f.o_scratch = ftake(f.scratch_bytes);
-            f.stage_hits_slots = (stage_bytes - head_bytes > f.s_slot) ? 1 : 0;   /* stage spills past racc */
-            f.smem_bytes = fo;
+            const long long cbytes = (long long)f.PH * f.PW + 32;
+            const FastLayout ly = fast_layout(A, L, HW, f.PH, f.PW, fslots, TF, max_enc, d.hw_words);
+            fast_apply_layout(f, ly);
+            const int fo = ly.smem_bytes;
             f.async_ok = (A % 16 == 0) && (L % 4 == 0);
             f.simd_ok = (A % 4 == 0);
             f.uniform_view = -1;
@@ -357,7 +330,7 @@ int bgw_create(const BgwSpec *sp, int device, bgw_handle *out)
                              q.obs_h == C::obs_h && q.obs_c == 1 && q.move_actor == C::move_actor && q.ravel == C::ravel &&
                              q.observe_self == C::observe_self && q.done_mask == C::done_mask && q.max_enc == C::max_enc &&
                              f.P == C::P && f.PL == C::PL && f.PW == C::PW && f.PH == C::PH && f.uniform_view == C::view &&
-                             f.simd_ok == C::simd_ok && f.async_ok == C::async_ok;
+                             f.simd_ok == C::simd_ok && f.async_ok == C::async_ok && q.slot_mask == C::slots - 1 && TF == C::T;
             if (const char *t = getenv("BGW_DYNAMIC_SHAPES")) if (atoi(t)) h->fast_static = false;
         }
     }

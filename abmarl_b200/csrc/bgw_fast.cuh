@@ -58,6 +58,74 @@ struct FastSpec {
     long long *prof;          /* debug (BGW_PROF_FILE): clock64 at phase boundaries, [cta][8 envs][16 marks] */
 };
 
+/* The shared-memory carve-up of the fast kernel: ONE definition used by bgw_create (run-time shapes) and by the
+ * compile-time-shape instantiation (where every offset folds into an immediate). */
+struct FastLayout {
+    int b_cell, b_next, b_flags, b_act, buf_bytes;
+    int o_enc, o_klass, o_tmp, o_lmask, o_head, o_cenc, o_rel, o_ragent, o_plist, o_ctr, o_wsum, o_buf, o_scratch;
+    int s_racc, s_slot, s_rkmask, s_eff, s_pstate, s_killrank, s_avail, scratch_bytes, smem_bytes, stage_hits_slots;
+};
+
+__host__ __device__ constexpr int fl_align16(int x) { return (x + 15) & ~15; }
+
+__host__ __device__ constexpr FastLayout fast_layout(int A, int L, int HW, int PH, int PW, int slots, int T, int max_enc,
+                                                     int hw_words)
+{
+    FastLayout y{};
+    int fo = 0;
+    y.o_enc = fo; fo += fl_align16(A);
+    y.o_klass = fo; fo += fl_align16(A);
+    y.o_tmp = fo; fo += fl_align16(A);
+    y.o_lmask = fo; fo += fl_align16(A);
+    y.o_cenc = fo; fo += fl_align16(PH * PW + 32);        /* + slack: the word gather reads past a row end */
+    y.o_rel = fo; fo += fl_align16(A * 2);
+    y.o_ragent = fo; fo += fl_align16(L * 2);
+    y.o_plist = fo; fo += fl_align16(L * 2);
+    y.o_ctr = fo; fo += fl_align16(CTR_COUNT * 4);
+    y.o_wsum = fo; fo += fl_align16(72 * 4);
+    int bo = 0;
+    y.b_cell = bo; bo += fl_align16(A * 2);
+    y.b_next = bo; bo += fl_align16(A * 2);
+    y.b_flags = bo; bo += fl_align16(A);
+    y.b_act = bo; bo += fl_align16(L * 4);
+    y.buf_bytes = bo;
+    y.o_buf = fo; fo += 2 * bo;
+    int so = 0;                                           /* scratch union */
+    y.s_racc = so; so += fl_align16(A * 8);
+    const int after_racc = so;
+    y.s_slot = so; so += fl_align16(slots * 4);
+    y.s_rkmask = so; so += fl_align16(L * 4);
+    y.s_eff = so; so += fl_align16(L * 2);
+    y.s_pstate = so; so += fl_align16(L);
+    y.s_killrank = so; so += fl_align16(A * 2);
+    const int actor_bytes = so;
+    y.s_avail = after_racc;
+    const int reset_bytes = after_racc + fl_align16((max_enc + 1) * hw_words * 4);
+    const int stage_bytes = (T / 32) * 32 * BGW_STAGE_ROW;
+    /* the observation stage spans `head` + scratch (the occupant lists are dead once the row gather starts; `head`
+     * is refilled with NONE afterwards), so head and scratch are laid out back to back */
+    const int head_bytes = fl_align16(HW * 2 + 2);
+    int sb = actor_bytes > reset_bytes ? actor_bytes : reset_bytes;
+    if (stage_bytes - head_bytes > sb) sb = stage_bytes - head_bytes;
+    y.scratch_bytes = sb;
+    y.o_head = fo; fo += head_bytes;
+    y.o_scratch = fo; fo += sb;
+    y.stage_hits_slots = (stage_bytes - head_bytes > y.s_slot) ? 1 : 0;   /* stage spills past racc */
+    y.smem_bytes = fo;
+    return y;
+}
+
+__host__ __device__ inline void fast_apply_layout(FastSpec &f, const FastLayout &y)
+{
+    f.b_cell = y.b_cell; f.b_next = y.b_next; f.b_flags = y.b_flags; f.b_act = y.b_act; f.buf_bytes = y.buf_bytes;
+    f.o_enc = y.o_enc; f.o_klass = y.o_klass; f.o_tmp = y.o_tmp; f.o_lmask = y.o_lmask; f.o_head = y.o_head;
+    f.o_cenc = y.o_cenc; f.o_rel = y.o_rel; f.o_ragent = y.o_ragent; f.o_plist = y.o_plist; f.o_ctr = y.o_ctr;
+    f.o_wsum = y.o_wsum; f.o_buf = y.o_buf; f.o_scratch = y.o_scratch;
+    f.s_racc = y.s_racc; f.s_slot = y.s_slot; f.s_rkmask = y.s_rkmask; f.s_eff = y.s_eff; f.s_pstate = y.s_pstate;
+    f.s_killrank = y.s_killrank; f.s_avail = y.s_avail; f.scratch_bytes = y.scratch_bytes; f.smem_bytes = y.smem_bytes;
+    f.stage_hits_slots = y.stage_hits_slots;
+}
+
 struct FastEnv {
     int8_t *cenc;
     uint16_t *killrank, *eff, *rel;
@@ -379,7 +447,7 @@ __device__ void fast_obs_rows(const DevSpec &s, const FastSpec &f, const Env &ev
 struct FastStaticC5 {
     static constexpr int A = 256, L = 256, H = 64, W = 64, P = 5, PL = 5, PW = 76, PH = 74, obs_stride = 128, nchunks = 8,
                          obs_h = 11, view = 5, move_actor = BGW_MOVE_BOX, ravel = 0, observe_self = 1, done_mask = BGW_DONE_ONE_TEAM,
-                         max_enc = 4, simd_ok = 1, async_ok = 1;
+                         max_enc = 4, simd_ok = 1, async_ok = 1, slots = 1024, T = 128;
 };
 
 template <bool STATIC>
@@ -397,8 +465,11 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
         s.manager = BGW_MANAGER_ALL_STEP; s.attack_actor = BGW_ATTACK_BINARY; s.hw_words = (C::H * C::W + 31) / 32;
         f.P = C::P; f.PL = C::PL; f.PW = C::PW; f.PH = C::PH; f.uniform_view = C::view; f.simd_ok = C::simd_ok; f.async_ok = C::async_ok;
         f.magic_w = (uint32_t)(((1ull << 32) + C::W - 1) / C::W);
+        s.slot_mask = C::slots - 1;
+        constexpr FastLayout LY = fast_layout(C::A, C::L, C::H * C::W, C::PH, C::PW, C::slots, C::T, C::max_enc, (C::H * C::W + 31) / 32);
+        fast_apply_layout(f, LY);
     }
-    const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = T >> 5;
+    const int tid = threadIdx.x, T = STATIC ? FastStaticC5::T : (int)blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = T >> 5;
     unsigned char *scratch = bgw_smem + f.o_scratch;
     Env ev;
     ev.enc = (int8_t *)(bgw_smem + f.o_enc);
