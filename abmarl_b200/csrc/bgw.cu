@@ -153,14 +153,18 @@ int bgw_create(const BgwSpec *sp, int device, bgw_handle *out)
 
     /* ---- per-entity tables ------------------------------------------------------------------ */
     std::vector<int16_t> learner_of(A, -1), agent_of;
-    std::vector<uint16_t> blk, var, init_cell(A, BGW_NONE);
+    std::vector<uint16_t> blk, blk_static, var, init_cell(A, BGW_NONE);
     int max_enc = 0, rmax_obs = 0, rmax_att = 0;
     for (int a = 0; a < A; ++a) {
         const int e = sp->encoding[a];
         if (e < 1 || e > BGW_MAX_ENCODING) return bail(fail(1, "bgw_create: entity %d has encoding %d, must be 1..%d", a, e, BGW_MAX_ENCODING));
         max_enc = std::max(max_enc, e);
         if (sp->klass[a] & BGW_AG_LEARNER) { learner_of[a] = (int16_t)agent_of.size(); agent_of.push_back((int16_t)a); }
-        if (sp->klass[a] & BGW_AG_BLOCKING) blk.push_back((uint16_t)a);
+        if (sp->klass[a] & BGW_AG_BLOCKING) {
+            /* static = never moves, never dies, fixed start cell (walls); dynamic blockers are listed first */
+            const bool is_static = !(sp->klass[a] & (BGW_AG_MOVING | BGW_AG_HEALTH)) && sp->init_row[a] >= 0;
+            (is_static ? blk_static : blk).push_back((uint16_t)a);
+        }
         if (sp->init_row[a] < 0) var.push_back((uint16_t)a);
         else {
             if (sp->init_row[a] >= H || sp->init_col[a] < 0 || sp->init_col[a] >= W)
@@ -180,6 +184,8 @@ int bgw_create(const BgwSpec *sp, int device, bgw_handle *out)
     }
     const int L = (int)agent_of.size();
     if (L < 1) return bail(fail(1, "bgw_create: the simulation has no learning agent"));
+    d.n_dyn_blk = (int)blk.size();
+    blk.insert(blk.end(), blk_static.begin(), blk_static.end());
     d.L = L; d.max_enc = max_enc; d.n_blk = (int)blk.size(); d.n_var = (int)var.size();
     if (sp->attack_actor != BGW_ATTACK_NONE && d.n_blk > 0 && (2 * rmax_att + 1) * (2 * rmax_att + 1) > 32 * BGW_ATT_MASK_WORDS)
         return bail(fail(1, "bgw_create: attack_range %d with view-blocking entities exceeds the attacker's LOS mask (range <= 7)", rmax_att));
@@ -269,6 +275,33 @@ int bgw_create(const BgwSpec *sp, int device, bgw_handle *out)
         if (d.n_blk) {
             if ((long long)d.mask_words * 4 > 96 * 1024) return bail(fail(1, "bgw_create: view range %d with view-blocking entities needs a %lld-bit LOS mask, too large for shared memory", reff, nbits));
             d.mask_batch = std::max(1, std::min(L, 32 * 1024 / (d.mask_words * 4)));
+        }
+        /* static-blocker table: one mask per viewer cell, when every observing learner has the same view range */
+        d.static_mask = nullptr;
+        bool uniform = true;
+        int ru = -1;
+        for (int a = 0; a < A; ++a)
+            if ((sp->klass[a] & BGW_AG_LEARNER) && (sp->klass[a] & BGW_AG_OBSERVING)) {
+                if (ru < 0) ru = sp->view_range[a]; else if (sp->view_range[a] != ru) uniform = false;
+            }
+        const size_t table_words = (size_t)HW * d.mask_words;
+        if (!blk_static.empty() && uniform && ru >= 0 && table_words * 4 <= (64u << 20) && !getenv("BGW_NO_STATIC_MASK")) {
+            const int R = reff, n = 2 * R + 1;
+            std::vector<uint32_t> table(table_words, 0xFFFFFFFFu);
+            std::vector<uint8_t> one((size_t)n * n);
+            for (int c = 0; c < HW; ++c) {
+                uint32_t *row = table.data() + (size_t)c * d.mask_words;
+                const int r0 = c / W, c0 = c % W;
+                for (uint16_t b : blk_static) {
+                    const int rd = sp->init_row[b] - r0, cd = sp->init_col[b] - c0;
+                    if (rd < -R || rd > R || cd < -R || cd > R) continue;
+                    memset(one.data(), 1, one.size());
+                    los_apply_host(one.data(), R, rd, cd);
+                    for (int i = 0; i < n * n; ++i) if (!one[i]) row[i >> 5] &= ~(1u << (i & 31));
+                }
+            }
+            int rc = upload(h, table.data(), table.size(), &d.static_mask);
+            if (rc) return bail(rc);
         }
     }
     int off = 0;

@@ -56,7 +56,9 @@ struct DevSpec {
     const int16_t *view_r, *move_r, *attack_r, *target, *learner_of, *agent_of;
     const double *init_health, *strength, *accuracy;
     const unsigned long long *overlap, *attack_map;
-    const uint16_t *blk_agents, *var_agents;
+    const uint16_t *blk_agents, *var_agents;   /* blk_agents: the n_dyn_blk dynamic blockers first, then the static ones */
+    const uint32_t *static_mask;   /* [HW][mask_words] LOS mask of all STATIC blockers per viewer cell, or NULL */
+    int n_dyn_blk;
     /* reset template: the env-independent result of placing the fixed-position entities (state.py:107-109) */
     const uint16_t *tpl_cell, *tpl_next;
     const uint8_t *tpl_flags;
@@ -723,10 +725,21 @@ __device__ void observe_learners(const DevSpec &s, Env &ev, int ne, int8_t *obs_
     for (int base = 0; base < ne; base += batch) {
         const int nb = min(batch, ne - base);
         if (blk) {
-            for (int w = tid; w < nb * s.mask_words; w += T) ev.mask[w] = 0xFFFFFFFFu;
+            /* view-blocking entities that never move, die or get re-placed (walls) hide the same cells from a given
+             * viewer cell in every env and every step: their combined mask comes from a table built at bgw_create;
+             * only the dynamic blockers are traced here */
+            const int nblk = s.static_mask ? s.n_dyn_blk : s.n_blk;
+            for (int w = tid; w < nb * s.mask_words; w += T) {
+                uint32_t v = 0xFFFFFFFFu;
+                if (s.static_mask) {
+                    const int li = w / s.mask_words, a = __ldg(&s.agent_of[ev.plist[base + li]]), c = ev.cell[a];
+                    if (c < s.HW) v = __ldg(&s.static_mask[(size_t)c * s.mask_words + (w - li * s.mask_words)]);
+                }
+                ev.mask[w] = v;
+            }
             __syncthreads();
-            for (int it = tid; it < nb * s.n_blk; it += T) {
-                const int li = it / s.n_blk, b = __ldg(&s.blk_agents[it % s.n_blk]);
+            for (int it = tid; it < nb * nblk; it += T) {
+                const int li = it / nblk, b = __ldg(&s.blk_agents[it % nblk]);
                 const int a = __ldg(&s.agent_of[ev.plist[base + li]]);
                 if (!(ev.klass[a] & BGW_AG_OBSERVING)) continue;
                 los_pair<true>(s, ev, ev.mask + (size_t)li * s.mask_words, ev.cell[a], view_range_eff(s, a), b,

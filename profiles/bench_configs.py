@@ -1,0 +1,49 @@
+#!/usr/bin/env python
+"""Side measurements of the other BASELINE configs (parity-test cases, not bench.py lines): device-resident
+rollouts with the keyed random policy, CUDA-event timing.
+
+    python profiles/bench_configs.py [tb_c2|pacman_c3|maze_c1|mm_allstep ...]
+"""
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from abmarl_b200 import _capi as K                      # noqa: E402
+from abmarl_b200.engine import BatchedGridWorld         # noqa: E402
+from abmarl_b200.spec import compile_sim                # noqa: E402
+from tests import scenarios                             # noqa: E402
+
+CONFIGS = {'tb_c2': (16384, 400), 'pacman_c3': (16384, 60), 'maze_c1': (16384, 400), 'tb_blocking': (16384, 200)}
+
+
+def main(names):
+    api = scenarios.mirror_api()
+    for name in names:
+        n_envs, steps = CONFIGS[name]
+        builder, manager, _ = scenarios.SCENARIOS[name]
+        spec = compile_sim(builder(api), manager=manager, n_envs=n_envs, seed=7, horizon=200, auto_reset=True)
+        eng = BatchedGridWorld(spec, device='cuda:0')
+        eng.reset()
+        for _ in range(10):
+            eng.step_sampled()
+        torch.cuda.synchronize()
+        n0 = int(eng.stats()[K.STAT_AGENT_STEPS])
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            eng.step_sampled()
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b)
+        n = int(eng.stats()[K.STAT_AGENT_STEPS]) - n0
+        print(json.dumps({"config": name, "envs": n_envs, "learners_per_env": eng.L, "entities_per_env": eng.A, "steps": steps,
+                          "ms_per_step": ms / steps, "agent_steps_per_s": n / (ms * 1e-3),
+                          "kernel": "bgw_step_fast_kernel" if eng.dims.threads_per_env <= 128 and spec.program == K.PROG_TEAM_BATTLE and not (spec.klass & K.AG_BLOCKING).any() else "bgw_step_kernel"}), flush=True)
+
+
+if __name__ == '__main__':
+    main(sys.argv[1:] or list(CONFIGS))

@@ -63,14 +63,20 @@ def make_spec(rows, cols, agents, overlapping=None, attack_mapping=None, program
 class Backend:
     """Uniform numpy view of the oracle (OracleEnv) or the CUDA engine (BatchedGridWorld)."""
 
-    def __init__(self, spec, kind):
+    def __init__(self, spec, kind, static_mask=True):
         self.kind = kind
         if kind == 'oracle':
             from oracle.oracle import OracleEnv
             self.env = OracleEnv(spec)
         else:
+            import os
             from abmarl_b200.engine import BatchedGridWorld
-            self.env = BatchedGridWorld(spec, device='cuda:0')
+            if not static_mask:              # the case flips `active` of a wall from outside, which no sim can do:
+                os.environ['BGW_NO_STATIC_MASK'] = '1'   # trace every blocker instead of using the static-wall table
+            try:
+                self.env = BatchedGridWorld(spec, device='cuda:0')
+            finally:
+                os.environ.pop('BGW_NO_STATIC_MASK', None)
         self.L, self.spec = self.env.L, spec
 
     def reset(self):
@@ -262,7 +268,8 @@ def case_absolute_encoding_observer(kind):                   # test_observer.py:
 
 
 def case_absolute_encoding_observer_blocking(kind):          # test_observer.py:106-191
-    be = Backend(make_spec(5, 5, _observer_agents(True, True), overlapping={1: {6}, 6: {1}}, observer=K.OBS_ABSOLUTE), kind)
+    be = Backend(make_spec(5, 5, _observer_agents(True, True), overlapping={1: {6}, 6: {1}}, observer=K.OBS_ABSOLUTE), kind,
+                 static_mask=False)
     be.reset()
     np.testing.assert_array_equal(be.obs(0), [[-2, -2, 0, 0, 0], [-2, 4, 0, 0, 0], [-2, 6, -1, 0, 0], [-2, 0, 0, 5, -2], [0, 0, 0, -2, -2]])
     np.testing.assert_array_equal(be.obs(1), [[-1, 0, -2, -2, -2], [0, 4, -2, -2, -2]] + [[-2] * 5] * 3)

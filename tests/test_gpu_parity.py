@@ -247,3 +247,14 @@ def test_c5_shape_static_and_dynamic_instantiations(mirror, dynamic, monkeypatch
     spec = compile_sim(scenarios.build_tb_c5(mirror), n_envs=6, env_offset=11, seed=0xB200, horizon=40, auto_reset=True)
     eng, ora = _pair(spec)
     run_lockstep(eng, ora, 90, label='tb_c5/dynamic=' + dynamic)
+
+
+@pytest.mark.parametrize('name', ['maze_c1', 'pacman_c3', 'tb_blocking'])
+def test_static_wall_table_and_traced_blockers_agree(mirror, name, monkeypatch):
+    """Walls use a per-viewer-cell LOS table built at bgw_create; BGW_NO_STATIC_MASK=1 traces every blocker
+    instead.  Both must equal the oracle (the default path is covered by test_engine_matches_oracle)."""
+    builder, manager, _ = scenarios.SCENARIOS[name]
+    spec = compile_sim(builder(mirror), manager=manager, n_envs=4, seed=17, horizon=20, auto_reset=True)
+    monkeypatch.setenv('BGW_NO_STATIC_MASK', '1')
+    eng, ora = _pair(spec)
+    run_lockstep(eng, ora, 30, label=name + '/traced')
