@@ -267,9 +267,9 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu:
             cores = 1
-            n, dt, envs = cpu_rollout(32, 200, cores)
+            n, dt, envs = cpu_rollout(1024, 200, cores)
             line["cpu_baseline"] = {"value": n / dt, "unit": "agent-steps/s", "cores": cores, "kind": "port",
-                                    "sample": f"oracle C port of the reference loop, {envs} envs x 200 steps (one full episode) of the same workload, 1 thread"}
+                                    "sample": f"oracle C port of the reference loop (scalar C, 1 thread), {envs} envs x 200 steps (one full episode) of the same workload, {dt:.1f} s of CPU work"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
