@@ -326,7 +326,7 @@ int bgw_create(const BgwSpec *sp, int device, bgw_handle *out)
                     sp->observer == BGW_OBS_POSITION_CENTERED && sp->attack_actor == BGW_ATTACK_BINARY &&
                     (2 * rmax_att + 1) * (2 * rmax_att + 1) <= 32;
         if (const char *t = getenv("BGW_GENERIC_KERNEL")) if (atoi(t)) fast = false;
-        int TF = A <= 32 ? 32 : A <= 64 ? 64 : 128;
+        int TF = A <= 32 ? 32 : A <= 64 ? 64 : 96;      /* 3 warps: 10 envs per SM fit (shared memory and registers) */
         if (const char *t = getenv("BGW_THREADS")) { const int v = atoi(t); if (v >= 32 && v <= 1024 && v % 32 == 0) TF = std::min(v, 128); }   /* __launch_bounds__(128, 7) */
         if (fast) {
             f.P = P;
@@ -334,7 +334,7 @@ int bgw_create(const BgwSpec *sp, int device, bgw_handle *out)
             f.PW = (W + 2 * P + 3) / 4 * 4;
             f.PH = H + 2 * P;
             f.magic_w = (uint32_t)(((1ull << 32) + (uint64_t)W - 1) / (uint64_t)W);
-            int fslots = std::min(std::max(pow2ceil(HW), 32), 1024);
+            int fslots = std::min(std::max(pow2ceil(HW), 32), 512);
             if (const char *t = getenv("BGW_SLOTS")) { const int v = atoi(t); if (v >= 32 && v <= 65536 && (v & (v - 1)) == 0) fslots = v; }
             h->dsf = d;
             h->dsf.slot_mask = fslots - 1;
@@ -371,13 +371,14 @@ int bgw_create(const BgwSpec *sp, int device, bgw_handle *out)
     if (off > 227 * 1024) return bail(fail(1, "bgw_create: one environment needs %d bytes of shared memory (limit 232448): grid or entity count too large", off));
     cudaError_t ce;
     if ((ce = cudaFuncSetAttribute(bgw_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, off)) != cudaSuccess ||
-        (h->fs.enabled && (ce = cudaFuncSetAttribute(bgw_step_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->fs.smem_bytes)) != cudaSuccess) ||
-        (h->fs.enabled && (ce = cudaFuncSetAttribute(bgw_step_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->fs.smem_bytes)) != cudaSuccess) ||
+        (h->fs.enabled && (ce = cudaFuncSetAttribute(bgw_step_fast_kernel<true, uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->fs.smem_bytes)) != cudaSuccess) ||
+        (h->fs.enabled && (ce = cudaFuncSetAttribute(bgw_step_fast_kernel<false, uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->fs.smem_bytes)) != cudaSuccess) ||
+        (h->fs.enabled && (ce = cudaFuncSetAttribute(bgw_step_fast_kernel<false, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->fs.smem_bytes)) != cudaSuccess) ||
         (ce = cudaFuncSetAttribute(bgw_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, off)) != cudaSuccess)
         return bail(fail(2, "bgw_create: cudaFuncSetAttribute: %s", cudaGetErrorString(ce)));
     if (h->fs.enabled) {
         int per_sm = 0, sms = 0;
-        if ((ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bgw_step_fast_kernel<false>, h->threads_fast, h->fs.smem_bytes)) != cudaSuccess ||
+        if ((ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bgw_step_fast_kernel<false, uint16_t>, h->threads_fast, h->fs.smem_bytes)) != cudaSuccess ||
             (ce = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess)
             return bail(fail(2, "bgw_create: occupancy query: %s", cudaGetErrorString(ce)));
         h->fs.grid_ctas = std::max(1, std::min(d.E, per_sm * sms));
@@ -436,12 +437,13 @@ static int step_impl(bgw_handle h, const int8_t *actions, int8_t *sampled, const
 {
     DeviceGuard guard(h->device);
     if (h->fs.enabled) {
-        if (h->fast_static)
-            bgw_step_fast_kernel<true><<<h->fs.grid_ctas, h->threads_fast, h->fs.smem_bytes, (cudaStream_t)stream>>>(
-                h->dsf, h->fs, h->st, (const uint32_t *)actions, (uint32_t *)sampled, order, obs, reward, done, all_done);
-        else
-            bgw_step_fast_kernel<false><<<h->fs.grid_ctas, h->threads_fast, h->fs.smem_bytes, (cudaStream_t)stream>>>(
-                h->dsf, h->fs, h->st, (const uint32_t *)actions, (uint32_t *)sampled, order, obs, reward, done, all_done);
+#define BGW_LAUNCH_FAST(ST, HT)                                                                                       \
+    bgw_step_fast_kernel<ST, HT><<<h->fs.grid_ctas, h->threads_fast, h->fs.smem_bytes, (cudaStream_t)stream>>>(          \
+        h->dsf, h->fs, h->st, (const uint32_t *)actions, (uint32_t *)sampled, order, obs, reward, done, all_done)
+        if (h->fast_static) BGW_LAUNCH_FAST(true, uint8_t);
+        else if (h->fs.head_elem == 1) BGW_LAUNCH_FAST(false, uint8_t);
+        else BGW_LAUNCH_FAST(false, uint16_t);
+#undef BGW_LAUNCH_FAST
     } else {
         if (sampled) {                                 /* general kernel: sample, then step (two launches) */
             const size_t n = (size_t)h->ds.E * h->ds.L;

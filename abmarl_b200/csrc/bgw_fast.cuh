@@ -51,10 +51,12 @@ struct FastSpec {
     int stage_hits_slots;     /* the observation stage overlaps the reservation slots: refill them after it */
     int b_cell, b_next, b_flags, b_act, buf_bytes;   /* layout of one staging buffer */
     /* shared-memory carve-up of the fast kernel.  `scratch` is a union: during the actor phases it holds
-     * racc | slot | rkmask | eff | pstate | killrank, during the observation phase the per-warp stage, and in
+     * rflag | slot | rkmask | eff | pstate | killrank, during the observation phase the per-warp stage, and in
      * the (general) reset path racc | avail. */
     int o_enc, o_klass, o_tmp, o_lmask, o_head, o_cenc, o_rel, o_ragent, o_plist, o_ctr, o_wsum, o_buf, o_scratch;
-    int s_racc, s_slot, s_rkmask, s_eff, s_pstate, s_killrank, s_avail, scratch_bytes, smem_bytes;
+    int s_rflag, s_slot, s_rkmask, s_eff, s_pstate, s_killrank, scratch_bytes, smem_bytes;
+    int r_racc, r_avail;      /* reset arena (over cenc | head | scratch, from o_cenc): u16 heads at 0, then racc, avail */
+    int head_elem;            /* bytes per list head: 1 when A <= 256, else 2 */
     long long *prof;          /* debug (BGW_PROF_FILE): clock64 at phase boundaries, [cta][8 envs][16 marks] */
 };
 
@@ -63,7 +65,8 @@ struct FastSpec {
 struct FastLayout {
     int b_cell, b_next, b_flags, b_act, buf_bytes;
     int o_enc, o_klass, o_tmp, o_lmask, o_head, o_cenc, o_rel, o_ragent, o_plist, o_ctr, o_wsum, o_buf, o_scratch;
-    int s_racc, s_slot, s_rkmask, s_eff, s_pstate, s_killrank, s_avail, scratch_bytes, smem_bytes, stage_hits_slots;
+    int s_rflag, s_slot, s_rkmask, s_eff, s_pstate, s_killrank, scratch_bytes, smem_bytes, stage_hits_slots;
+    int r_racc, r_avail, head_elem;
 };
 
 __host__ __device__ constexpr int fl_align16(int x) { return (x + 15) & ~15; }
@@ -77,7 +80,6 @@ __host__ __device__ constexpr FastLayout fast_layout(int A, int L, int HW, int P
     y.o_klass = fo; fo += fl_align16(A);
     y.o_tmp = fo; fo += fl_align16(A);
     y.o_lmask = fo; fo += fl_align16(A);
-    y.o_cenc = fo; fo += fl_align16(PH * PW + 32);        /* + slack: the word gather reads past a row end */
     y.o_rel = fo; fo += fl_align16(A * 2);
     y.o_ragent = fo; fo += fl_align16(L * 2);
     y.o_plist = fo; fo += fl_align16(L * 2);
@@ -90,27 +92,32 @@ __host__ __device__ constexpr FastLayout fast_layout(int A, int L, int HW, int P
     y.b_act = bo; bo += fl_align16(L * 4);
     y.buf_bytes = bo;
     y.o_buf = fo; fo += 2 * bo;
-    int so = 0;                                           /* scratch union */
-    y.s_racc = so; so += fl_align16(A * 8);
-    const int after_racc = so;
-    y.s_slot = so; so += fl_align16(slots * 4);
+    /* scratch union, actor phases: rflag | rkmask | eff | pstate | killrank | slot */
+    int so = 0;
+    y.s_rflag = so; so += fl_align16(A);
     y.s_rkmask = so; so += fl_align16(L * 4);
     y.s_eff = so; so += fl_align16(L * 2);
     y.s_pstate = so; so += fl_align16(L);
     y.s_killrank = so; so += fl_align16(A * 2);
+    y.s_slot = so; so += fl_align16(slots * 4);           /* last: the observation stage may spill over the arrays before it */
     const int actor_bytes = so;
-    y.s_avail = after_racc;
-    const int reset_bytes = after_racc + fl_align16((max_enc + 1) * hw_words * 4);
+    /* cenc | head | scratch are contiguous: the observation stage spans head + scratch (the lists are dead once the
+     * row gather starts), and the general reset path uses all three as one arena: u16 heads | racc | avail */
+    const int cenc_bytes = fl_align16(PH * PW + 32);      /* + slack: the word gather reads past a row end */
+    y.head_elem = A <= 256 ? 1 : 2;
+    const int head_bytes = fl_align16(HW * y.head_elem + 2);
     const int stage_bytes = (T / 32) * 32 * BGW_STAGE_ROW;
-    /* the observation stage spans `head` + scratch (the occupant lists are dead once the row gather starts; `head`
-     * is refilled with NONE afterwards), so head and scratch are laid out back to back */
-    const int head_bytes = fl_align16(HW * 2 + 2);
-    int sb = actor_bytes > reset_bytes ? actor_bytes : reset_bytes;
+    y.r_racc = fl_align16(HW * 2 + 2);
+    y.r_avail = y.r_racc + fl_align16(A * 8);
+    const int reset_bytes = y.r_avail + fl_align16((max_enc + 1) * hw_words * 4);
+    int sb = actor_bytes;
     if (stage_bytes - head_bytes > sb) sb = stage_bytes - head_bytes;
+    if (reset_bytes - cenc_bytes - head_bytes > sb) sb = reset_bytes - cenc_bytes - head_bytes;
     y.scratch_bytes = sb;
+    y.o_cenc = fo; fo += cenc_bytes;
     y.o_head = fo; fo += head_bytes;
     y.o_scratch = fo; fo += sb;
-    y.stage_hits_slots = (stage_bytes - head_bytes > y.s_slot) ? 1 : 0;   /* stage spills past racc */
+    y.stage_hits_slots = (stage_bytes - head_bytes > y.s_slot) ? 1 : 0;   /* the stage reaches the slots */
     y.smem_bytes = fo;
     return y;
 }
@@ -121,12 +128,21 @@ __host__ __device__ inline void fast_apply_layout(FastSpec &f, const FastLayout 
     f.o_enc = y.o_enc; f.o_klass = y.o_klass; f.o_tmp = y.o_tmp; f.o_lmask = y.o_lmask; f.o_head = y.o_head;
     f.o_cenc = y.o_cenc; f.o_rel = y.o_rel; f.o_ragent = y.o_ragent; f.o_plist = y.o_plist; f.o_ctr = y.o_ctr;
     f.o_wsum = y.o_wsum; f.o_buf = y.o_buf; f.o_scratch = y.o_scratch;
-    f.s_racc = y.s_racc; f.s_slot = y.s_slot; f.s_rkmask = y.s_rkmask; f.s_eff = y.s_eff; f.s_pstate = y.s_pstate;
-    f.s_killrank = y.s_killrank; f.s_avail = y.s_avail; f.scratch_bytes = y.scratch_bytes; f.smem_bytes = y.smem_bytes;
+    f.s_rflag = y.s_rflag; f.s_slot = y.s_slot; f.s_rkmask = y.s_rkmask; f.s_eff = y.s_eff; f.s_pstate = y.s_pstate;
+    f.s_killrank = y.s_killrank; f.scratch_bytes = y.scratch_bytes; f.smem_bytes = y.smem_bytes;
+    f.r_racc = y.r_racc; f.r_avail = y.r_avail; f.head_elem = y.head_elem;
     f.stage_hits_slots = y.stage_hits_slots;
 }
 
+/* what happened to an entity this step, in the order the reference adds the rewards (team_battle_example.py:38-59):
+ * its own attack (failed attempt or kill, at its turn), its death (at the killer's turn), its failed move */
+enum { RF_ATTACK_FAIL = 1, RF_KILL = 2, RF_DIED = 4, RF_MOVE_FAIL = 8 };
+
 struct FastEnv {
+    void *head;               /* [HW] first occupant of a cell, uint8_t when A <= 256 else uint16_t; an entry is
+                                 meaningful only while the summary says the cell is occupied, so the array is
+                                 never cleared */
+    uint8_t *rflag;           /* [A] RF_* bits of this step (replaces float64 accumulators: the sum is formed once, in order) */
     int8_t *cenc;
     uint16_t *killrank, *eff, *rel;
     uint32_t *rkmask, *act;
@@ -147,14 +163,55 @@ __device__ __forceinline__ int pad_index(const DevSpec &s, const FastSpec &f, in
     return (r + f.P) * f.PW + (c + f.PL);
 }
 
-/* summary of a cell from its occupant list */
-__device__ __forceinline__ int8_t cenc_of_list(const Env &ev, int cell)
+/* ---- occupant lists of the fast kernel: `next` threads the entities of a cell in arrival order (as everywhere),
+ * the first occupant is head[cell], valid iff cenc says the cell is occupied ------------------------------------ */
+template <typename HT>
+__device__ __forceinline__ unsigned fl_first(const FastEnv &fe, int cell, int pidx)
 {
-    unsigned o = ev.head[cell];
-    if (o == BGW_NONE16) return 0;
-    const int8_t e = ev.enc[o];
-    for (o = ev.next[o]; o != BGW_NONE16; o = ev.next[o]) if (ev.enc[o] != e) return (int8_t)BGW_MIXED;
+    return fe.cenc[pidx] != 0 ? (unsigned)((const HT *)fe.head)[cell] : BGW_NONE16;
+}
+
+/* summary of the list that starts at `first` */
+__device__ __forceinline__ int8_t fl_summary(const Env &ev, unsigned first)
+{
+    if (first == BGW_NONE16) return 0;
+    const int8_t e = ev.enc[first];
+    for (unsigned o = ev.next[first]; o != BGW_NONE16; o = ev.next[o]) if (ev.enc[o] != e) return (int8_t)BGW_MIXED;
     return e;
+}
+
+/* Grid.remove grid.py:131-140 for an entity that is in the grid; returns the first occupant that remains */
+template <typename HT>
+__device__ __forceinline__ unsigned fl_unlink(Env &ev, FastEnv &fe, int a)
+{
+    const int cell = ev.cell[a];
+    unsigned first = ((const HT *)fe.head)[cell];
+    if (first == (unsigned)a) {
+        first = ev.next[a];
+        if (first != BGW_NONE16) ((HT *)fe.head)[cell] = (HT)first;
+    } else {
+        unsigned p = first;
+        while (ev.next[p] != (unsigned)a) p = ev.next[p];
+        ev.next[p] = ev.next[a];
+    }
+    ev.next[a] = BGW_NONE16;
+    ev.flags[a] &= ~BGW_ST_IN_GRID;
+    return first;
+}
+
+/* dict insert of Grid.place grid.py:124-126 (append at the tail) */
+template <typename HT>
+__device__ __forceinline__ void fl_append(Env &ev, FastEnv &fe, int a, int cell, bool occupied)
+{
+    ev.next[a] = BGW_NONE16;
+    if (!occupied) ((HT *)fe.head)[cell] = (HT)a;
+    else {
+        unsigned p = ((const HT *)fe.head)[cell];
+        for (unsigned q = ev.next[p]; q != BGW_NONE16; q = ev.next[p]) p = q;
+        ev.next[p] = (uint16_t)a;
+    }
+    ev.cell[a] = (uint16_t)cell;
+    ev.flags[a] |= BGW_ST_IN_GRID;
 }
 
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
@@ -192,6 +249,7 @@ __device__ __forceinline__ void fast_issue_env(const DevSpec &s, const FastSpec 
 }
 
 /* BinaryAttackActor for one attacker with a candidate-cell bit mask (row-major window order, actor.py:489-496) */
+template <typename HT>
 __device__ void fast_exec_attack(const DevSpec &s, const FastSpec &f, Env &ev, FastEnv &fe, int rank, int a, uint32_t mask)
 {
     if (!(ev.flags[a] & BGW_ST_ACTIVE)) return;                   /* team_battle_example.py:37 */
@@ -202,27 +260,27 @@ __device__ void fast_exec_attack(const DevSpec &s, const FastSpec &f, Env &ev, F
     int ncand = 0;
     for (uint32_t m = mask; m; m &= m - 1) {
         const int b = __ffs(m) - 1, wr = b / n, wc = b - wr * n;
-        for (unsigned o = ev.head[own + (wr - R) * s.W + (wc - R)]; o != BGW_NONE16; o = ev.next[o])
+        const int cc = own + (wr - R) * s.W + (wc - R);
+        for (unsigned o = fl_first<HT>(fe, cc, pad_index(s, f, cc)); o != BGW_NONE16; o = ev.next[o])
             ncand += basic_criteria(s, ev, a, (int)o, row, acc) ? 1 : 0;
     }
-    if (ncand == 0) { ev.racc[a] += s.reward[BGW_RW_ATTACK_FAIL]; return; }
+    if (ncand == 0) { fe.rflag[a] |= RF_ATTACK_FAIL; return; }
     int j = (int)bgw_index(dev_draw(s, ev, BGW_SITE_SUBSET, (uint32_t)a, 0), (uint32_t)ncand);
     int v = -1, vcell = 0;
     for (uint32_t m = mask; m && v < 0; m &= m - 1) {
         const int b = __ffs(m) - 1, wr = b / n, wc = b - wr * n;
         vcell = own + (wr - R) * s.W + (wc - R);
-        for (unsigned o = ev.head[vcell]; o != BGW_NONE16; o = ev.next[o])
+        for (unsigned o = fl_first<HT>(fe, vcell, pad_index(s, f, vcell)); o != BGW_NONE16; o = ev.next[o])
             if (basic_criteria(s, ev, a, (int)o, row, acc) && j-- == 0) { v = (int)o; break; }
     }
     /* actor.py:353-358; HealthAgent.health setter agent.py:192-196 (health stays in HBM, touched only on a hit) */
     set_health(ev, v, __ldcg(&ev.health[v]) - __ldg(&s.strength[a]));
     if (!(ev.flags[v] & BGW_ST_ACTIVE)) {
-        grid_unlink(ev, v);
-        fe.cenc[pad_index(s, f, vcell)] = cenc_of_list(ev, vcell);
+        fe.cenc[pad_index(s, f, vcell)] = fl_summary(ev, fl_unlink<HT>(ev, fe, v));
         fe.killrank[v] = (uint16_t)rank;
         atomicAdd(&ev.ctr[CTR_KILLS], 1);
-        ev.racc[v] += s.reward[BGW_RW_DIE];                       /* team_battle_example.py:44-47 */
-        ev.racc[a] += s.reward[BGW_RW_KILL];
+        fe.rflag[v] |= RF_DIED;                                   /* team_battle_example.py:44-47 */
+        fe.rflag[a] |= RF_KILL;
     }
 }
 
@@ -231,7 +289,7 @@ __device__ void fast_exec_attack(const DevSpec &s, const FastSpec &f, Env &ev, F
  * barrier an attacker that holds all its slots executes and frees them (losers only read slots, so the check
  * and the execution need no barrier between them); a second barrier separates the frees from the next round's
  * reservations.  WARP = run by one warp with __syncwarp. */
-template <bool WARP>
+template <bool WARP, typename HT>
 __device__ void fast_attack_rounds(const DevSpec &s, const FastSpec &f, Env &ev, FastEnv &fe, int n_eff, int tid, int T)
 {
     const int stride = WARP ? 32 : T;
@@ -260,7 +318,7 @@ __device__ void fast_attack_rounds(const DevSpec &s, const FastSpec &f, Env &ev,
                 win &= *slot_of(s, ev, own + (wr - R) * s.W + (wc - R)) == (uint32_t)i;
             }
             if (!win) { lost = 1; continue; }
-            fast_exec_attack(s, f, ev, fe, i, a, mask);
+            fast_exec_attack<HT>(s, f, ev, fe, i, a, mask);
             *slot_of(s, ev, own) = BGW_SLOT_FREE;
             for (uint32_t m = mask; m; m &= m - 1) {
                 const int b = __ffs(m) - 1, wr = b / n, wc = b - wr * n;
@@ -273,18 +331,22 @@ __device__ void fast_attack_rounds(const DevSpec &s, const FastSpec &f, Env &ev,
 }
 
 /* one move: Grid.query through the summary, then remove / place (actor.py:99-114) */
+template <typename HT>
 __device__ __forceinline__ void fast_exec_move(const DevSpec &s, const FastSpec &f, Env &ev, FastEnv &fe, int a, int to)
 {
     const int from = ev.cell[a], pto = pad_index(s, f, to);
     const int8_t summary = fe.cenc[pto], me = ev.enc[a];
-    bool ok;
-    if (summary == 0) ok = true;
-    else if (summary != (int8_t)BGW_MIXED) ok = (__ldg(&s.overlap[me]) >> summary) & 1ull;
-    else ok = grid_query(s, ev, a, to);
-    if (!ok) { ev.racc[a] += s.reward[BGW_RW_MOVE_FAIL]; return; }
-    grid_unlink(ev, a);
-    fe.cenc[pad_index(s, f, from)] = cenc_of_list(ev, from);
-    grid_append(ev, a, to);
+    bool ok = true;
+    if (summary != 0) {
+        const unsigned long long row = __ldg(&s.overlap[me]);
+        if (summary != (int8_t)BGW_MIXED) ok = (row >> summary) & 1ull;
+        else                                                        /* Grid.query grid.py:81-105 over a mixed cell */
+            for (unsigned o = ((const HT *)fe.head)[to]; o != BGW_NONE16; o = ev.next[o])
+                if (!((row >> ev.enc[o]) & 1ull)) { ok = false; break; }
+    }
+    if (!ok) { fe.rflag[a] |= RF_MOVE_FAIL; return; }
+    if (ev.flags[a] & BGW_ST_IN_GRID) fe.cenc[pad_index(s, f, from)] = fl_summary(ev, fl_unlink<HT>(ev, fe, a));
+    fl_append<HT>(ev, fe, a, to, summary != 0);
     const int8_t ns = summary == 0 ? me : (summary == me ? me : (int8_t)BGW_MIXED);
     fe.cenc[pto] = ns;
     if (ns == (int8_t)BGW_MIXED) ev.ctr[CTR_MIXED] = 1;
@@ -292,7 +354,7 @@ __device__ __forceinline__ void fast_exec_move(const DevSpec &s, const FastSpec 
 
 /* Ordered rounds over the pending movers (pstate == 1; targets in rkmask[], the attack masks are dead by
  * then): each reserves its source and destination cell; same two-barrier round as the attack phase. */
-template <bool WARP>
+template <bool WARP, typename HT>
 __device__ void fast_move_rounds(const DevSpec &s, const FastSpec &f, Env &ev, FastEnv &fe, int n_act, int pending, int tid, int T)
 {
     const int stride = WARP ? 32 : T;
@@ -308,7 +370,7 @@ __device__ void fast_move_rounds(const DevSpec &s, const FastSpec &f, Env &ev, F
             if (ev.pstate[i] != 1) continue;
             const int a = ev.ragent[i], from = ev.cell[a], to = (int)fe.rkmask[i];
             if (*slot_of(s, ev, from) != (uint32_t)i || *slot_of(s, ev, to) != (uint32_t)i) { lost = 1; continue; }
-            fast_exec_move(s, f, ev, fe, a, to);
+            fast_exec_move<HT>(s, f, ev, fe, a, to);
             *slot_of(s, ev, from) = BGW_SLOT_FREE;
             *slot_of(s, ev, to) = BGW_SLOT_FREE;
             ev.pstate[i] = 0;
@@ -317,13 +379,11 @@ __device__ void fast_move_rounds(const DevSpec &s, const FastSpec &f, Env &ev, F
     }
 }
 
-/* (re)initialise the dense per-cell arrays of this CTA: empty lists, clean head-detection marks, free
- * reservation slots, empty summary with a -1 border */
+/* (re)initialise the dense per-cell arrays of this CTA: clean head-detection marks, free reservation slots, empty
+ * summary with a -1 border (the list heads need no initialisation: the summary says which are meaningful) */
 __device__ void fast_init_dense(const DevSpec &s, const FastSpec &f, Env &ev, FastEnv &fe, int tid, int T)
 {
-    uint4 *h4 = (uint4 *)ev.head;
     const uint4 ones = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
-    for (int i = tid; i < (s.HW * 2 + 15) / 16; i += T) h4[i] = ones;
     for (int a = tid; a < s.A; a += T) ev.tmp[a] = 0;
     {   /* reservation slots: every round frees what it reserved, so they only need filling here (and after a
          * reset, whose availability maps share the scratch union) */
@@ -349,6 +409,7 @@ __device__ void fast_init_dense(const DevSpec &s, const FastSpec &f, Env &ev, Fa
 
 /* the general per-cell observation chunk on top of the summary: used when the env holds a mixed cell, an
  * observer does not observe itself, or the compile-time gather does not apply */
+template <typename HT>
 __device__ void fast_obs_chunk_slow(const DevSpec &s, const FastSpec &f, const Env &ev, const FastEnv &fe, int a, int ch,
                                     uint32_t w[4])
 {
@@ -362,8 +423,21 @@ __device__ void fast_obs_chunk_slow(const DevSpec &s, const FastSpec &f, const E
     for (int t = 0; t < 16 && k0 + t < valid; ++t) {
         int v = win[wr * f.PW + wc];
         const bool centre = (wr == R && wc == R);
-        if (v == BGW_MIXED || (centre && !s.observe_self && v > 0))
-            v = choose_encoding(s, ev, a, (r0 - R + wr) * s.W + (c0 - R + wc), s.observe_self ? -1 : a);
+        if (v == BGW_MIXED || (centre && !s.observe_self && v > 0)) {
+            /* np.random.choice over the encodings of the occupants in arrival order (observer.py:233-246) */
+            const int cell = (r0 - R + wr) * s.W + (c0 - R + wc), skip = s.observe_self ? -1 : a;
+            const unsigned first = ((const HT *)fe.head)[cell];
+            int cnt = 0;
+            for (unsigned o = first; o != BGW_NONE16; o = ev.next[o]) cnt += ((int)o != skip);
+            v = 0;
+            if (cnt > 0) {
+                int k = (cnt == 1) ? 0 : (int)bgw_index(dev_draw(s, ev, BGW_SITE_OBS, (uint32_t)a, (uint32_t)cell), (uint32_t)cnt);
+                for (unsigned o = first; o != BGW_NONE16; o = ev.next[o]) {
+                    if ((int)o == skip) continue;
+                    if (k-- == 0) { v = ev.enc[o]; break; }
+                }
+            }
+        }
         w[t >> 2] |= (uint32_t)(uint8_t)(int8_t)v << ((t & 3) * 8);
         if (++wc == n) { wc = 0; ++wr; }
     }
@@ -447,10 +521,10 @@ __device__ void fast_obs_rows(const DevSpec &s, const FastSpec &f, const Env &ev
 struct FastStaticC5 {
     static constexpr int A = 256, L = 256, H = 64, W = 64, P = 5, PL = 5, PW = 76, PH = 74, obs_stride = 128, nchunks = 8,
                          obs_h = 11, view = 5, move_actor = BGW_MOVE_BOX, ravel = 0, observe_self = 1, done_mask = BGW_DONE_ONE_TEAM,
-                         max_enc = 4, simd_ok = 1, async_ok = 1, slots = 1024, T = 128;
+                         max_enc = 4, simd_ok = 1, async_ok = 1, slots = 512, T = 96;
 };
 
-template <bool STATIC>
+template <bool STATIC, typename HT>
 __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_in, const FastSpec f_in, const BgwState st, const uint32_t *actions,
                                      uint32_t *sampled, const int16_t *order, int8_t *obs, float *reward, uint8_t *done,
                                      uint8_t *all_done)
@@ -475,16 +549,18 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
     ev.enc = (int8_t *)(bgw_smem + f.o_enc);
     ev.klass = bgw_smem + f.o_klass;
     ev.tmp = bgw_smem + f.o_tmp;
-    ev.head = (uint16_t *)(bgw_smem + f.o_head);
+    ev.head = nullptr;                                     /* the fast kernel keeps its own typed heads (fe.head) */
     ev.ragent = (uint16_t *)(bgw_smem + f.o_ragent);
     ev.plist = (uint16_t *)(bgw_smem + f.o_plist);
     ev.ctr = (int *)(bgw_smem + f.o_ctr);
-    ev.racc = (double *)(scratch + f.s_racc);
+    ev.racc = nullptr;                                     /* float64 accumulators exist only in the reset arena */
     ev.slot = (uint32_t *)(scratch + f.s_slot);
     ev.pstate = scratch + f.s_pstate;
-    ev.avail = (uint32_t *)(scratch + f.s_avail);
+    ev.avail = nullptr;
     ev.mask = nullptr; ev.act = nullptr;
     FastEnv fe;
+    fe.head = bgw_smem + f.o_head;
+    fe.rflag = scratch + f.s_rflag;
     fe.cenc = (int8_t *)(bgw_smem + f.o_cenc);
     fe.rel = (uint16_t *)(bgw_smem + f.o_rel);
     fe.lmask = (const uint32_t *)(bgw_smem + f.o_lmask);
@@ -572,15 +648,23 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
             }
             /* sim.reset() on this env's staging buffer (general code: placement, health, orientation), state to
              * HBM, then the first observations through the same summary + row-gather path as a step */
-            sim_reset(s, st, ev, tid, T);
-            store_env(s, st, ev, true, tid, T);
+            {
+                unsigned char *arena = bgw_smem + f.o_cenc;         /* cenc | head | scratch as one arena */
+                Env evr = ev;
+                evr.head = (uint16_t *)arena;
+                evr.racc = (double *)(arena + f.r_racc);
+                evr.avail = (uint32_t *)(arena + f.r_avail);
+                sim_reset(s, st, evr, tid, T);
+                store_env(s, st, evr, true, tid, T);
+                ev.episode = evr.episode; ev.step = evr.step;
+            }
             if (tid == 0) {
                 const uint8_t fl = (uint8_t)((ev.ctr[CTR_ERR] ? BGW_ENV_ERROR : 0) | BGW_ENV_RESET);
                 st.error[e] = (uint32_t)ev.ctr[CTR_ERR];
                 st.env_flags[e] = fl; all_done[e] = fl;
             }
             __syncthreads();
-            fast_init_dense(s, f, ev, fe, tid, T);                  /* sim_reset left its lists in `head` */
+            fast_init_dense(s, f, ev, fe, tid, T);                  /* the reset arena ran over summary and slots */
             if (tid < CTR_COUNT) ev.ctr[tid] = 0;
             __syncthreads();
             fresh = true;
@@ -674,7 +758,7 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
         /* ---- occupant lists and summary from the relevant entities --------------------------------- */
         for (int x = tid; x < n_rel; x += T) {
             const int a = fe.rel[x];
-            ev.racc[a] = (!fresh && racc_persists(ev.klass[a])) ? st.reward_acc[off + a] : 0.0;
+            fe.rflag[a] = 0;
             fe.killrank[a] = BGW_NONE16;
             if (ev.flags[a] & BGW_ST_IN_GRID) {
                 if (ev.next[a] != BGW_NONE16) ev.tmp[ev.next[a]] = 1;
@@ -685,7 +769,7 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
         for (int x = tid; x < n_rel; x += T) {
             const int a = fe.rel[x];
             if (ev.flags[a] & BGW_ST_IN_GRID) {
-                if (!ev.tmp[a]) ev.head[ev.cell[a]] = (uint16_t)a;
+                if (!ev.tmp[a]) ((HT *)fe.head)[ev.cell[a]] = (HT)a;
                 ev.tmp[a] = 0;
                 const int p = pad_index(s, f, ev.cell[a]);
                 if (fe.cenc[p] != ev.enc[a]) { fe.cenc[p] = (int8_t)BGW_MIXED; ev.ctr[CTR_MIXED] = 1; }
@@ -736,8 +820,8 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
             BGW_PROF_MARK(5);
             {
                 const int n_eff = ev.ctr[CTR_NEMIT];
-                if (n_eff > 32) fast_attack_rounds<false>(s, f, ev, fe, n_eff, tid, T);
-                else if (n_eff > 0 && warp == 0) fast_attack_rounds<true>(s, f, ev, fe, n_eff, tid, T);
+                if (n_eff > 32) fast_attack_rounds<false, HT>(s, f, ev, fe, n_eff, tid, T);
+                else if (n_eff > 0 && warp == 0) fast_attack_rounds<true, HT>(s, f, ev, fe, n_eff, tid, T);
                 if (n_eff > 0 && n_eff <= 32) __syncthreads();
             }
             BGW_PROF_MARK(6);
@@ -749,7 +833,7 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
                 const bool active = ev.flags[a] & BGW_ST_ACTIVE;
                 if (ev.pstate[i] == 3) {
                     const unsigned kr = fe.killrank[a];
-                    if (active || (kr != BGW_NONE16 && kr > (unsigned)i)) ev.racc[a] += rw[BGW_RW_ATTACK_FAIL];   /* :41-42 */
+                    if (active || (kr != BGW_NONE16 && kr > (unsigned)i)) fe.rflag[a] |= RF_ATTACK_FAIL;   /* :41-42 */
                 }
                 uint8_t p = 0;
                 if (active) {
@@ -764,16 +848,16 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
                             else { p = 1; fe.rkmask[i] = (uint32_t)(r * s.W + c); }
                         }
                     }
-                    if (!p && !ok) ev.racc[a] += rw[BGW_RW_MOVE_FAIL];
+                    if (!p && !ok) fe.rflag[a] |= RF_MOVE_FAIL;
                 }
                 ev.pstate[i] = p;
                 pend |= p;
             }
             pend = __syncthreads_or(pend);
             BGW_PROF_MARK(7);
-            if (n_act > 32) fast_move_rounds<false>(s, f, ev, fe, n_act, pend, tid, T);
+            if (n_act > 32) fast_move_rounds<false, HT>(s, f, ev, fe, n_act, pend, tid, T);
             else {
-                if (warp == 0) fast_move_rounds<true>(s, f, ev, fe, n_act, pend, tid, T);
+                if (warp == 0) fast_move_rounds<true, HT>(s, f, ev, fe, n_act, pend, tid, T);
                 __syncthreads();
             }
             BGW_PROF_MARK(8);
@@ -781,18 +865,25 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
             /* ---- entropy :58-59, rewards / dones of the acting learners (all_step_manager.py:68-87) -------- */
             for (int i = tid; i < n_act; i += T) {
                 const int a = ev.ragent[i], l = ev.plist[i];
-                const double r = ev.racc[a] + rw[BGW_RW_ENTROPY];
+                /* the reference's float64 sum, term by term in the order it adds them (:42,:47,:46,:55,:59) */
+                const unsigned rf = fe.rflag[a];
+                double r = 0.0;
+                if (rf & RF_ATTACK_FAIL) r += rw[BGW_RW_ATTACK_FAIL];
+                if (rf & RF_KILL) r += rw[BGW_RW_KILL];
+                if (rf & RF_DIED) r += rw[BGW_RW_DIE];
+                if (rf & RF_MOVE_FAIL) r += rw[BGW_RW_MOVE_FAIL];
+                r += rw[BGW_RW_ENTROPY];
                 const bool dd = prog_done(s, ev, a);
                 rew[l] = (float)r;
                 dn[l] = (uint8_t)(BGW_OUT_VALID | (dd ? BGW_OUT_DONE : 0));
                 if (dd) ev.flags[a] |= BGW_ST_DONE_REPORTED; else atomicAdd(&ev.ctr[CTR_REMAINING], 1);
             }
         }
-        /* racc of entities whose accumulator persists (non-learners with health) goes back before the scratch is reused */
+        /* entities whose accumulator persists (non-learners with health, never read): add this step's 'die' in HBM */
         if (!fresh)
             for (int x = tid; x < n_rel; x += T) {
                 const int a = fe.rel[x];
-                if (racc_persists(ev.klass[a])) st.reward_acc[off + a] = ev.racc[a];
+                if (racc_persists(ev.klass[a]) && (fe.rflag[a] & RF_DIED)) st.reward_acc[off + a] += rw[BGW_RW_DIE];
             }
         __syncthreads();                                            /* the scratch union becomes the observation stage */
         BGW_PROF_MARK(9);
@@ -803,18 +894,18 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
             const bool direct = s.observe_self && !ev.ctr[CTR_MIXED];
             const int R = direct ? f.uniform_view : -1;
             switch (R) {
-            case 1: fast_obs_rows<1>(s, f, ev, fe, n_act, obs_env, (unsigned char *)ev.head, tid, T); staged = true; break;
-            case 2: fast_obs_rows<2>(s, f, ev, fe, n_act, obs_env, (unsigned char *)ev.head, tid, T); staged = true; break;
-            case 3: fast_obs_rows<3>(s, f, ev, fe, n_act, obs_env, (unsigned char *)ev.head, tid, T); staged = true; break;
-            case 4: fast_obs_rows<4>(s, f, ev, fe, n_act, obs_env, (unsigned char *)ev.head, tid, T); staged = true; break;
-            case 5: fast_obs_rows<5>(s, f, ev, fe, n_act, obs_env, (unsigned char *)ev.head, tid, T); staged = true; break;
+            case 1: fast_obs_rows<1>(s, f, ev, fe, n_act, obs_env, (unsigned char *)fe.head, tid, T); staged = true; break;
+            case 2: fast_obs_rows<2>(s, f, ev, fe, n_act, obs_env, (unsigned char *)fe.head, tid, T); staged = true; break;
+            case 3: fast_obs_rows<3>(s, f, ev, fe, n_act, obs_env, (unsigned char *)fe.head, tid, T); staged = true; break;
+            case 4: fast_obs_rows<4>(s, f, ev, fe, n_act, obs_env, (unsigned char *)fe.head, tid, T); staged = true; break;
+            case 5: fast_obs_rows<5>(s, f, ev, fe, n_act, obs_env, (unsigned char *)fe.head, tid, T); staged = true; break;
             default: {
                 const int items = n_act * nch;
                 for (int it = tid; it < items; it += T) {
                     const int li = it / nch, ch = it - li * nch;
                     const int l = ev.plist[li], a = ev.ragent[li];
                     uint32_t w[4];
-                    fast_obs_chunk_slow(s, f, ev, fe, a, ch, w);
+                    fast_obs_chunk_slow<HT>(s, f, ev, fe, a, ch, w);
                     *reinterpret_cast<uint4 *>(obs_env + (size_t)l * s.obs_stride + ch * 16) = make_uint4(w[0], w[1], w[2], w[3]);
                 }
             }
@@ -824,14 +915,10 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
         BGW_PROF_MARK(10);
 
         /* ---- store the relevant entities, get_all_done (done.py:49-56,147-153), clean the dense arrays ---- */
-        if (staged) {                                               /* `head` held the observation stage: empty lists again */
-            uint4 *h4 = (uint4 *)ev.head;
+        if (staged && f.stage_hits_slots) {                         /* the observation stage ran over the reservation slots */
+            uint4 *s4 = (uint4 *)ev.slot;
             const uint4 ones = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
-            for (int i = tid; i < (s.HW * 2 + 15) / 16; i += T) h4[i] = ones;
-            if (f.stage_hits_slots) {
-                uint4 *s4 = (uint4 *)ev.slot;
-                for (int i = tid; i < (s.slot_mask + 1) / 4; i += T) s4[i] = ones;
-            }
+            for (int i = tid; i < (s.slot_mask + 1) / 4; i += T) s4[i] = ones;
         }
         {
             uint32_t lo = 0, hi = 0;
@@ -846,10 +933,7 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
                     if ((s.done_mask & BGW_DONE_TARGET_AGENT) && t >= 0 && !same_position(ev, a, t)) ok = 0;
                     if ((s.done_mask & BGW_DONE_TARGET_DESTROYED) && t >= 0 && (ev.flags[t] & BGW_ST_ACTIVE)) ok = 0;
                 }
-                if (fl & BGW_ST_IN_GRID) {
-                    if (!staged) ev.head[ev.cell[a]] = BGW_NONE16;
-                    fe.cenc[pad_index(s, f, ev.cell[a])] = 0;
-                }
+                if (fl & BGW_ST_IN_GRID) fe.cenc[pad_index(s, f, ev.cell[a])] = 0;
             }
             lo = __reduce_or_sync(0xFFFFFFFFu, lo);
             hi = __reduce_or_sync(0xFFFFFFFFu, hi);

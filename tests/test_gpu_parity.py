@@ -63,7 +63,7 @@ def test_general_kernel_on_fast_path_scenarios(mirror, name, monkeypatch):
     run_lockstep(eng, ora, 60, label=name + '/general')
 
 
-@pytest.mark.parametrize('threads', ['32', '64', '256'])
+@pytest.mark.parametrize('threads', ['32', '64', '96', '256'])
 def test_thread_count_does_not_change_results(mirror, threads, monkeypatch):
     spec = compile_sim(scenarios.build_tb_c5_small(mirror), n_envs=16, seed=9, horizon=30, auto_reset=True)
     monkeypatch.setenv('BGW_THREADS', threads)
@@ -258,3 +258,11 @@ def test_static_wall_table_and_traced_blockers_agree(mirror, name, monkeypatch):
     monkeypatch.setenv('BGW_NO_STATIC_MASK', '1')
     eng, ora = _pair(spec)
     run_lockstep(eng, ora, 30, label=name + '/traced')
+
+
+def test_more_than_256_entities_use_16_bit_list_heads(mirror):
+    """The specialised kernel keeps 8-bit list heads up to 256 entities and 16-bit ones beyond."""
+    sim = scenarios.build_tb_c5(mirror, rows=40, cols=36, n_agents=300, view_range=4)
+    spec = compile_sim(sim, n_envs=5, env_offset=2, seed=99, horizon=30, auto_reset=True)
+    eng, ora = _pair(spec)
+    run_lockstep(eng, ora, 70, label='tb_300_agents')
