@@ -353,29 +353,45 @@ __device__ __forceinline__ void fast_exec_move(const DevSpec &s, const FastSpec 
 }
 
 /* Ordered rounds over the pending movers (pstate == 1; targets in rkmask[], the attack masks are dead by
- * then): each reserves its source and destination cell; same two-barrier round as the attack phase. */
+ * then): each reserves its source and destination cell; same two-barrier round as the attack phase.  The first
+ * round walks all ranks; its losers are appended to a list and later rounds walk only the list of the round
+ * before (two lists in the storage of eff[] / killrank[], both dead by now). */
 template <bool WARP, typename HT>
 __device__ void fast_move_rounds(const DevSpec &s, const FastSpec &f, Env &ev, FastEnv &fe, int n_act, int pending, int tid, int T)
 {
     const int stride = WARP ? 32 : T;
+    int which = 0, n_cur = -1;                                     /* -1: walk the ranks themselves */
     while (pending) {
-        for (int i = tid; i < n_act; i += stride) {
+        const int n_it = n_cur < 0 ? n_act : n_cur;
+        for (int x = tid; x < n_it; x += stride) {
+            const int i = n_cur < 0 ? x : (which ? fe.killrank : fe.eff)[x];
             if (ev.pstate[i] != 1) continue;
             atomicMin(slot_of(s, ev, ev.cell[ev.ragent[i]]), (uint32_t)i);
             atomicMin(slot_of(s, ev, (int)fe.rkmask[i]), (uint32_t)i);
         }
         if (WARP) __syncwarp(); else __syncthreads();
         int lost = 0;
-        for (int i = tid; i < n_act; i += stride) {
+        for (int x = tid; x < n_it; x += stride) {
+            const int i = n_cur < 0 ? x : (which ? fe.killrank : fe.eff)[x];
             if (ev.pstate[i] != 1) continue;
             const int a = ev.ragent[i], from = ev.cell[a], to = (int)fe.rkmask[i];
-            if (*slot_of(s, ev, from) != (uint32_t)i || *slot_of(s, ev, to) != (uint32_t)i) { lost = 1; continue; }
+            if (*slot_of(s, ev, from) != (uint32_t)i || *slot_of(s, ev, to) != (uint32_t)i) {
+                lost = 1;
+                if (!WARP) (which ? fe.eff : fe.killrank)[atomicAdd(&ev.ctr[CTR_PA + (which ^ 1)], 1)] = (uint16_t)i;
+                continue;
+            }
             fast_exec_move<HT>(s, f, ev, fe, a, to);
             *slot_of(s, ev, from) = BGW_SLOT_FREE;
             *slot_of(s, ev, to) = BGW_SLOT_FREE;
             ev.pstate[i] = 0;
         }
-        if (WARP) { pending = __any_sync(0xFFFFFFFFu, lost); __syncwarp(); } else pending = __syncthreads_or(lost);
+        if (WARP) { pending = __any_sync(0xFFFFFFFFu, lost); __syncwarp(); }
+        else {
+            pending = __syncthreads_or(lost);
+            n_cur = ev.ctr[CTR_PA + (which ^ 1)];                  /* the losers of this round */
+            if (tid == 0) ev.ctr[CTR_PA + which] = 0;              /* next round appends here (after its barrier) */
+            which ^= 1;
+        }
     }
 }
 
