@@ -32,6 +32,9 @@ def make_spec(rows, cols, agents, overlapping=None, attack_mapping=None, program
     sp.init_col[:] = -1
     sp.init_health[:] = math.nan
     sp.target[:] = -1
+    for i, a in enumerate(agents):
+        if a.get('target') is not None:
+            sp.target[i] = a['target']
     sp.agent_ids = [f'agent{i}' for i in range(len(agents))]
     for i, a in enumerate(agents):
         sp.encoding[i], sp.klass[i] = a['enc'], a['klass']
@@ -346,6 +349,46 @@ def case_active_done(kind):                                  # test_done.py: Act
     done = be._np(be.env.done)[0]
     assert list(done & K.OUT_DONE) == [0, 1, 0] and all(done & K.OUT_VALID)
     assert not be._np(be.env.all_done)[0] & K.ENV_ALL_DONE       # two entities are still active
+
+
+def case_target_agent_done(kind):                            # test_done.py:45-118 (TargetAgentDone) through the manager
+    pos = [(0, 0), (0, 1), (1, 0), (1, 1)]
+    agents = [dict(enc=1 + (i >= 2), pos=pos[i], klass=LRN | OBS | MOV, move=1, view=1, target=(i + 1) % 4) for i in range(4)]
+    be = Backend(make_spec(2, 2, agents, overlapping={1: {1, 2}, 2: {1, 2}}, done_mask=K.DONE_TARGET_AGENT,
+                           attack_actor=K.ATTACK_BINARY), kind)
+    be.reset()
+    script = [  # (mover, move) -> learners reported done this step, __all__
+        ((0, (0, 1)), [0], False),       # agent0 steps onto agent1's cell
+        ((1, (1, -1)), [1], False),      # agent1 onto agent2's cell (agent0 is done and no longer reported)
+        ((3, (-1, 0)), [3], False),      # agent3 onto agent0's cell
+        ((2, (-1, 1)), [2], True),       # agent2 onto agent3's cell: every learner has been reported done
+    ]
+    reported = set()
+    for (mover, mv), newly_done, all_done in script:
+        be.step([mv if l == mover else (0, 0) for l in range(4)])
+        done = be._np(be.env.done)[0]
+        for l in range(4):
+            assert bool(done[l] & K.OUT_VALID) == (l not in reported)
+            assert bool(done[l] & K.OUT_DONE) == (l in newly_done)
+        reported |= set(newly_done)
+        assert bool(be._np(be.env.all_done)[0] & K.ENV_ALL_DONE) == all_done
+
+
+def case_target_destroyed_done(kind):                        # test_done.py:120-189 (TargetDestroyedDone) through attacks
+    agents = [dict(enc=1, pos=(0, 0), klass=LRN | OBS | ATT, att_range=1, strength=1, accuracy=1, view=1, target=2),
+              dict(enc=1, pos=(0, 3), klass=LRN | OBS | ATT, att_range=1, strength=1, accuracy=1, view=1, target=3),
+              dict(enc=3, pos=(1, 0), klass=HEA, health=1), dict(enc=3, pos=(1, 3), klass=HEA, health=0.5)]
+    be = Backend(make_spec(2, 4, agents, attack_mapping={1: {3}}, attack_actor=K.ATTACK_BINARY,
+                           done_mask=K.DONE_TARGET_DESTROYED), kind)
+    be.reset()
+    be.step([(0, 0, 0), (0, 0, 1)])                            # agent1 destroys its target
+    done = be._np(be.env.done)[0]
+    assert [bool(d & K.OUT_DONE) for d in done] == [False, True]
+    assert not be._np(be.env.all_done)[0] & K.ENV_ALL_DONE     # agent0's target is still active
+    be.step([(0, 0, 1), (0, 0, 0)])
+    done = be._np(be.env.done)[0]
+    assert bool(done[0] & K.OUT_DONE) and not done[1] & K.OUT_VALID
+    assert be._np(be.env.all_done)[0] & K.ENV_ALL_DONE         # every target destroyed (done.py:133-137)
 
 
 CASES = [v for k, v in sorted(globals().items()) if k.startswith('case_')]

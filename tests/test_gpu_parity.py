@@ -266,3 +266,24 @@ def test_more_than_256_entities_use_16_bit_list_heads(mirror):
     spec = compile_sim(sim, n_envs=5, env_offset=2, seed=99, horizon=30, auto_reset=True)
     eng, ora = _pair(spec)
     run_lockstep(eng, ora, 70, label='tb_300_agents')
+
+
+@pytest.mark.parametrize('name', ['tb_c2', 'maze_c1'])
+def test_masked_reset_touches_only_the_selected_envs(mirror, name):
+    """bgw_reset(env_mask): AllStepManager.reset for a subset of the batch, the rest keeps running."""
+    builder, manager, _ = scenarios.SCENARIOS[name]
+    spec = compile_sim(builder(mirror), manager=manager, n_envs=10, seed=8, horizon=0, auto_reset=False)
+    eng, ora = _pair(spec)
+    eng.reset()
+    ora.reset()
+    rng = np.random.default_rng(3)
+    for t in range(30):
+        act = ora.sample_actions()
+        ora.step(act)
+        eng.step(torch.from_numpy(act).cuda())
+        if t % 7 == 6:
+            mask = (rng.random(10) < 0.4).astype(np.uint8)
+            ora.reset(mask)
+            eng.reset(mask)
+        assert np.array_equal(eng.obs.cpu().numpy(), ora.obs), f'{name} step {t}'
+        assert_state_equal(eng.state_numpy(), ora.state, f'{name} step {t}')
