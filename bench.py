@@ -207,7 +207,7 @@ def run_ours(args):
     def host_step(i):
         # public host-facing call: pinned host actions -> H2D, step, on-device compaction of the rows the
         # reference's manager would return, D2H of exactly those rows (+ all_done); returns when they are on the host
-        eng.step_host(pool[i % len(pool)])
+        eng.step_host(pool[i % len(pool)], zero_copy=args.e2e_zero_copy)
         d2h_total[0] += eng.last_d2h_bytes
 
     for i in range(3):
@@ -284,6 +284,7 @@ def main():
     ap.add_argument('--envs-per-gpu', type=int, default=ENVS_PER_GPU)
     ap.add_argument('--e2e-steps', type=int, default=200, help='steps of the host-buffer loop (one full episode)')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--e2e-zero-copy', action='store_true', help='e2e: the gather kernel writes the pinned host buffers directly instead of compacting on the device and copying')
     ap.add_argument('--dump-steps', default=None, help='write the per-step kernel times (ms) to this JSON file')
     args = ap.parse_args()
     if args.impl == 'reference':

@@ -194,7 +194,8 @@ def test_full_size_c5_properties(mirror):
     assert (own >= 1).all()                                            # a live agent sees its own team on its cell
 
 
-def test_step_host_returns_exactly_the_valid_rows(mirror):
+@pytest.mark.parametrize('zero_copy', [True, False])
+def test_step_host_returns_exactly_the_valid_rows(mirror, zero_copy):
     """bgw_gather_valid / BatchedGridWorld.step_host: the compacted host buffers hold the rows with BGW_OUT_VALID
     (and every row of an env that was auto-reset), identical to the dense device outputs."""
     spec = compile_sim(scenarios.build_tb_dense(mirror), n_envs=48, seed=13, horizon=12, auto_reset=True)
@@ -204,7 +205,7 @@ def test_step_host_returns_exactly_the_valid_rows(mirror):
     seen_reset = False
     for t in range(40):
         act = eng.sample_actions().cpu().pin_memory()
-        n, index, obs_c, rew_c, done_c, all_done = eng.step_host(act)
+        n, index, obs_c, rew_c, done_c, all_done = eng.step_host(act, zero_copy=zero_copy)
         dense_obs, dense_rew = eng.obs.cpu().numpy().reshape(-1, eng.dims.obs_stride), eng.reward.cpu().numpy().ravel()
         dense_done, flags = eng.done.cpu().numpy().ravel(), eng.all_done.cpu().numpy()
         want = ((dense_done & K.OUT_VALID) != 0).reshape(eng.E, eng.L) | ((flags & K.ENV_RESET) != 0)[:, None]
