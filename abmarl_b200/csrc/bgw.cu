@@ -317,6 +317,7 @@ int bgw_create(const BgwSpec *sp, int device, bgw_handle *out)
     d.o_avail = take((max_enc + 1) * d.hw_words * 4);
     d.o_mask = take(d.mask_batch * d.mask_words * 4);
     d.o_ctr = take(CTR_COUNT * 4);
+    d.o_csum = take(HW);
     /* ---- specialised team-battle kernel (bgw_fast.cuh) when the sim qualifies: own launch geometry and its
      *      own shared-memory carve-up ------------------------------------------------------------------- */
     {

@@ -30,6 +30,7 @@
 
 #define BGW_NONE16 0xFFFFu
 #define BGW_SLOT_FREE 0xFFFFFFFFu
+#define BGW_CSUM_MIXED (-128)
 #define BGW_ATT_MASK_WORDS 8   /* thread-local LOS mask of an attacker: (2R+1)^2 <= 256 bits -> attack_range <= 7 */
 
 enum { CTR_KILLS = 0, CTR_ALLDONE, CTR_REMAINING, CTR_ENC_LO, CTR_ENC_HI, CTR_AND, CTR_NEMIT, CTR_ENVDONE,
@@ -65,7 +66,7 @@ struct DevSpec {
     const uint32_t *tpl_avail;     /* [(max_enc+1)][hw_words] availability bit maps after the fixed placements */
     /* shared memory carve-up (byte offsets) */
     int o_head, o_slot, o_cell, o_next, o_flags, o_enc, o_klass, o_tmp, o_racc, o_act, o_ragent, o_plist,
-        o_pstate, o_avail, o_mask, o_ctr, smem_bytes;
+        o_pstate, o_avail, o_mask, o_ctr, o_csum, smem_bytes;
 };
 
 struct Env {
@@ -73,6 +74,7 @@ struct Env {
     uint32_t *slot, *act, *avail, *mask;
     uint8_t *flags, *klass, *tmp, *pstate;
     int8_t *enc;
+    int8_t *csum;     /* [HW] per-cell summary for the observers: 0 empty, e = every occupant has encoding e, CSUM_MIXED */
     double *racc;
     int *ctr;
     double *health;   /* this env's row of BgwState.health (global) */
@@ -98,6 +100,7 @@ __device__ __forceinline__ void env_init(Env &ev, const DevSpec &s, unsigned cha
     ev.avail = (uint32_t *)(sm + s.o_avail);
     ev.mask = (uint32_t *)(sm + s.o_mask);
     ev.ctr = (int *)(sm + s.o_ctr);
+    ev.csum = (int8_t *)(sm + s.o_csum);
 }
 
 __device__ __forceinline__ uint32_t dev_draw(const DevSpec &s, const Env &ev, uint32_t site, uint32_t slot, uint32_t k)
@@ -684,9 +687,9 @@ __device__ void obs_chunk(const DevSpec &s, const Env &ev, int a, int ch, const 
             else if (maskp && !((maskp[(wr * n + wc) >> 5] >> ((wr * n + wc) & 31)) & 1u)) v = -2;   /* :135-136 */
             else {
                 const int cell = gr * s.W + gc;
-                if (ev.head[cell] == BGW_NONE16) v = 0;                                   /* :127-128 */
-                else if (in_own && cell == own) v = -1;                                   /* :130-131 */
-                else v = choose_encoding(s, ev, a, cell, -1);                             /* :133-134 */
+                v = ev.csum[cell];                                                        /* 0 = empty :127-128 */
+                if (v != 0 && in_own && cell == own) v = -1;                              /* :130-131 */
+                else if (v == BGW_CSUM_MIXED) v = choose_encoding(s, ev, a, cell, -1);    /* :133-134 */
             }
             out[t >> 2] |= (uint32_t)(uint8_t)(int8_t)v << ((t & 3) * 8);
             if (++gc == s.W) { gc = 0; ++gr; }
@@ -703,12 +706,15 @@ __device__ void obs_chunk(const DevSpec &s, const Env &ev, int a, int ch, const 
         else {
             const int cell = gr * s.W + gc;
             if (s.observer == BGW_OBS_POSITION_CENTERED) {
-                if (ev.head[cell] == BGW_NONE16) v = 0;                                     /* :230-231 */
-                else v = choose_encoding(s, ev, a, cell, s.observe_self ? -1 : a);          /* :233-246 */
+                v = ev.csum[cell];                                                          /* 0 = empty :230-231 */
+                if (v == BGW_CSUM_MIXED || (v != 0 && !s.observe_self && cell == own))
+                    v = choose_encoding(s, ev, a, cell, s.observe_self ? -1 : a);           /* :233-246 */
             } else {                                                                        /* :316-326 */
                 v = 0;
-                for (unsigned o = ev.head[cell]; o != BGW_NONE16; o = ev.next[o]) v += (ev.enc[o] == ech + 1);
-                v = min(v, 127);
+                if (ev.csum[cell] != 0) {
+                    for (unsigned o = ev.head[cell]; o != BGW_NONE16; o = ev.next[o]) v += (ev.enc[o] == ech + 1);
+                    v = min(v, 127);
+                }
             }
         }
         out[t >> 2] |= (uint32_t)(uint8_t)(int8_t)v << ((t & 3) * 8);
@@ -722,6 +728,15 @@ __device__ void observe_learners(const DevSpec &s, Env &ev, int ne, int8_t *obs_
     const int nch = s.nchunks;
     const bool blk = s.n_blk > 0;
     const int batch = blk ? s.mask_batch : ne;
+    /* per-cell summary of the occupant lists: the observers read one byte per cell and only walk a list when the
+     * cell holds mixed encodings (np.random.choice, observer.py:131-134,233-236) or counts are wanted */
+    for (int i = tid; i < s.HW; i += T) ev.csum[i] = 0;
+    __syncthreads();
+    for (int a = tid; a < s.A; a += T) if (ev.flags[a] & BGW_ST_IN_GRID) ev.csum[ev.cell[a]] = ev.enc[a];
+    __syncthreads();
+    for (int a = tid; a < s.A; a += T)
+        if ((ev.flags[a] & BGW_ST_IN_GRID) && ev.csum[ev.cell[a]] != ev.enc[a]) ev.csum[ev.cell[a]] = (int8_t)BGW_CSUM_MIXED;
+    __syncthreads();
     for (int base = 0; base < ne; base += batch) {
         const int nb = min(batch, ne - base);
         if (blk) {
