@@ -352,10 +352,12 @@ __device__ __forceinline__ void fast_exec_move(const DevSpec &s, const FastSpec 
     if (ns == (int8_t)BGW_MIXED) ev.ctr[CTR_MIXED] = 1;
 }
 
-/* Ordered rounds over the pending movers (pstate == 1; targets in rkmask[], the attack masks are dead by
- * then): each reserves its source and destination cell; same two-barrier round as the attack phase.  The first
- * round walks all ranks; its losers are appended to a list and later rounds walk only the list of the round
- * before (two lists in the storage of eff[] / killrank[], both dead by now). */
+#define BGW_NO_MOVE 0xFFFFFFFFu
+/* Ordered rounds over the pending movers.  rkmask[i] = (source cell << 16 | destination cell) for a pending rank,
+ * BGW_NO_MOVE otherwise (the attack masks are dead by then): each reserves its source and destination cell; same
+ * two-barrier round as the attack phase.  The first round walks all ranks; its losers are appended to a list and
+ * later rounds walk only the list of the round before (two lists in the storage of eff[] / killrank[], both dead
+ * by now).  The common move -- alone in its cell, destination empty -- touches no list. */
 template <bool WARP, typename HT>
 __device__ void fast_move_rounds(const DevSpec &s, const FastSpec &f, Env &ev, FastEnv &fe, int n_act, int pending, int tid, int T)
 {
@@ -365,25 +367,37 @@ __device__ void fast_move_rounds(const DevSpec &s, const FastSpec &f, Env &ev, F
         const int n_it = n_cur < 0 ? n_act : n_cur;
         for (int x = tid; x < n_it; x += stride) {
             const int i = n_cur < 0 ? x : (which ? fe.killrank : fe.eff)[x];
-            if (ev.pstate[i] != 1) continue;
-            atomicMin(slot_of(s, ev, ev.cell[ev.ragent[i]]), (uint32_t)i);
-            atomicMin(slot_of(s, ev, (int)fe.rkmask[i]), (uint32_t)i);
+            const uint32_t ft = fe.rkmask[i];
+            if (ft == BGW_NO_MOVE) continue;
+            atomicMin(slot_of(s, ev, (int)(ft >> 16)), (uint32_t)i);
+            atomicMin(slot_of(s, ev, (int)(ft & 0xFFFFu)), (uint32_t)i);
         }
         if (WARP) __syncwarp(); else __syncthreads();
         int lost = 0;
         for (int x = tid; x < n_it; x += stride) {
             const int i = n_cur < 0 ? x : (which ? fe.killrank : fe.eff)[x];
-            if (ev.pstate[i] != 1) continue;
-            const int a = ev.ragent[i], from = ev.cell[a], to = (int)fe.rkmask[i];
-            if (*slot_of(s, ev, from) != (uint32_t)i || *slot_of(s, ev, to) != (uint32_t)i) {
+            const uint32_t ft = fe.rkmask[i];
+            if (ft == BGW_NO_MOVE) continue;
+            const int from = (int)(ft >> 16), to = (int)(ft & 0xFFFFu);
+            uint32_t *sf = slot_of(s, ev, from), *sto = slot_of(s, ev, to);
+            if (*sf != (uint32_t)i || *sto != (uint32_t)i) {
                 lost = 1;
                 if (!WARP) (which ? fe.eff : fe.killrank)[atomicAdd(&ev.ctr[CTR_PA + (which ^ 1)], 1)] = (uint16_t)i;
                 continue;
             }
-            fast_exec_move<HT>(s, f, ev, fe, a, to);
-            *slot_of(s, ev, from) = BGW_SLOT_FREE;
-            *slot_of(s, ev, to) = BGW_SLOT_FREE;
-            ev.pstate[i] = 0;
+            const int a = ev.ragent[i], pto = pad_index(s, f, to);
+            const int8_t summary = fe.cenc[pto], me = ev.enc[a];
+            if (summary == 0 && (ev.flags[a] & BGW_ST_IN_GRID) && ((const HT *)fe.head)[from] == (HT)a && ev.next[a] == BGW_NONE16) {
+                fe.cenc[pad_index(s, f, from)] = 0;                /* Grid.remove: the cell is empty again */
+                fe.cenc[pto] = me;                                 /* Grid.place into an empty cell */
+                ((HT *)fe.head)[to] = (HT)a;
+                ev.cell[a] = (uint16_t)to;
+            } else {
+                fast_exec_move<HT>(s, f, ev, fe, a, to);
+            }
+            *sf = BGW_SLOT_FREE;
+            *sto = BGW_SLOT_FREE;
+            fe.rkmask[i] = BGW_NO_MOVE;
         }
         if (WARP) { pending = __any_sync(0xFFFFFFFFu, lost); __syncwarp(); }
         else {
@@ -851,23 +865,24 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
                     const unsigned kr = fe.killrank[a];
                     if (active || (kr != BGW_NONE16 && kr > (unsigned)i)) fe.rflag[a] |= RF_ATTACK_FAIL;   /* :41-42 */
                 }
-                uint8_t p = 0;
+                uint32_t ft = BGW_NO_MOVE;                          /* (source << 16 | destination) of a pending move */
                 if (active) {
                     bool ok = false;
                     if (ev.klass[a] & BGW_AG_MOVING) {
                         int dr, dc, r0, c0;
+                        const int from = ev.cell[a];
                         decode_move(s, a, fe.act[ev.plist[i]], dr, dc);
-                        cell_rc(s, f, ev.cell[a], r0, c0);
+                        cell_rc(s, f, from, r0, c0);
                         const int r = r0 + dr, c = c0 + dc;
                         if (r >= 0 && r < s.H && c >= 0 && c < s.W) {
                             if (dr == 0 && dc == 0) ok = true;
-                            else { p = 1; fe.rkmask[i] = (uint32_t)(r * s.W + c); }
+                            else ft = ((uint32_t)from << 16) | (uint32_t)(r * s.W + c);
                         }
                     }
-                    if (!p && !ok) fe.rflag[a] |= RF_MOVE_FAIL;
+                    if (ft == BGW_NO_MOVE && !ok) fe.rflag[a] |= RF_MOVE_FAIL;
                 }
-                ev.pstate[i] = p;
-                pend |= p;
+                fe.rkmask[i] = ft;
+                pend |= (ft != BGW_NO_MOVE);
             }
             pend = __syncthreads_or(pend);
             BGW_PROF_MARK(7);
