@@ -354,6 +354,17 @@ int bgw_create(const BgwSpec *sp, int device, bgw_handle *out)
                     else if (sp->view_range[a] != f.uniform_view) uniform = false;
                 }
             if (!uniform) f.uniform_view = -1;
+            f.uniform_att = -1;
+            {
+                bool firsta = true, unia = true;
+                for (int a = 0; a < A; ++a)
+                    if (sp->klass[a] & BGW_AG_ATTACKING) {
+                        if (firsta) { f.uniform_att = sp->attack_range[a]; firsta = false; }
+                        else if (sp->attack_range[a] != f.uniform_att) unia = false;
+                    }
+                if (!unia) f.uniform_att = -1;
+            }
+            f.identity_learners = (L == A);
             if (cbytes > 96 * 1024 || fo > 227 * 1024) fast = false;
         }
         f.enabled = fast;
@@ -365,7 +376,8 @@ int bgw_create(const BgwSpec *sp, int device, bgw_handle *out)
                              q.obs_h == C::obs_h && q.obs_c == 1 && q.move_actor == C::move_actor && q.ravel == C::ravel &&
                              q.observe_self == C::observe_self && q.done_mask == C::done_mask && q.max_enc == C::max_enc &&
                              f.P == C::P && f.PL == C::PL && f.PW == C::PW && f.PH == C::PH && f.uniform_view == C::view &&
-                             f.simd_ok == C::simd_ok && f.async_ok == C::async_ok && q.slot_mask == C::slots - 1 && TF == C::T;
+                             f.simd_ok == C::simd_ok && f.async_ok == C::async_ok && q.slot_mask == C::slots - 1 && TF == C::T &&
+                             f.uniform_att == C::att && f.identity_learners == C::identity;
             if (const char *t = getenv("BGW_DYNAMIC_SHAPES")) if (atoi(t)) h->fast_static = false;
         }
     }

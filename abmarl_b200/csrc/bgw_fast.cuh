@@ -45,6 +45,8 @@ struct FastSpec {
                                  padded width (multiple of 16) / height */
     uint32_t magic_w;         /* ceil(2^32 / W): r = umulhi(cell, magic_w) for cell < 65536 */
     int uniform_view;         /* view range shared by every observing learner, or -1 */
+    int uniform_att;          /* attack range shared by every attacking entity, or -1 */
+    int identity_learners;    /* every entity is a learner: learner index == entity index */
     int grid_ctas;            /* persistent grid size */
     int async_ok;             /* rows are 16-byte aligned: stage with cp.async */
     int simd_ok;              /* A % 4 == 0: byte-parallel compaction */
@@ -253,25 +255,29 @@ template <typename HT>
 __device__ void fast_exec_attack(const DevSpec &s, const FastSpec &f, Env &ev, FastEnv &fe, int rank, int a, uint32_t mask)
 {
     if (!(ev.flags[a] & BGW_ST_ACTIVE)) return;                   /* team_battle_example.py:37 */
-    const int R = __ldg(&s.attack_r[a]), n = 2 * R + 1;
+    const int R = f.uniform_att >= 0 ? f.uniform_att : __ldg(&s.attack_r[a]), n = 2 * R + 1;
     const int own = ev.cell[a];
     const unsigned long long row = __ldg(&s.attack_map[ev.enc[a]]);
     const double acc = __ldg(&s.accuracy[a]);
-    int ncand = 0;
+    int ncand = 0, v = -1, vcell = 0;                              /* v: the first candidate in scan order */
     for (uint32_t m = mask; m; m &= m - 1) {
         const int b = __ffs(m) - 1, wr = b / n, wc = b - wr * n;
         const int cc = own + (wr - R) * s.W + (wc - R);
         for (unsigned o = fl_first<HT>(fe, cc, pad_index(s, f, cc)); o != BGW_NONE16; o = ev.next[o])
-            ncand += basic_criteria(s, ev, a, (int)o, row, acc) ? 1 : 0;
+            if (basic_criteria(s, ev, a, (int)o, row, acc) && ncand++ == 0) { v = (int)o; vcell = cc; }
     }
     if (ncand == 0) { fe.rflag[a] |= RF_ATTACK_FAIL; return; }
-    int j = (int)bgw_index(dev_draw(s, ev, BGW_SITE_SUBSET, (uint32_t)a, 0), (uint32_t)ncand);
-    int v = -1, vcell = 0;
-    for (uint32_t m = mask; m && v < 0; m &= m - 1) {
-        const int b = __ffs(m) - 1, wr = b / n, wc = b - wr * n;
-        vcell = own + (wr - R) * s.W + (wc - R);
-        for (unsigned o = fl_first<HT>(fe, vcell, pad_index(s, f, vcell)); o != BGW_NONE16; o = ev.next[o])
-            if (basic_criteria(s, ev, a, (int)o, row, acc) && j-- == 0) { v = (int)o; break; }
+    if (ncand > 1) {
+        /* _subset_attackables actor.py:394-414: one keyed draw over the candidate list (with a single candidate the
+         * choice is forced and, the stream being keyed, the draw is skipped) */
+        int j = (int)bgw_index(dev_draw(s, ev, BGW_SITE_SUBSET, (uint32_t)a, 0), (uint32_t)ncand);
+        v = -1;
+        for (uint32_t m = mask; m && v < 0; m &= m - 1) {
+            const int b = __ffs(m) - 1, wr = b / n, wc = b - wr * n;
+            vcell = own + (wr - R) * s.W + (wc - R);
+            for (unsigned o = fl_first<HT>(fe, vcell, pad_index(s, f, vcell)); o != BGW_NONE16; o = ev.next[o])
+                if (basic_criteria(s, ev, a, (int)o, row, acc) && j-- == 0) { v = (int)o; break; }
+        }
     }
     /* actor.py:353-358; HealthAgent.health setter agent.py:192-196 (health stays in HBM, touched only on a hit) */
     set_health(ev, v, __ldcg(&ev.health[v]) - __ldg(&s.strength[a]));
@@ -298,7 +304,7 @@ __device__ void fast_attack_rounds(const DevSpec &s, const FastSpec &f, Env &ev,
         for (int x = tid; x < n_eff; x += stride) {
             const int i = fe.eff[x];
             if (ev.pstate[i] != 1) continue;
-            const int a = ev.ragent[i], R = __ldg(&s.attack_r[a]), n = 2 * R + 1, own = ev.cell[a];
+            const int a = ev.ragent[i], R = f.uniform_att >= 0 ? f.uniform_att : __ldg(&s.attack_r[a]), n = 2 * R + 1, own = ev.cell[a];
             atomicMin(slot_of(s, ev, own), (uint32_t)i);
             for (uint32_t m = fe.rkmask[i]; m; m &= m - 1) {
                 const int b = __ffs(m) - 1, wr = b / n, wc = b - wr * n;
@@ -310,7 +316,7 @@ __device__ void fast_attack_rounds(const DevSpec &s, const FastSpec &f, Env &ev,
         for (int x = tid; x < n_eff; x += stride) {
             const int i = fe.eff[x];
             if (ev.pstate[i] != 1) continue;
-            const int a = ev.ragent[i], R = __ldg(&s.attack_r[a]), n = 2 * R + 1, own = ev.cell[a];
+            const int a = ev.ragent[i], R = f.uniform_att >= 0 ? f.uniform_att : __ldg(&s.attack_r[a]), n = 2 * R + 1, own = ev.cell[a];
             const uint32_t mask = fe.rkmask[i];
             bool win = *slot_of(s, ev, own) == (uint32_t)i;
             for (uint32_t m = mask; m; m &= m - 1) {
@@ -551,7 +557,7 @@ __device__ void fast_obs_rows(const DevSpec &s, const FastSpec &f, const Env &ev
 struct FastStaticC5 {
     static constexpr int A = 256, L = 256, H = 64, W = 64, P = 5, PL = 5, PW = 76, PH = 74, obs_stride = 128, nchunks = 8,
                          obs_h = 11, view = 5, move_actor = BGW_MOVE_BOX, ravel = 0, observe_self = 1, done_mask = BGW_DONE_ONE_TEAM,
-                         max_enc = 4, simd_ok = 1, async_ok = 1, slots = 512, T = 96;
+                         max_enc = 4, simd_ok = 1, async_ok = 1, slots = 512, T = 96, att = 1, identity = 1;
 };
 
 template <bool STATIC, typename HT>
@@ -568,6 +574,7 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
         s.done_mask = C::done_mask; s.max_enc = C::max_enc; s.n_blk = 0; s.program = BGW_PROG_TEAM_BATTLE;
         s.manager = BGW_MANAGER_ALL_STEP; s.attack_actor = BGW_ATTACK_BINARY; s.hw_words = (C::H * C::W + 31) / 32;
         f.P = C::P; f.PL = C::PL; f.PW = C::PW; f.PH = C::PH; f.uniform_view = C::view; f.simd_ok = C::simd_ok; f.async_ok = C::async_ok;
+        f.uniform_att = C::att; f.identity_learners = C::identity;
         f.magic_w = (uint32_t)(((1ull << 32) + C::W - 1) / C::W);
         s.slot_mask = C::slots - 1;
         constexpr FastLayout LY = fast_layout(C::A, C::L, C::H * C::W, C::PH, C::PW, C::slots, C::T, C::max_enc, (C::H * C::W + 31) / 32);
@@ -645,6 +652,8 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
         ev.flags = buf + f.b_flags;
         fe.act = (uint32_t *)(buf + f.b_act);
         ev.health = st.health + (size_t)e * s.A;
+        for (int i = tid; i < (s.A * 8 + 127) / 128; i += T)       /* hits read health from HBM on demand: warm L2 now */
+            asm volatile("prefetch.global.L2 [%0];" ::"l"((const char *)ev.health + (size_t)i * 128));
         ev.e = e; ev.genv = (uint32_t)(s.env_offset + e);
         int8_t *obs_env = obs ? obs + (size_t)e * s.L * s.obs_stride : nullptr;
         float *rew = reward + (size_t)e * s.L;
@@ -809,11 +818,11 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
         BGW_PROF_MARK(4);
 
         if (fresh) {
-            for (int i = tid; i < n_act; i += T) ev.plist[i] = (uint16_t)__ldg(&s.learner_of[ev.ragent[i]]);
+            for (int i = tid; i < n_act; i += T) ev.plist[i] = f.identity_learners ? ev.ragent[i] : (uint16_t)__ldg(&s.learner_of[ev.ragent[i]]);
         } else {
             /* ---- attack phase team_battle_example.py:35-47 ---------------------------------------------- */
             for (int i = tid; i < n_act; i += T) {
-                const int a = ev.ragent[i], l = __ldg(&s.learner_of[a]);
+                const int a = ev.ragent[i], l = f.identity_learners ? a : __ldg(&s.learner_of[a]);
                 ev.plist[i] = (uint16_t)l;
                 if (sampled) {                                   /* bgw_step_sampled: the keyed random policy, fused */
                     const uint32_t w = sample_action_word(s, a, ev.klass[a], ev.genv, ev.episode, ev.step - 1u);
@@ -823,7 +832,7 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
                 uint8_t p = 0;
                 if ((ev.flags[a] & BGW_ST_ACTIVE) && (ev.klass[a] & BGW_AG_ATTACKING) && (int8_t)((fe.act[l] >> 16) & 0xFF) != 0) {
                     /* candidate cells: the summary says an attackable encoding (or a mix) is present */
-                    const int R = __ldg(&s.attack_r[a]), n = 2 * R + 1;
+                    const int R = f.uniform_att >= 0 ? f.uniform_att : __ldg(&s.attack_r[a]), n = 2 * R + 1;
                     const unsigned long long row = __ldg(&s.attack_map[ev.enc[a]]);
                     const int8_t *w = fe.cenc + pad_index(s, f, ev.cell[a]) - R * f.PW - R;
                     uint32_t mask = 0;
