@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 SRC = os.path.join(HERE, 'bgw.cu')
 OUT = os.path.join(HERE, 'libbgw.so')
-DEPS = [SRC, os.path.join(HERE, 'bgw_dev.cuh'), os.path.join(ROOT, 'include', 'bgw.h'),
+DEPS = [SRC, os.path.join(HERE, 'bgw_dev.cuh'), os.path.join(HERE, 'bgw_fast.cuh'), os.path.join(ROOT, 'include', 'bgw.h'),
         os.path.join(ROOT, 'include', 'bgw_philox.h'), os.path.abspath(__file__)]
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 
