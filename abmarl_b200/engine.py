@@ -143,17 +143,11 @@ class BatchedGridWorld:
                 h_all=torch.empty(E, dtype=torch.uint8).pin_memory(), d_act=torch.empty((E, L, 4), dtype=torch.int8, device=dev))
         return self._hb
 
-    def step_host(self, actions_host, order=None, zero_copy=False):
-        """One manager step for a HOST caller: `actions_host` int8 [E, L, 4] (pinned for speed) is copied to the
-        device, the batch is stepped, and the rows of the learners that received (obs, reward, done) -- plus all
-        rows of envs that were auto-reset -- are compacted and land in pinned host buffers.  Returns
-        (n, index[:n], obs[:n], reward[:n], done[:n], all_done[E]) as pinned host tensors; index = env * L + learner.
-        With zero_copy the gather kernel writes the compacted rows straight into the pinned buffers (they are
-        device-addressable under UVA): one stream synchronisation per call and no separate copies; measured equal to
-        the staged copies on this pool (both PCIe-bound), so staged is the default.
-        Bytes over PCIe per call: 4*E*L in, n*(obs_stride + 9) + E + 4 out."""
+    def enqueue_host(self, actions_host, order=None, zero_copy=False):
+        """The device side of step_host, enqueued on the current stream without waiting: H2D of the pinned action
+        buffer, the step, the compaction of the valid rows (with zero_copy straight into the pinned host buffers)
+        and the D2H of the row count and all_done."""
         hb = self._host_buffers()
-        stream = torch.cuda.current_stream(self.device)
         hb['d_act'].copy_(actions_host, non_blocking=True)
         self.step(hb['d_act'], order)
         p = lambda t: t.data_ptr()
@@ -163,6 +157,11 @@ class BatchedGridWorld:
                                           self._stream()), self.lib)
         hb['h_count'].copy_(hb['count'], non_blocking=True)
         hb['h_all'].copy_(self.all_done, non_blocking=True)
+
+    def collect_host(self, zero_copy=False):
+        """Wait for the work enqueue_host put on the current stream; returns what step_host returns."""
+        hb = self._hb
+        stream = torch.cuda.current_stream(self.device)
         stream.synchronize()
         n = int(hb['h_count'][0])
         if not zero_copy:
@@ -171,6 +170,18 @@ class BatchedGridWorld:
             stream.synchronize()
         self.last_d2h_bytes = n * (self.dims.obs_stride + 9) + self.E + 4
         return n, hb['h_index'][:n], hb['h_obs'][:n], hb['h_reward'][:n], hb['h_done'][:n], hb['h_all']
+
+    def step_host(self, actions_host, order=None, zero_copy=False):
+        """One manager step for a HOST caller: `actions_host` int8 [E, L, 4] (pinned for speed) is copied to the
+        device, the batch is stepped, and the rows of the learners that received (obs, reward, done) -- plus all
+        rows of envs that were auto-reset -- are compacted and land in pinned host buffers.  Returns
+        (n, index[:n], obs[:n], reward[:n], done[:n], all_done[E]) as pinned host tensors; index = env * L + learner.
+        With zero_copy the gather kernel writes the compacted rows straight into the pinned buffers (they are
+        device-addressable under UVA): one stream synchronisation per call and no separate copies; measured equal to
+        the staged copies on this pool (both PCIe-bound), so staged is the default.
+        Bytes over PCIe per call: 4*E*L in, n*(obs_stride + 9) + E + 4 out."""
+        self.enqueue_host(actions_host, order, zero_copy)
+        return self.collect_host(zero_copy)
 
     # ---- views / introspection -------------------------------------------------------------------
     def obs_view(self, obs=None):
@@ -213,3 +224,69 @@ class BatchedGridWorld:
     @property
     def launches(self):
         return int(self.lib.bgw_launch_count(self._h))
+
+
+class HostPipeline:
+    """K sub-batches of one compiled simulation, each a BatchedGridWorld on its own CUDA stream, for HOST callers
+    that keep several sub-batches in flight (the send / recv pattern of asynchronous vector envs): while the
+    host consumes sub-batch k, the other sub-batches' action upload (H2D), step kernel and compacted result rows
+    (the gather kernel writes them straight into pinned host memory) overlap on the device and on both PCIe
+    directions.  Sub-batch k owns the global envs [env_offset + k*E/K, env_offset + (k+1)*E/K): the Philox key is
+    global, so the results are those of one BatchedGridWorld over all E envs (tests/test_gpu_parity.py).
+
+        pipe.reset()
+        for k in range(pipe.K): pipe.send(k, actions[k])          # prime
+        loop: for k in range(pipe.K): out = pipe.recv(k); ...; pipe.send(k, next_actions[k])
+    """
+
+    def __init__(self, spec, shards=4, device=None):
+        assert spec.n_envs % shards == 0, "n_envs must divide evenly over the sub-batches"
+        self.K, self.Ek = shards, spec.n_envs // shards
+        self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        self.engines = [BatchedGridWorld(spec.with_envs(self.Ek, spec.env_offset + k * self.Ek), device=self.device)
+                        for k in range(shards)]
+        self.streams = [torch.cuda.Stream(self.device) for _ in range(shards)]
+        self.E, self.L, self.A = spec.n_envs, self.engines[0].L, self.engines[0].A
+        self.in_flight = [False] * shards
+
+    def reset(self):
+        for eng, s in zip(self.engines, self.streams):
+            with torch.cuda.stream(s):
+                eng.reset()
+        for s in self.streams:
+            s.synchronize()
+
+    def send(self, k, actions_host, order=None):
+        """Enqueue one manager step of sub-batch k: actions_host int8 [E/K, L, 4] in pinned host memory."""
+        assert not self.in_flight[k], "recv(k) the previous step of this sub-batch first"
+        with torch.cuda.stream(self.streams[k]):
+            self.engines[k].enqueue_host(actions_host, order, zero_copy=True)
+        self.in_flight[k] = True
+
+    def recv(self, k):
+        """Wait for sub-batch k's step; (n, index, obs, reward, done, all_done) as step_host, index = local env * L +
+        learner (global env = env_offset + k * E/K + local env)."""
+        assert self.in_flight[k]
+        with torch.cuda.stream(self.streams[k]):
+            out = self.engines[k].collect_host(zero_copy=True)
+        self.in_flight[k] = False
+        return out
+
+    def step_host(self, actions_host):
+        """All sub-batches one step: actions_host int8 [E, L, 4] pinned; returns the K recv() tuples."""
+        for k in range(self.K):
+            self.send(k, actions_host[k * self.Ek:(k + 1) * self.Ek])
+        return [self.recv(k) for k in range(self.K)]
+
+    @property
+    def last_d2h_bytes(self):
+        return sum(e.last_d2h_bytes for e in self.engines)
+
+    @property
+    def launches(self):
+        return sum(e.launches for e in self.engines)
+
+    def stats(self):
+        for s in self.streams:
+            s.synchronize()
+        return sum(e.stats() for e in self.engines)

@@ -203,27 +203,55 @@ def run_ours(args):
         a[..., 2] = rng.integers(0, 2, size=(E, L), dtype=np.int8)
         pool.append(torch.from_numpy(a).pin_memory())
     d2h_total = [0]
+    KS = args.e2e_shards
+    if KS > 1:
+        # public host-facing API for callers that keep several sub-batches in flight (send / recv, as asynchronous
+        # vector envs do): HostPipeline = KS sub-batches of E/KS envs, each on its own stream.  Every step of every
+        # sub-batch uploads its pinned host actions (H2D) and lands its compacted rows in pinned host memory (D2H)
+        # inside the timed region; the timed region also contains the pipeline's fill and drain.
+        from abmarl_b200.engine import HostPipeline
+        pipe = HostPipeline(build_spec(E, rank * E), shards=KS, device=dev)
+        Ek = E // KS
+        pipe.reset()
 
-    def host_step(i):
-        # public host-facing call: pinned host actions -> H2D, step, on-device compaction of the rows the
-        # reference's manager would return, D2H of exactly those rows (+ all_done); returns when they are on the host
-        eng.step_host(pool[i % len(pool)], zero_copy=args.e2e_zero_copy)
-        d2h_total[0] += eng.last_d2h_bytes
+        def pipe_steps(i0, n):
+            for k in range(KS):
+                pipe.send(k, pool[i0 % len(pool)][k * Ek:(k + 1) * Ek])
+            for i in range(i0 + 1, i0 + n):
+                for k in range(KS):
+                    pipe.recv(k)
+                    d2h_total[0] += pipe.engines[k].last_d2h_bytes
+                    pipe.send(k, pool[i % len(pool)][k * Ek:(k + 1) * Ek])
+            for k in range(KS):
+                pipe.recv(k)
+                d2h_total[0] += pipe.engines[k].last_d2h_bytes
 
-    for i in range(3):
-        host_step(i)
+        e2e_stats = lambda: int(pipe.stats()[K.STAT_AGENT_STEPS].item())
+        e2e_api = (f"HostPipeline.send/recv: {KS} sub-batches of {Ek} envs in flight on their own streams; per step pinned "
+                   "host actions in (H2D), valid rows compacted by the gather kernel straight into pinned host memory (D2H)")
+    else:
+        def pipe_steps(i0, n):
+            # pinned host actions -> H2D, step, on-device compaction of the rows the reference's manager would
+            # return, D2H of exactly those rows (+ all_done); each call returns when they are on the host
+            for i in range(i0, i0 + n):
+                eng.step_host(pool[i % len(pool)], zero_copy=args.e2e_zero_copy)
+                d2h_total[0] += eng.last_d2h_bytes
+
+        e2e_stats = agent_steps
+        e2e_api = "BatchedGridWorld.step_host: pinned host actions in, valid rows compacted on the device and copied out"
+
+    pipe_steps(0, 3)
     barrier()
-    n1 = agent_steps()
+    n1 = e2e_stats()
     d2h_total[0] = 0
-    launches_e2e0 = eng.launches
     e_beg, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
     e_beg.record(stream)
-    for i in range(e2e_steps):
-        host_step(i)
+    pipe_steps(3, e2e_steps)
     e_end.record(stream)
     barrier()
     e2e_ms = e_beg.elapsed_time(e_end)
-    n_e2e = agent_steps() - n1
+    n_e2e = e2e_stats() - n1
     h2d = E * L * 4
     d2h = d2h_total[0] / e2e_steps
 
@@ -257,7 +285,7 @@ def run_ours(args):
                        "agent_steps_per_step": n_dev_all / args.steps},
             "e2e": {"value": n_e2e_all / (e2e_ms * 1e-3), "unit": "agent-steps/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                    "api": "BatchedGridWorld.step_host: pinned host actions in, valid rows compacted on the device and copied out"},
+                    "api": e2e_api},
             "gpu_launches": int(launches_all),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "bgw_step_fast_kernel (bgw_step_sampled)", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -283,6 +311,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--envs-per-gpu', type=int, default=ENVS_PER_GPU)
     ap.add_argument('--e2e-steps', type=int, default=200, help='steps of the host-buffer loop (one full episode)')
+    ap.add_argument('--e2e-shards', type=int, default=2, help='sub-batches the e2e loop keeps in flight (1 = one blocking step_host call per step)')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--e2e-zero-copy', action='store_true', help='e2e: the gather kernel writes the pinned host buffers directly instead of compacting on the device and copying')
     ap.add_argument('--dump-steps', default=None, help='write the per-step kernel times (ms) to this JSON file')

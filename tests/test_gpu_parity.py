@@ -219,6 +219,44 @@ def test_step_host_returns_exactly_the_valid_rows(mirror, zero_copy):
     assert seen_reset
 
 
+def test_host_pipeline_equals_one_batch(mirror):
+    """HostPipeline (K sub-batches on their own streams, send / recv) returns, sub-batch by sub-batch, the rows one
+    BatchedGridWorld over all the envs returns for the same actions: the Philox key is the global env index."""
+    from abmarl_b200.engine import BatchedGridWorld, HostPipeline
+    spec = compile_sim(scenarios.build_tb_dense(mirror), n_envs=48, env_offset=5, seed=13, horizon=12, auto_reset=True)
+    eng = BatchedGridWorld(spec, device='cuda:0')
+    pipe = HostPipeline(spec, shards=3, device='cuda:0')
+    eng.reset()
+    pipe.reset()
+    Ek, L = pipe.Ek, pipe.L
+    act = eng.sample_actions().cpu().pin_memory()
+    for k in range(pipe.K):
+        pipe.send(k, act[k * Ek:(k + 1) * Ek])
+    for t in range(30):
+        n, index, obs_c, rew_c, done_c, all_done = eng.step_host(act)
+        order = np.argsort(index.numpy(), kind='stable')
+        idx, obs_c, rew_c, done_c = index.numpy()[order], obs_c.numpy()[order], rew_c.numpy()[order], done_c.numpy()[order]
+        nxt = eng.sample_actions().cpu().pin_memory()
+        got = 0
+        for k in range(pipe.K):
+            nk, ik, ok, rk, dk, ak = pipe.recv(k)
+            o = np.argsort(ik.numpy(), kind='stable')
+            sel = (idx >= k * Ek * L) & (idx < (k + 1) * Ek * L)
+            np.testing.assert_array_equal(ik.numpy()[o] + k * Ek * L, idx[sel])
+            np.testing.assert_array_equal(ok.numpy()[o], obs_c[sel])
+            np.testing.assert_array_equal(rk.numpy()[o], rew_c[sel])
+            np.testing.assert_array_equal(dk.numpy()[o], done_c[sel])
+            np.testing.assert_array_equal(ak.numpy(), all_done.numpy()[k * Ek:(k + 1) * Ek])
+            got += nk
+            pipe.send(k, nxt[k * Ek:(k + 1) * Ek])
+        assert got == n
+        act = nxt
+    eng.step_host(act)                                                  # the step the pipeline still has in flight
+    for k in range(pipe.K):
+        pipe.recv(k)
+    assert int(pipe.stats()[K.STAT_AGENT_STEPS]) == int(eng.stats()[K.STAT_AGENT_STEPS])
+
+
 @pytest.mark.parametrize('name', ['tb_c2', 'tb_c5_small', 'tb_blocking', 'maze_c1'])
 def test_step_sampled_equals_sample_then_step(mirror, name):
     """bgw_step_sampled (fused on the specialised kernel, two launches on the general one) against the oracle's
