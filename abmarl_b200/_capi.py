@@ -6,7 +6,7 @@ is missing or does not load, importing the engine raises.
 import ctypes as C
 import os
 
-BGW_ABI_VERSION = 1
+BGW_ABI_VERSION = 2
 BGW_MAX_ENCODING = 63
 BGW_MAX_AGENTS = 4096
 BGW_NONE = 0xFFFF
@@ -14,11 +14,12 @@ BGW_RW_COUNT = 8
 BGW_STAT_COUNT = 4
 
 # enums (include/bgw.h)
-AG_OBSERVING, AG_MOVING, AG_ATTACKING, AG_HEALTH, AG_ORIENT, AG_LEARNER, AG_BLOCKING = (1 << i for i in range(7))
+AG_OBSERVING, AG_MOVING, AG_ATTACKING, AG_HEALTH, AG_ORIENT, AG_LEARNER, AG_BLOCKING, AG_AMMO = (1 << i for i in range(8))
 ROLE_NONE, ROLE_NAVIGATOR, ROLE_TARGET, ROLE_PACMAN, ROLE_FOOD, ROLE_BADDIE, ROLE_WALL = range(7)
 PROG_TEAM_BATTLE, PROG_MAZE, PROG_MULTI_MAZE, PROG_PACMAN = range(4)
 MOVE_NONE, MOVE_BOX, MOVE_CROSS, MOVE_DRIFT = range(4)
-ATTACK_NONE, ATTACK_BINARY = range(2)
+ATTACK_NONE, ATTACK_BINARY, ATTACK_ENCODING, ATTACK_RESTRICTED, ATTACK_SELECTIVE = range(5)
+BGW_MAX_VICTIMS, BGW_MAX_SIMATT = 256, 16
 OBS_POSITION_CENTERED, OBS_ABSOLUTE, OBS_STACKED = range(3)
 DONE_ACTIVE, DONE_ONE_TEAM, DONE_TARGET_AGENT, DONE_TARGET_DESTROYED = (1 << i for i in range(4))
 MANAGER_ALL_STEP, MANAGER_TURN_BASED = range(2)
@@ -28,7 +29,7 @@ ST_ORIENT_SHIFT = 4
 OUT_DONE, OUT_VALID = 1, 2
 ENV_ALL_DONE, ENV_RESET, ENV_TRUNCATED, ENV_ERROR = 1, 2, 4, 8
 STAT_AGENT_STEPS, STAT_EPISODES, STAT_KILLS, STAT_ENV_STEPS = range(4)
-SITE_PLACE, SITE_HEALTH, SITE_ORIENT, SITE_ACC, SITE_SUBSET, SITE_OBS, SITE_ACTION, SITE_MAZE = range(8)
+SITE_PLACE, SITE_HEALTH, SITE_ORIENT, SITE_ACC, SITE_SUBSET, SITE_OBS, SITE_ACTION, SITE_MAZE, SITE_AMMO = range(9)
 
 _p = C.c_void_p
 
@@ -40,23 +41,23 @@ class BgwSpec(C.Structure):
         ('attack_actor', C.c_int32), ('observer', C.c_int32), ('observe_self', C.c_int32),
         ('done_mask', C.c_int32), ('manager', C.c_int32), ('ravel_actions', C.c_int32),
         ('no_overlap_at_reset', C.c_int32), ('stacked_attacks', C.c_int32), ('horizon', C.c_int32),
-        ('auto_reset', C.c_int32), ('seed', C.c_uint64), ('reward', C.c_double * BGW_RW_COUNT),
+        ('auto_reset', C.c_int32), ('ammo_observer', C.c_int32), ('seed', C.c_uint64), ('reward', C.c_double * BGW_RW_COUNT),
         ('encoding', _p), ('klass', _p), ('role', _p), ('init_row', _p), ('init_col', _p),
         ('init_health', _p), ('init_orient', _p), ('view_range', _p), ('move_range', _p),
         ('attack_range', _p), ('attack_strength', _p), ('attack_accuracy', _p),
-        ('simultaneous_attacks', _p), ('target', _p), ('overlap', _p), ('attack_map', _p),
+        ('simultaneous_attacks', _p), ('target', _p), ('initial_ammo', _p), ('overlap', _p), ('attack_map', _p),
     ]
 
 
 class BgwState(C.Structure):
     _fields_ = [(n, _p) for n in ('cell', 'next', 'flags', 'health', 'reward_acc', 'episode', 'step',
-                                  'env_flags', 'turn', 'error', 'layout', 'stats')]
+                                  'env_flags', 'turn', 'error', 'layout', 'stats', 'ammo')]
 
 
 class BgwDims(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ('n_envs', 'n_agents', 'n_learners', 'obs_h', 'obs_w', 'obs_c',
                                          'obs_stride', 'action_stride', 'threads_per_env', 'envs_per_cta',
-                                         'smem_bytes')]
+                                         'smem_bytes', 'ammo_offset')]
 
 
 EXPORTS = ('bgw_create', 'bgw_destroy', 'bgw_dims', 'bgw_bind_state', 'bgw_reset', 'bgw_step',

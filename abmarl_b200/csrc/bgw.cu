@@ -154,11 +154,12 @@ int bgw_create(const BgwSpec *sp, int device, bgw_handle *out)
     /* ---- per-entity tables ------------------------------------------------------------------ */
     std::vector<int16_t> learner_of(A, -1), agent_of;
     std::vector<uint16_t> blk, blk_static, var, init_cell(A, BGW_NONE);
-    int max_enc = 0, rmax_obs = 0, rmax_att = 0;
+    int max_enc = 0, rmax_obs = 0, rmax_att = 0, n_ammo = 0, att_payload = 1;
+    for (int a = 0; a < A; ++a) if (sp->encoding[a] > max_enc) max_enc = std::min((int)sp->encoding[a], BGW_MAX_ENCODING);
+    if (sp->attack_actor < BGW_ATTACK_NONE || sp->attack_actor > BGW_ATTACK_SELECTIVE) return bail(fail(1, "bgw_create: unknown attack actor %d", sp->attack_actor));
     for (int a = 0; a < A; ++a) {
         const int e = sp->encoding[a];
         if (e < 1 || e > BGW_MAX_ENCODING) return bail(fail(1, "bgw_create: entity %d has encoding %d, must be 1..%d", a, e, BGW_MAX_ENCODING));
-        max_enc = std::max(max_enc, e);
         if (sp->klass[a] & BGW_AG_LEARNER) { learner_of[a] = (int16_t)agent_of.size(); agent_of.push_back((int16_t)a); }
         if (sp->klass[a] & BGW_AG_BLOCKING) {
             /* static = never moves, never dies, fixed start cell (walls); dynamic blockers are listed first */
@@ -176,10 +177,28 @@ int bgw_create(const BgwSpec *sp, int device, bgw_handle *out)
             if (R < 0) return bail(fail(1, "bgw_create: negative view range"));
             rmax_obs = std::max(rmax_obs, R);
         }
-        if (sp->klass[a] & BGW_AG_ATTACKING) {
-            rmax_att = std::max(rmax_att, (int)sp->attack_range[a]);
-            if (sp->program == BGW_PROG_TEAM_BATTLE && sp->simultaneous_attacks[a] > 1)
-                return bail(fail(1, "bgw_create: TeamBattleSim.step is only defined for simultaneous_attacks == 1 (team_battle_example.py:41)"));
+        if (sp->klass[a] & BGW_AG_AMMO) {
+            ++n_ammo;
+            if (!sp->initial_ammo || sp->initial_ammo[a] < 0) return bail(fail(1, "bgw_create: entity %d is an AmmoAgent without a non-negative initial_ammo", a));
+        }
+        if ((sp->klass[a] & BGW_AG_ATTACKING) && sp->attack_actor != BGW_ATTACK_NONE) {
+            const int R = sp->attack_range[a], n = 2 * R + 1, sim = sp->simultaneous_attacks[a];
+            rmax_att = std::max(rmax_att, R);
+            if (R < 0) return bail(fail(1, "bgw_create: negative attack range"));
+            /* Binary / EncodingBased hand TeamBattleSim.step an ndarray: `not attacked_agents` raises for more than
+             * one element (team_battle_example.py:41); the two selective actors return lists */
+            if (sp->program == BGW_PROG_TEAM_BATTLE && sp->attack_actor == BGW_ATTACK_BINARY && sim > 1)
+                return bail(fail(1, "bgw_create: TeamBattleSim.step with the BinaryAttackActor is only defined for simultaneous_attacks == 1 (team_battle_example.py:41)"));
+            if (sim > BGW_MAX_SIMATT) return bail(fail(1, "bgw_create: simultaneous_attacks %d exceeds %d", sim, BGW_MAX_SIMATT));
+            /* attack bytes of the action row and the most agents one attack can name */
+            int w = 1, groups = 1;
+            if (sp->attack_actor == BGW_ATTACK_ENCODING) { w = max_enc; groups = 0; for (int e = 1; e <= max_enc; ++e) groups += (int)((sp->attack_map[sp->encoding[a]] >> e) & 1); }
+            else if (sp->attack_actor == BGW_ATTACK_RESTRICTED) { w = sim; groups = 1; }
+            else if (sp->attack_actor == BGW_ATTACK_SELECTIVE) { w = n * n; groups = n * n; }
+            if (n * n > 256 && sp->attack_actor >= BGW_ATTACK_RESTRICTED) return bail(fail(1, "bgw_create: attack range %d: a ravelled window cell must fit one byte (range <= 7)", R));
+            if (groups * std::max(sim, 1) > BGW_MAX_VICTIMS)
+                return bail(fail(1, "bgw_create: entity %d could attack %d agents in one step, the limit is %d", a, groups * sim, BGW_MAX_VICTIMS));
+            att_payload = std::max(att_payload, w);
         }
     }
     const int L = (int)agent_of.size();
@@ -210,8 +229,13 @@ int bgw_create(const BgwSpec *sp, int device, bgw_handle *out)
     if (sp->observer == BGW_OBS_STACKED) dm.obs_c = max_enc;                        /* observer.py:264 */
     const long long ncell = (long long)dm.obs_h * dm.obs_w * dm.obs_c;
     if (ncell > (1 << 24)) return bail(fail(1, "bgw_create: observation of %lld cells is too large", ncell));
-    dm.obs_stride = (int)((ncell + 15) / 16 * 16);
-    dm.action_stride = 4;
+    dm.ammo_offset = -1;
+    long long obs_bytes = ncell;
+    if (sp->ammo_observer) { dm.ammo_offset = (int)((ncell + 3) / 4 * 4); obs_bytes = dm.ammo_offset + 4; }   /* observer.py:376-413 */
+    dm.obs_stride = (int)((obs_bytes + 15) / 16 * 16);
+    dm.action_stride = (2 + att_payload + 3) / 4 * 4;
+    d.act_words = dm.action_stride / 4; d.ammo_offset = dm.ammo_offset; d.n_ammo = n_ammo;
+    d.obs_cells = (int)ncell;
     d.obs_h = dm.obs_h; d.obs_w = dm.obs_w; d.obs_c = dm.obs_c; d.obs_stride = dm.obs_stride; d.nchunks = dm.obs_stride / 16;
 
     /* ---- reset template: place the fixed-position entities once (state.py:107-109,143-150) ------- */
@@ -254,6 +278,8 @@ int bgw_create(const BgwSpec *sp, int device, bgw_handle *out)
             (rc = upload(h, ov.data(), ov.size(), &d.overlap)) || (rc = upload(h, am.data(), am.size(), &d.attack_map)) ||
             (rc = upload(h, blk.data(), blk.size(), &d.blk_agents)) || (rc = upload(h, var.data(), var.size(), &d.var_agents)))
             return bail(rc);
+        d.init_ammo = nullptr;
+        if (n_ammo && (rc = upload(h, sp->initial_ammo, A, &d.init_ammo))) return bail(rc);
     }
 
     /* ---- launch geometry and the shared-memory carve-up ------------------------------------------ */
@@ -312,7 +338,7 @@ int bgw_create(const BgwSpec *sp, int device, bgw_handle *out)
     d.o_cell = take(A * 2); d.o_next = take(A * 2);
     d.o_flags = take(A); d.o_enc = take(A); d.o_klass = take(A); d.o_tmp = take(A);
     d.o_racc = take(A * 8);
-    d.o_act = take(L * 4);
+    d.o_act = take(L * dm.action_stride);
     d.o_ragent = take(L * 2); d.o_plist = take(L * 2); d.o_pstate = take(L);
     d.o_avail = take((max_enc + 1) * d.hw_words * 4);
     d.o_mask = take(d.mask_batch * d.mask_words * 4);
@@ -325,7 +351,8 @@ int bgw_create(const BgwSpec *sp, int device, bgw_handle *out)
         const int P = std::max(rmax_obs, rmax_att);
         bool fast = sp->program == BGW_PROG_TEAM_BATTLE && sp->manager == BGW_MANAGER_ALL_STEP &&
                     (sp->move_actor == BGW_MOVE_BOX || sp->move_actor == BGW_MOVE_CROSS) && d.n_blk == 0 &&
-                    sp->observer == BGW_OBS_POSITION_CENTERED && sp->attack_actor == BGW_ATTACK_BINARY &&
+                    sp->observer == BGW_OBS_POSITION_CENTERED && sp->attack_actor == BGW_ATTACK_BINARY && n_ammo == 0 &&
+                    !sp->ammo_observer &&
                     (2 * rmax_att + 1) * (2 * rmax_att + 1) <= 32;
         if (const char *t = getenv("BGW_GENERIC_KERNEL")) if (atoi(t)) fast = false;
         int TF = A <= 32 ? 32 : A <= 64 ? 64 : 96;      /* 3 warps: 10 envs per SM fit (shared memory and registers) */
@@ -429,7 +456,8 @@ int bgw_bind_state(bgw_handle h, const BgwState *state)
     if (!h || !state) return fail(1, "bgw_bind_state: null argument");
     if (!state->cell || !state->next || !state->flags || !state->health || !state->reward_acc || !state->episode ||
         !state->step || !state->env_flags || !state->turn || !state->error || !state->stats)
-        return fail(1, "bgw_bind_state: every array except `layout` is required");
+        return fail(1, "bgw_bind_state: every array except `layout` and `ammo` is required");
+    if (h->ds.n_ammo && !state->ammo) return fail(1, "bgw_bind_state: the simulation has AmmoAgents: `ammo` is required");
     h->st = *state;
     h->bound = true;
     return 0;

@@ -49,6 +49,10 @@ struct DevSpec {
     int slot_mask;                 /* reservation slots - 1 (power of two) */
     int mask_words, mask_batch;    /* LOS scratch of the observation pass */
     int parallel_actors;           /* 1: reservation rounds (team battle, Box/Cross moves); 0: rank-order loop */
+    int act_words;                 /* 32-bit words per learner action row (BgwDims.action_stride / 4) */
+    int ammo_offset, n_ammo;       /* AmmoObserver slot in the obs row (-1 none); number of AmmoAgents */
+    int obs_cells;                 /* obs_h * obs_w * obs_c: grid bytes of an obs row */
+    const int32_t *init_ammo;
     unsigned long long seed;
     double reward[BGW_RW_COUNT];
     /* per-entity tables in global memory (shared by all envs, L1/L2 resident) */
@@ -78,6 +82,7 @@ struct Env {
     double *racc;
     int *ctr;
     double *health;   /* this env's row of BgwState.health (global) */
+    int32_t *ammo;    /* this env's row of BgwState.ammo (global), or NULL */
     int e;
     uint32_t genv, episode, step;
 };
@@ -312,13 +317,13 @@ __device__ bool process_move(const DevSpec &s, Env &ev, int a, uint32_t act)
  * (attacker, candidate); with accuracy >= 1 the comparison u > accuracy can never hold, so the draw is
  * skipped (keyed streams: skipping a draw does not shift any other). */
 __device__ __forceinline__ bool basic_criteria(const DevSpec &s, const Env &ev, int attacker, int cand,
-                                               unsigned long long map_row, double acc)
+                                               unsigned long long map_row, double acc, uint32_t occ = 0)
 {
     if (cand == attacker) return false;
     if (!(ev.flags[cand] & BGW_ST_ACTIVE)) return false;
     if (!((map_row >> ev.enc[cand]) & 1ull)) return false;
     if (acc < 1.0) {
-        const double u = bgw_u01(dev_draw(s, ev, BGW_SITE_ACC, (uint32_t)attacker, (uint32_t)cand));
+        const double u = bgw_u01(dev_draw(s, ev, BGW_SITE_ACC, (uint32_t)attacker, (uint32_t)cand + 4096u * occ));
         if (u > acc) return false;
     }
     return true;
@@ -375,6 +380,198 @@ __device__ void exec_attack(const DevSpec &s, Env &ev, int a)
     }
 }
 
+/* ---- the other attack actors (and the ammo filter) --------------------------------------------------------- */
+/* attack bytes of entity a's action row (layout: bgw.h, bgw_step) and how many of them its action has */
+__device__ __forceinline__ const uint8_t *attack_bytes(const DevSpec &s, const Env &ev, int a)
+{
+    return reinterpret_cast<const uint8_t *>(ev.act + (size_t)__ldg(&s.learner_of[a]) * s.act_words) + 2;
+}
+
+__device__ __forceinline__ int attack_width(const DevSpec &s, int a)
+{
+    if (s.attack_actor == BGW_ATTACK_ENCODING) return s.max_enc;                       /* actor.py:513-519 */
+    if (s.attack_actor == BGW_ATTACK_RESTRICTED) return __ldg(&s.simatt[a]);           /* :593-599 */
+    if (s.attack_actor == BGW_ATTACK_SELECTIVE) { const int n = 2 * __ldg(&s.attack_r[a]) + 1; return n * n; }   /* :669-679 */
+    return 1;                                                                          /* :451-453 */
+}
+
+/* `if not attack` / `not any(...)` / `not np.any(attack)` actor.py:478,542,622,703 */
+__device__ __forceinline__ bool attack_requested(const DevSpec &s, const Env &ev, int a)
+{
+    const uint8_t *att = attack_bytes(s, ev, a);
+    const int w = attack_width(s, a);
+    unsigned any = 0;
+    for (int j = 0; j < w; ++j) any |= att[j];
+    return any != 0;
+}
+
+struct AttackView {                      /* gu.create_grid_and_mask(agent, grid, attack_range, agents) for one attacker */
+    int a, R, n, r0, c0;
+    unsigned long long row;
+    double acc;
+    bool use_mask;
+    uint32_t m[BGW_ATT_MASK_WORDS];
+};
+
+/* grid cell of window cell (wr, wc), or -1 when it is masked or outside the grid (local_grid[r, c] is None) */
+__device__ __forceinline__ int attack_window_cell(const DevSpec &s, const AttackView &v, int wr, int wc)
+{
+    if (v.use_mask) { const int idx = wr * v.n + wc; if (!((v.m[idx >> 5] >> (idx & 31)) & 1u)) return -1; }
+    const int gr = v.r0 - v.R + wr, gc = v.c0 - v.R + wc;
+    if (gr < 0 || gr >= s.H || gc < 0 || gc >= s.W) return -1;
+    return gr * s.W + gc;
+}
+
+/* Walk the attackable agents of window cells [wr0..wr1] x [wc0..wc1] in the reference's scan order (cells row-major,
+ * occupants in dict order; actor.py:489-496): those that pass _basic_criteria, have encoding enc_only (if > 0) and
+ * are not in skip[0..nskip).  f(agent) returns true to stop. */
+template <typename F>
+__device__ __forceinline__ void for_attackables(const DevSpec &s, const Env &ev, const AttackView &v, int wr0, int wr1, int wc0,
+                                                int wc1, int enc_only, uint32_t occ, const uint16_t *skip, int nskip, F f)
+{
+    for (int wr = wr0; wr <= wr1; ++wr)
+        for (int wc = wc0; wc <= wc1; ++wc) {
+            const int cell = attack_window_cell(s, v, wr, wc);
+            if (cell < 0) continue;
+            for (unsigned o = ev.head[cell]; o != BGW_NONE16; o = ev.next[o]) {
+                if (enc_only > 0 && ev.enc[o] != enc_only) continue;
+                if (!basic_criteria(s, ev, v.a, (int)o, v.row, v.acc, occ)) continue;
+                bool skipped = false;
+                for (int q = 0; q < nskip; ++q) skipped |= (skip[q] == (uint16_t)o);
+                if (skipped) continue;
+                if (f((int)o)) return;
+            }
+        }
+}
+
+/* _subset_attackables actor.py:394-414 over the attackables of a window region: appends the chosen agents to
+ * victims[nv..] and returns the new count.  Draw keys: BGW_SITE_SUBSET, slot = attacker, k = group << 8 | draw#.  The
+ * choice without replacement is a partial Fisher-Yates over the candidate list, kept as a sparse map of the
+ * displaced positions (k <= BGW_MAX_SIMATT picks), the positions are resolved by walking the region again. */
+__device__ int subset_attackables_dev(const DevSpec &s, const Env &ev, const AttackView &v, int wr0, int wr1, int wc0, int wc1,
+                                      int enc_only, uint32_t group, int k, uint16_t *victims, int nv)
+{
+    int ncand = 0;
+    for_attackables(s, ev, v, wr0, wr1, wc0, wc1, enc_only, 0, nullptr, 0, [&](int) { ++ncand; return false; });
+    if (ncand == 0 || k <= 0) return nv;
+    if (!s.stacked && k > ncand) {                                  /* the whole list, no draw :410-411 */
+        for_attackables(s, ev, v, wr0, wr1, wc0, wc1, enc_only, 0, nullptr, 0,
+                        [&](int o) { if (nv < BGW_MAX_VICTIMS) victims[nv++] = (uint16_t)o; return false; });
+        return nv;
+    }
+    k = min(k, BGW_MAX_SIMATT);
+    int pos[BGW_MAX_SIMATT];
+    if (s.stacked) {
+        for (int t = 0; t < k; ++t)
+            pos[t] = ncand == 1 ? 0 : (int)bgw_index(dev_draw(s, ev, BGW_SITE_SUBSET, (uint32_t)v.a, (group << 8) | (uint32_t)t), (uint32_t)ncand);
+    } else {
+        int mk[BGW_MAX_SIMATT], mv[BGW_MAX_SIMATT], nm = 0;
+        for (int t = 0; t < k; ++t) {
+            const int rem = ncand - t;
+            const int j = t + (rem == 1 ? 0 : (int)bgw_index(dev_draw(s, ev, BGW_SITE_SUBSET, (uint32_t)v.a, (group << 8) | (uint32_t)t), (uint32_t)rem));
+            int vj = j, vt = t, at = -1;
+            for (int q = 0; q < nm; ++q) { if (mk[q] == j) { vj = mv[q]; at = q; } if (mk[q] == t) vt = mv[q]; }
+            pos[t] = vj;
+            if (at >= 0) mv[at] = vt; else { mk[nm] = j; mv[nm] = vt; ++nm; }
+        }
+    }
+    for (int t = 0; t < k; ++t) {
+        int want = pos[t], found = -1;
+        for_attackables(s, ev, v, wr0, wr1, wc0, wc1, enc_only, 0, nullptr, 0,
+                        [&](int o) { if (want-- == 0) { found = o; return true; } return false; });
+        if (found >= 0 && nv < BGW_MAX_VICTIMS) victims[nv++] = (uint16_t)found;
+    }
+    return nv;
+}
+
+/* <attack actor>._determine_attack (actor.py:455-501 Binary, 521-582 EncodingBased, 601-658 RestrictedSelective,
+ * 681-728 Selective) + AttackActorBaseComponent.process_action (:306-361, with the ammo filter :343-351) + the
+ * reward lines of TeamBattleSim.step (team_battle_example.py:38-47) for ONE attacker that requested an attack. */
+__device__ void exec_attack_ext(const DevSpec &s, Env &ev, int a)
+{
+    if (!(ev.flags[a] & BGW_ST_ACTIVE)) return;                   /* team_battle_example.py:37 */
+    AttackView v;
+    v.a = a; v.R = __ldg(&s.attack_r[a]); v.n = 2 * v.R + 1;
+    v.r0 = ev.cell[a] / s.W; v.c0 = ev.cell[a] % s.W;
+    v.row = __ldg(&s.attack_map[ev.enc[a]]);
+    v.acc = __ldg(&s.accuracy[a]);
+    v.use_mask = s.n_blk > 0;
+    if (v.use_mask) {
+#pragma unroll
+        for (int i = 0; i < BGW_ATT_MASK_WORDS; ++i) v.m[i] = 0xFFFFFFFFu;
+        for (int i = 0; i < s.n_blk; ++i) los_pair<false>(s, ev, v.m, ev.cell[a], v.R, __ldg(&s.blk_agents[i]), false);
+    }
+    const uint8_t *att = attack_bytes(s, ev, a);
+    const int n = v.n, last = n - 1;
+    uint16_t victims[BGW_MAX_VICTIMS];
+    int nv = 0;
+    switch (s.attack_actor) {
+    case BGW_ATTACK_BINARY:
+        nv = subset_attackables_dev(s, ev, v, 0, last, 0, last, 0, 0u, att[0], victims, nv);
+        break;
+    case BGW_ATTACK_ENCODING:                                      /* `for encoding, num_attacks in attack.items()`, ascending */
+        for (int enc = 1; enc <= s.max_enc; ++enc)
+            if (((v.row >> enc) & 1ull) && att[enc - 1])
+                nv = subset_attackables_dev(s, ev, v, 0, last, 0, last, enc, (uint32_t)enc, att[enc - 1], victims, nv);
+        break;
+    case BGW_ATTACK_RESTRICTED: {
+        const int width = __ldg(&s.simatt[a]);
+        for (int j = 0; j < width; ++j) {
+            const int code = att[j];
+            if (code == 0) continue;                               /* :635-637 */
+            const int rav = code - 1, wr = rav % n, wc = rav / n;  /* :641-643: row = remainder, column = quotient */
+            if (wr >= n || wc >= n) continue;
+            uint32_t occ = 0;                                      /* earlier attacks of this action on the same cell */
+            for (int q = 0; q < j; ++q) occ += (att[q] == code);
+            const uint16_t *skip = s.stacked ? nullptr : victims;  /* :652-654 */
+            const int nskip = s.stacked ? 0 : nv;
+            int ncand = 0;
+            for_attackables(s, ev, v, wr, wr, wc, wc, 0, occ, skip, nskip, [&](int) { ++ncand; return false; });
+            if (ncand == 0 || nv >= BGW_MAX_VICTIMS) continue;
+            int want = ncand == 1 ? 0 : (int)bgw_index(dev_draw(s, ev, BGW_SITE_SUBSET, (uint32_t)a, (uint32_t)nv << 8), (uint32_t)ncand);
+            int found = -1;
+            for_attackables(s, ev, v, wr, wr, wc, wc, 0, occ, skip, nskip, [&](int o) { if (want-- == 0) { found = o; return true; } return false; });
+            if (found >= 0) victims[nv++] = (uint16_t)found;
+        }
+        break;
+    }
+    case BGW_ATTACK_SELECTIVE:
+        for (int wr = 0; wr < n; ++wr)
+            for (int wc = 0; wc < n; ++wc)
+                if (att[wr * n + wc])
+                    nv = subset_attackables_dev(s, ev, v, wr, wr, wc, wc, 0, (uint32_t)(wr * n + wc), att[wr * n + wc], victims, nv);
+        break;
+    default: break;
+    }
+    if ((ev.klass[a] & BGW_AG_AMMO) && ev.ammo) {                  /* actor.py:343-351 */
+        int ammo = ev.ammo[a];
+        if (nv > ammo) {                                           /* np.random.choice(size=ammo, replace=False) */
+            for (int t = 0; t < ammo; ++t) {
+                const int j = t + (int)bgw_index(dev_draw(s, ev, BGW_SITE_AMMO, (uint32_t)a, (uint32_t)t), (uint32_t)(nv - t));
+                const uint16_t tmp = victims[t]; victims[t] = victims[j]; victims[j] = tmp;
+            }
+            nv = ammo;
+        }
+        ev.ammo[a] = max(ammo - nv, 0);
+    }
+    if (nv == 0) { ev.racc[a] += s.reward[BGW_RW_ATTACK_FAIL]; return; }   /* team_battle_example.py:41-42 */
+    const double strength = __ldg(&s.strength[a]);
+    for (int t = 0; t < nv; ++t) {                                  /* actor.py:353-358 */
+        const int x = victims[t];
+        if (!(ev.flags[x] & BGW_ST_ACTIVE)) continue;
+        set_health(ev, x, __ldcg(&ev.health[x]) - strength);
+        if (!(ev.flags[x] & BGW_ST_ACTIVE)) { grid_unlink(ev, x); atomicAdd(&ev.ctr[CTR_KILLS], 1); }
+    }
+    for (int t = 0; t < nv; ++t)                                    /* team_battle_example.py:44-47 */
+        if (!(ev.flags[victims[t]] & BGW_ST_ACTIVE)) { ev.racc[victims[t]] += s.reward[BGW_RW_DIE]; ev.racc[a] += s.reward[BGW_RW_KILL]; }
+}
+
+/* one attacker's turn in the attack phase */
+__device__ __forceinline__ void run_attack(const DevSpec &s, Env &ev, int a)
+{
+    if (s.attack_actor == BGW_ATTACK_BINARY && s.n_ammo == 0) exec_attack(s, ev, a); else exec_attack_ext(s, ev, a);
+}
+
 /* reservation helpers: slot of a cell */
 __device__ __forceinline__ uint32_t *slot_of(const DevSpec &s, const Env &ev, int cell) { return &ev.slot[cell & s.slot_mask]; }
 
@@ -390,13 +587,12 @@ __device__ void team_battle_step(const DevSpec &s, Env &ev, int nrank, int tid, 
             for (int i = 0; i < nrank; ++i) {
                 const int a = ev.ragent[i];
                 if (a == BGW_NONE16) continue;
-                const uint32_t act = ev.act[__ldg(&s.learner_of[a])];
-                if ((ev.klass[a] & BGW_AG_ATTACKING) && (int8_t)((act >> 16) & 0xFF) != 0) exec_attack(s, ev, a);
+                if ((ev.klass[a] & BGW_AG_ATTACKING) && attack_requested(s, ev, a)) run_attack(s, ev, a);
             }
             for (int i = 0; i < nrank; ++i) {
                 const int a = ev.ragent[i];
                 if (a == BGW_NONE16 || !(ev.flags[a] & BGW_ST_ACTIVE)) continue;
-                if (!process_move(s, ev, a, ev.act[__ldg(&s.learner_of[a])])) ev.racc[a] += rw[BGW_RW_MOVE_FAIL];
+                if (!process_move(s, ev, a, ev.act[(size_t)__ldg(&s.learner_of[a]) * s.act_words])) ev.racc[a] += rw[BGW_RW_MOVE_FAIL];
             }
             for (int i = 0; i < nrank; ++i) if (ev.ragent[i] != BGW_NONE16) ev.racc[ev.ragent[i]] += rw[BGW_RW_ENTROPY];
         }
@@ -409,8 +605,7 @@ __device__ void team_battle_step(const DevSpec &s, Env &ev, int nrank, int tid, 
     for (int i = tid; i < nrank; i += T) {
         const int a = ev.ragent[i];
         uint8_t p = 0;
-        if (a != BGW_NONE16 && (ev.flags[a] & BGW_ST_ACTIVE) && (ev.klass[a] & BGW_AG_ATTACKING) &&
-            (int8_t)((ev.act[__ldg(&s.learner_of[a])] >> 16) & 0xFF) != 0) p = 1;
+        if (a != BGW_NONE16 && (ev.flags[a] & BGW_ST_ACTIVE) && (ev.klass[a] & BGW_AG_ATTACKING) && attack_requested(s, ev, a)) p = 1;
         ev.pstate[i] = p;
         mine |= p;
     }
@@ -441,7 +636,7 @@ __device__ void team_battle_step(const DevSpec &s, Env &ev, int nrank, int tid, 
             if (ev.pstate[i] == 2) {
                 const int a = ev.ragent[i], R = __ldg(&s.attack_r[a]);
                 const int r0 = ev.cell[a] / s.W, c0 = ev.cell[a] % s.W;
-                exec_attack(s, ev, a);
+                run_attack(s, ev, a);
                 for (int gr = max(0, r0 - R); gr <= min(s.H - 1, r0 + R); ++gr)
                     for (int gc = max(0, c0 - R); gc <= min(s.W - 1, c0 + R); ++gc)
                         *slot_of(s, ev, gr * s.W + gc) = BGW_SLOT_FREE;
@@ -461,7 +656,7 @@ __device__ void team_battle_step(const DevSpec &s, Env &ev, int nrank, int tid, 
             bool ok = false;
             if (ev.klass[a] & BGW_AG_MOVING) {
                 int dr, dc;
-                decode_move(s, a, ev.act[__ldg(&s.learner_of[a])], dr, dc);
+                decode_move(s, a, ev.act[(size_t)__ldg(&s.learner_of[a]) * s.act_words], dr, dc);
                 const int from = ev.cell[a], r = from / s.W + dr, c = from % s.W + dc;
                 if (r >= 0 && r < s.H && c >= 0 && c < s.W) {
                     const int to = r * s.W + c;
@@ -546,7 +741,7 @@ __device__ void pacman_overlaps(const DevSpec &s, Env &ev, int p, bool eat_food)
 __device__ void serial_program_step(const DevSpec &s, Env &ev, int nrank)
 {
     const double *rw = s.reward;
-#define ACT(a) ev.act[__ldg(&s.learner_of[(a)])]
+#define ACT(a) ev.act[(size_t)__ldg(&s.learner_of[(a)]) * s.act_words]
     if (s.program == BGW_PROG_MAZE) {
         const int nav = s.a_nav;
         if (!process_move(s, ev, nav, ACT(nav))) ev.racc[nav] += rw[BGW_RW_MOVE_FAIL];
@@ -767,6 +962,8 @@ __device__ void observe_learners(const DevSpec &s, Env &ev, int ne, int8_t *obs_
             const int l = ev.plist[base + li], a = __ldg(&s.agent_of[l]);
             uint32_t w[4];
             obs_chunk(s, ev, a, ch, blk ? ev.mask + (size_t)li * s.mask_words : nullptr, w);
+            if (s.ammo_offset >= 0 && ch == (s.ammo_offset >> 4) && (ev.klass[a] & BGW_AG_AMMO) && ev.ammo)   /* AmmoObserver observer.py:406-413 */
+                w[(s.ammo_offset & 15) >> 2] = (uint32_t)ev.ammo[a];
             *reinterpret_cast<uint4 *>(obs_env + (size_t)l * s.obs_stride + ch * 16) = make_uint4(w[0], w[1], w[2], w[3]);
         }
         if (blk) __syncthreads();
@@ -881,6 +1078,7 @@ __device__ void sim_reset(const DevSpec &s, const BgwState &st, Env &ev, int tid
             f = (uint8_t)((f & 0x8F) | (o << BGW_ST_ORIENT_SHIFT));
         }
         if (!(ev.klass[a] & BGW_AG_LEARNER)) f |= BGW_ST_DONE_REPORTED;   /* all_step_manager.py:41-44 */
+        if (ev.ammo) ev.ammo[a] = ((ev.klass[a] & BGW_AG_AMMO) && s.init_ammo) ? __ldg(&s.init_ammo[a]) : 0;   /* AmmoState.reset state.py:649-656 */
         ev.flags[a] = f;
     }
     __syncthreads();
@@ -932,6 +1130,7 @@ __global__ void bgw_reset_kernel(const DevSpec s, const BgwState st, const uint8
     env_init(ev, s, bgw_smem);
     ev.e = e; ev.genv = (uint32_t)(s.env_offset + e);
     ev.health = st.health + (size_t)e * s.A;
+    ev.ammo = st.ammo ? st.ammo + (size_t)e * s.A : nullptr;
     env_reset(s, st, ev, obs ? obs + (size_t)e * s.L * s.obs_stride : nullptr, tid, T);
     if (tid == 0) st.env_flags[e] = (uint8_t)(ev.ctr[CTR_ERR] ? BGW_ENV_ERROR : 0);
 }
@@ -944,6 +1143,7 @@ __global__ void bgw_step_kernel(const DevSpec s, const BgwState st, const uint32
     env_init(ev, s, bgw_smem);
     ev.e = e; ev.genv = (uint32_t)(s.env_offset + e);
     ev.health = st.health + (size_t)e * s.A;
+    ev.ammo = st.ammo ? st.ammo + (size_t)e * s.A : nullptr;
     int8_t *obs_env = obs ? obs + (size_t)e * s.L * s.obs_stride : nullptr;
     float *rew = reward + (size_t)e * s.L;
     uint8_t *dn = done + (size_t)e * s.L;
@@ -971,7 +1171,7 @@ __global__ void bgw_step_kernel(const DevSpec s, const BgwState st, const uint32
         ev.enc[a] = __ldg(&s.enc[a]); ev.klass[a] = __ldg(&s.klass[a]);
         ev.racc[a] = (turn_based || racc_persists(ev.klass[a])) ? st.reward_acc[off + a] : 0.0;
     }
-    for (int l = tid; l < s.L; l += T) ev.act[l] = actions[(size_t)e * s.L + l];
+    for (int w = tid; w < s.L * s.act_words; w += T) ev.act[w] = actions[(size_t)e * s.L * s.act_words + w];
     for (int i = tid; i <= s.slot_mask; i += T) ev.slot[i] = BGW_SLOT_FREE;
     if (tid < CTR_COUNT) ev.ctr[tid] = 0;
     __syncthreads();
@@ -1096,18 +1296,37 @@ __device__ __forceinline__ uint32_t sample_action_word(const DevSpec &s, int a, 
             o = bgw_index(x[0], 5);
         }
     }
-    if ((klass & BGW_AG_ATTACKING) && s.attack_actor != BGW_ATTACK_NONE)
+    if ((klass & BGW_AG_ATTACKING) && s.attack_actor == BGW_ATTACK_BINARY)
         o |= (bgw_index(x[2], (uint32_t)__ldg(&s.simatt[a]) + 1) & 0xFF) << 16;   /* Discrete(n+1) actor.py:452 */
     return o;
 }
 
-/* one thread per (env, learner) */
+/* one thread per (env, learner).  The wider attack actions (EncodingBased / RestrictedSelective / Selective): attack
+ * byte j draws word j%4 of the Philox block k = 1 + j/4 of the same (env, step, agent) key. */
 __global__ void bgw_sample_actions_kernel(const DevSpec s, const BgwState st, uint32_t *actions)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)s.E * s.L) return;
     const int e = (int)(i / s.L), l = (int)(i % s.L), a = __ldg(&s.agent_of[l]);
-    actions[i] = sample_action_word(s, a, __ldg(&s.klass[a]), (uint32_t)(s.env_offset + e), st.episode[e], st.step[e]);
+    const int klass = __ldg(&s.klass[a]);
+    const uint32_t genv = (uint32_t)(s.env_offset + e), episode = st.episode[e], step = st.step[e];
+    uint32_t *row = actions + i * s.act_words;
+    row[0] = sample_action_word(s, a, klass, genv, episode, step);
+    for (int w = 1; w < s.act_words; ++w) row[w] = 0;
+    if (!(klass & BGW_AG_ATTACKING) || s.attack_actor <= BGW_ATTACK_BINARY) return;
+    const uint32_t sim = __ldg(&s.simatt[a]);
+    const int n = 2 * __ldg(&s.attack_r[a]) + 1;
+    const int width = s.attack_actor == BGW_ATTACK_ENCODING ? s.max_enc : s.attack_actor == BGW_ATTACK_RESTRICTED ? (int)sim : n * n;
+    const unsigned long long map_row = __ldg(&s.attack_map[__ldg(&s.enc[a])]);
+    uint32_t x[4];
+    for (int j = 0; j < width; ++j) {
+        if ((j & 3) == 0) bgw_draw4(s.seed, genv, episode, step, BGW_SITE_ACTION, (uint32_t)a, 1u + ((uint32_t)j >> 2), x);
+        uint32_t v;
+        if (s.attack_actor == BGW_ATTACK_ENCODING) v = ((map_row >> (j + 1)) & 1ull) ? bgw_index(x[j & 3], sim + 1) : 0;   /* actor.py:513-519 */
+        else if (s.attack_actor == BGW_ATTACK_RESTRICTED) v = bgw_index(x[j & 3], (uint32_t)(n * n) + 1);                  /* :593-599 */
+        else v = bgw_index(x[j & 3], sim + 1);                                                                            /* :669-679 */
+        row[(2 + j) >> 2] |= (v & 0xFFu) << (((2 + j) & 3) * 8);
+    }
 }
 
 /* bgw_gather_valid: one CTA per env; rows are claimed with one global atomicAdd per env and copied as 16-byte chunks */

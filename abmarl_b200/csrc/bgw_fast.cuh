@@ -595,6 +595,7 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
     ev.pstate = scratch + f.s_pstate;
     ev.avail = nullptr;
     ev.mask = nullptr; ev.act = nullptr;
+    ev.ammo = nullptr;                                     /* sims with AmmoAgents run the general kernel */
     FastEnv fe;
     fe.head = bgw_smem + f.o_head;
     fe.rflag = scratch + f.s_rflag;

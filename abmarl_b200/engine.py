@@ -15,14 +15,15 @@ from abmarl_b200 import _capi as K
 _STATE_FIELDS = (('cell', torch.int16, 'EA'), ('next', torch.int16, 'EA'), ('flags', torch.uint8, 'EA'),
                  ('health', torch.float64, 'EA'), ('reward_acc', torch.float64, 'EA'),
                  ('episode', torch.int32, 'E'), ('step', torch.int32, 'E'), ('env_flags', torch.uint8, 'E'),
-                 ('turn', torch.int16, 'E'), ('error', torch.int32, 'E'))
+                 ('turn', torch.int16, 'E'), ('error', torch.int32, 'E'), ('ammo', torch.int32, 'EA'))
 _NP_VIEW = {'cell': np.uint16, 'next': np.uint16, 'episode': np.uint32, 'step': np.uint32, 'error': np.uint32}
 
 
 class BatchedGridWorld:
     """reset() / step(actions) over device tensors.
 
-    actions  int8  [E, L, 4]   byte 0,1 = move (dr, dc | cross 0..4 | ravelled), byte 2 = attack
+    actions  int8  [E, L, action_stride]   byte 0,1 = move (dr, dc | cross 0..4 | ravelled), from byte 2 the attack
+                   action (layout: include/bgw.h, bgw_step; action_stride = 4 for the BinaryAttackActor)
     obs      int8  [E, L, obs_stride]   (see obs_view)
     reward   f32   [E, L];  done uint8 [E, L] (OUT_VALID | OUT_DONE);  all_done uint8 [E] (ENV_* bits)
     """
@@ -55,14 +56,15 @@ class BatchedGridWorld:
         self.reward = torch.zeros((self.E, self.L), dtype=torch.float32, device=dev)
         self.done = torch.zeros((self.E, self.L), dtype=torch.uint8, device=dev)
         self.all_done = torch.zeros((self.E,), dtype=torch.uint8, device=dev)
-        self.actions = torch.zeros((self.E, self.L, 4), dtype=torch.int8, device=dev)
+        self.action_stride = d.action_stride
+        self.actions = torch.zeros((self.E, self.L, d.action_stride), dtype=torch.int8, device=dev)
         self._bind()
 
     # ---- plumbing -------------------------------------------------------------------------------
     def _bind(self):
         s = K.BgwState()
         for name in ('cell', 'next', 'flags', 'health', 'reward_acc', 'episode', 'step', 'env_flags', 'turn',
-                     'error', 'layout', 'stats'):
+                     'error', 'layout', 'stats', 'ammo'):
             t = self.state[name]
             setattr(s, name, None if t is None else t.data_ptr())
         K.check(self.lib.bgw_bind_state(self._h, C.byref(s)), self.lib)
@@ -106,8 +108,8 @@ class BatchedGridWorld:
         return out
 
     def step(self, actions, order=None):
-        assert actions.dtype == torch.int8 and tuple(actions.shape) == (self.E, self.L, 4) and actions.is_cuda \
-            and actions.is_contiguous(), "actions must be a contiguous int8 CUDA tensor [E, L, 4]"
+        assert actions.dtype == torch.int8 and tuple(actions.shape) == (self.E, self.L, self.action_stride) and actions.is_cuda \
+            and actions.is_contiguous(), "actions must be a contiguous int8 CUDA tensor [E, L, action_stride]"
         o = None
         if order is not None:
             o = torch.as_tensor(order, dtype=torch.int16, device=self.device).contiguous()
@@ -140,7 +142,7 @@ class BatchedGridWorld:
                 h_count=torch.zeros(1, dtype=torch.int32).pin_memory(), h_index=torch.empty(n, dtype=torch.int32).pin_memory(),
                 h_obs=torch.empty((n, self.dims.obs_stride), dtype=torch.int8).pin_memory(),
                 h_reward=torch.empty(n, dtype=torch.float32).pin_memory(), h_done=torch.empty(n, dtype=torch.uint8).pin_memory(),
-                h_all=torch.empty(E, dtype=torch.uint8).pin_memory(), d_act=torch.empty((E, L, 4), dtype=torch.int8, device=dev))
+                h_all=torch.empty(E, dtype=torch.uint8).pin_memory(), d_act=torch.empty((E, L, self.action_stride), dtype=torch.int8, device=dev))
         return self._hb
 
     def enqueue_host(self, actions_host, order=None, zero_copy=False):
@@ -191,6 +193,14 @@ class BatchedGridWorld:
         v = obs[..., :d.obs_h * d.obs_w * d.obs_c]
         shape = tuple(obs.shape[:-1]) + ((d.obs_h, d.obs_w) if d.obs_c == 1 else (d.obs_h, d.obs_w, d.obs_c))
         return v.reshape(shape)
+
+    def ammo_view(self, obs=None):
+        """[E, L] int32: the AmmoObserver's 'ammo' observation stored in the obs rows (None without an AmmoObserver)."""
+        obs = self.obs if obs is None else obs
+        off = self.dims.ammo_offset
+        if off < 0:
+            return None
+        return obs[..., off:off + 4].contiguous().view(torch.int32).squeeze(-1)
 
     def state_numpy(self):
         """Host copy of the state in the oracle's numpy layout (tests)."""

@@ -60,7 +60,7 @@ class SimulationManager(ABC):
         return self.engine.obs_view()
 
     def step(self, actions, order=None):
-        """actions int8 [E, L, 4] on the device -> (obs, reward f32 [E, L], done uint8 [E, L], all_done uint8 [E]).
+        """actions int8 [E, L, action_stride] on the device -> (obs, reward f32 [E, L], done uint8 [E, L], all_done uint8 [E]).
 
         `done` carries OUT_VALID for the learners that received (obs, reward, done) this call and OUT_DONE for
         those that are done; rows of learners already reported done are ignored on input (the reference
@@ -79,9 +79,10 @@ class SimulationManager(ABC):
         return self.engine.sample_actions()
 
     def encode_actions(self, action_dicts):
-        """[{agent_id: {'move': ..., 'attack': ...}}, ...] (one dict per env, reference format) -> int8 [E, L, 4]."""
+        """[{agent_id: {'move': ..., 'attack': ...}}, ...] (one dict per env, reference format) -> int8
+        [E, L, action_stride] (layout: include/bgw.h, bgw_step)."""
         sp = self.spec
-        act = np.zeros((self.engine.E, self.engine.L, 4), dtype=np.int8)
+        act = np.zeros((self.engine.E, self.engine.L, self.engine.action_stride), dtype=np.uint8)
         index = {aid: l for l, aid in enumerate(self.learner_ids)}
         for e, d in enumerate(action_dicts):
             for agent_id, a in d.items():
@@ -89,12 +90,23 @@ class SimulationManager(ABC):
                 if 'move' in a:
                     mv = a['move']
                     if sp.move_actor == K.MOVE_BOX and not sp.ravel_actions:
-                        act[e, l, 0], act[e, l, 1] = int(mv[0]), int(mv[1])
+                        act[e, l, 0], act[e, l, 1] = np.int8(int(mv[0])).view(np.uint8), np.int8(int(mv[1])).view(np.uint8)
                     else:
-                        act[e, l, 0] = np.uint8(int(mv)).view(np.int8)
+                        act[e, l, 0] = int(mv)
                 if 'attack' in a:
-                    act[e, l, 2] = int(a['attack'])
-        return torch.from_numpy(act).to(self.engine.device)
+                    att = a['attack']
+                    if sp.attack_actor == K.ATTACK_ENCODING:          # {encoding: count} actor.py:513-519
+                        for enc, count in att.items():
+                            act[e, l, 2 + int(enc) - 1] = int(count)
+                    elif sp.attack_actor == K.ATTACK_RESTRICTED:       # [cell + 1 | 0] * simultaneous_attacks :593-599
+                        att = np.asarray(att, dtype=int).ravel()
+                        act[e, l, 2:2 + att.size] = att
+                    elif sp.attack_actor == K.ATTACK_SELECTIVE:        # (n, n) counts :669-679
+                        att = np.asarray(att, dtype=int).ravel()
+                        act[e, l, 2:2 + att.size] = att
+                    else:
+                        act[e, l, 2] = int(att)
+        return torch.from_numpy(act.view(np.int8)).to(self.engine.device)
 
     # -- reference-shaped view of one env --------------------------------------------------------
     def as_dicts(self, env=0, after_reset=False):
@@ -103,6 +115,8 @@ class SimulationManager(ABC):
         key = {K.OBS_POSITION_CENTERED: 'position_centered_encoding', K.OBS_ABSOLUTE: 'absolute_encoding',
                K.OBS_STACKED: 'stacked_position_centered_encoding'}[self.spec.observer]
         obs_all = eng.obs_view()[env].cpu().numpy().astype(np.int64)
+        ammo = eng.ammo_view()
+        ammo = None if ammo is None else ammo[env].cpu().numpy()
         done = eng.done[env].cpu().numpy()
         reward = eng.reward[env].cpu().numpy()
         flags = int(eng.all_done[env].item())
@@ -115,7 +129,9 @@ class SimulationManager(ABC):
                 if self.spec.observer != K.OBS_ABSOLUTE and o.shape[0] != n:     # agent with a smaller view
                     flat = o.reshape(-1)[:n * n * (o.shape[2] if o.ndim == 3 else 1)]
                     o = flat.reshape((n, n) + o.shape[2:])
-                obs[agent_id] = {key: o}
+                obs[agent_id] = {key: o} if self.spec.klass[a] & K.AG_OBSERVING else {}
+                if ammo is not None and self.spec.klass[a] & K.AG_AMMO:      # AmmoObserver observer.py:406-413
+                    obs[agent_id]['ammo'] = int(ammo[l])
                 if not after_reset:
                     rew[agent_id] = float(reward[l])
                     dn[agent_id] = bool(done[l] & K.OUT_DONE)

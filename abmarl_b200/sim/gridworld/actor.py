@@ -8,7 +8,7 @@ from abc import ABC, abstractmethod
 
 import numpy as np
 
-from abmarl_b200.spaces import Box, Discrete
+from abmarl_b200.spaces import Box, Discrete, MultiDiscrete, Dict
 from abmarl_b200.sim.gridworld.base import GridWorldBaseComponent
 from abmarl_b200.sim.gridworld.agent import MovingAgent, AttackingAgent, OrientationAgent
 
@@ -90,6 +90,35 @@ class BinaryAttackActor(AttackActorBaseComponent):
     def _assign_space(self, agent):
         agent.action_space[self.key] = Discrete(agent.simultaneous_attacks + 1)
         agent.null_action[self.key] = 0
+
+
+class EncodingBasedAttackActor(AttackActorBaseComponent):
+    """actor.py:504-582: Dict{encoding: Discrete(simultaneous_attacks + 1)} over the encodings the agent can attack;
+    the count is an upper bound per encoding."""
+
+    def _assign_space(self, agent):
+        attackable_encodings = self.attack_mapping[agent.encoding]
+        agent.action_space[self.key] = Dict({i: Discrete(agent.simultaneous_attacks + 1) for i in sorted(attackable_encodings)})
+        agent.null_action[self.key] = {i: 0 for i in sorted(attackable_encodings)}
+
+
+class RestrictedSelectiveAttackActor(AttackActorBaseComponent):
+    """actor.py:585-658: MultiDiscrete([cells + 1] * simultaneous_attacks): each entry names one cell of the attack
+    window (0 = attack not used, else 1 + ravelled cell with row = (v-1) % n, column = (v-1) // n)."""
+
+    def _assign_space(self, agent):
+        grid_cells = (2 * agent.attack_range + 1) ** 2
+        agent.action_space[self.key] = MultiDiscrete([grid_cells + 1] * agent.simultaneous_attacks)
+        agent.null_action[self.key] = np.zeros((agent.simultaneous_attacks,), dtype=int)
+
+
+class SelectiveAttackActor(AttackActorBaseComponent):
+    """actor.py:661-728: Box(0, simultaneous_attacks, (n, n), int): attacks per cell of the attack window."""
+
+    def _assign_space(self, agent):
+        n = 2 * agent.attack_range + 1
+        agent.action_space[self.key] = Box(0, agent.simultaneous_attacks, (n, n), int)
+        agent.null_action[self.key] = np.zeros((n, n), dtype=int)
 
 
 AttackActor = BinaryAttackActor   # pre-0.2.6 name (docs/src/release.rst:96-99)

@@ -109,12 +109,24 @@ class AttackingAgent(ActingAgent, GridWorldAgent):
 
 
 class AmmoAgent(GridWorldAgent):
-    """agent.py:291-322 (declared for API completeness; ammo accounting is not on the device path yet)."""
+    """agent.py:291-322.  `ammo` lives in BgwState.ammo on the device: AmmoState.reset gives initial_ammo, every
+    agent an attack names costs one round (actor.py:343-351)."""
     initial_ammo = _Checked(_is_int, "Initial ammo must be an integer.")
 
     def __init__(self, initial_ammo=None, **kwargs):
         super().__init__(**kwargs)
         self.initial_ammo = initial_ammo
+
+
+class _AmmoObservingMeta(type(GridWorldAgent)):
+    """agent.py:324-332: anything that is both an AmmoAgent and an ObservingAgent."""
+
+    def __instancecheck__(cls, instance):
+        return isinstance(instance, ObservingAgent) and isinstance(instance, AmmoAgent)
+
+
+class AmmoObservingAgent(AmmoAgent, ObservingAgent, metaclass=_AmmoObservingMeta):
+    """agent.py:335-339: boilerplate required by the AmmoObserver."""
 
 
 class OrientationAgent(GridWorldAgent):

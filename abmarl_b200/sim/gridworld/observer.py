@@ -11,7 +11,7 @@ import numpy as np
 
 from abmarl_b200.spaces import Box
 from abmarl_b200.sim.gridworld.base import GridWorldBaseComponent
-from abmarl_b200.sim.gridworld.agent import GridObservingAgent
+from abmarl_b200.sim.gridworld.agent import GridObservingAgent, AmmoObservingAgent
 
 
 class ObserverBaseComponent(GridWorldBaseComponent, ABC):
@@ -74,6 +74,19 @@ class StackedPositionCenteredEncodingObserver(ObserverBaseComponent):
 
     def _shape(self, agent):
         return (agent.view_range * 2 + 1, agent.view_range * 2 + 1, self.number_of_encodings)
+
+
+class AmmoObserver(ObserverBaseComponent):
+    """observer.py:376-413: agents observe their own ammo (an int32 slot at BgwDims.ammo_offset of the obs row)."""
+    key = 'ammo'
+    supported_agent_type = AmmoObservingAgent
+
+    def __init__(self, **kwargs):
+        super().__init__(**kwargs)
+        for agent in self.agents.values():
+            if isinstance(agent, self.supported_agent_type):
+                agent.observation_space[self.key] = Box(0, agent.initial_ammo, (1,), int)
+                agent.null_observation[self.key] = 0
 
 
 # pre-0.2.6 names (docs/src/release.rst:96-99; still used by tests/sim/gridworld/test_observer.py)

@@ -80,6 +80,30 @@ class Discrete(Space):
         return f"Discrete({self.n})"
 
 
+class MultiDiscrete(Space):
+    """gym.spaces.MultiDiscrete(nvec): a vector whose j-th entry is in [0, nvec[j])."""
+
+    def __init__(self, nvec):
+        self.nvec = np.asarray(nvec, dtype=int)
+        self.shape, self.dtype = self.nvec.shape, np.dtype(int)
+
+    def contains(self, x):
+        x = np.asarray(x)
+        return x.shape == self.nvec.shape and bool(np.all(x >= 0) and np.all(x < self.nvec))
+
+    def sample(self):
+        return np.array([self.rng().integers(0, n) for n in self.nvec], dtype=int)
+
+    def __len__(self):
+        return len(self.nvec)
+
+    def __eq__(self, other):
+        return isinstance(other, MultiDiscrete) and np.array_equal(self.nvec, other.nvec)
+
+    def __repr__(self):
+        return f"MultiDiscrete({self.nvec.tolist()})"
+
+
 class Dict(Space):
     def __init__(self, spaces):
         self.spaces = dict(spaces)
@@ -125,7 +149,7 @@ class Dict(Space):
 
 def check_space(space, strict=False):
     """abmarl/tools/gym_utils.py:27-55."""
-    if isinstance(space, (Box, Discrete)):
+    if isinstance(space, (Box, Discrete, MultiDiscrete)):
         return True
     if isinstance(space, Dict):
         return all(check_space(s) for s in space.spaces.values())

@@ -34,12 +34,12 @@ class CompiledSpec:
 
     SCALARS = ('rows', 'cols', 'n_agents', 'n_envs', 'env_offset', 'program', 'move_actor', 'attack_actor',
                'observer', 'observe_self', 'done_mask', 'manager', 'ravel_actions', 'no_overlap_at_reset',
-               'stacked_attacks', 'horizon', 'auto_reset', 'seed')
+               'stacked_attacks', 'horizon', 'auto_reset', 'ammo_observer', 'seed')
     TABLES = (('encoding', np.int8), ('klass', np.uint8), ('role', np.uint8), ('init_row', np.int16),
               ('init_col', np.int16), ('init_health', np.float64), ('init_orient', np.uint8),
               ('view_range', np.int16), ('move_range', np.int16), ('attack_range', np.int16),
               ('attack_strength', np.float64), ('attack_accuracy', np.float64),
-              ('simultaneous_attacks', np.uint8), ('target', np.int16))
+              ('simultaneous_attacks', np.uint8), ('target', np.int16), ('initial_ammo', np.int32))
 
     def __init__(self):
         for s in self.SCALARS:
@@ -163,6 +163,9 @@ def compile_sim(sim, manager='all_step', n_envs=1, env_offset=0, seed=0, horizon
         if hasattr(ag, 'initial_orientation'):
             k |= K.AG_ORIENT
             sp.init_orient[i] = ag.initial_orientation or 0
+        if hasattr(ag, 'initial_ammo'):
+            k |= K.AG_AMMO
+            sp.initial_ammo[i] = int(ag.initial_ammo)
         if acting and observing:
             k |= K.AG_LEARNER
         if ag.blocking:
@@ -191,7 +194,9 @@ def compile_sim(sim, manager='all_step', n_envs=1, env_offset=0, seed=0, horizon
                 "ravelled move must fit one byte: move_range <= 7"
     attack = getattr(sim, 'attack_actor', None)
     if attack is not None:
-        sp.attack_actor = _first(_mro_names(attack), (('BinaryAttackActor', K.ATTACK_BINARY),), 'attack actor')
+        sp.attack_actor = _first(_mro_names(attack), (
+            ('BinaryAttackActor', K.ATTACK_BINARY), ('EncodingBasedAttackActor', K.ATTACK_ENCODING),
+            ('RestrictedSelectiveAttackActor', K.ATTACK_RESTRICTED), ('SelectiveAttackActor', K.ATTACK_SELECTIVE)), 'attack actor')
         sp.attack_map = _rows(attack.attack_mapping)
         sp.stacked_attacks = int(bool(attack.stacked_attacks))
 
@@ -199,6 +204,9 @@ def compile_sim(sim, manager='all_step', n_envs=1, env_offset=0, seed=0, horizon
     observers = list(getattr(sim, '_observers', None) or [])
     if hasattr(sim, 'grid_observer'):
         observers.append(sim.grid_observer)
+    if any('AmmoObserver' in _mro_names(o) for o in observers):            # observer.py:376-413
+        sp.ammo_observer = 1
+        observers = [o for o in observers if 'AmmoObserver' not in _mro_names(o)]
     assert len(observers) == 1, "exactly one grid observer per compiled sim is supported"
     sp.observer = _first(_mro_names(observers[0]), _OBSERVERS, 'observer')
     sp.observe_self = int(getattr(observers[0], 'observe_self', True))
@@ -234,8 +242,9 @@ def compile_sim(sim, manager='all_step', n_envs=1, env_offset=0, seed=0, horizon
         sp.reward[K.RW_DIE] = rc.get('die', -1.0)
         sp.reward[K.RW_MOVE_FAIL] = rc.get('move_fail', -0.1)
         sp.reward[K.RW_ENTROPY] = rc.get('entropy', -0.01)
-        assert int(sp.simultaneous_attacks.max(initial=0)) <= 1, \
-            "TeamBattleSim.step is only defined for simultaneous_attacks == 1 (team_battle_example.py:41)"
+        # Binary hands TeamBattleSim.step an ndarray: `not attacked_agents` raises for more than one element
+        assert sp.attack_actor != K.ATTACK_BINARY or int(sp.simultaneous_attacks.max(initial=0)) <= 1, \
+            "TeamBattleSim.step with the BinaryAttackActor is only defined for simultaneous_attacks == 1 (team_battle_example.py:41)"
     elif sp.program in (K.PROG_MAZE, K.PROG_MULTI_MAZE):   # maze_navigation.py:29-36, multi_maze_navigation.py:45-59
         sp.reward[K.RW_MOVE_FAIL] = rc.get('move_fail', -0.1)
         sp.reward[K.RW_TARGET] = rc.get('target', 1.0)

@@ -35,11 +35,13 @@
 extern "C" {
 #endif
 
-#define BGW_ABI_VERSION 1
+#define BGW_ABI_VERSION 2
 #define BGW_MAX_ENCODING 63   /* encodings are bit positions in 64-bit overlap / attack rows */
 #define BGW_MAX_AGENTS 4096   /* Philox slot field (bgw_philox.h)                           */
 #define BGW_MAX_CELLS 65535   /* cell index is u16, 0xFFFF = none                           */
 #define BGW_NONE 0xFFFFu
+#define BGW_MAX_VICTIMS 256   /* attacked agents one attacker can name in one step (simultaneous_attacks x groups) */
+#define BGW_MAX_SIMATT 16     /* AttackingAgent.simultaneous_attacks                                             */
 
 /* ---- per-agent class flags (which reference mixins the entity derives from) ------------------- */
 enum {
@@ -49,7 +51,8 @@ enum {
     BGW_AG_HEALTH = 1 << 3,     /* HealthAgent          agent.py:160-196 */
     BGW_AG_ORIENT = 1 << 4,     /* OrientationAgent     agent.py:342-373 */
     BGW_AG_LEARNER = 1 << 5,    /* isinstance(x, Agent) agent_based_simulation.py:174-186 */
-    BGW_AG_BLOCKING = 1 << 6    /* GridWorldAgent.blocking  agent.py:60-68 */
+    BGW_AG_BLOCKING = 1 << 6,   /* GridWorldAgent.blocking  agent.py:60-68 */
+    BGW_AG_AMMO = 1 << 7        /* AmmoAgent            agent.py:291-321 */
 };
 
 /* ---- per-agent role inside a sim program ----------------------------------------------------- */
@@ -73,7 +76,10 @@ enum {
 
 enum { BGW_MOVE_NONE = 0, BGW_MOVE_BOX = 1 /* MoveActor actor.py:55 */, BGW_MOVE_CROSS = 2 /* :117 */,
        BGW_MOVE_DRIFT = 3 /* :197 */ };
-enum { BGW_ATTACK_NONE = 0, BGW_ATTACK_BINARY = 1 /* BinaryAttackActor actor.py:441 */ };
+enum { BGW_ATTACK_NONE = 0, BGW_ATTACK_BINARY = 1 /* BinaryAttackActor actor.py:441 */,
+       BGW_ATTACK_ENCODING = 2 /* EncodingBasedAttackActor actor.py:504 */,
+       BGW_ATTACK_RESTRICTED = 3 /* RestrictedSelectiveAttackActor actor.py:585 */,
+       BGW_ATTACK_SELECTIVE = 4 /* SelectiveAttackActor actor.py:661 */ };
 enum {
     BGW_OBS_POSITION_CENTERED = 0, /* PositionCenteredEncodingObserver (SingleGridObserver) observer.py:153 */
     BGW_OBS_ABSOLUTE = 1,          /* AbsoluteEncodingObserver                              observer.py:55  */
@@ -143,6 +149,8 @@ typedef struct BgwSpec {
     int32_t stacked_attacks;     /* AttackActorBaseComponent(stacked_attacks=) actor.py:245 */
     int32_t horizon;       /* 0 = none; else all_done|TRUNCATED once the episode has this many steps */
     int32_t auto_reset;    /* 1: an env that reported __all__ is reset by the NEXT bgw_step call */
+    int32_t ammo_observer; /* 1: the sim has an AmmoObserver (observer.py:376-413): learners with BGW_AG_AMMO
+                              also observe their ammo (BgwDims.ammo_offset) */
     uint64_t seed;         /* Philox key */
     double reward[BGW_RW_COUNT];
 
@@ -161,6 +169,8 @@ typedef struct BgwSpec {
     const double *attack_accuracy;
     const uint8_t *simultaneous_attacks;
     const int16_t *target;        /* TargetAgentDone / TargetDestroyedDone mapping: agent -> target agent, -1 none */
+    const int32_t *initial_ammo;  /* AmmoAgent.initial_ammo (agent.py:311-321) of entities with BGW_AG_AMMO; may be
+                                     NULL when no entity has the flag */
 
     /* per-encoding bit rows, length BGW_MAX_ENCODING+1; row e bit f set <=> f in map[e] */
     const uint64_t *overlap;      /* Grid.overlapping, already symmetrised        grid.py:53-71 */
@@ -188,6 +198,8 @@ typedef struct BgwState {
                             for MazePlacementState layouts generated host-side (state.py:385-619)          */
     uint64_t *stats;     /* [E][BGW_STAT_COUNT] per-env running counters, see below (sum over E on demand;
                             per-env rows avoid same-address atomics in the step kernel)                 */
+    int32_t *ammo;       /* [E][A] AmmoAgent.ammo (agent.py:299-309; AmmoState.reset state.py:644-656);
+                            required only when some entity has BGW_AG_AMMO, else may be NULL             */
 } BgwState;
 
 enum {
@@ -202,9 +214,11 @@ enum {
 typedef struct BgwDims {
     int32_t n_envs, n_agents, n_learners;
     int32_t obs_h, obs_w, obs_c; /* logical observation shape per learner (obs_c = 1 unless STACKED) */
-    int32_t obs_stride;          /* bytes per learner in the int8 obs buffer = roundup(h*w*c, 16)     */
-    int32_t action_stride;       /* bytes per learner in the action buffer (4)                        */
+    int32_t obs_stride;          /* bytes per learner in the int8 obs buffer = roundup(h*w*c (+4), 16) */
+    int32_t action_stride;       /* bytes per learner in the action buffer, a multiple of 4 (see bgw_step) */
     int32_t threads_per_env, envs_per_cta, smem_bytes; /* launch geometry (informational)             */
+    int32_t ammo_offset;         /* AmmoObserver (observer.py:376-413): byte offset inside a learner's obs row of
+                                    its int32 'ammo' observation (little endian, 4-byte aligned), or -1       */
 } BgwDims;
 
 typedef struct BgwEngine *bgw_handle;
@@ -226,7 +240,15 @@ int bgw_reset(bgw_handle h, const uint8_t *env_mask, int8_t *obs, void *stream);
 
 /*
  * One manager step for every env (all_step_manager.py:51-95 / turn_based_manager.py:34-94):
- *   actions  [E][L][4] i8   byte0,1 = move (dr,dc | cross 0..4 | ravelled), byte2 = attack count, byte3 pad;
+ *   actions  [E][L][action_stride] i8
+ *                           byte0,1 = move (dr,dc | cross 0..4 | ravelled); from byte 2 the attack action:
+ *                             BinaryAttackActor               byte2 = number of attacks (actor.py:451-453)
+ *                             EncodingBasedAttackActor        byte 2+(e-1) = attacks on encoding e (:513-519)
+ *                             RestrictedSelectiveAttackActor  byte 2+j = ravelled cell + 1 of attack j, 0 = unused
+ *                                                             (:593-599; j < simultaneous_attacks)
+ *                             SelectiveAttackActor            byte 2+(r*n+c) = attacks on window cell (r,c),
+ *                                                             n = 2*attack_range+1 of that agent (:669-679)
+ *                           action_stride = roundup(2 + widest attack action, 4): 4 for the Binary actor;
  *                           rows of learners already reported done are ignored (the reference asserts
  *                           they are absent, all_step_manager.py:59-61)
  *   order    [E][L] i16     optional processing order of learners (randomize_action_input,
@@ -238,7 +260,7 @@ int bgw_step(bgw_handle h, const int8_t *actions, const int16_t *order, int8_t *
              uint8_t *done, uint8_t *all_done, void *stream);
 
 /* bgw_sample_actions + bgw_step in one call: every acting learner draws its action from the keyed random policy
- * and the batch is stepped with them.  actions_out[E][L][4] receives the sampled actions of the learners that acted
+ * and the batch is stepped with them.  actions_out[E][L][action_stride] receives the sampled actions of the learners that acted
  * (rows of learners already reported done are not written).  Same results as the two calls made separately. */
 int bgw_step_sampled(bgw_handle h, int8_t *actions_out, const int16_t *order, int8_t *obs, float *reward,
                      uint8_t *done, uint8_t *all_done, void *stream);
@@ -257,7 +279,7 @@ int bgw_gather_valid(bgw_handle h, const int8_t *obs, const float *reward, const
                      int32_t *count, int32_t *index, int8_t *obs_c, float *reward_c, uint8_t *done_c, void *stream);
 
 /* Synthetic random policy (policies/policy.py:81-92 `action_space.sample()`), keyed Philox site ACTION:
- * fills actions[E][L][4] for the CURRENT step of every env.  Used by bench.py and the parity tests. */
+ * fills actions[E][L][action_stride] for the CURRENT step of every env.  Used by bench.py and the parity tests. */
 int bgw_sample_actions(bgw_handle h, int8_t *actions, void *stream);
 
 /* Host-callable Philox draw, identical to the device stream (used by the replay shim). */

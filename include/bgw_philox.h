@@ -37,11 +37,16 @@ enum {
     BGW_SITE_PLACE = 0,   /* PositionState._place_variable_position_agent   state.py:159  slot=agent k=0 */
     BGW_SITE_HEALTH = 1,  /* HealthState.reset                                state.py:641  slot=agent k=0 */
     BGW_SITE_ORIENT = 2,  /* OrientationState.reset                           state.py:675  slot=agent k=0 */
-    BGW_SITE_ACC = 3,     /* AttackActorBaseComponent._basic_criteria         actor.py:388  slot=attacker k=candidate */
-    BGW_SITE_SUBSET = 4,  /* AttackActorBaseComponent._subset_attackables     actor.py:412  slot=attacker k=draw# */
+    BGW_SITE_ACC = 3,     /* AttackActorBaseComponent._basic_criteria         actor.py:388  slot=attacker
+                             k = candidate + 4096 * (how often this step the pair was evaluated before; only the
+                             RestrictedSelectiveAttackActor evaluates a pair more than once) */
+    BGW_SITE_SUBSET = 4,  /* _subset_attackables actor.py:412 and RestrictedSelectiveAttackActor's choice :655
+                             slot=attacker  k = group << 8 | draw#;  group = 0 (Binary), the encoding (EncodingBased),
+                             window cell r*n+c (Selective), number of agents attacked so far (RestrictedSelective) */
     BGW_SITE_OBS = 5,     /* observers' np.random.choice            observer.py:131,234,246 slot=observer k=absolute cell */
     BGW_SITE_ACTION = 6,  /* synthetic random policy (bench / tests)          policies/policy.py:81-92 slot=agent */
-    BGW_SITE_MAZE = 7     /* reserved: MazePlacementState                     state.py:529, utils.py:193,198 */
+    BGW_SITE_MAZE = 7,    /* MazePlacementState                               state.py:529, utils.py:193,198 */
+    BGW_SITE_AMMO = 8     /* ammo filter of process_action                    actor.py:346-350 slot=attacker k=draw# */
 };
 
 BGW_HD void bgw_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,

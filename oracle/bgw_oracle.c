@@ -28,6 +28,9 @@ typedef struct {
     uint16_t *cell, *next;
     uint8_t *flags;
     double *health, *racc;
+    int32_t *ammo;    /* NULL when the state has no ammo array */
+    int astride;      /* bytes per learner action row */
+    uint8_t *acc_occ; /* [A] how often the current attacker evaluated each candidate this step (ACC draw key) */
     /* work arrays */
     uint16_t *head, *tail, *prev;
     int *learner_of;  /* [A] learner index or -1 */
@@ -53,6 +56,22 @@ static int max_encoding(const BgwSpec *sp)
     return m;
 }
 
+/* bytes of one learner's action row: 2 move bytes + the widest attack action (layout: bgw.h, bgw_step) */
+static int action_stride_of(const BgwSpec *sp)
+{
+    int payload = 1;                                                        /* Discrete(n+1) actor.py:452 */
+    for (int a = 0; a < sp->n_agents; ++a) {
+        if (!(sp->klass[a] & BGW_AG_ATTACKING)) continue;
+        const int n = 2 * sp->attack_range[a] + 1;
+        int w = 1;
+        if (sp->attack_actor == BGW_ATTACK_ENCODING) w = max_encoding(sp);             /* Dict per encoding :513-519 */
+        else if (sp->attack_actor == BGW_ATTACK_RESTRICTED) w = sp->simultaneous_attacks[a];   /* MultiDiscrete :593-599 */
+        else if (sp->attack_actor == BGW_ATTACK_SELECTIVE) w = n * n;                  /* Box (n, n) :669-679 */
+        if (w > payload) payload = w;
+    }
+    return (2 + payload + 3) / 4 * 4;
+}
+
 int bgwo_dims(const BgwSpec *sp, BgwDims *d)
 {
     memset(d, 0, sizeof(*d));
@@ -66,8 +85,10 @@ int bgwo_dims(const BgwSpec *sp, BgwDims *d)
     else { d->obs_h = d->obs_w = 2 * rmax + 1; }                                          /* observer.py:170,266 */
     if (sp->observer == BGW_OBS_STACKED) d->obs_c = max_encoding(sp);                     /* observer.py:264 */
     int n = d->obs_h * d->obs_w * d->obs_c;
+    d->ammo_offset = -1;
+    if (sp->ammo_observer) { d->ammo_offset = (n + 3) / 4 * 4; n = d->ammo_offset + 4; }   /* observer.py:376-413 */
     d->obs_stride = (n + 15) / 16 * 16;
-    d->action_stride = 4;
+    d->action_stride = action_stride_of(sp);
     return 0;
 }
 
@@ -256,6 +277,11 @@ static void observe_agent(Ctx *c, int a, int8_t *out, int stride)
 {
     const BgwSpec *sp = c->sp;
     memset(out, 0, (size_t)stride);
+    if (sp->ammo_observer && (sp->klass[a] & BGW_AG_AMMO) && c->ammo) {      /* AmmoObserver.get_obs observer.py:406-413 */
+        BgwDims dd; bgwo_dims(sp, &dd);
+        const int32_t v = c->ammo[a];
+        memcpy(out + dd.ammo_offset, &v, 4);
+    }
     if (!(sp->klass[a] & BGW_AG_OBSERVING)) return;          /* get_obs returns {} observer.py:103,213,301 */
     const int R = sp->view_range[a], n = 2 * R + 1;
     const int r0 = c->cell[a] / c->W, c0 = c->cell[a] % c->W;
@@ -361,59 +387,140 @@ static int process_move(Ctx *c, int a, const int8_t *act)
     return 0;
 }
 
-/* AttackActorBaseComponent._basic_criteria actor.py:381-392 */
+/* AttackActorBaseComponent._basic_criteria actor.py:381-392.  The accuracy draw is keyed by (attacker,
+ * candidate, how often the pair was evaluated before in this call) -- see BGW_SITE_ACC. */
 static int basic_criteria(Ctx *c, int attacker, int cand)
 {
     const BgwSpec *sp = c->sp;
     if (cand == attacker) return 0;
     if (!(c->flags[cand] & BGW_ST_ACTIVE)) return 0;
     if (!((sp->attack_map[sp->encoding[attacker]] >> sp->encoding[cand]) & 1)) return 0;
-    const double u = bgw_u01(draw(c, BGW_SITE_ACC, (uint32_t)attacker, (uint32_t)cand));
+    const uint32_t occ = c->acc_occ[cand]++;
+    const double u = bgw_u01(draw(c, BGW_SITE_ACC, (uint32_t)attacker, (uint32_t)cand + 4096u * occ));
     if (u > sp->attack_accuracy[attacker]) return 0;
     return 1;
 }
 
-/* BinaryAttackActor._determine_attack + AttackActorBaseComponent.process_action
- * actor.py:455-501, 306-361.  Returns attack_status; victims[] / *nv receive attacked_agents. */
-static int process_attack(Ctx *c, int a, int attack, int *victims, int *nv, int cap)
+/* AttackActorBaseComponent._subset_attackables actor.py:394-414: appends the chosen agents to out[*nv..] */
+static void subset_attackables(Ctx *c, int a, uint32_t group, int *cand, int ncand, int k, int *out, int *nv)
+{
+    const BgwSpec *sp = c->sp;
+    if (!sp->stacked_attacks && k > ncand) {                      /* whole list, no draw :410-411 */
+        for (int t = 0; t < ncand && *nv < BGW_MAX_VICTIMS; ++t) out[(*nv)++] = cand[t];
+    } else if (sp->stacked_attacks) {                             /* choice with replacement */
+        for (int t = 0; t < k && *nv < BGW_MAX_VICTIMS; ++t)
+            out[(*nv)++] = cand[bgw_index(draw(c, BGW_SITE_SUBSET, (uint32_t)a, (group << 8) | (uint32_t)t), (uint32_t)ncand)];
+    } else {
+        /* choice without replacement == partial Fisher-Yates over the candidate list (the replay shim
+         * implements np.random.choice(replace=False) the same way) */
+        for (int t = 0; t < k; ++t) {
+            int j = t + (int)bgw_index(draw(c, BGW_SITE_SUBSET, (uint32_t)a, (group << 8) | (uint32_t)t), (uint32_t)(ncand - t));
+            int tmp = cand[t]; cand[t] = cand[j]; cand[j] = tmp;
+            if (*nv < BGW_MAX_VICTIMS) out[(*nv)++] = cand[t];
+        }
+    }
+}
+
+/* candidates of one window cell (r, cc) of attacker a: visible, inside the grid, occupants in dict order that pass
+ * _basic_criteria; optionally only those with encoding enc_only (> 0) */
+static int cell_candidates(Ctx *c, int a, int R, const uint8_t *mask, int r, int cc, int *cand, int ncand)
+{
+    const int n = 2 * R + 1, r0 = c->cell[a] / c->W, c0 = c->cell[a] % c->W;
+    if (!mask[r * n + cc]) return ncand;
+    const int gr = r0 - R + r, gc = c0 - R + cc;
+    if (gr < 0 || gr >= c->H || gc < 0 || gc >= c->W) return ncand;          /* local_grid[r, c] is None */
+    for (uint16_t o = c->head[gr * c->W + gc]; o != NONE; o = c->next[o])
+        if (basic_criteria(c, a, o) && ncand < c->A) cand[ncand++] = o;
+    return ncand;
+}
+
+/* <Attack actor>._determine_attack + AttackActorBaseComponent.process_action (actor.py:306-361) for the four
+ * attack actors (:455-501 Binary, :521-582 EncodingBased, :601-658 RestrictedSelective, :681-728 Selective).
+ * `att` points at the attack bytes of the agent's action row (layout: bgw.h, bgw_step).  Returns attack_status;
+ * victims[0..*nv) receives attacked_agents (at most BGW_MAX_VICTIMS, possibly with repeats). */
+static int process_attack(Ctx *c, int a, const uint8_t *att, int *victims, int *nv)
 {
     const BgwSpec *sp = c->sp;
     *nv = 0;
     if (!(sp->klass[a] & BGW_AG_ATTACKING)) return 0;             /* actor.py:360-361 */
-    if (!attack) return 0;                                        /* actor.py:478-479 */
     const int R = sp->attack_range[a], n = 2 * R + 1;
-    const int r0 = c->cell[a] / c->W, c0 = c->cell[a] % c->W;
-    uint8_t *mask = los_mask_for(c, a, R, 0);
-    int ncand = 0, *cand = victims;   /* reuse caller storage for the candidate list */
-    for (int r = 0; r < n; ++r) for (int cc = 0; cc < n; ++cc) {  /* actor.py:489-496 */
-        if (!mask[r * n + cc]) continue;
-        const int gr = r0 - R + r, gc = c0 - R + cc;
-        if (gr < 0 || gr >= c->H || gc < 0 || gc >= c->W) continue;
-        for (uint16_t o = c->head[gr * c->W + gc]; o != NONE; o = c->next[o])
-            if (basic_criteria(c, a, o) && ncand < cap) cand[ncand++] = o;
-    }
-    if (ncand == 0) return 1;                                     /* actor.py:500-501 */
-    /* _subset_attackables actor.py:394-414 */
-    int k = attack;
-    if (!sp->stacked_attacks && k > ncand) {
-        k = ncand;                                                /* whole list, no draw */
-    } else if (sp->stacked_attacks) {
-        int *tmp = (int *)malloc(sizeof(int) * (size_t)k);
-        for (int t = 0; t < k; ++t)
-            tmp[t] = cand[bgw_index(draw(c, BGW_SITE_SUBSET, (uint32_t)a, (uint32_t)t), (uint32_t)ncand)];
-        for (int t = 0; t < k; ++t) cand[t] = tmp[t];
-        free(tmp);
-    } else {
-        /* choice without replacement == partial Fisher-Yates over the candidate list (replay shim
-         * implements np.random.choice(replace=False) the same way) */
-        for (int t = 0; t < k; ++t) {
-            int j = t + (int)bgw_index(draw(c, BGW_SITE_SUBSET, (uint32_t)a, (uint32_t)t), (uint32_t)(ncand - t));
-            int tmp = cand[t]; cand[t] = cand[j]; cand[j] = tmp;
+    int width = 1;
+    if (sp->attack_actor == BGW_ATTACK_ENCODING) width = c->max_enc;
+    else if (sp->attack_actor == BGW_ATTACK_RESTRICTED) width = sp->simultaneous_attacks[a];
+    else if (sp->attack_actor == BGW_ATTACK_SELECTIVE) width = n * n;
+    int any = 0;
+    for (int j = 0; j < width; ++j) any |= att[j];
+    if (!any) return 0;                                           /* actor.py:478-479,542-543,622-623,703-704 */
+    memset(c->acc_occ, 0, (size_t)c->A);
+    uint8_t *mask = los_mask_for(c, a, R, 0);                     /* gu.create_grid_and_mask */
+    int *cand = (int *)malloc(sizeof(int) * (size_t)(c->A + 1));
+    int ncand;
+    switch (sp->attack_actor) {
+    case BGW_ATTACK_BINARY:                                        /* actor.py:489-501 */
+        ncand = 0;
+        for (int r = 0; r < n; ++r) for (int cc = 0; cc < n; ++cc) ncand = cell_candidates(c, a, R, mask, r, cc, cand, ncand);
+        if (ncand) subset_attackables(c, a, 0, cand, ncand, att[0], victims, nv);
+        break;
+    case BGW_ATTACK_ENCODING: {                                    /* actor.py:554-582: one scan, one list per encoding */
+        int *all = (int *)malloc(sizeof(int) * (size_t)(c->A + 1));
+        int nall = 0;
+        for (int r = 0; r < n; ++r) for (int cc = 0; cc < n; ++cc) nall = cell_candidates(c, a, R, mask, r, cc, all, nall);
+        for (int enc = 1; enc <= c->max_enc; ++enc) {             /* `for encoding, num_attacks in attack.items()`, ascending */
+            if (!((sp->attack_map[sp->encoding[a]] >> enc) & 1)) continue;   /* not a key of the action space :513-519 */
+            ncand = 0;
+            for (int t = 0; t < nall; ++t) if (sp->encoding[all[t]] == enc) cand[ncand++] = all[t];
+            if (ncand == 0) continue;                              /* :576-577 */
+            subset_attackables(c, a, (uint32_t)enc, cand, ncand, att[enc - 1], victims, nv);
         }
+        free(all);
+        break;
     }
-    *nv = k;
+    case BGW_ATTACK_RESTRICTED:                                    /* actor.py:633-657 */
+        for (int j = 0; j < width; ++j) {
+            if (att[j] == 0) continue;                             /* :635-637 */
+            const int rav = att[j] - 1, r = rav % n, cc = rav / n; /* :641-643 (row = remainder, column = quotient) */
+            if (r >= n || cc >= n) continue;                       /* outside the action space */
+            int *all = (int *)malloc(sizeof(int) * (size_t)(c->A + 1));
+            const int nall = cell_candidates(c, a, R, mask, r, cc, all, 0);
+            ncand = 0;
+            for (int t = 0; t < nall; ++t) {                       /* :649-654 */
+                int seen = 0;
+                for (int q = 0; q < *nv; ++q) seen |= (victims[q] == all[t]);
+                if (seen && !sp->stacked_attacks) continue;
+                cand[ncand++] = all[t];
+            }
+            free(all);
+            if (ncand && *nv < BGW_MAX_VICTIMS) {                  /* np.random.choice(attackable_agents) :655-656 */
+                const uint32_t x = draw(c, BGW_SITE_SUBSET, (uint32_t)a, (uint32_t)*nv << 8);
+                victims[(*nv)++] = cand[bgw_index(x, (uint32_t)ncand)];
+            }
+        }
+        break;
+    case BGW_ATTACK_SELECTIVE:                                     /* actor.py:711-727 */
+        for (int r = 0; r < n; ++r) for (int cc = 0; cc < n; ++cc) {
+            if (!att[r * n + cc]) continue;
+            ncand = cell_candidates(c, a, R, mask, r, cc, cand, 0);
+            if (ncand) subset_attackables(c, a, (uint32_t)(r * n + cc), cand, ncand, att[r * n + cc], victims, nv);
+        }
+        break;
+    default: break;
+    }
+    free(cand);
+    /* ammo filter actor.py:343-351 */
+    if ((sp->klass[a] & BGW_AG_AMMO) && c->ammo) {
+        int ammo = c->ammo[a];
+        if (*nv > ammo) {                                          /* choice(size=ammo, replace=False): partial Fisher-Yates */
+            for (int t = 0; t < ammo; ++t) {
+                int j = t + (int)bgw_index(draw(c, BGW_SITE_AMMO, (uint32_t)a, (uint32_t)t), (uint32_t)(*nv - t));
+                int tmp = victims[t]; victims[t] = victims[j]; victims[j] = tmp;
+            }
+            *nv = ammo;
+        }
+        ammo -= *nv;
+        c->ammo[a] = ammo < 0 ? 0 : ammo;                          /* setter agent.py:306-309 */
+    }
     /* actor.py:353-358 */
-    for (int t = 0; t < k; ++t) {
+    for (int t = 0; t < *nv; ++t) {
         const int v = victims[t];
         if (!(c->flags[v] & BGW_ST_ACTIVE)) continue;
         set_health(c, v, c->health[v] - sp->attack_strength[a]);
@@ -542,15 +649,15 @@ static void prog_step(Ctx *c, const int *acting, int n_act, const int8_t *action
 {
     const BgwSpec *sp = c->sp;
     const double *rw = sp->reward;
-#define ACT(a) (actions + (size_t)c->learner_of[(a)] * 4)
+#define ACT(a) (actions + (size_t)c->learner_of[(a)] * c->astride)
     switch (sp->program) {
     case BGW_PROG_TEAM_BATTLE: {                               /* team_battle_example.py:33-59 */
-        int *victims = (int *)malloc(sizeof(int) * (size_t)(c->A + 8));
+        int victims[BGW_MAX_VICTIMS + 1];
         for (int i = 0; i < n_act; ++i) {                      /* :35-47 */
             const int a = acting[i];
             if (!(c->flags[a] & BGW_ST_ACTIVE)) continue;
             int nv = 0;
-            const int status = process_attack(c, a, ACT(a)[2], victims, &nv, c->A);
+            const int status = process_attack(c, a, (const uint8_t *)ACT(a) + 2, victims, &nv);
             if (status) {
                 if (nv == 0) c->racc[a] += rw[BGW_RW_ATTACK_FAIL];
                 else for (int t = 0; t < nv; ++t)
@@ -560,7 +667,6 @@ static void prog_step(Ctx *c, const int *acting, int n_act, const int8_t *action
                     }
             }
         }
-        free(victims);
         for (int i = 0; i < n_act; ++i) {                      /* :50-55 */
             const int a = acting[i];
             if (!(c->flags[a] & BGW_ST_ACTIVE)) continue;
@@ -667,6 +773,7 @@ static void sim_reset(Ctx *c)
             c->flags[a] = (uint8_t)((c->flags[a] & 0x8F) | (o << BGW_ST_ORIENT_SHIFT));
         }
         if (!(sp->klass[a] & BGW_AG_LEARNER)) c->flags[a] |= BGW_ST_DONE_REPORTED;  /* all_step_manager.py:41-44 */
+        if (c->ammo) c->ammo[a] = (sp->klass[a] & BGW_AG_AMMO) && sp->initial_ammo ? sp->initial_ammo[a] : 0;   /* AmmoState.reset state.py:649-656 */
     }
 }
 
@@ -685,6 +792,8 @@ static void ctx_init(Ctx *c, const BgwSpec *sp, BgwState *st)
     c->prev = (uint16_t *)malloc(sizeof(uint16_t) * (size_t)c->A);
     c->learner_of = (int *)malloc(sizeof(int) * (size_t)c->A);
     c->agent_of = (int *)malloc(sizeof(int) * (size_t)(c->L + 1));
+    c->acc_occ = (uint8_t *)calloc((size_t)c->A + 1, 1);
+    c->astride = action_stride_of(sp);
     int l = 0;
     for (int a = 0; a < c->A; ++a) {
         if (sp->klass[a] & BGW_AG_LEARNER) { c->learner_of[a] = l; c->agent_of[l++] = a; }
@@ -694,7 +803,7 @@ static void ctx_init(Ctx *c, const BgwSpec *sp, BgwState *st)
 
 static void ctx_free(Ctx *c)
 {
-    free(c->head); free(c->tail); free(c->prev); free(c->learner_of); free(c->agent_of); free(c->mask);
+    free(c->head); free(c->tail); free(c->prev); free(c->learner_of); free(c->agent_of); free(c->mask); free(c->acc_occ);
 }
 
 static void ctx_env(Ctx *c, int e)
@@ -703,6 +812,7 @@ static void ctx_env(Ctx *c, int e)
     const size_t off = (size_t)e * c->A;
     c->cell = c->st->cell + off; c->next = c->st->next + off; c->flags = c->st->flags + off;
     c->health = c->st->health + off; c->racc = c->st->reward_acc + off;
+    c->ammo = c->st->ammo ? c->st->ammo + off : NULL;
 }
 
 /* reset one env + first observations (AllStepManager.reset all_step_manager.py:37-49,
@@ -759,7 +869,7 @@ int bgwo_step(const BgwSpec *sp, BgwState *st, const int8_t *actions, const int1
         float *rew = reward ? reward + (size_t)e * L : NULL;
         double *rew64 = reward64 ? reward64 + (size_t)e * L : NULL;
         uint8_t *dn = done + (size_t)e * L;
-        const int8_t *act = actions + (size_t)e * L * 4;
+        const int8_t *act = actions + (size_t)e * L * c.astride;
         for (int l = 0; l < L; ++l) { dn[l] = 0; if (rew) rew[l] = 0.f; if (rew64) rew64[l] = 0.0; }
 
         if (st->env_flags[e] & BGW_ENV_ALL_DONE) {
@@ -850,16 +960,16 @@ int bgwo_observe(const BgwSpec *sp, BgwState *st, int env, int8_t *obs_env)
  * stream: one Philox block per (env, step, agent); words 0,1 -> move, word 2 -> attack. */
 int bgwo_sample_actions(const BgwSpec *sp, const BgwState *st, int8_t *actions)
 {
-    const int A = sp->n_agents, L = count_learners(sp);
+    const int A = sp->n_agents, L = count_learners(sp), stride = action_stride_of(sp), menc = max_encoding(sp);
     for (int e = 0; e < sp->n_envs; ++e) {
         int l = 0;
         for (int a = 0; a < A; ++a) {
             if (!(sp->klass[a] & BGW_AG_LEARNER)) continue;
-            int8_t *o = actions + ((size_t)e * L + l) * 4;
+            int8_t *o = actions + ((size_t)e * L + l) * stride;
             ++l;
             uint32_t x[4];
             bgw_draw4(sp->seed, (uint32_t)(sp->env_offset + e), st->episode[e], st->step[e], BGW_SITE_ACTION, (uint32_t)a, 0, x);
-            o[0] = o[1] = o[2] = o[3] = 0;
+            memset(o, 0, (size_t)stride);
             if (sp->klass[a] & BGW_AG_MOVING) {
                 if (sp->move_actor == BGW_MOVE_BOX) {            /* Box(-m, m, (2,), int) actor.py:63-65 */
                     const int m = sp->move_range[a], w = 2 * m + 1;
@@ -870,12 +980,33 @@ int bgwo_sample_actions(const BgwSpec *sp, const BgwState *st, int8_t *actions)
                     o[0] = (int8_t)bgw_index(x[0], 5);
                 }
             }
-            if ((sp->klass[a] & BGW_AG_ATTACKING) && sp->attack_actor != BGW_ATTACK_NONE)
-                o[2] = (int8_t)bgw_index(x[2], (uint32_t)sp->simultaneous_attacks[a] + 1);   /* Discrete(n+1) actor.py:452 */
+            if (!(sp->klass[a] & BGW_AG_ATTACKING) || sp->attack_actor == BGW_ATTACK_NONE) continue;
+            const uint32_t sim = sp->simultaneous_attacks[a];
+            if (sp->attack_actor == BGW_ATTACK_BINARY) {
+                o[2] = (int8_t)bgw_index(x[2], sim + 1);         /* Discrete(n+1) actor.py:452 */
+                continue;
+            }
+            /* wider attack actions: attack byte j draws word j%4 of the block k = 1 + j/4 */
+            const int n = 2 * sp->attack_range[a] + 1;
+            const int width = sp->attack_actor == BGW_ATTACK_ENCODING ? menc : sp->attack_actor == BGW_ATTACK_RESTRICTED ? (int)sim : n * n;
+            for (int j = 0; j < width; ++j) {
+                if ((j & 3) == 0) bgw_draw4(sp->seed, (uint32_t)(sp->env_offset + e), st->episode[e], st->step[e], BGW_SITE_ACTION, (uint32_t)a, 1u + ((uint32_t)j >> 2), x);
+                uint32_t v;
+                if (sp->attack_actor == BGW_ATTACK_ENCODING)      /* Dict{enc: Discrete(n+1)} actor.py:513-519 */
+                    v = ((sp->attack_map[sp->encoding[a]] >> (j + 1)) & 1) ? bgw_index(x[j & 3], sim + 1) : 0;
+                else if (sp->attack_actor == BGW_ATTACK_RESTRICTED)   /* MultiDiscrete([cells+1]*n) actor.py:593-599 */
+                    v = bgw_index(x[j & 3], (uint32_t)(n * n) + 1);
+                else                                              /* Box(0, n, (w, w)) actor.py:669-679 */
+                    v = bgw_index(x[j & 3], sim + 1);
+                o[2 + j] = (int8_t)(uint8_t)v;
+            }
         }
     }
     return 0;
 }
+
+/* sizeof the three ABI structs as this C compiler lays them out (tests/test_capi.py checks the ctypes mirrors) */
+int bgwo_sizeof(int which) { return which == 0 ? (int)sizeof(BgwSpec) : which == 1 ? (int)sizeof(BgwState) : (int)sizeof(BgwDims); }
 
 /* host-callable draw, same stream as include/bgw_philox.h (used by the replay shim and the Philox KATs) */
 int bgwo_rng_draw(uint64_t seed, uint32_t env, uint32_t episode, uint32_t step, uint32_t site, uint32_t slot,

@@ -48,6 +48,7 @@ def alloc_state(E, A):
     st['turn'][:] = -1
     st['stats'] = np.zeros((E, K.BGW_STAT_COUNT), dtype=np.uint64)
     st['layout'] = None
+    st['ammo'] = np.zeros((E, A), dtype=np.int32)
     return st
 
 
@@ -76,7 +77,7 @@ class OracleEnv:
     def _state_struct(self):
         s = K.BgwState()
         for name in ('cell', 'next', 'flags', 'health', 'reward_acc', 'episode', 'step', 'env_flags', 'turn',
-                     'error', 'layout', 'stats'):
+                     'error', 'layout', 'stats', 'ammo'):
             setattr(s, name, _ptr(self.state[name]))
         return s
 
@@ -90,14 +91,14 @@ class OracleEnv:
         return self.obs
 
     def sample_actions(self):
-        act = np.zeros((self.E, self.L, 4), dtype=np.int8)
+        act = np.zeros((self.E, self.L, self.dims.action_stride), dtype=np.int8)
         s = self._state_struct()
         lib().bgwo_sample_actions(C.byref(self._c), C.byref(s), _ptr(act))
         return act
 
     def step(self, actions, order=None):
         actions = np.ascontiguousarray(actions, dtype=np.int8)
-        assert actions.shape == (self.E, self.L, 4)
+        assert actions.shape == (self.E, self.L, self.dims.action_stride)
         o = None if order is None else np.ascontiguousarray(order, dtype=np.int16)
         s = self._state_struct()
         lib().bgwo_step(C.byref(self._c), C.byref(s), _ptr(actions), _ptr(o), _ptr(self.obs), _ptr(self.reward),

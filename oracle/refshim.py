@@ -42,6 +42,7 @@ class PhiloxReplay:
         self.index = {agent_id: i for i, agent_id in enumerate(sim.agents)}
         self.episode, self.step = -1, 0
         self.maze_k, self.maze_episode = 0, None                  # position in the episode's maze draw sequence
+        self.acc_seen = {}                  # (episode, step, attacker, candidate) -> evaluations so far (ACC draw key)
         self.log = []                       # (site, slot, k) of every replayed draw, for debugging
 
     # -- keyed draw -------------------------------------------------------------------------------
@@ -55,7 +56,13 @@ class PhiloxReplay:
         name, loc = f.f_code.co_name, f.f_locals
         assert size is None
         if name == '_basic_criteria':                        # actor.py:388
-            x = self._x(K.SITE_ACC, self.index[loc['attacking_agent'].id], self.index[loc['candidate'].id])
+            att, cand = self.index[loc['attacking_agent'].id], self.index[loc['candidate'].id]
+            key = (self.episode, self.step, att, cand)
+            occ = self.acc_seen.get(key, 0)                  # only RestrictedSelective evaluates a pair twice
+            if len(self.acc_seen) > 4096:
+                self.acc_seen.clear()
+            self.acc_seen[key] = occ + 1
+            x = self._x(K.SITE_ACC, att, cand + 4096 * occ)
         elif name == 'reset' and 'agent' in loc:             # HealthState.reset state.py:641
             x = self._x(K.SITE_HEALTH, self.index[loc['agent'].id])
         else:
@@ -74,19 +81,43 @@ class PhiloxReplay:
             x = self._x(K.SITE_PLACE, self.index[loc['var_agent_to_place'].id])
             return np.array([seq[philox.index(x, n)]])
         if name == '_subset_attackables':                    # actor.py:412
-            attacker = sys._getframe(2).f_locals['agent']    # _determine_attack(self, agent, attack)
+            outer = sys._getframe(2).f_locals                # _determine_attack(self, agent, attack)
+            attacker = outer['agent']
             slot = self.index[attacker.id]
+            actor = type(outer['self']).__name__
+            if actor == 'EncodingBasedAttackActor':          # one call per encoding :575-581
+                group = int(outer['encoding'])
+            elif actor == 'SelectiveAttackActor':            # one call per attacked cell :711-726
+                group = int(outer['r']) * (2 * attacker.attack_range + 1) + int(outer['c'])
+            else:
+                group = 0
+            size = int(size)
             out = np.empty(size, dtype=object)
             if replace:
                 for t in range(size):
-                    out[t] = seq[philox.index(self._x(K.SITE_SUBSET, slot, t), n)]
+                    out[t] = seq[philox.index(self._x(K.SITE_SUBSET, slot, (group << 8) | t), n)]
             else:                                            # partial Fisher-Yates, as the oracle/engine
                 if size > n:
                     raise ValueError("Cannot take a larger sample than population when 'replace=False'")
                 for t in range(size):
-                    j = t + philox.index(self._x(K.SITE_SUBSET, slot, t), n - t)
+                    j = t + philox.index(self._x(K.SITE_SUBSET, slot, (group << 8) | t), n - t)
                     seq[t], seq[j] = seq[j], seq[t]
                     out[t] = seq[t]
+            return out
+        if name == '_determine_attack':                      # RestrictedSelectiveAttackActor actor.py:655-656
+            assert size is None
+            slot = self.index[loc['agent'].id]
+            group = len(loc['attacked_agents'])
+            return seq[philox.index(self._x(K.SITE_SUBSET, slot, group << 8), n)]
+        if name == 'process_action':                         # ammo filter actor.py:346-350
+            assert not replace
+            slot = self.index[loc['attacking_agent'].id]
+            size = int(size)
+            out = np.empty(size, dtype=object)
+            for t in range(size):
+                j = t + philox.index(self._x(K.SITE_AMMO, slot, t), n - t)
+                seq[t], seq[j] = seq[j], seq[t]
+                out[t] = seq[t]
             return out
         if name == 'get_obs':                                # observer.py:131,234,246
             agent = loc['agent']
@@ -145,7 +176,10 @@ def extract_state(sim, done_agents=()):
     nxt = np.full(A, K.BGW_NONE, dtype=np.uint16)
     flags = np.zeros(A, dtype=np.uint8)
     health = np.zeros(A, dtype=np.float64)
+    ammo = np.zeros(A, dtype=np.int32)
     for i, agent in enumerate(sim.agents.values()):
+        if hasattr(agent, 'initial_ammo'):
+            ammo[i] = int(getattr(agent, '_ammo', 0))
         pos = getattr(agent, 'position', None)
         if pos is not None:
             cell[i] = int(pos[0]) * cols + int(pos[1])
@@ -167,4 +201,4 @@ def extract_state(sim, done_agents=()):
                 flags[a] |= K.ST_IN_GRID
                 assert cell[a] == r * cols + c, "grid / position mismatch in the reference sim"
                 nxt[a] = order[j + 1] if j + 1 < len(order) else K.BGW_NONE
-    return dict(cell=cell, next=nxt, flags=flags, health=health)
+    return dict(cell=cell, next=nxt, flags=flags, health=health, ammo=ammo)

@@ -46,19 +46,33 @@ def action_dict(spec, sim, done_agents, act, only=None):
             else:
                 d['move'] = int(np.uint8(act[l, 0]))
         if 'attack' in agent.action_space.spaces:
-            d['attack'] = int(act[l, 2])
+            att = act[l, 2:].view(np.uint8).astype(int)
+            n = 2 * int(getattr(agent, 'attack_range', 0)) + 1
+            if spec.attack_actor == K.ATTACK_ENCODING:        # {encoding: count}, ascending (actor.py:513-519)
+                d['attack'] = {int(enc): int(att[enc - 1]) for enc in sorted(agent.action_space.spaces['attack'].spaces)}
+            elif spec.attack_actor == K.ATTACK_RESTRICTED:     # actor.py:593-599
+                d['attack'] = att[:agent.simultaneous_attacks].copy()
+            elif spec.attack_actor == K.ATTACK_SELECTIVE:      # actor.py:669-679
+                d['attack'] = att[:n * n].reshape(n, n).copy()
+            else:
+                d['attack'] = int(att[0])
         out[agent_id] = d
     return out
 
 
-def ref_obs_rows(spec, ref_obs, stride):
-    """reference obs dict -> (rows [L, stride] int8 zero padded, present [L] bool)"""
+def ref_obs_rows(spec, ref_obs, stride, ammo_offset=-1):
+    """reference obs dict -> (rows [L, stride] int8 zero padded, present [L] bool); the AmmoObserver's 'ammo' entry
+    (observer.py:406-413) goes to the int32 slot at ammo_offset"""
     rows = np.zeros((spec.n_learners, stride), dtype=np.int8)
     present = np.zeros(spec.n_learners, dtype=bool)
     for l, a in enumerate(spec.learner_agents):
         agent_id = spec.agent_ids[a]
         if agent_id in ref_obs:
-            (key, arr), = ref_obs[agent_id].items()
+            entries = dict(ref_obs[agent_id])
+            if 'ammo' in entries:
+                assert ammo_offset >= 0
+                rows[l, ammo_offset:ammo_offset + 4] = np.array([entries.pop('ammo')], dtype=np.int32).view(np.int8)
+            (key, arr), = entries.items()
             assert arr.min() >= -128 and arr.max() <= 127
             flat = np.asarray(arr).astype(np.int8).ravel()
             rows[l, :flat.size] = flat
@@ -79,11 +93,11 @@ def record(name, builder, manager, n_steps):
     mgr = {'all_step': api.managers.AllStepManager, 'turn_based': api.managers.TurnBasedManager}[manager](sim)
     spec = compile_sim(sim, manager=manager, n_envs=1, seed=SEED, auto_reset=False)
     ora = OracleEnv(spec)
-    L, stride = spec.n_learners, ora.dims.obs_stride
+    L, stride, astride, ammo_off = spec.n_learners, ora.dims.obs_stride, ora.dims.action_stride, ora.dims.ammo_offset
     learner_ids = spec.learner_ids
 
     rec = {k: [] for k in ('kind', 'actions', 'obs', 'obs_present', 'reward', 'done', 'all_done', 'cell', 'next',
-                           'flags', 'health')}
+                           'flags', 'health', 'ammo')}
 
     def snapshot(kind, act, obs_rows, present, reward, done, all_done):
         st = extract_state(sim, mgr.done_agents)
@@ -94,7 +108,7 @@ def record(name, builder, manager, n_steps):
         rec['reward'].append(reward)
         rec['done'].append(done)
         rec['all_done'].append(all_done)
-        for k in ('cell', 'next', 'flags', 'health'):
+        for k in ('cell', 'next', 'flags', 'health', 'ammo'):
             rec[k].append(st[k])
         return st
 
@@ -105,6 +119,7 @@ def record(name, builder, manager, n_steps):
         check(name, 'cell', t, o['cell'][0], st['cell'])
         check(name, 'next(in grid)', t, o['next'][0][in_grid], st['next'][in_grid])
         check(name, 'health', t, o['health'][0], st['health'])
+        check(name, 'ammo', t, o['ammo'][0], st['ammo'])
 
     with PhiloxReplay(sim, SEED) as rp:
         t = 0
@@ -117,8 +132,8 @@ def record(name, builder, manager, n_steps):
                     ora.set_layout(layouts_for(spec, [0], [rp.episode]))
                 ref_obs = mgr.reset()
                 ora.reset()
-                rows, present = ref_obs_rows(spec, ref_obs, stride)
-                st = snapshot(0, np.zeros((L, 4), np.int8), rows, present, np.zeros(L), np.zeros(L, np.uint8), 0)
+                rows, present = ref_obs_rows(spec, ref_obs, stride, ammo_off)
+                st = snapshot(0, np.zeros((L, astride), np.int8), rows, present, np.zeros(L), np.zeros(L, np.uint8), 0)
                 compare_state(t, st)
                 check(name, 'reset obs', t, ora.obs[0][present], rows[present])
                 need_reset = False
@@ -128,7 +143,7 @@ def record(name, builder, manager, n_steps):
             only = int(ora.state['turn'][0]) if manager == 'turn_based' else None
             ref_obs, ref_rew, ref_done, _ = mgr.step(action_dict(spec, sim, mgr.done_agents, act, only))
             ora.step(act[None])
-            rows, present = ref_obs_rows(spec, ref_obs, stride)
+            rows, present = ref_obs_rows(spec, ref_obs, stride, ammo_off)
             reward = np.zeros(L)
             done = np.zeros(L, np.uint8)
             for l, agent_id in enumerate(learner_ids):
@@ -145,6 +160,9 @@ def record(name, builder, manager, n_steps):
             check(name, '__all__', t, int(ora.all_done[0] & K.ENV_ALL_DONE), all_done)
             need_reset = bool(all_done)
         n_draws = len(rp.log)
+        n_ammo_draws = sum(1 for site, _, _ in rp.log if site == K.SITE_AMMO)
+        n_repeat_acc = sum(1 for site, _, k in rp.log if site == K.SITE_ACC and k >= 4096)
+        n_multi_subset = sum(1 for site, _, k in rp.log if site == K.SITE_SUBSET and (k & 0xFF) > 0)
 
     out = {k: np.stack(v) for k, v in rec.items()}
     out['seed'] = np.uint64(SEED)
@@ -157,7 +175,8 @@ def record(name, builder, manager, n_steps):
     path = os.path.join(OUT, name + '.npz')
     np.savez_compressed(path, **out)
     resets = int((out['kind'] == 0).sum())
-    print(f"{name}: {n_steps} steps, {resets} episodes, {n_draws} replayed draws, "
+    print(f"{name}: {n_steps} steps, {resets} episodes, {n_draws} replayed draws ({n_ammo_draws} ammo-filter, "
+          f"{n_repeat_acc} repeated-pair accuracy, {n_multi_subset} 2nd+ subset), "
           f"{int(out['done'].astype(bool).sum())} agent-steps -> {os.path.getsize(path) / 1024:.0f} KiB   oracle == reference")
 
 

@@ -3,7 +3,7 @@ import numpy as np
 
 from abmarl_b200 import _capi as K
 
-STATE_KEYS = ('flags', 'cell', 'health', 'reward_acc', 'episode', 'step', 'env_flags', 'turn', 'error', 'stats')
+STATE_KEYS = ('flags', 'cell', 'health', 'reward_acc', 'episode', 'step', 'env_flags', 'turn', 'error', 'stats', 'ammo')
 
 
 def assert_state_equal(eng_state, ora_state, where):

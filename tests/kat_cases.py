@@ -12,15 +12,15 @@ import numpy as np
 from abmarl_b200 import _capi as K
 from abmarl_b200.spec import CompiledSpec
 
-OBS, MOV, ATT, HEA, ORI, LRN, BLK = (K.AG_OBSERVING, K.AG_MOVING, K.AG_ATTACKING, K.AG_HEALTH, K.AG_ORIENT,
-                                     K.AG_LEARNER, K.AG_BLOCKING)
+OBS, MOV, ATT, HEA, ORI, LRN, BLK, AMM = (K.AG_OBSERVING, K.AG_MOVING, K.AG_ATTACKING, K.AG_HEALTH, K.AG_ORIENT,
+                                          K.AG_LEARNER, K.AG_BLOCKING, K.AG_AMMO)
 
 
 def make_spec(rows, cols, agents, overlapping=None, attack_mapping=None, program=K.PROG_TEAM_BATTLE,
               move_actor=K.MOVE_BOX, attack_actor=K.ATTACK_NONE, observer=K.OBS_POSITION_CENTERED, observe_self=True,
               done_mask=K.DONE_ACTIVE, manager=K.MANAGER_ALL_STEP, ravel=False, stacked=False, n_envs=1, seed=24):
     """agents: list of dicts(enc, pos=(r, c) | None, klass, view=0, move=0, att_range=0, strength=0, accuracy=1,
-    health=None | float, orient=0)."""
+    health=None | float, orient=0, simatt=1, ammo=0)."""
     sp = CompiledSpec()
     sp.rows, sp.cols, sp.n_agents, sp.n_envs, sp.seed = rows, cols, len(agents), n_envs, seed
     sp.program, sp.move_actor, sp.attack_actor, sp.observer = program, move_actor, attack_actor, observer
@@ -42,7 +42,8 @@ def make_spec(rows, cols, agents, overlapping=None, attack_mapping=None, program
             sp.init_row[i], sp.init_col[i] = a['pos']
         sp.view_range[i], sp.move_range[i] = a.get('view', 0), a.get('move', 0)
         sp.attack_range[i], sp.attack_strength[i] = a.get('att_range', 0), a.get('strength', 0)
-        sp.attack_accuracy[i], sp.simultaneous_attacks[i] = a.get('accuracy', 1), 1 if a['klass'] & ATT else 0
+        sp.attack_accuracy[i], sp.simultaneous_attacks[i] = a.get('accuracy', 1), a.get('simatt', 1) if a['klass'] & ATT else 0
+        sp.initial_ammo[i] = a.get('ammo', 0)
         if a.get('health') is not None:
             sp.init_health[i] = a['health']
         sp.init_orient[i] = a.get('orient', 0)
@@ -86,7 +87,7 @@ class Backend:
         self.env.reset()
 
     def step(self, actions):
-        act = np.zeros((1, self.L, 4), dtype=np.int8)
+        act = np.zeros((1, self.L, self.env.dims.action_stride), dtype=np.int8)
         for l, a in enumerate(actions):
             a = (a,) if np.isscalar(a) else a
             for j, v in enumerate(a):
@@ -127,6 +128,9 @@ class Backend:
     def health(self):
         return self.state()['health'][0]
 
+    def ammo(self):
+        return self.state()['ammo'][0]
+
     def set_flags(self, agent, clear=0):
         st = {k: (None if v is None else np.array(v)) for k, v in self.state().items()}
         st['flags'][0, agent] &= ~np.uint8(clear)
@@ -143,7 +147,7 @@ class Backend:
             self.env.obs[0] = self.env.observe(0)
         else:
             import torch
-            self.env.step(torch.zeros((1, self.L, 4), dtype=torch.int8, device='cuda'))
+            self.env.step(torch.zeros((1, self.L, self.env.dims.action_stride), dtype=torch.int8, device='cuda'))
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -244,6 +248,125 @@ def case_stacked_attack_exact_health(kind):                  # test_actor.py:701
     assert be.health()[2] == 0.5 and be.flags()[2] & K.ST_ACTIVE
     be.step([(0, 0, 1)])
     assert be.health()[2] == 0.0 and not be.flags()[2] & K.ST_IN_GRID
+
+
+def _sel(*cells, n=5):
+    """(move 0, 0) + an n x n SelectiveAttackActor action with one attack on each listed window cell"""
+    m = np.zeros((n, n), dtype=int)
+    for r, c in cells:
+        m[r, c] += 1
+    return (0, 0) + tuple(m.ravel())
+
+
+def _selective_agents(**attacker):
+    return [dict(enc=1, pos=(4, 4), klass=HEA),
+            dict(enc=1, pos=(2, 2), klass=LRN | OBS | ATT | attacker.pop('klass', 0), att_range=2, strength=1, accuracy=1, view=1, **attacker),
+            dict(enc=2, pos=(2, 3), klass=HEA), dict(enc=1, pos=(3, 2), klass=HEA)]
+
+
+def case_selective_attack_actor(kind):                       # test_actor.py:724-882
+    be = Backend(make_spec(5, 6, _selective_agents(), attack_mapping={1: {1}}, attack_actor=K.ATTACK_SELECTIVE), kind)
+    everywhere = [(r, c) for r in range(5) for c in range(5)]
+    alive = lambda: [bool(f & K.ST_ACTIVE) and bool(f & K.ST_IN_GRID) for f in be.flags()]
+    be.reset()
+    be.step([_sel((4, 4))])                                   # attacking agent0
+    np.testing.assert_allclose(be.rewards(), [1 - 0.1 - 0.01], atol=1e-6)
+    assert alive() == [False, True, True, True] and be.health()[0] <= 0
+    be.step([_sel((3, 2))])                                   # attacking agent3
+    np.testing.assert_allclose(be.rewards(), [1 - 0.1 - 0.01], atol=1e-6)
+    assert alive() == [False, True, True, False] and be.health()[3] <= 0
+    be.reset()
+    be.step([_sel((3, 2), (4, 4))])                           # both at once
+    np.testing.assert_allclose(be.rewards(), [2 - 0.1 - 0.01], atol=1e-6)
+    assert alive() == [False, True, True, False]
+    be.reset()
+    be.step([_sel(*[rc for rc in everywhere if rc not in ((3, 2), (4, 4))])])   # everywhere but agent0 / agent3
+    np.testing.assert_allclose(be.rewards(), [-0.1 - 0.1 - 0.01], atol=1e-6)   # attempted, nobody attacked
+    assert alive() == [True, True, True, True]
+    be.step([_sel(*everywhere)])                              # everywhere: agent2 (encoding 2) is not attackable
+    np.testing.assert_allclose(be.rewards(), [2 - 0.1 - 0.01], atol=1e-6)
+    assert alive() == [False, True, True, False]
+    be.reset()
+    be.step([_sel()])                                         # nowhere: no attack attempted
+    np.testing.assert_allclose(be.rewards(), [-0.1 - 0.01], atol=1e-6)
+    assert alive() == [True, True, True, True]
+
+
+def case_selective_attack_actor_ammo(kind):                  # test_actor.py:885-987
+    spec = make_spec(5, 6, _selective_agents(klass=AMM, ammo=3), attack_mapping={1: {1}}, attack_actor=K.ATTACK_SELECTIVE)
+    be = Backend(spec, kind)
+    be.reset()
+    assert be.ammo()[1] == 3
+    be.step([_sel((4, 4))])
+    assert be.ammo()[1] == 2 and not be.flags()[0] & K.ST_ACTIVE
+    be.step([_sel((3, 2))])
+    assert be.ammo()[1] == 1 and not be.flags()[3] & K.ST_ACTIVE
+    # "attacking both agent0 and agent3" with one round left, then everywhere with none (:957-986)
+    be = Backend(make_spec(5, 6, _selective_agents(klass=AMM, ammo=1), attack_mapping={1: {1}}, attack_actor=K.ATTACK_SELECTIVE), kind)
+    be.reset()
+    be.step([_sel((3, 2), (4, 4))])
+    np.testing.assert_allclose(be.rewards(), [1 - 0.1 - 0.01], atol=1e-6)      # len(attacked_agents) == 1
+    assert be.ammo()[1] == 0
+    assert sorted(bool(be.flags()[a] & K.ST_ACTIVE) for a in (0, 3)) == [False, True]
+    be.step([_sel(*[(r, c) for r in range(5) for c in range(5)])])
+    np.testing.assert_allclose(be.rewards(), [-0.1 - 0.1 - 0.01], atol=1e-6)   # attack_status, not attacked_agents
+    assert be.ammo()[1] == 0
+
+
+def _enc_attackers(strength):
+    return [dict(enc=1, pos=(0, 0), klass=HEA), dict(enc=2, pos=(0, 1), klass=HEA), dict(enc=2, pos=(1, 0), klass=HEA),
+            dict(enc=3, pos=(1, 1), klass=LRN | OBS | ATT | AMM, att_range=1, strength=strength, accuracy=1, view=1, ammo=100),
+            dict(enc=1, pos=(1, 1), klass=HEA)]
+
+
+def case_encoding_based_attack_actor(kind):                  # test_actor.py:1175-1247
+    kw = dict(overlapping={1: {3}, 3: {1}}, attack_mapping={3: {1, 2}}, attack_actor=K.ATTACK_ENCODING)
+    be = Backend(make_spec(2, 2, _enc_attackers(0), **kw), kind)   # "should still be active because attacking agent is weak"
+    be.reset()
+    be.step([(0, 0, 0, 1)])                                   # {1: 0, 2: 1}
+    np.testing.assert_allclose(be.rewards(), [-0.1 - 0.01], atol=1e-6)          # one agent attacked, none killed
+    assert be.ammo()[3] == 99 and all(f & K.ST_ACTIVE for f in be.flags())
+    be = Backend(make_spec(2, 2, _enc_attackers(1), **kw), kind)
+    be.reset()
+    dead = lambda: [a for a in range(5) if not be.flags()[a] & K.ST_ACTIVE]
+    be.step([(0, 0, 1, 0)])                                   # {1: 1, 2: 0}: one of the two encoding-1 agents
+    np.testing.assert_allclose(be.rewards(), [1 - 0.1 - 0.01], atol=1e-6)
+    assert len(dead()) == 1 and dead()[0] in (0, 4)
+    be.step([(0, 0, 1, 1)])                                   # the other encoding 1 and one encoding 2
+    np.testing.assert_allclose(be.rewards(), [2 - 0.1 - 0.01], atol=1e-6)
+    assert len(dead()) == 3 and {0, 4} <= set(dead())
+    be.step([(0, 0, 1, 1)])                                   # only an encoding 2 is left
+    np.testing.assert_allclose(be.rewards(), [1 - 0.1 - 0.01], atol=1e-6)
+    assert dead() == [0, 1, 2, 4]
+    be.step([(0, 0, 1, 1)])                                   # attack_status True, len(attacked_agents) == 0
+    np.testing.assert_allclose(be.rewards(), [-0.1 - 0.1 - 0.01], atol=1e-6)
+    assert be.ammo()[3] == 96
+
+
+def case_restricted_selective_attack_actor(kind):            # test_actor.py:1505-1573 (+ stacked :1576-1645)
+    agents = [dict(enc=1, pos=(0, 0), klass=HEA), dict(enc=2, pos=(0, 1), klass=HEA), dict(enc=2, pos=(1, 0), klass=HEA),
+              dict(enc=3, pos=(1, 1), klass=LRN | OBS | ATT | AMM, att_range=1, strength=0, accuracy=1, view=1, simatt=2, ammo=100),
+              dict(enc=1, pos=(0, 0), klass=HEA)]
+    kw = dict(overlapping={1: {1}}, attack_mapping={3: {1, 2}}, attack_actor=K.ATTACK_RESTRICTED)
+    be = Backend(make_spec(2, 2, agents, **kw), kind)
+    be.reset()
+    be.step([(0, 0, 0, 0)])                                   # [0, 0]: not attack_status
+    np.testing.assert_allclose(be.rewards(), [-0.1 - 0.01], atol=1e-6)
+    assert be.ammo()[3] == 100
+    be.step([(0, 0, 1, 1)])                                   # twice the cell (0, 0): two different encoding-1 agents
+    np.testing.assert_allclose(be.rewards(), [-0.1 - 0.01], atol=1e-6)
+    assert be.ammo()[3] == 98
+    be.step([(0, 0, 2, 2)])                                   # twice the cell (1, 0): its one agent only once
+    assert be.ammo()[3] == 97
+    be.step([(0, 0, 1, 4)])                                   # cells (0, 0) and (0, 1)
+    assert be.ammo()[3] == 95
+    be.step([(0, 0, 5, 9)])                                   # own cell and an off-grid cell: attempted, nobody attacked
+    np.testing.assert_allclose(be.rewards(), [-0.1 - 0.1 - 0.01], atol=1e-6)
+    assert be.ammo()[3] == 95
+    be = Backend(make_spec(2, 2, agents, stacked=True, **kw), kind)   # stacked_attacks: the same agent may be named twice
+    be.reset()
+    be.step([(0, 0, 2, 2)])
+    assert be.ammo()[3] == 98
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -143,6 +143,77 @@ def build_tb_noself(api):
 
 
 # ---------------------------------------------------------------------------------------------------
+# team battle with the other attack actors / ammo (actor.py:504-728, agent.py:291-339)
+# ---------------------------------------------------------------------------------------------------
+def _tb_attack_variant(api, actor_name, stacked, n_agents=18, rows=6, cols=7, sim_attacks=2, ammo=None,
+                       ammo_observer=False, blocking=()):
+    """TeamBattleSim (its step() only needs process_action's (status, attacked_agents) contract) with the attack
+    actor swapped for `actor_name`; three teams, teams 1 and 2 may share cells, mixed ranges / strength /
+    accuracy so that several hits, misses and repeated evaluations of the same pair all occur."""
+    base = api.ex.BattleAgent
+    if ammo is not None:
+        class AmmoBattleAgent(api.ex.BattleAgent, api.agent.AmmoAgent):
+            pass
+        base = AmmoBattleAgent
+    agents = {}
+    for i in range(n_agents):
+        kw = dict(id=f'a{i}', encoding=i % 3 + 1, initial_health=1.0 if i % 2 else None, blocking=i in blocking)
+        if ammo is not None:
+            kw['initial_ammo'] = ammo + i % 3
+        ag = base(**kw)
+        ag.view_range = 2
+        ag.attack_range = 1 + (i % 4 == 0)
+        ag.simultaneous_attacks = sim_attacks + (i % 5 == 0 and actor_name != 'BinaryAttackActor')
+        ag.attack_strength = 0.5 if i % 3 else 1
+        ag.attack_accuracy = 0.7 if i % 2 else 1
+        agents[ag.id] = ag
+    attack = {1: {2, 3}, 2: {1, 3}, 3: {1, 2}}
+    states = {'PositionState', 'HealthState'} | ({'AmmoState'} if ammo is not None else set())
+    observers = {'PositionCenteredEncodingObserver'} | ({'AmmoObserver'} if ammo_observer else set())
+    sim = api.ex.TeamBattleSim.build_sim(
+        rows, cols, agents=agents, overlapping={1: {1, 2}, 2: {2}, 3: {3}}, attack_mapping=attack,
+        states=states, observers=observers, dones={'OneTeamRemainingDone'})
+    if actor_name != 'BinaryAttackActor' or stacked:
+        sim.attack_actor = getattr(api.actor, actor_name)(
+            agents=sim.agents, grid=sim.grid, attack_mapping=attack, stacked_attacks=stacked)
+    return sim
+
+
+def build_tb_encoding(api):
+    return _tb_attack_variant(api, 'EncodingBasedAttackActor', False)
+
+
+def build_tb_encoding_stacked(api):
+    return _tb_attack_variant(api, 'EncodingBasedAttackActor', True)
+
+
+def build_tb_restricted(api):
+    return _tb_attack_variant(api, 'RestrictedSelectiveAttackActor', False, sim_attacks=3, rows=4, cols=5)
+
+
+def build_tb_restricted_stacked(api):
+    return _tb_attack_variant(api, 'RestrictedSelectiveAttackActor', True, sim_attacks=3, rows=4, cols=5, blocking=(2, 8))
+
+
+def build_tb_selective(api):
+    return _tb_attack_variant(api, 'SelectiveAttackActor', False, blocking=(0, 4, 7))
+
+
+def build_tb_selective_stacked(api):
+    return _tb_attack_variant(api, 'SelectiveAttackActor', True)
+
+
+def build_tb_ammo(api):
+    """BinaryAttackActor + AmmoAgent / AmmoState / AmmoObserver: attacks stop when the ammo is spent."""
+    return _tb_attack_variant(api, 'BinaryAttackActor', False, sim_attacks=1, ammo=2, ammo_observer=True, n_agents=15)
+
+
+def build_tb_ammo_selective(api):
+    """SelectiveAttackActor naming more agents than the attacker has ammo left: the ammo filter's choice."""
+    return _tb_attack_variant(api, 'SelectiveAttackActor', True, ammo=3, ammo_observer=True)
+
+
+# ---------------------------------------------------------------------------------------------------
 # maze (maze_navigation.py; examples/rllib_maze_navigation.py:7-38)
 # ---------------------------------------------------------------------------------------------------
 def build_maze_c1(api):
@@ -240,6 +311,14 @@ SCENARIOS = {
     'tb_blocking': (build_tb_blocking, 'all_step', 30),
     'tb_stacked': (build_tb_stacked, 'all_step', 25),
     'tb_noself': (build_tb_noself, 'all_step', 25),
+    'tb_encoding': (build_tb_encoding, 'all_step', 40),
+    'tb_encoding_stacked': (build_tb_encoding_stacked, 'all_step', 40),
+    'tb_restricted': (build_tb_restricted, 'all_step', 40),
+    'tb_restricted_stacked': (build_tb_restricted_stacked, 'all_step', 40),
+    'tb_selective': (build_tb_selective, 'all_step', 40),
+    'tb_selective_stacked': (build_tb_selective_stacked, 'all_step', 40),
+    'tb_ammo': (build_tb_ammo, 'all_step', 40),
+    'tb_ammo_selective': (build_tb_ammo_selective, 'all_step', 40),
     'maze_c1': (build_maze_c1, 'all_step', 60),
     'pacman_c3': (build_pacman_c3, 'all_step', 12),
     'mm_c4': (build_mm_c4, 'turn_based', 120),

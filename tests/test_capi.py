@@ -29,9 +29,10 @@ def test_every_declared_symbol_is_exported():
 def test_struct_layouts_match_the_header():
     """ctypes mirrors of BgwSpec / BgwState / BgwDims have the C sizes (checked against the oracle build,
     which includes the same header)."""
-    assert C.sizeof(K.BgwState) == 12 * 8
-    assert C.sizeof(K.BgwDims) == 11 * 4
-    assert C.sizeof(K.BgwSpec) == 18 * 4 + 8 + 8 * K.BGW_RW_COUNT + 16 * 8
+    from oracle.oracle import lib
+    assert C.sizeof(K.BgwSpec) == lib().bgwo_sizeof(0) == 19 * 4 + 4 + 8 + 8 * K.BGW_RW_COUNT + 17 * 8
+    assert C.sizeof(K.BgwState) == lib().bgwo_sizeof(1) == 13 * 8
+    assert C.sizeof(K.BgwDims) == lib().bgwo_sizeof(2) == 12 * 4
 
 
 def test_host_rng_draw_matches_python_philox():

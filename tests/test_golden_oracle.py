@@ -55,6 +55,7 @@ def test_oracle_reproduces_reference_transcript(mirror, name):
         np.testing.assert_array_equal(st['flags'][0], g['flags'][t], err_msg=f'call {t} flags')
         np.testing.assert_array_equal(st['cell'][0], g['cell'][t], err_msg=f'call {t} cell')
         np.testing.assert_array_equal(st['health'][0], g['health'][t], err_msg=f'call {t} health')
+        np.testing.assert_array_equal(st['ammo'][0], g['ammo'][t], err_msg=f'call {t} ammo')
         in_grid = (g['flags'][t] & K.ST_IN_GRID) != 0
         np.testing.assert_array_equal(st['next'][0][in_grid], g['next'][t][in_grid], err_msg=f'call {t} next')
     assert n_valid > 0

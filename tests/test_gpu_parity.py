@@ -31,6 +31,14 @@ CASES = [
     ('tb_blocking', 48, 100, 40),
     ('tb_stacked', 48, 80, 30),
     ('tb_noself', 48, 80, 30),
+    ('tb_encoding', 48, 100, 30),
+    ('tb_encoding_stacked', 48, 100, 30),
+    ('tb_restricted', 48, 100, 30),
+    ('tb_restricted_stacked', 48, 100, 30),
+    ('tb_selective', 48, 100, 30),
+    ('tb_selective_stacked', 48, 100, 30),
+    ('tb_ammo', 48, 100, 30),
+    ('tb_ammo_selective', 48, 100, 30),
     ('maze_c1', 32, 150, 60),
     ('pacman_c3', 6, 40, 25),
     ('mm_c4', 12, 150, 60),
@@ -71,7 +79,7 @@ def test_thread_count_does_not_change_results(mirror, threads, monkeypatch):
     run_lockstep(eng, ora, 45, label='tb_c5_small/T' + threads)
 
 
-@pytest.mark.parametrize('name', ['tb_c2', 'tb_dense', 'tb_blocking'])
+@pytest.mark.parametrize('name', ['tb_c2', 'tb_dense', 'tb_blocking', 'tb_restricted_stacked', 'tb_ammo_selective'])
 def test_serial_and_reservation_actor_paths_agree(mirror, name, monkeypatch):
     """The rank-order loop (one thread) and the reservation rounds must both equal the oracle."""
     builder, manager, _ = scenarios.SCENARIOS[name]
@@ -129,6 +137,7 @@ def test_engine_reproduces_reference_transcript(mirror, name):
         np.testing.assert_array_equal(st['flags'][0], g['flags'][t], err_msg=f'{name} call {t} flags')
         np.testing.assert_array_equal(st['cell'][0], g['cell'][t], err_msg=f'{name} call {t} cell')
         np.testing.assert_array_equal(st['health'][0], g['health'][t], err_msg=f'{name} call {t} health')
+        np.testing.assert_array_equal(st['ammo'][0], g['ammo'][t], err_msg=f'{name} call {t} ammo')
         in_grid = (g['flags'][t] & K.ST_IN_GRID) != 0
         np.testing.assert_array_equal(st['next'][0][in_grid], g['next'][t][in_grid], err_msg=f'{name} call {t} next')
 

@@ -69,6 +69,43 @@ def test_attack_actor_validation():                            # test_actor.py:5
     assert agents['a'].action_space['attack'] == Discrete(2) and agents['a'].null_action['attack'] == 0
 
 
+def test_other_attack_actor_spaces():          # test_actor.py:743-750, 1196-1203, 1528-1535; test_observer (ammo) :376-413
+    from abmarl_b200.spaces import Dict, MultiDiscrete
+    mk = lambda **kw: {'a': agent.AttackingAgent(id='a', encoding=3, attack_range=2, attack_strength=1, attack_accuracy=1,
+                                                 initial_position=np.array([0, 0]), **kw)}
+    grid = Grid(5, 6)
+    ag = mk()
+    actor.SelectiveAttackActor(agents=ag, grid=grid, attack_mapping={3: {1}})
+    assert ag['a'].action_space['attack'] == Box(0, 1, (5, 5), int)
+    np.testing.assert_array_equal(ag['a'].null_action['attack'], np.zeros((5, 5), dtype=int))
+    ag = mk()
+    actor.EncodingBasedAttackActor(agents=ag, grid=grid, attack_mapping={3: {1, 2}})
+    assert ag['a'].action_space['attack'] == Dict({1: Discrete(2), 2: Discrete(2)})
+    assert ag['a'].null_action['attack'] == {1: 0, 2: 0}
+    ag = mk(simultaneous_attacks=2)
+    ag['a'].attack_range = 1
+    actor.RestrictedSelectiveAttackActor(agents=ag, grid=grid, attack_mapping={3: {1, 2}})
+    assert ag['a'].action_space['attack'] == MultiDiscrete([10, 10])
+    np.testing.assert_array_equal(ag['a'].null_action['attack'], np.zeros((2,), dtype=int))
+
+    class AmmoObserving(agent.AmmoAgent, agent.GridObservingAgent):
+        pass
+    from abmarl_b200.sim.gridworld import observer
+    watchers = {'w': AmmoObserving(id='w', encoding=1, view_range=1, initial_ammo=7), 'x': agent.AmmoAgent(id='x', encoding=1, initial_ammo=2)}
+    assert isinstance(watchers['w'], agent.AmmoObservingAgent) and not isinstance(watchers['x'], agent.AmmoObservingAgent)
+    observer.AmmoObserver(agents=watchers, grid=grid)
+    assert watchers['w'].observation_space['ammo'] == Box(0, 7, (1,), int) and watchers['w'].null_observation['ammo'] == 0
+
+
+def test_attack_variants_compile_and_encode(mirror):
+    """compile_sim + the managers' action encoding for the wider attack actions (layout: include/bgw.h, bgw_step)."""
+    spec = compile_sim(scenarios.build_tb_ammo_selective(mirror))
+    assert spec.attack_actor == K.ATTACK_SELECTIVE and spec.stacked_attacks == 1 and spec.ammo_observer == 1
+    assert all(spec.klass[a] & K.AG_AMMO for a in range(spec.n_agents)) and list(spec.initial_ammo[:4]) == [3, 4, 5, 3]
+    assert compile_sim(scenarios.build_tb_encoding(mirror)).attack_actor == K.ATTACK_ENCODING
+    assert compile_sim(scenarios.build_tb_restricted(mirror)).attack_actor == K.ATTACK_RESTRICTED
+
+
 def test_build_sim_from_file_counts_registered_characters(mirror):   # base.py:178-191
     sim = scenarios.build_maze_c1(mirror)
     assert list(sim.agents)[0].startswith('wall') and 'navigator' in sim.agents and 'target' in sim.agents
@@ -89,7 +126,7 @@ def test_team_battle_spec_tables(mirror):
     assert np.isnan(spec.init_health).all()                     # rllib_team_battle.py leaves initial_health unset
 
 
-def test_team_battle_rejects_simultaneous_attacks(mirror):     # ValueError in the reference
+def test_team_battle_rejects_simultaneous_attacks(mirror):     # ValueError in the reference (Binary only)
     agents = {'a0': ex.BattleAgent(id='a0', encoding=1), 'a1': ex.BattleAgent(id='a1', encoding=2)}
     agents['a0'].simultaneous_attacks = 2
     sim = ex.TeamBattleSim.build_sim(4, 4, agents=agents, overlapping={1: {1}}, attack_mapping={1: {2}, 2: {1}},
