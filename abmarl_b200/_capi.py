@@ -68,7 +68,8 @@ _LIB = None
 
 
 def lib_path():
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), 'csrc', 'libbgw.so')
+    # BGW_LIB: an alternative build of the same sources (A/B measurements of kernel variants)
+    return os.environ.get('BGW_LIB') or os.path.join(os.path.dirname(os.path.abspath(__file__)), 'csrc', 'libbgw.so')
 
 
 def load():

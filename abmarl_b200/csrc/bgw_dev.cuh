@@ -34,7 +34,7 @@
 #define BGW_ATT_MASK_WORDS 8   /* thread-local LOS mask of an attacker: (2R+1)^2 <= 256 bits -> attack_range <= 7 */
 
 enum { CTR_KILLS = 0, CTR_ALLDONE, CTR_REMAINING, CTR_ENC_LO, CTR_ENC_HI, CTR_AND, CTR_NEMIT, CTR_ENVDONE,
-       CTR_ERR, CTR_TURN, CTR_MIXED, CTR_PA, CTR_PB, CTR_COUNT = 16 };
+       CTR_ERR, CTR_TURN, CTR_MIXED, CTR_PA, CTR_PB, CTR_EPOCH, CTR_COUNT = 16 };
 
 struct DevSpec {
     int H, W, HW, A, L, E, env_offset;

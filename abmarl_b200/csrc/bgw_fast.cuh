@@ -290,50 +290,82 @@ __device__ void fast_exec_attack(const DevSpec &s, const FastSpec &f, Env &ev, F
     }
 }
 
-/* Ordered rounds over the effective attackers eff[0..n_eff) (all of them pending on entry).  Per round: every
- * pending attacker atomicMin()s its rank into the slots of its own cell and of its candidate cells; after a
- * barrier an attacker that holds all its slots executes and frees them (losers only read slots, so the check
- * and the execution need no barrier between them); a second barrier separates the frees from the next round's
- * reservations.  WARP = run by one warp with __syncwarp. */
+/* ---- ordered rounds ---------------------------------------------------------------------------------------
+ * Agents whose actions touch disjoint cells commute; agents that share a cell must act in rank order.  Every
+ * pending agent atomicMin()s a TAGGED rank (epoch << 12 | rank) into the slot of every cell its action may read
+ * or write; after ONE barrier an agent that finds its own value in all its slots executes, the others retry in
+ * the next round.  The epoch decreases from round to round, so whatever earlier rounds (or earlier phases, or
+ * earlier envs of this CTA) left in a slot is larger than any current value and reads as free: slots are never
+ * released or cleared.  The slot array is split in two tables used by alternate rounds: a loser reserves for the
+ * next round right away, in the other table, while the winners of this round are still reading this one -- the
+ * barrier that ends a round is the barrier that publishes the next round's reservations. */
+#define BGW_TAG_SHIFT 12                      /* ranks < BGW_MAX_AGENTS = 4096 */
+
+struct SlotTables {
+    uint32_t *t0, *t1;
+    uint32_t mask;
+    __device__ __forceinline__ uint32_t *tab(int p) const { return p ? t1 : t0; }
+};
+
+__device__ __forceinline__ SlotTables slot_tables(const DevSpec &s, const Env &ev)
+{
+    SlotTables t;
+    const uint32_t half = (uint32_t)(s.slot_mask + 1) >> 1;
+    t.t0 = ev.slot; t.t1 = ev.slot + half; t.mask = half - 1u;
+    return t;
+}
+
+/* reserve / test the slots of an attacker: its own cell and the cells of its candidate mask */
+__device__ __forceinline__ void attack_reserve(const DevSpec &s, uint32_t *tab, uint32_t smask, int own, int R, uint32_t mask, uint32_t v)
+{
+    const int n = 2 * R + 1;
+    atomicMin(&tab[own & smask], v);
+    for (uint32_t m = mask; m; m &= m - 1) {
+        const int b = __ffs(m) - 1, wr = b / n, wc = b - wr * n;
+        atomicMin(&tab[(own + (wr - R) * s.W + (wc - R)) & smask], v);
+    }
+}
+
+__device__ __forceinline__ bool attack_holds(const DevSpec &s, const uint32_t *tab, uint32_t smask, int own, int R, uint32_t mask, uint32_t v)
+{
+    const int n = 2 * R + 1;
+    bool win = tab[own & smask] == v;
+    for (uint32_t m = mask; m; m &= m - 1) {
+        const int b = __ffs(m) - 1, wr = b / n, wc = b - wr * n;
+        win &= tab[(own + (wr - R) * s.W + (wc - R)) & smask] == v;
+    }
+    return win;
+}
+
+/* Ordered rounds over the effective attackers eff[0..n_eff): all of them pending on entry, with their first
+ * reservation already made in table 0 under `epoch` (by the attack pre-pass) and published by a barrier.
+ * WARP = run by one warp with __syncwarp.  Returns the next unused epoch. */
 template <bool WARP, typename HT>
-__device__ void fast_attack_rounds(const DevSpec &s, const FastSpec &f, Env &ev, FastEnv &fe, int n_eff, int tid, int T)
+__device__ uint32_t fast_attack_rounds(const DevSpec &s, const FastSpec &f, Env &ev, FastEnv &fe, int n_eff, uint32_t epoch, int tid, int T)
 {
     const int stride = WARP ? 32 : T;
-    int pending = 1;
+    const SlotTables st = slot_tables(s, ev);
+    int pending = 1, p = 0;
     while (pending) {
-        for (int x = tid; x < n_eff; x += stride) {
-            const int i = fe.eff[x];
-            if (ev.pstate[i] != 1) continue;
-            const int a = ev.ragent[i], R = f.uniform_att >= 0 ? f.uniform_att : __ldg(&s.attack_r[a]), n = 2 * R + 1, own = ev.cell[a];
-            atomicMin(slot_of(s, ev, own), (uint32_t)i);
-            for (uint32_t m = fe.rkmask[i]; m; m &= m - 1) {
-                const int b = __ffs(m) - 1, wr = b / n, wc = b - wr * n;
-                atomicMin(slot_of(s, ev, own + (wr - R) * s.W + (wc - R)), (uint32_t)i);
-            }
-        }
-        if (WARP) __syncwarp(); else __syncthreads();
+        const uint32_t tag = epoch << BGW_TAG_SHIFT, next_tag = (epoch - 1u) << BGW_TAG_SHIFT;
         int lost = 0;
         for (int x = tid; x < n_eff; x += stride) {
             const int i = fe.eff[x];
             if (ev.pstate[i] != 1) continue;
-            const int a = ev.ragent[i], R = f.uniform_att >= 0 ? f.uniform_att : __ldg(&s.attack_r[a]), n = 2 * R + 1, own = ev.cell[a];
+            const int a = ev.ragent[i], R = f.uniform_att >= 0 ? f.uniform_att : __ldg(&s.attack_r[a]), own = ev.cell[a];
             const uint32_t mask = fe.rkmask[i];
-            bool win = *slot_of(s, ev, own) == (uint32_t)i;
-            for (uint32_t m = mask; m; m &= m - 1) {
-                const int b = __ffs(m) - 1, wr = b / n, wc = b - wr * n;
-                win &= *slot_of(s, ev, own + (wr - R) * s.W + (wc - R)) == (uint32_t)i;
+            if (!attack_holds(s, st.tab(p), st.mask, own, R, mask, tag | (uint32_t)i)) {
+                lost = 1;
+                attack_reserve(s, st.tab(p ^ 1), st.mask, own, R, mask, next_tag | (uint32_t)i);
+                continue;
             }
-            if (!win) { lost = 1; continue; }
             fast_exec_attack<HT>(s, f, ev, fe, i, a, mask);
-            *slot_of(s, ev, own) = BGW_SLOT_FREE;
-            for (uint32_t m = mask; m; m &= m - 1) {
-                const int b = __ffs(m) - 1, wr = b / n, wc = b - wr * n;
-                *slot_of(s, ev, own + (wr - R) * s.W + (wc - R)) = BGW_SLOT_FREE;
-            }
             ev.pstate[i] = 0;
         }
         if (WARP) { pending = __any_sync(0xFFFFFFFFu, lost); __syncwarp(); } else pending = __syncthreads_or(lost);
+        p ^= 1; --epoch;
     }
+    return epoch;
 }
 
 /* one move: Grid.query through the summary, then remove / place (actor.py:99-114) */
@@ -360,35 +392,34 @@ __device__ __forceinline__ void fast_exec_move(const DevSpec &s, const FastSpec 
 
 #define BGW_NO_MOVE 0xFFFFFFFFu
 /* Ordered rounds over the pending movers.  rkmask[i] = (source cell << 16 | destination cell) for a pending rank,
- * BGW_NO_MOVE otherwise (the attack masks are dead by then): each reserves its source and destination cell; same
- * two-barrier round as the attack phase.  The first round walks all ranks; its losers are appended to a list and
- * later rounds walk only the list of the round before (two lists in the storage of eff[] / killrank[], both dead
- * by now).  The common move -- alone in its cell, destination empty -- touches no list. */
+ * BGW_NO_MOVE otherwise (the attack masks are dead by then); each reserves its source and destination cell, the first
+ * reservation (table 0, `epoch`) was made by the classification loop.  The first round walks all ranks; its losers
+ * are appended to a list and later rounds walk only the list of the round before (two lists in the storage of
+ * eff[] / killrank[], both dead by now).  The common move -- alone in its cell, destination empty -- touches no
+ * occupant list.  Returns the next unused epoch. */
 template <bool WARP, typename HT>
-__device__ void fast_move_rounds(const DevSpec &s, const FastSpec &f, Env &ev, FastEnv &fe, int n_act, int pending, int tid, int T)
+__device__ uint32_t fast_move_rounds(const DevSpec &s, const FastSpec &f, Env &ev, FastEnv &fe, int n_act, int pending, uint32_t epoch,
+                                     int tid, int T)
 {
     const int stride = WARP ? 32 : T;
-    int which = 0, n_cur = -1;                                     /* -1: walk the ranks themselves */
+    const SlotTables st = slot_tables(s, ev);
+    int which = 0, n_cur = -1, p = 0;                              /* n_cur -1: walk the ranks themselves */
+    int base0 = 0, base1 = 0;                                      /* the list counters only grow: entries before base are consumed */
     while (pending) {
+        const uint32_t tag = epoch << BGW_TAG_SHIFT, next_tag = (epoch - 1u) << BGW_TAG_SHIFT;
         const int n_it = n_cur < 0 ? n_act : n_cur;
-        for (int x = tid; x < n_it; x += stride) {
-            const int i = n_cur < 0 ? x : (which ? fe.killrank : fe.eff)[x];
-            const uint32_t ft = fe.rkmask[i];
-            if (ft == BGW_NO_MOVE) continue;
-            atomicMin(slot_of(s, ev, (int)(ft >> 16)), (uint32_t)i);
-            atomicMin(slot_of(s, ev, (int)(ft & 0xFFFFu)), (uint32_t)i);
-        }
-        if (WARP) __syncwarp(); else __syncthreads();
         int lost = 0;
         for (int x = tid; x < n_it; x += stride) {
             const int i = n_cur < 0 ? x : (which ? fe.killrank : fe.eff)[x];
             const uint32_t ft = fe.rkmask[i];
             if (ft == BGW_NO_MOVE) continue;
             const int from = (int)(ft >> 16), to = (int)(ft & 0xFFFFu);
-            uint32_t *sf = slot_of(s, ev, from), *sto = slot_of(s, ev, to);
-            if (*sf != (uint32_t)i || *sto != (uint32_t)i) {
+            const uint32_t mine = tag | (uint32_t)i;
+            if (st.tab(p)[from & st.mask] != mine || st.tab(p)[to & st.mask] != mine) {
                 lost = 1;
-                if (!WARP) (which ? fe.eff : fe.killrank)[atomicAdd(&ev.ctr[CTR_PA + (which ^ 1)], 1)] = (uint16_t)i;
+                atomicMin(&st.tab(p ^ 1)[from & st.mask], next_tag | (uint32_t)i);
+                atomicMin(&st.tab(p ^ 1)[to & st.mask], next_tag | (uint32_t)i);
+                if (!WARP) (which ? fe.eff : fe.killrank)[atomicAdd(&ev.ctr[CTR_PA + (which ^ 1)], 1) - (which ? base0 : base1)] = (uint16_t)i;
                 continue;
             }
             const int a = ev.ragent[i], pto = pad_index(s, f, to);
@@ -401,18 +432,18 @@ __device__ void fast_move_rounds(const DevSpec &s, const FastSpec &f, Env &ev, F
             } else {
                 fast_exec_move<HT>(s, f, ev, fe, a, to);
             }
-            *sf = BGW_SLOT_FREE;
-            *sto = BGW_SLOT_FREE;
             fe.rkmask[i] = BGW_NO_MOVE;
         }
         if (WARP) { pending = __any_sync(0xFFFFFFFFu, lost); __syncwarp(); }
         else {
             pending = __syncthreads_or(lost);
-            n_cur = ev.ctr[CTR_PA + (which ^ 1)];                  /* the losers of this round */
-            if (tid == 0) ev.ctr[CTR_PA + which] = 0;              /* next round appends here (after its barrier) */
+            if (n_cur >= 0) { if (which) base1 += n_cur; else base0 += n_cur; }   /* the list walked in this round is consumed */
+            n_cur = ev.ctr[CTR_PA + (which ^ 1)] - (which ? base0 : base1);       /* the losers of this round */
             which ^= 1;
         }
+        p ^= 1; --epoch;
     }
+    return epoch;
 }
 
 /* (re)initialise the dense per-cell arrays of this CTA: clean head-detection marks, free reservation slots, empty
@@ -636,6 +667,7 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
     }
     cp_async_commit();
 
+    uint32_t epoch = 0xFFFFEu;                            /* tag of the next reservation round (ordered rounds, above) */
     int it_no = -1;
     for (; e < s.E; e += gridDim.x) {
         ++it_no;
@@ -675,6 +707,10 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
             for (int l = tid; l < s.L; l += T) { dn[l] = 0; rew[l] = 0.f; }
         }
         if (tid < CTR_COUNT) ev.ctr[tid] = 0;
+        if (epoch < 4096u) {                                        /* (never in practice) the epochs are used up: start over */
+            for (int i = tid; i <= s.slot_mask; i += T) ev.slot[i] = BGW_SLOT_FREE;
+            epoch = 0xFFFFEu;
+        }
         cp_async_wait<1>();
         __syncthreads();
         BGW_PROF_MARK(1);
@@ -851,7 +887,11 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
                             }
                     }
                     fe.rkmask[i] = mask;
-                    if (mask) { p = 1; fe.eff[atomicAdd(&ev.ctr[CTR_NEMIT], 1)] = (uint16_t)i; }
+                    if (mask) {                                         /* effective attacker: first reservation right here */
+                        p = 1; fe.eff[atomicAdd(&ev.ctr[CTR_NEMIT], 1)] = (uint16_t)i;
+                        const SlotTables stt = slot_tables(s, ev);
+                        attack_reserve(s, stt.t0, stt.mask, ev.cell[a], R, mask, (epoch << BGW_TAG_SHIFT) | (uint32_t)i);
+                    }
                     else p = 3;                                         /* no possible victim: settled after the rounds */
                 }
                 ev.pstate[i] = p;
@@ -860,9 +900,15 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
             BGW_PROF_MARK(5);
             {
                 const int n_eff = ev.ctr[CTR_NEMIT];
-                if (n_eff > 32) fast_attack_rounds<false, HT>(s, f, ev, fe, n_eff, tid, T);
-                else if (n_eff > 0 && warp == 0) fast_attack_rounds<true, HT>(s, f, ev, fe, n_eff, tid, T);
-                if (n_eff > 0 && n_eff <= 32) __syncthreads();
+                if (n_eff > 32) epoch = fast_attack_rounds<false, HT>(s, f, ev, fe, n_eff, epoch, tid, T);
+                else if (n_eff > 0) {                               /* one warp runs the rounds; every thread keeps the same epoch */
+                    uint32_t e2 = epoch;
+                    if (warp == 0) e2 = fast_attack_rounds<true, HT>(s, f, ev, fe, n_eff, epoch, tid, T);
+                    if (tid == 0) ev.ctr[CTR_EPOCH] = (int)e2;
+                    __syncthreads();
+                    epoch = (uint32_t)ev.ctr[CTR_EPOCH];
+                }
+                else --epoch;
             }
             BGW_PROF_MARK(6);
 
@@ -892,15 +938,25 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
                     if (ft == BGW_NO_MOVE && !ok) fe.rflag[a] |= RF_MOVE_FAIL;
                 }
                 fe.rkmask[i] = ft;
-                pend |= (ft != BGW_NO_MOVE);
+                if (ft != BGW_NO_MOVE) {                            /* first reservation of the move rounds */
+                    const SlotTables stt = slot_tables(s, ev);
+                    const uint32_t mine = (epoch << BGW_TAG_SHIFT) | (uint32_t)i;
+                    atomicMin(&stt.t0[(ft >> 16) & stt.mask], mine);
+                    atomicMin(&stt.t0[(ft & 0xFFFFu) & stt.mask], mine);
+                    pend = 1;
+                }
             }
             pend = __syncthreads_or(pend);
             BGW_PROF_MARK(7);
-            if (n_act > 32) fast_move_rounds<false, HT>(s, f, ev, fe, n_act, pend, tid, T);
+            if (n_act > 32) epoch = fast_move_rounds<false, HT>(s, f, ev, fe, n_act, pend, epoch, tid, T);
             else {
-                if (warp == 0) fast_move_rounds<true, HT>(s, f, ev, fe, n_act, pend, tid, T);
+                uint32_t e2 = epoch;
+                if (warp == 0) e2 = fast_move_rounds<true, HT>(s, f, ev, fe, n_act, pend, epoch, tid, T);
+                if (tid == 0) ev.ctr[CTR_EPOCH] = (int)e2;
                 __syncthreads();
+                epoch = (uint32_t)ev.ctr[CTR_EPOCH];
             }
+            if (!pend) --epoch;
             BGW_PROF_MARK(8);
 
             /* ---- entropy :58-59, rewards / dones of the acting learners (all_step_manager.py:68-87) -------- */

@@ -27,6 +27,10 @@ def build(force=False, verbose=False):
            '-I', os.path.join(ROOT, 'include'), '-o', OUT, SRC, '-lcudart']
     if os.environ.get('BGW_PROFILE'):
         cmd.insert(1, '-DBGW_PROFILE')
+    for d in os.environ.get('BGW_DEFINES', '').split():          # kernel variants for A/B measurements
+        cmd.insert(1, '-D' + d)
+    if os.environ.get('BGW_OUT'):
+        cmd[cmd.index('-o') + 1] = os.environ['BGW_OUT']
     if verbose:
         cmd.insert(1, '-Xptxas=-v')
         print(' '.join(cmd))
