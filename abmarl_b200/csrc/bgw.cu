@@ -187,7 +187,7 @@ int bgw_create(const BgwSpec *sp, int device, bgw_handle *out)
             if (R < 0) return bail(fail(1, "bgw_create: negative attack range"));
             /* Binary / EncodingBased hand TeamBattleSim.step an ndarray: `not attacked_agents` raises for more than
              * one element (team_battle_example.py:41); the two selective actors return lists */
-            if (sp->program == BGW_PROG_TEAM_BATTLE && sp->attack_actor == BGW_ATTACK_BINARY && sim > 1)
+            if ((sp->program == BGW_PROG_TEAM_BATTLE || sp->program == BGW_PROG_REACH_TARGET) && sp->attack_actor == BGW_ATTACK_BINARY && sim > 1)
                 return bail(fail(1, "bgw_create: TeamBattleSim.step with the BinaryAttackActor is only defined for simultaneous_attacks == 1 (team_battle_example.py:41)"));
             if (sim > BGW_MAX_SIMATT) return bail(fail(1, "bgw_create: simultaneous_attacks %d exceeds %d", sim, BGW_MAX_SIMATT));
             /* attack bytes of the action row and the most agents one attack can name */
@@ -218,7 +218,9 @@ int bgw_create(const BgwSpec *sp, int device, bgw_handle *out)
     if (sp->program == BGW_PROG_MULTI_MAZE && d.a_target < 0) return bail(fail(1, "bgw_create: MultiMazeNavigationSim needs a target"));
     if (sp->program == BGW_PROG_PACMAN && (d.a_pacman < 0 || learner_of[d.a_pacman] < 0 || H <= 9 || W <= 20))
         return bail(fail(1, "bgw_create: PacmanSim needs a learning pacman and the (9,0)<->(9,20) tunnel (pacman.py:87-92)"));
-    if (sp->program < BGW_PROG_TEAM_BATTLE || sp->program > BGW_PROG_PACMAN) return bail(fail(1, "bgw_create: unknown program %d", sp->program));
+    if (sp->program == BGW_PROG_REACH_TARGET && (d.a_target < 0 || learner_of[d.a_target] < 0))
+        return bail(fail(1, "bgw_create: ReachTheTargetSim needs a learning target agent"));
+    if (sp->program < BGW_PROG_TEAM_BATTLE || sp->program > BGW_PROG_REACH_TARGET) return bail(fail(1, "bgw_create: unknown program %d", sp->program));
 
     /* ---- observation geometry (same rule as the oracle's bgwo_dims) ------------------------------ */
     BgwDims &dm = h->dims;
@@ -288,7 +290,7 @@ int bgw_create(const BgwSpec *sp, int device, bgw_handle *out)
     int T = A <= 128 ? 32 : A <= 1024 ? 64 : 128;
     if (const char *t = getenv("BGW_THREADS")) { const int v = atoi(t); if (v >= 32 && v <= 1024 && v % 32 == 0) T = v; }
     h->threads = T;
-    d.parallel_actors = (sp->program == BGW_PROG_TEAM_BATTLE && (sp->move_actor == BGW_MOVE_BOX || sp->move_actor == BGW_MOVE_CROSS));
+    d.parallel_actors = ((sp->program == BGW_PROG_TEAM_BATTLE || sp->program == BGW_PROG_REACH_TARGET) && (sp->move_actor == BGW_MOVE_BOX || sp->move_actor == BGW_MOVE_CROSS));
     if (const char *t = getenv("BGW_SERIAL_ACTORS")) if (atoi(t)) d.parallel_actors = 0;
     int slots = std::min(std::max(pow2ceil(HW), 32), 2048);
     if (const char *t = getenv("BGW_SLOTS")) { const int v = atoi(t); if (v >= 32 && v <= 65536 && (v & (v - 1)) == 0) slots = v; }

@@ -578,10 +578,24 @@ __device__ __forceinline__ uint32_t *slot_of(const DevSpec &s, const Env &ev, in
 /* ------------------------------------------------------------------------------------------------- */
 /* sim programs: the user-written step()                                                             */
 /* ------------------------------------------------------------------------------------------------- */
-/* TeamBattleSim.step team_battle_example.py:33-59, ranks 0..nrank-1 hold the acting agents (ragent) */
+/* ReachTheTargetSim.step reach_the_target.py:141-144: a runner standing on the target's cell has reached it.  A runner
+ * that is no longer in the grid (killed on that cell) would make the reference's grid.remove raise; it is left alone. */
+__device__ __forceinline__ void reach_check(const DevSpec &s, Env &ev, int a)
+{
+    if (a != s.a_target && (ev.flags[a] & BGW_ST_IN_GRID) && ev.cell[a] == ev.cell[s.a_target]) {
+        ev.racc[a] += s.reward[BGW_RW_TARGET];
+        grid_unlink(ev, a);
+        ev.flags[a] &= ~BGW_ST_ACTIVE;
+    }
+}
+
+/* TeamBattleSim.step team_battle_example.py:33-59 and ReachTheTargetSim.step reach_the_target.py:117-152 (same attack
+ * phase; only MovingAgents move, a runner that reaches the target leaves the grid, only runners pay the entropy
+ * penalty); ranks 0..nrank-1 hold the acting agents (ragent) */
 __device__ void team_battle_step(const DevSpec &s, Env &ev, int nrank, int tid, int T)
 {
     const double *rw = s.reward;
+    const bool reach = s.program == BGW_PROG_REACH_TARGET;
     if (!s.parallel_actors) {
         if (tid == 0) {
             for (int i = 0; i < nrank; ++i) {
@@ -591,10 +605,13 @@ __device__ void team_battle_step(const DevSpec &s, Env &ev, int nrank, int tid, 
             }
             for (int i = 0; i < nrank; ++i) {
                 const int a = ev.ragent[i];
-                if (a == BGW_NONE16 || !(ev.flags[a] & BGW_ST_ACTIVE)) continue;
-                if (!process_move(s, ev, a, ev.act[(size_t)__ldg(&s.learner_of[a]) * s.act_words])) ev.racc[a] += rw[BGW_RW_MOVE_FAIL];
+                if (a == BGW_NONE16 || (reach && !(ev.klass[a] & BGW_AG_MOVING))) continue;
+                if (ev.flags[a] & BGW_ST_ACTIVE)
+                    if (!process_move(s, ev, a, ev.act[(size_t)__ldg(&s.learner_of[a]) * s.act_words])) ev.racc[a] += rw[BGW_RW_MOVE_FAIL];
+                if (reach) reach_check(s, ev, a);
             }
-            for (int i = 0; i < nrank; ++i) if (ev.ragent[i] != BGW_NONE16) ev.racc[ev.ragent[i]] += rw[BGW_RW_ENTROPY];
+            for (int i = 0; i < nrank; ++i)
+                if (ev.ragent[i] != BGW_NONE16 && (!reach || __ldg(&s.role[ev.ragent[i]]) == BGW_ROLE_RUNNER)) ev.racc[ev.ragent[i]] += rw[BGW_RW_ENTROPY];
         }
         __syncthreads();
         return;
@@ -652,7 +669,7 @@ __device__ void team_battle_step(const DevSpec &s, Env &ev, int nrank, int tid, 
     for (int i = tid; i < nrank; i += T) {
         const int a = ev.ragent[i];
         uint8_t p = 0;
-        if (a != BGW_NONE16 && (ev.flags[a] & BGW_ST_ACTIVE)) {
+        if (a != BGW_NONE16 && (ev.flags[a] & BGW_ST_ACTIVE) && (!reach || (ev.klass[a] & BGW_AG_MOVING))) {
             bool ok = false;
             if (ev.klass[a] & BGW_AG_MOVING) {
                 int dr, dc;
@@ -665,6 +682,9 @@ __device__ void team_battle_step(const DevSpec &s, Env &ev, int nrank, int tid, 
                 }
             }
             if (!p && !ok) ev.racc[a] += rw[BGW_RW_MOVE_FAIL];
+            /* a runner that does not move but stands on the target's cell (placed there) still reaches it: the removal
+             * goes through the ordered rounds as a move to its own cell */
+            if (reach && !p && (ev.flags[a] & BGW_ST_IN_GRID) && a != s.a_target && ev.cell[a] == ev.cell[s.a_target]) { p = 1; ev.plist[i] = ev.cell[a]; }
         }
         ev.pstate[i] = p;
         mine |= p;
@@ -688,8 +708,11 @@ __device__ void team_battle_step(const DevSpec &s, Env &ev, int nrank, int tid, 
         for (int i = tid; i < nrank; i += T) {
             if (ev.pstate[i] == 2) {
                 const int a = ev.ragent[i], from = ev.cell[a], to = ev.plist[i];
-                if (grid_query(s, ev, a, to)) { grid_unlink(ev, a); grid_append(ev, a, to); }
-                else ev.racc[a] += rw[BGW_RW_MOVE_FAIL];
+                if (to != from) {
+                    if (grid_query(s, ev, a, to)) { grid_unlink(ev, a); grid_append(ev, a, to); }
+                    else ev.racc[a] += rw[BGW_RW_MOVE_FAIL];
+                }
+                if (reach) reach_check(s, ev, a);
                 *slot_of(s, ev, from) = BGW_SLOT_FREE;
                 *slot_of(s, ev, to) = BGW_SLOT_FREE;
                 ev.pstate[i] = 0;
@@ -699,7 +722,8 @@ __device__ void team_battle_step(const DevSpec &s, Env &ev, int nrank, int tid, 
         any = __syncthreads_or(mine);
     }
     /* ---- entropy :58-59 ------------------------------------------------------------------------ */
-    for (int i = tid; i < nrank; i += T) if (ev.ragent[i] != BGW_NONE16) ev.racc[ev.ragent[i]] += rw[BGW_RW_ENTROPY];
+    for (int i = tid; i < nrank; i += T)
+        if (ev.ragent[i] != BGW_NONE16 && (!reach || __ldg(&s.role[ev.ragent[i]]) == BGW_ROLE_RUNNER)) ev.racc[ev.ragent[i]] += rw[BGW_RW_ENTROPY];
     __syncthreads();
 }
 
@@ -783,6 +807,15 @@ __device__ void compute_all_done(const DevSpec &s, Env &ev, int tid, int T)
         if (tid == 0) ev.ctr[CTR_ALLDONE] = same_position(ev, s.a_nav, s.a_target);
     } else if (s.program == BGW_PROG_PACMAN) {                       /* pacman.py:140-151 */
         if (tid == 0) ev.ctr[CTR_ALLDONE] = !(ev.flags[s.a_pacman] & BGW_ST_ACTIVE) ? 1 : (s.has_food ? 0 : 1);
+    } else if (s.program == BGW_PROG_REACH_TARGET) {                 /* OnlyAgentLeftDone reach_the_target.py:43-57 */
+        if (tid == 0) ev.ctr[CTR_AND] = 0;
+        __syncthreads();
+        int n = 0;
+        for (int l = tid; l < s.L; l += T) n += (ev.flags[__ldg(&s.agent_of[l])] & BGW_ST_ACTIVE) ? 1 : 0;
+        n = __reduce_add_sync(0xFFFFFFFFu, n);
+        if ((tid & 31) == 0 && n) atomicAdd(&ev.ctr[CTR_AND], n);
+        __syncthreads();
+        if (tid == 0) ev.ctr[CTR_ALLDONE] = ev.ctr[CTR_AND] <= 1;
     } else {
         if (tid == 0) { ev.ctr[CTR_ENC_LO] = 0; ev.ctr[CTR_ENC_HI] = 0; ev.ctr[CTR_AND] = 1; }
         __syncthreads();
@@ -827,6 +860,9 @@ __device__ __forceinline__ bool prog_done(const DevSpec &s, const Env &ev, int a
     switch (s.program) {
     case BGW_PROG_MAZE: case BGW_PROG_PACMAN: return ev.ctr[CTR_ALLDONE] != 0;      /* maze:38-39, pacman:137-138 */
     case BGW_PROG_MULTI_MAZE: return same_position(ev, a, s.a_target);              /* multi_maze:61-64 */
+    case BGW_PROG_REACH_TARGET:                                                     /* reach_the_target.py:161-168 */
+        if (__ldg(&s.role[a]) == BGW_ROLE_RUNNER) return !(ev.flags[a] & BGW_ST_ACTIVE) || (a != s.a_target && same_position(ev, a, s.a_target));
+        return a == s.a_target && ev.ctr[CTR_ALLDONE] != 0;
     default: {
         bool d = true;
         const int t = __ldg(&s.target[a]);
@@ -1194,7 +1230,7 @@ __global__ void bgw_step_kernel(const DevSpec s, const BgwState st, const uint32
     __syncthreads();
 
     /* ---- sim.step(action_dict) ------------------------------------------------------------------ */
-    if (s.program == BGW_PROG_TEAM_BATTLE) team_battle_step(s, ev, nrank, tid, T);
+    if (s.program == BGW_PROG_TEAM_BATTLE || s.program == BGW_PROG_REACH_TARGET) team_battle_step(s, ev, nrank, tid, T);
     else { if (tid == 0) serial_program_step(s, ev, nrank); __syncthreads(); }
 
     compute_all_done(s, ev, tid, T);

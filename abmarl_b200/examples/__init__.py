@@ -1,7 +1,8 @@
-"""Example simulations (definitions) -- the four sims named by the BASELINE configs."""
+"""Example simulations (definitions): the four sims named by the BASELINE configs and ReachTheTargetSim."""
 from .sims import (  # noqa: F401
     BattleAgent, TeamBattleSim,
     MazeNavigationAgent, MazeNavigationSim,
     MultiMazeNavigationAgent, MultiMazeNavigationSim,
     PacmanAgent, WallAgent, FoodAgent, BaddieAgent, PacmanSim,
+    BarrierAgent, TargetAgent, RunningAgent, ReachTheTargetSim, TargetDone, OnlyAgentLeftDone,
 )

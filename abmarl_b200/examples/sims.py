@@ -7,13 +7,16 @@ step()/get_reward()/get_done()/get_all_done(), and carries that sim's reward con
   MazeNavigationSim       abmarl/examples/sim/maze_navigation.py:14-42
   MultiMazeNavigationSim  abmarl/examples/sim/multi_maze_navigation.py:17-74
   PacmanSim               abmarl/examples/sim/pacman.py:29-151
+  ReachTheTargetSim       abmarl/examples/sim/reach_the_target.py:90-176
 """
 from abmarl_b200.sim.gridworld.smart import SmartGridWorldSimulation
 from abmarl_b200.sim.gridworld.base import GridWorldSimulation
 from abmarl_b200.sim.gridworld.agent import (
     GridObservingAgent, MovingAgent, AttackingAgent, HealthAgent, OrientationAgent, GridWorldAgent,
 )
-from abmarl_b200.sim.gridworld.actor import MoveActor, BinaryAttackActor, DriftMoveActor
+from abmarl_b200.sim.gridworld.actor import MoveActor, BinaryAttackActor, DriftMoveActor, SelectiveAttackActor
+from abmarl_b200.sim.gridworld.state import PositionState, HealthState
+from abmarl_b200.sim.gridworld.done import ActiveDone, DoneBaseComponent
 from abmarl_b200.sim.gridworld.state import MazePlacementState
 from abmarl_b200.sim.gridworld.observer import PositionCenteredEncodingObserver
 
@@ -123,3 +126,58 @@ class PacmanSim(SmartGridWorldSimulation):
 
     def program(self):
         return 'pacman'
+
+
+class TargetDone(ActiveDone):
+    """reach_the_target.py:14-40: an agent is done when it stands on the target's cell."""
+
+    def __init__(self, target=None, **kwargs):
+        super().__init__(**kwargs)
+        assert target in self.agents.values(), "Target must be an agent."
+        self.target = target
+
+
+class OnlyAgentLeftDone(DoneBaseComponent):
+    """reach_the_target.py:43-57: agent and simulation are done when at most one learning agent is active."""
+
+
+class BarrierAgent(GridWorldAgent):
+    """reach_the_target.py:60-67"""
+
+    def __init__(self, **kwargs):
+        super().__init__(encoding=1, blocking=True, render_shape='s', **kwargs)
+
+
+class TargetAgent(AttackingAgent, GridObservingAgent):
+    """reach_the_target.py:70-77"""
+
+    def __init__(self, **kwargs):
+        super().__init__(id='target', encoding=2, render_color='g', **kwargs)
+
+
+class RunningAgent(MovingAgent, GridObservingAgent, HealthAgent):
+    """reach_the_target.py:80-87"""
+
+    def __init__(self, **kwargs):
+        super().__init__(encoding=3, render_color='b', **kwargs)
+
+
+class ReachTheTargetSim(GridWorldSimulation):
+    """reach_the_target.py:90-176: runners try to reach the target, which shoots at them (SelectiveAttackActor)."""
+    reward_constants = dict(attack_fail=-0.1, kill=1.0, die=-1.0, move_fail=-0.1, target=1.0, entropy=-0.01)
+
+    def __init__(self, **kwargs):
+        super().__init__(**kwargs)
+        self.target = self.agents['target']
+        self.position_state = PositionState(**kwargs)
+        self.health_state = HealthState(**kwargs)
+        self.move_actor = MoveActor(**kwargs)
+        self.attack_actor = SelectiveAttackActor(**kwargs)
+        self.grid_observer = PositionCenteredEncodingObserver(**kwargs)
+        self.active_done = ActiveDone(**kwargs)
+        self.target_done = TargetDone(target=self.target, **kwargs)
+        self.only_agent_done = OnlyAgentLeftDone(**kwargs)
+        self.finalize()
+
+    def program(self):
+        return 'reach_the_target'

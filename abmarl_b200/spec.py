@@ -98,7 +98,7 @@ class CompiledSpec:
         return s
 
 
-_PROGRAMS = (('TeamBattleSim', K.PROG_TEAM_BATTLE), ('MultiMazeNavigationSim', K.PROG_MULTI_MAZE),
+_PROGRAMS = (('ReachTheTargetSim', K.PROG_REACH_TARGET), ('TeamBattleSim', K.PROG_TEAM_BATTLE), ('MultiMazeNavigationSim', K.PROG_MULTI_MAZE),
              ('MazeNavigationSim', K.PROG_MAZE), ('PacmanSim', K.PROG_PACMAN))
 _OBSERVERS = (('StackedPositionCenteredEncodingObserver', K.OBS_STACKED),
               ('PositionCenteredEncodingObserver', K.OBS_POSITION_CENTERED),
@@ -245,6 +245,18 @@ def compile_sim(sim, manager='all_step', n_envs=1, env_offset=0, seed=0, horizon
         # Binary hands TeamBattleSim.step an ndarray: `not attacked_agents` raises for more than one element
         assert sp.attack_actor != K.ATTACK_BINARY or int(sp.simultaneous_attacks.max(initial=0)) <= 1, \
             "TeamBattleSim.step with the BinaryAttackActor is only defined for simultaneous_attacks == 1 (team_battle_example.py:41)"
+    elif sp.program == K.PROG_REACH_TARGET:     # reach_the_target.py:117-152
+        sp.reward[K.RW_ATTACK_FAIL] = rc.get('attack_fail', -0.1)
+        sp.reward[K.RW_KILL] = rc.get('kill', 1.0)
+        sp.reward[K.RW_DIE] = rc.get('die', -1.0)
+        sp.reward[K.RW_MOVE_FAIL] = rc.get('move_fail', -0.1)
+        sp.reward[K.RW_TARGET] = rc.get('target', 1.0)
+        sp.reward[K.RW_ENTROPY] = rc.get('entropy', -0.01)
+        sp.role[index[sim.target.id]] = K.ROLE_TARGET
+        for i, ag in enumerate(agents):
+            if 'RunningAgent' in _mro_names(ag):
+                sp.role[i] = K.ROLE_RUNNER
+        assert sp.attack_actor != K.ATTACK_BINARY or int(sp.simultaneous_attacks.max(initial=0)) <= 1
     elif sp.program in (K.PROG_MAZE, K.PROG_MULTI_MAZE):   # maze_navigation.py:29-36, multi_maze_navigation.py:45-59
         sp.reward[K.RW_MOVE_FAIL] = rc.get('move_fail', -0.1)
         sp.reward[K.RW_TARGET] = rc.get('target', 1.0)

@@ -63,7 +63,8 @@ enum {
     BGW_ROLE_PACMAN = 3,    /* pacman.py:11                                          */
     BGW_ROLE_FOOD = 4,      /* pacman.py:19                                          */
     BGW_ROLE_BADDIE = 5,    /* pacman.py:24                                          */
-    BGW_ROLE_WALL = 6
+    BGW_ROLE_WALL = 6,
+    BGW_ROLE_RUNNER = 7     /* reach_the_target.py:80-87 RunningAgent                */
 };
 
 /* ---- sim program: the user-written step()/get_* the engine reproduces ------------------------ */
@@ -71,7 +72,8 @@ enum {
     BGW_PROG_TEAM_BATTLE = 0, /* abmarl/examples/sim/team_battle_example.py:23-59 */
     BGW_PROG_MAZE = 1,        /* abmarl/examples/sim/maze_navigation.py:14-42     */
     BGW_PROG_MULTI_MAZE = 2,  /* abmarl/examples/sim/multi_maze_navigation.py:17-74 */
-    BGW_PROG_PACMAN = 3       /* abmarl/examples/sim/pacman.py:29-151             */
+    BGW_PROG_PACMAN = 3,      /* abmarl/examples/sim/pacman.py:29-151             */
+    BGW_PROG_REACH_TARGET = 4 /* abmarl/examples/sim/reach_the_target.py:90-176   */
 };
 
 enum { BGW_MOVE_NONE = 0, BGW_MOVE_BOX = 1 /* MoveActor actor.py:55 */, BGW_MOVE_CROSS = 2 /* :117 */,
@@ -100,7 +102,7 @@ enum {
     BGW_RW_DIE = 2,         /* -1    :46 / pacman 'die'        */
     BGW_RW_MOVE_FAIL = 3,   /* -0.1  :55 / pacman 'bad_move'   */
     BGW_RW_ENTROPY = 4,     /* -0.01 :59 / pacman 'entropy'    */
-    BGW_RW_TARGET = 5,      /* +1    maze_navigation.py:33 / multi_maze_navigation.py:57 */
+    BGW_RW_TARGET = 5,      /* +1    maze_navigation.py:33 / multi_maze_navigation.py:57 / reach_the_target.py:142 */
     BGW_RW_EAT_FOOD = 6,    /* pacman 'eat_food' pacman.py:97  */
     BGW_RW_COUNT = 8
 };

@@ -571,9 +571,24 @@ static int smart_all_done(const Ctx *c)      /* smart.py:113-117 */
     return d;
 }
 
+/* OnlyAgentLeftDone._agents_remaining reach_the_target.py:47-51: active learning agents */
+static int learners_remaining(const Ctx *c)
+{
+    int n = 0;
+    for (int l = 0; l < c->L; ++l) n += (c->flags[c->agent_of[l]] & BGW_ST_ACTIVE) ? 1 : 0;
+    return n;
+}
+
 static int prog_done(const Ctx *c, int a)
 {
     switch (c->sp->program) {
+    case BGW_PROG_REACH_TARGET: {                                                   /* reach_the_target.py:161-168 */
+        const int t = find_role(c, BGW_ROLE_TARGET);
+        if (c->sp->role[a] == BGW_ROLE_RUNNER)                                      /* ActiveDone or TargetDone :26-40 */
+            return !(c->flags[a] & BGW_ST_ACTIVE) || (a != t && same_position(c, a, t));
+        if (a == t) return learners_remaining(c) <= 1;                              /* OnlyAgentLeftDone :53-54 */
+        return 0;
+    }
     case BGW_PROG_MAZE: return prog_all_done(c);                                    /* maze_navigation.py:38-39 */
     case BGW_PROG_MULTI_MAZE: return same_position(c, a, find_role(c, BGW_ROLE_TARGET)); /* multi_maze_navigation.py:61-64 */
     case BGW_PROG_PACMAN: return prog_all_done(c);                                  /* pacman.py:137-138 */
@@ -584,6 +599,7 @@ static int prog_done(const Ctx *c, int a)
 static int prog_all_done(const Ctx *c)
 {
     switch (c->sp->program) {
+    case BGW_PROG_REACH_TARGET: return learners_remaining(c) <= 1;                  /* reach_the_target.py:170-171,56-57 */
     case BGW_PROG_MAZE:                                                             /* maze_navigation.py:41-42 */
         return same_position(c, find_role(c, BGW_ROLE_NAVIGATOR), find_role(c, BGW_ROLE_TARGET));
     case BGW_PROG_MULTI_MAZE: {                                                     /* multi_maze_navigation.py:66-71 */
@@ -673,6 +689,40 @@ static void prog_step(Ctx *c, const int *acting, int n_act, const int8_t *action
             if (!process_move(c, a, ACT(a))) c->racc[a] += rw[BGW_RW_MOVE_FAIL];
         }
         for (int i = 0; i < n_act; ++i) c->racc[acting[i]] += rw[BGW_RW_ENTROPY];   /* :58-59 */
+        break;
+    }
+    case BGW_PROG_REACH_TARGET: {                              /* reach_the_target.py:117-152 */
+        int victims[BGW_MAX_VICTIMS + 1];
+        const int tgt = find_role(c, BGW_ROLE_TARGET);
+        for (int i = 0; i < n_act; ++i) {                      /* :119-131 (same shape as the team battle) */
+            const int a = acting[i];
+            if (!(c->flags[a] & BGW_ST_ACTIVE)) continue;
+            int nv = 0;
+            const int status = process_attack(c, a, (const uint8_t *)ACT(a) + 2, victims, &nv);
+            if (status) {
+                if (nv == 0) c->racc[a] += rw[BGW_RW_ATTACK_FAIL];
+                else for (int t = 0; t < nv; ++t)
+                    if (!(c->flags[victims[t]] & BGW_ST_ACTIVE)) {
+                        c->racc[victims[t]] += rw[BGW_RW_DIE];
+                        c->racc[a] += rw[BGW_RW_KILL];
+                    }
+            }
+        }
+        for (int i = 0; i < n_act; ++i) {                      /* :134-145 */
+            const int a = acting[i];
+            if (!(sp->klass[a] & BGW_AG_MOVING)) continue;
+            if (c->flags[a] & BGW_ST_ACTIVE)
+                if (!process_move(c, a, ACT(a))) c->racc[a] += rw[BGW_RW_MOVE_FAIL];
+            /* TargetDone.get_done :33-40.  A runner that is no longer in the grid (killed while standing on the
+             * target's cell) would make the reference's grid.remove raise; it is left alone here */
+            if (a != tgt && (c->flags[a] & BGW_ST_IN_GRID) && same_position(c, a, tgt)) {
+                c->racc[a] += rw[BGW_RW_TARGET];
+                grid_remove(c, a);
+                c->flags[a] &= (uint8_t)~BGW_ST_ACTIVE;
+            }
+        }
+        for (int i = 0; i < n_act; ++i)                         /* :148-150 */
+            if (sp->role[acting[i]] == BGW_ROLE_RUNNER) c->racc[acting[i]] += rw[BGW_RW_ENTROPY];
         break;
     }
     case BGW_PROG_MAZE: {                                      /* maze_navigation.py:25-36 */

@@ -214,6 +214,37 @@ def build_tb_ammo_selective(api):
 
 
 # ---------------------------------------------------------------------------------------------------
+# reach the target (reach_the_target.py:90-176; examples/rllib_reach_the_target.py:7-56)
+# ---------------------------------------------------------------------------------------------------
+def build_reach_target(api, grid_size=7, n_barriers=10, n_runners=4, corners=True, move_range=2, sim_attacks=1):
+    """examples/rllib_reach_the_target.py: ten view-blocking barriers at random cells, four runners starting in the
+    corners, the target in the middle shooting with the SelectiveAttackActor."""
+    ex = api.ex
+    corner = [np.array([0, 0]), np.array([grid_size - 1, 0]), np.array([0, grid_size - 1]), np.array([grid_size - 1, grid_size - 1])]
+    agents = {f'barrier{i}': ex.BarrierAgent(id=f'barrier{i}') for i in range(n_barriers)}
+    for i in range(n_runners):
+        agents[f'runner{i}'] = ex.RunningAgent(
+            id=f'runner{i}', move_range=move_range, view_range=grid_size // 2, initial_health=1,
+            initial_position=corner[i] if corners and i < 4 else None)
+    agents['target'] = ex.TargetAgent(
+        view_range=grid_size, attack_range=1, attack_strength=1, attack_accuracy=1, simultaneous_attacks=sim_attacks,
+        initial_position=np.array([grid_size // 2, grid_size // 2]))
+    return ex.ReachTheTargetSim.build_sim(
+        grid_size, grid_size, agents=agents, overlapping={2: {3}, 3: {1, 2, 3}}, attack_mapping={2: {3}})
+
+
+def build_reach_target_crowd(api):
+    """A busier variant: more runners placed at random (some may start on the target's cell), weaker and less
+    accurate shots from a target that may shoot twice per cell, move range 1."""
+    sim = build_reach_target(api, grid_size=6, n_barriers=6, n_runners=9, corners=False, move_range=1, sim_attacks=2)
+    sim.target.attack_strength = 0.6
+    sim.target.attack_accuracy = 0.8
+    sim.target.attack_range = 2
+    sim.attack_actor = api.actor.SelectiveAttackActor(agents=sim.agents, grid=sim.grid, attack_mapping={2: {3}})
+    return sim
+
+
+# ---------------------------------------------------------------------------------------------------
 # maze (maze_navigation.py; examples/rllib_maze_navigation.py:7-38)
 # ---------------------------------------------------------------------------------------------------
 def build_maze_c1(api):
@@ -319,6 +350,8 @@ SCENARIOS = {
     'tb_selective_stacked': (build_tb_selective_stacked, 'all_step', 40),
     'tb_ammo': (build_tb_ammo, 'all_step', 40),
     'tb_ammo_selective': (build_tb_ammo_selective, 'all_step', 40),
+    'reach_target': (build_reach_target, 'all_step', 60),
+    'reach_target_crowd': (build_reach_target_crowd, 'all_step', 60),
     'maze_c1': (build_maze_c1, 'all_step', 60),
     'pacman_c3': (build_pacman_c3, 'all_step', 12),
     'mm_c4': (build_mm_c4, 'turn_based', 120),
