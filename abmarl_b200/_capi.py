@@ -16,7 +16,7 @@ BGW_STAT_COUNT = 4
 # enums (include/bgw.h)
 AG_OBSERVING, AG_MOVING, AG_ATTACKING, AG_HEALTH, AG_ORIENT, AG_LEARNER, AG_BLOCKING, AG_AMMO = (1 << i for i in range(8))
 ROLE_NONE, ROLE_NAVIGATOR, ROLE_TARGET, ROLE_PACMAN, ROLE_FOOD, ROLE_BADDIE, ROLE_WALL, ROLE_RUNNER = range(8)
-PROG_TEAM_BATTLE, PROG_MAZE, PROG_MULTI_MAZE, PROG_PACMAN, PROG_REACH_TARGET = range(5)
+PROG_TEAM_BATTLE, PROG_MAZE, PROG_MULTI_MAZE, PROG_PACMAN, PROG_REACH_TARGET, PROG_TRAFFIC = range(6)
 MOVE_NONE, MOVE_BOX, MOVE_CROSS, MOVE_DRIFT = range(4)
 ATTACK_NONE, ATTACK_BINARY, ATTACK_ENCODING, ATTACK_RESTRICTED, ATTACK_SELECTIVE = range(5)
 BGW_MAX_VICTIMS, BGW_MAX_SIMATT = 256, 16

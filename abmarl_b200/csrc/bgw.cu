@@ -220,7 +220,7 @@ int bgw_create(const BgwSpec *sp, int device, bgw_handle *out)
         return bail(fail(1, "bgw_create: PacmanSim needs a learning pacman and the (9,0)<->(9,20) tunnel (pacman.py:87-92)"));
     if (sp->program == BGW_PROG_REACH_TARGET && (d.a_target < 0 || learner_of[d.a_target] < 0))
         return bail(fail(1, "bgw_create: ReachTheTargetSim needs a learning target agent"));
-    if (sp->program < BGW_PROG_TEAM_BATTLE || sp->program > BGW_PROG_REACH_TARGET) return bail(fail(1, "bgw_create: unknown program %d", sp->program));
+    if (sp->program < BGW_PROG_TEAM_BATTLE || sp->program > BGW_PROG_TRAFFIC) return bail(fail(1, "bgw_create: unknown program %d", sp->program));
 
     /* ---- observation geometry (same rule as the oracle's bgwo_dims) ------------------------------ */
     BgwDims &dm = h->dims;
@@ -290,7 +290,9 @@ int bgw_create(const BgwSpec *sp, int device, bgw_handle *out)
     int T = A <= 128 ? 32 : A <= 1024 ? 64 : 128;
     if (const char *t = getenv("BGW_THREADS")) { const int v = atoi(t); if (v >= 32 && v <= 1024 && v % 32 == 0) T = v; }
     h->threads = T;
-    d.parallel_actors = ((sp->program == BGW_PROG_TEAM_BATTLE || sp->program == BGW_PROG_REACH_TARGET) && (sp->move_actor == BGW_MOVE_BOX || sp->move_actor == BGW_MOVE_CROSS));
+    d.parallel_actors = ((sp->program == BGW_PROG_TEAM_BATTLE || sp->program == BGW_PROG_REACH_TARGET || sp->program == BGW_PROG_TRAFFIC) && (sp->move_actor == BGW_MOVE_BOX || sp->move_actor == BGW_MOVE_CROSS));
+    if (sp->program == BGW_PROG_TRAFFIC)         /* the +1 looks at the target's cell right after the own move: rank order if a target can move */
+        for (int a = 0; a < A; ++a) if (sp->target[a] >= 0 && (sp->klass[sp->target[a]] & BGW_AG_MOVING)) d.parallel_actors = 0;
     if (const char *t = getenv("BGW_SERIAL_ACTORS")) if (atoi(t)) d.parallel_actors = 0;
     int slots = std::min(std::max(pow2ceil(HW), 32), 2048);
     if (const char *t = getenv("BGW_SLOTS")) { const int v = atoi(t); if (v >= 32 && v <= 65536 && (v & (v - 1)) == 0) slots = v; }

@@ -578,6 +578,8 @@ __device__ __forceinline__ uint32_t *slot_of(const DevSpec &s, const Env &ev, in
 /* ------------------------------------------------------------------------------------------------- */
 /* sim programs: the user-written step()                                                             */
 /* ------------------------------------------------------------------------------------------------- */
+__device__ __forceinline__ bool prog_done(const DevSpec &s, const Env &ev, int a);
+
 /* ReachTheTargetSim.step reach_the_target.py:141-144: a runner standing on the target's cell has reached it.  A runner
  * that is no longer in the grid (killed on that cell) would make the reference's grid.remove raise; it is left alone. */
 __device__ __forceinline__ void reach_check(const DevSpec &s, Env &ev, int a)
@@ -589,13 +591,14 @@ __device__ __forceinline__ void reach_check(const DevSpec &s, Env &ev, int a)
     }
 }
 
-/* TeamBattleSim.step team_battle_example.py:33-59 and ReachTheTargetSim.step reach_the_target.py:117-152 (same attack
+/* TeamBattleSim.step team_battle_example.py:33-59, ReachTheTargetSim.step reach_the_target.py:117-152 (same attack
  * phase; only MovingAgents move, a runner that reaches the target leaves the grid, only runners pay the entropy
- * penalty); ranks 0..nrank-1 hold the acting agents (ragent) */
+ * penalty) and TrafficCorridorSimulation.step traffic_corridor.py:46-53 (moves only; +1 while on the own target, no
+ * entropy penalty); ranks 0..nrank-1 hold the acting agents (ragent) */
 __device__ void team_battle_step(const DevSpec &s, Env &ev, int nrank, int tid, int T)
 {
     const double *rw = s.reward;
-    const bool reach = s.program == BGW_PROG_REACH_TARGET;
+    const bool reach = s.program == BGW_PROG_REACH_TARGET, traffic = s.program == BGW_PROG_TRAFFIC;
     if (!s.parallel_actors) {
         if (tid == 0) {
             for (int i = 0; i < nrank; ++i) {
@@ -609,8 +612,9 @@ __device__ void team_battle_step(const DevSpec &s, Env &ev, int nrank, int tid, 
                 if (ev.flags[a] & BGW_ST_ACTIVE)
                     if (!process_move(s, ev, a, ev.act[(size_t)__ldg(&s.learner_of[a]) * s.act_words])) ev.racc[a] += rw[BGW_RW_MOVE_FAIL];
                 if (reach) reach_check(s, ev, a);
+                if (traffic && prog_done(s, ev, a)) ev.racc[a] += rw[BGW_RW_TARGET];
             }
-            for (int i = 0; i < nrank; ++i)
+            for (int i = 0; i < nrank && !traffic; ++i)
                 if (ev.ragent[i] != BGW_NONE16 && (!reach || __ldg(&s.role[ev.ragent[i]]) == BGW_ROLE_RUNNER)) ev.racc[ev.ragent[i]] += rw[BGW_RW_ENTROPY];
         }
         __syncthreads();
@@ -685,6 +689,7 @@ __device__ void team_battle_step(const DevSpec &s, Env &ev, int nrank, int tid, 
             /* a runner that does not move but stands on the target's cell (placed there) still reaches it: the removal
              * goes through the ordered rounds as a move to its own cell */
             if (reach && !p && (ev.flags[a] & BGW_ST_IN_GRID) && a != s.a_target && ev.cell[a] == ev.cell[s.a_target]) { p = 1; ev.plist[i] = ev.cell[a]; }
+            if (traffic && !p && prog_done(s, ev, a)) ev.racc[a] += rw[BGW_RW_TARGET];     /* :52-53, it did not move */
         }
         ev.pstate[i] = p;
         mine |= p;
@@ -713,6 +718,7 @@ __device__ void team_battle_step(const DevSpec &s, Env &ev, int nrank, int tid, 
                     else ev.racc[a] += rw[BGW_RW_MOVE_FAIL];
                 }
                 if (reach) reach_check(s, ev, a);
+                if (traffic && prog_done(s, ev, a)) ev.racc[a] += rw[BGW_RW_TARGET];
                 *slot_of(s, ev, from) = BGW_SLOT_FREE;
                 *slot_of(s, ev, to) = BGW_SLOT_FREE;
                 ev.pstate[i] = 0;
@@ -722,7 +728,7 @@ __device__ void team_battle_step(const DevSpec &s, Env &ev, int nrank, int tid, 
         any = __syncthreads_or(mine);
     }
     /* ---- entropy :58-59 ------------------------------------------------------------------------ */
-    for (int i = tid; i < nrank; i += T)
+    for (int i = tid; i < nrank && !traffic; i += T)
         if (ev.ragent[i] != BGW_NONE16 && (!reach || __ldg(&s.role[ev.ragent[i]]) == BGW_ROLE_RUNNER)) ev.racc[ev.ragent[i]] += rw[BGW_RW_ENTROPY];
     __syncthreads();
 }
@@ -1230,7 +1236,7 @@ __global__ void bgw_step_kernel(const DevSpec s, const BgwState st, const uint32
     __syncthreads();
 
     /* ---- sim.step(action_dict) ------------------------------------------------------------------ */
-    if (s.program == BGW_PROG_TEAM_BATTLE || s.program == BGW_PROG_REACH_TARGET) team_battle_step(s, ev, nrank, tid, T);
+    if (s.program == BGW_PROG_TEAM_BATTLE || s.program == BGW_PROG_REACH_TARGET || s.program == BGW_PROG_TRAFFIC) team_battle_step(s, ev, nrank, tid, T);
     else { if (tid == 0) serial_program_step(s, ev, nrank); __syncthreads(); }
 
     compute_all_done(s, ev, tid, T);

@@ -98,7 +98,7 @@ class CompiledSpec:
         return s
 
 
-_PROGRAMS = (('ReachTheTargetSim', K.PROG_REACH_TARGET), ('TeamBattleSim', K.PROG_TEAM_BATTLE), ('MultiMazeNavigationSim', K.PROG_MULTI_MAZE),
+_PROGRAMS = (('ReachTheTargetSim', K.PROG_REACH_TARGET), ('TrafficCorridorSimulation', K.PROG_TRAFFIC), ('TeamBattleSim', K.PROG_TEAM_BATTLE), ('MultiMazeNavigationSim', K.PROG_MULTI_MAZE),
              ('MazeNavigationSim', K.PROG_MAZE), ('PacmanSim', K.PROG_PACMAN))
 _OBSERVERS = (('StackedPositionCenteredEncodingObserver', K.OBS_STACKED),
               ('PositionCenteredEncodingObserver', K.OBS_POSITION_CENTERED),
@@ -245,6 +245,10 @@ def compile_sim(sim, manager='all_step', n_envs=1, env_offset=0, seed=0, horizon
         # Binary hands TeamBattleSim.step an ndarray: `not attacked_agents` raises for more than one element
         assert sp.attack_actor != K.ATTACK_BINARY or int(sp.simultaneous_attacks.max(initial=0)) <= 1, \
             "TeamBattleSim.step with the BinaryAttackActor is only defined for simultaneous_attacks == 1 (team_battle_example.py:41)"
+    elif sp.program == K.PROG_TRAFFIC:          # traffic_corridor.py:46-53
+        sp.reward[K.RW_MOVE_FAIL] = rc.get('move_fail', -0.1)
+        sp.reward[K.RW_TARGET] = rc.get('target', 1.0)
+        assert sp.done_mask == K.DONE_TARGET_AGENT, "TrafficCorridorSimulation.step rewards TargetAgentDone.get_done"
     elif sp.program == K.PROG_REACH_TARGET:     # reach_the_target.py:117-152
         sp.reward[K.RW_ATTACK_FAIL] = rc.get('attack_fail', -0.1)
         sp.reward[K.RW_KILL] = rc.get('kill', 1.0)

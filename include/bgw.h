@@ -73,7 +73,8 @@ enum {
     BGW_PROG_MAZE = 1,        /* abmarl/examples/sim/maze_navigation.py:14-42     */
     BGW_PROG_MULTI_MAZE = 2,  /* abmarl/examples/sim/multi_maze_navigation.py:17-74 */
     BGW_PROG_PACMAN = 3,      /* abmarl/examples/sim/pacman.py:29-151             */
-    BGW_PROG_REACH_TARGET = 4 /* abmarl/examples/sim/reach_the_target.py:90-176   */
+    BGW_PROG_REACH_TARGET = 4,/* abmarl/examples/sim/reach_the_target.py:90-176   */
+    BGW_PROG_TRAFFIC = 5      /* abmarl/examples/sim/traffic_corridor.py:24-53    */
 };
 
 enum { BGW_MOVE_NONE = 0, BGW_MOVE_BOX = 1 /* MoveActor actor.py:55 */, BGW_MOVE_CROSS = 2 /* :117 */,
@@ -102,7 +103,7 @@ enum {
     BGW_RW_DIE = 2,         /* -1    :46 / pacman 'die'        */
     BGW_RW_MOVE_FAIL = 3,   /* -0.1  :55 / pacman 'bad_move'   */
     BGW_RW_ENTROPY = 4,     /* -0.01 :59 / pacman 'entropy'    */
-    BGW_RW_TARGET = 5,      /* +1    maze_navigation.py:33 / multi_maze_navigation.py:57 / reach_the_target.py:142 */
+    BGW_RW_TARGET = 5,      /* +1    maze_navigation.py:33 / multi_maze_navigation.py:57 / reach_the_target.py:142 / traffic_corridor.py:53 */
     BGW_RW_EAT_FOOD = 6,    /* pacman 'eat_food' pacman.py:97  */
     BGW_RW_COUNT = 8
 };

@@ -725,6 +725,13 @@ static void prog_step(Ctx *c, const int *acting, int n_act, const int8_t *action
             if (sp->role[acting[i]] == BGW_ROLE_RUNNER) c->racc[acting[i]] += rw[BGW_RW_ENTROPY];
         break;
     }
+    case BGW_PROG_TRAFFIC:                                     /* traffic_corridor.py:46-53 */
+        for (int i = 0; i < n_act; ++i) {
+            const int a = acting[i];
+            if (!process_move(c, a, ACT(a))) c->racc[a] += rw[BGW_RW_MOVE_FAIL];
+            if (smart_done(c, a)) c->racc[a] += rw[BGW_RW_TARGET];
+        }
+        break;
     case BGW_PROG_MAZE: {                                      /* maze_navigation.py:25-36 */
         const int nav = find_role(c, BGW_ROLE_NAVIGATOR);
         if (!process_move(c, nav, ACT(nav))) c->racc[nav] += rw[BGW_RW_MOVE_FAIL];

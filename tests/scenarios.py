@@ -17,9 +17,10 @@ LAYOUTS = os.path.join(HERE, 'golden', 'layouts')
 def mirror_api():
     from abmarl_b200 import examples as ex, managers
     from abmarl_b200.sim.gridworld import agent, actor, observer, state, done, wrapper
+    from abmarl_b200.examples import traffic_corridor
     return types.SimpleNamespace(
         name='mirror', ex=ex, agent=agent, actor=actor, observer=observer, state=state, done=done,
-        wrapper=wrapper, managers=managers, pacman=ex)
+        wrapper=wrapper, managers=managers, pacman=ex, traffic=traffic_corridor)
 
 
 def reference_api():
@@ -29,9 +30,10 @@ def reference_api():
     import abmarl.managers as managers
     from abmarl.examples.sim import pacman
     from abmarl.sim.gridworld import agent, actor, observer, state, done, wrapper
+    from abmarl.examples.sim import traffic_corridor
     return types.SimpleNamespace(
         name='reference', ex=ex, agent=agent, actor=actor, observer=observer, state=state, done=done,
-        wrapper=wrapper, managers=managers, pacman=pacman)
+        wrapper=wrapper, managers=managers, pacman=pacman, traffic=traffic_corridor)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -245,6 +247,28 @@ def build_reach_target_crowd(api):
 
 
 # ---------------------------------------------------------------------------------------------------
+# traffic corridor (traffic_corridor.py:24-53; examples/rllib_traffic_corridor_2_teams.py:7-66)
+# ---------------------------------------------------------------------------------------------------
+def build_traffic(api):
+    """examples/rllib_traffic_corridor_2_teams.py: two teams cross a one-cell-wide corridor in opposite directions."""
+    tc = api.traffic
+    grid = np.array([['G', 'W', 'W', 'W', 'R'],
+                     ['r', '_', '_', '_', 'g'],
+                     ['G', 'W', 'W', 'W', 'R']])
+    registry = {
+        'R': lambda n: tc.TrafficAgent(id=f'red{n}', encoding=1),
+        'G': lambda n: tc.TrafficAgent(id=f'green{n}', encoding=2),
+        'r': lambda n: tc.TargetAgent(id='red_target', encoding=1),
+        'g': lambda n: tc.TargetAgent(id='green_target', encoding=2),
+        'W': lambda n: tc.WallAgent(id=f'wall{n}', encoding=3),
+    }
+    return tc.TrafficCorridorSimulation.build_sim_from_array(
+        grid, registry, overlapping={1: {1}, 2: {2}}, states={'PositionState'}, dones={'TargetAgentDone'},
+        observers={'PositionCenteredEncodingObserver'},
+        target_mapping={'red4': 'red_target', 'red11': 'red_target', 'green0': 'green_target', 'green7': 'green_target'})
+
+
+# ---------------------------------------------------------------------------------------------------
 # maze (maze_navigation.py; examples/rllib_maze_navigation.py:7-38)
 # ---------------------------------------------------------------------------------------------------
 def build_maze_c1(api):
@@ -352,6 +376,7 @@ SCENARIOS = {
     'tb_ammo_selective': (build_tb_ammo_selective, 'all_step', 40),
     'reach_target': (build_reach_target, 'all_step', 60),
     'reach_target_crowd': (build_reach_target_crowd, 'all_step', 60),
+    'traffic': (build_traffic, 'all_step', 120),
     'maze_c1': (build_maze_c1, 'all_step', 60),
     'pacman_c3': (build_pacman_c3, 'all_step', 12),
     'mm_c4': (build_mm_c4, 'turn_based', 120),

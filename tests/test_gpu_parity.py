@@ -41,6 +41,7 @@ CASES = [
     ('tb_ammo_selective', 48, 100, 30),
     ('reach_target', 64, 150, 40),
     ('reach_target_crowd', 64, 150, 40),
+    ('traffic', 64, 200, 50),
     ('maze_c1', 32, 150, 60),
     ('pacman_c3', 6, 40, 25),
     ('mm_c4', 12, 150, 60),
@@ -81,7 +82,7 @@ def test_thread_count_does_not_change_results(mirror, threads, monkeypatch):
     run_lockstep(eng, ora, 45, label='tb_c5_small/T' + threads)
 
 
-@pytest.mark.parametrize('name', ['tb_c2', 'tb_dense', 'tb_blocking', 'tb_restricted_stacked', 'tb_ammo_selective', 'reach_target_crowd'])
+@pytest.mark.parametrize('name', ['tb_c2', 'tb_dense', 'tb_blocking', 'tb_restricted_stacked', 'tb_ammo_selective', 'reach_target_crowd', 'traffic'])
 def test_serial_and_reservation_actor_paths_agree(mirror, name, monkeypatch):
     """The rank-order loop (one thread) and the reservation rounds must both equal the oracle."""
     builder, manager, _ = scenarios.SCENARIOS[name]
