@@ -44,7 +44,7 @@ def main(names):
         n = int(eng.stats()[K.STAT_AGENT_STEPS]) - n0
         print(json.dumps({"config": name, "envs": n_envs, "learners_per_env": eng.L, "entities_per_env": eng.A, "steps": steps,
                           "ms_per_step": ms / steps, "agent_steps_per_s": n / (ms * 1e-3),
-                          "kernel": "bgw_step_fast_kernel" if eng.dims.threads_per_env <= 128 and spec.program == K.PROG_TEAM_BATTLE and not (spec.klass & K.AG_BLOCKING).any() else "bgw_step_kernel"}), flush=True)
+                          "kernel": "bgw_step_fast_kernel" if eng.dims.threads_per_env <= 128 and spec.program == K.PROG_TEAM_BATTLE and not (spec.klass & (K.AG_BLOCKING | K.AG_AMMO)).any() and spec.attack_actor <= K.ATTACK_BINARY else "bgw_step_kernel"}), flush=True)
 
 
 if __name__ == '__main__':
