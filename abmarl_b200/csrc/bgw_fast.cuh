@@ -37,11 +37,6 @@
 #else
 #define BGW_PROF_MARK(k) do { } while (0)
 #endif
-#ifdef BGW_DIRECT_OBS
-#define BGW_OBS_STAGED false
-#else
-#define BGW_OBS_STAGED true
-#endif
 #define BGW_STAGE_ROW 80        /* bytes per lane in the observation stage: 64 payload + 16 pad (conflict-free 128-bit) */
 
 struct FastSpec {
@@ -567,17 +562,6 @@ __device__ void fast_obs_rows(const DevSpec &s, const FastSpec &f, const Env &ev
                     }
                 }
             }
-#ifdef BGW_DIRECT_OBS
-            /* every lane stores its own row: 16-byte stores, 128 bytes apart across the warp (the L2 merges the two
-             * halves of a sector); no staging, no transposition */
-            if (have) {
-                const int nchg = min(4, s.nchunks - 4 * g);              /* 16-byte chunks of this group that exist */
-                uint4 *dst = reinterpret_cast<uint4 *>(obs_env + (size_t)ev.plist[li] * s.obs_stride + g * 64);
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (j < nchg) dst[j] = make_uint4(out[4 * j], out[4 * j + 1], out[4 * j + 2], out[4 * j + 3]);
-            }
-#else
             uint4 *sp4 = reinterpret_cast<uint4 *>(stage + lane * BGW_STAGE_ROW);
 #pragma unroll
             for (int j = 0; j < 4; ++j) sp4[j] = make_uint4(out[4 * j], out[4 * j + 1], out[4 * j + 2], out[4 * j + 3]);
@@ -593,7 +577,6 @@ __device__ void fast_obs_rows(const DevSpec &s, const FastSpec &f, const Env &ev
                 }
             }
             __syncwarp();
-#endif
         }
     }
 }
@@ -999,9 +982,7 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
                 const int a = fe.rel[x];
                 if (racc_persists(ev.klass[a]) && (fe.rflag[a] & RF_DIED)) st.reward_acc[off + a] += rw[BGW_RW_DIE];
             }
-#ifndef BGW_DIRECT_OBS
         __syncthreads();                                            /* the scratch union becomes the observation stage */
-#endif
         BGW_PROF_MARK(9);
 
         /* ---- observations ------------------------------------------------------------------------------ */
@@ -1010,11 +991,11 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
             const bool direct = s.observe_self && !ev.ctr[CTR_MIXED];
             const int R = direct ? f.uniform_view : -1;
             switch (R) {
-            case 1: fast_obs_rows<1>(s, f, ev, fe, n_act, obs_env, (unsigned char *)fe.head, tid, T); staged = BGW_OBS_STAGED; break;
-            case 2: fast_obs_rows<2>(s, f, ev, fe, n_act, obs_env, (unsigned char *)fe.head, tid, T); staged = BGW_OBS_STAGED; break;
-            case 3: fast_obs_rows<3>(s, f, ev, fe, n_act, obs_env, (unsigned char *)fe.head, tid, T); staged = BGW_OBS_STAGED; break;
-            case 4: fast_obs_rows<4>(s, f, ev, fe, n_act, obs_env, (unsigned char *)fe.head, tid, T); staged = BGW_OBS_STAGED; break;
-            case 5: fast_obs_rows<5>(s, f, ev, fe, n_act, obs_env, (unsigned char *)fe.head, tid, T); staged = BGW_OBS_STAGED; break;
+            case 1: fast_obs_rows<1>(s, f, ev, fe, n_act, obs_env, (unsigned char *)fe.head, tid, T); staged = true; break;
+            case 2: fast_obs_rows<2>(s, f, ev, fe, n_act, obs_env, (unsigned char *)fe.head, tid, T); staged = true; break;
+            case 3: fast_obs_rows<3>(s, f, ev, fe, n_act, obs_env, (unsigned char *)fe.head, tid, T); staged = true; break;
+            case 4: fast_obs_rows<4>(s, f, ev, fe, n_act, obs_env, (unsigned char *)fe.head, tid, T); staged = true; break;
+            case 5: fast_obs_rows<5>(s, f, ev, fe, n_act, obs_env, (unsigned char *)fe.head, tid, T); staged = true; break;
             default: {
                 const int items = n_act * nch;
                 for (int it = tid; it < items; it += T) {
@@ -1039,21 +1020,10 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
         {
             uint32_t lo = 0, hi = 0;
             int ok = 1;
-#ifdef BGW_VEC_STORE
-            const bool rows = !fresh && f.async_ok;                 /* the staged rows go back whole: 16-byte coalesced stores */
-            if (rows) {
-                const uint4 *c4 = (const uint4 *)ev.cell, *n4 = (const uint4 *)ev.next, *f4 = (const uint4 *)ev.flags;
-                uint4 *gc = (uint4 *)(st.cell + off), *gn = (uint4 *)(st.next + off), *gf = (uint4 *)(st.flags + off);
-                for (int i = tid; i < s.A / 8; i += T) { gc[i] = c4[i]; gn[i] = n4[i]; }
-                for (int i = tid; i < s.A / 16; i += T) gf[i] = f4[i];
-            }
-#else
-            const bool rows = false;
-#endif
             for (int x = tid; x < n_rel; x += T) {
                 const int a = fe.rel[x];
                 const uint8_t fl = ev.flags[a];
-                if (!fresh && !rows) { st.cell[off + a] = ev.cell[a]; st.next[off + a] = ev.next[a]; st.flags[off + a] = fl; }
+                if (!fresh) { st.cell[off + a] = ev.cell[a]; st.next[off + a] = ev.next[a]; st.flags[off + a] = fl; }
                 if (fl & BGW_ST_ACTIVE) { const int en2 = ev.enc[a]; if (en2 < 32) lo |= 1u << en2; else hi |= 1u << (en2 - 32); }
                 if (s.done_mask & (BGW_DONE_TARGET_AGENT | BGW_DONE_TARGET_DESTROYED)) {
                     const int t = __ldg(&s.target[a]);
