@@ -55,23 +55,28 @@ class ClockSampler(threading.Thread):
     def run(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                          '--format=csv,noheader,nounits', '-lms', '50'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
-                self.rows.append([x.strip() for x in line.split(',')])
+                self.rows.append([x.strip() for x in line.split(',')] + [time.perf_counter()])
         except Exception:
             pass
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Summary of the samples read between host times t0 and t1 (the measured period); all samples if too few."""
         if self.proc is not None:
             self.proc.terminate()
         self.join(timeout=2)
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace('.', '').isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace('.', '').isdigit()]
+        rows = [r for r in self.rows if len(r) >= 10]
+        inside = [r for r in rows if t0 is not None and t0 - 0.06 <= r[-1] <= t1 + 0.06]
+        if len(inside) >= 2:
+            rows = inside
+        sm = [float(r[1]) for r in rows if r[1].replace('.', '').isdigit()]
+        mx = [float(r[2]) for r in rows if r[2].replace('.', '').isdigit()]
         names = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')
-        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower().startswith('active')})
+        reasons = sorted({n for r in rows for n, v in zip(names, r[5:9]) if v.lower().startswith('active')})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "period_ms": 50}
 
 
 def measured_peak():
@@ -164,15 +169,18 @@ def run_ours(args):
         return int(eng.stats()[K.STAT_AGENT_STEPS].item())
 
     # ---------------- device-resident rollout: `value` + roofline of the step kernel -----------------
+    # clocks / throttle reasons are sampled from before the warm-up until after the end-to-end loop (50 ms period):
+    # the timed regions are tens of milliseconds long, so the samples taken while the GPU is busy bracket them
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.5)
     eng.reset()
     for _ in range(args.warmup):
         eng.step_sampled()
     barrier()
     n0, launches0 = agent_steps(), eng.launches
-    sampler = ClockSampler(local) if rank == 0 else None
-    if sampler:
-        sampler.start()
-        time.sleep(0.3)
+    host_t0 = time.perf_counter()
     k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     t_beg, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -183,7 +191,6 @@ def run_ours(args):
         k_ev[i][1].record(stream)
     t_end.record(stream)
     barrier()
-    clocks = sampler.stop() if sampler else None
     ms = t_beg.elapsed_time(t_end)
     n_dev = agent_steps() - n0
     launches = eng.launches - launches0
@@ -252,6 +259,7 @@ def run_ours(args):
     barrier()
     e2e_ms = e_beg.elapsed_time(e_end)
     n_e2e = e2e_stats() - n1
+    clocks = sampler.stop(host_t0, time.perf_counter()) if sampler else None
     h2d = E * L * 4
     d2h = d2h_total[0] / e2e_steps
 
