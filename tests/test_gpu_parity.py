@@ -206,6 +206,44 @@ def test_full_size_c5_properties(mirror):
     assert (own >= 1).all()                                            # a live agent sees its own team on its cell
 
 
+@pytest.mark.parametrize('name,steps', [('tb_c2', 60), ('pacman_c3', 12)])
+def test_full_size_16k_envs(mirror, name, steps):
+    """BASELINE configs 2 and 3 at their full batch (16384 envs per GPU): oracle parity on the first and the last envs
+    of the batch (the Philox key is the global env index) plus invariants over all envs."""
+    E, S = 16384, 6
+    builder, manager, _ = scenarios.SCENARIOS[name]
+    spec = compile_sim(builder(mirror), manager=manager, n_envs=E, seed=0xB200, horizon=40, auto_reset=True)
+    from abmarl_b200.engine import BatchedGridWorld
+    from oracle.oracle import OracleEnv
+    eng = BatchedGridWorld(spec, device='cuda:0')
+    head, tail = OracleEnv(spec.with_envs(S, 0)), OracleEnv(spec.with_envs(S, E - S))
+    eng.reset()
+    for o in (head, tail):
+        o.reset()
+    assert np.array_equal(eng.obs[:S].cpu().numpy(), head.obs) and np.array_equal(eng.obs[E - S:].cpu().numpy(), tail.obs)
+    total = 0
+    for t in range(steps):
+        act = eng.sample_actions()
+        eng.step(act)
+        for o, sl in ((head, slice(0, S)), (tail, slice(E - S, E))):
+            a = o.sample_actions()
+            assert np.array_equal(act[sl].cpu().numpy(), a)
+            o.step(a)
+            assert np.array_equal(eng.obs[sl].cpu().numpy(), o.obs), f'{name} step {t}'
+            assert np.array_equal(eng.done[sl].cpu().numpy(), o.done)
+            assert np.array_equal(eng.reward[sl].cpu().numpy(), o.reward)
+            assert np.array_equal(eng.all_done[sl].cpu().numpy(), o.all_done)
+        total += int(((eng.done.cpu().numpy() & K.OUT_VALID) != 0).sum())
+    st = eng.state_numpy()
+    assert_state_equal({k: (None if v is None else v[:S]) for k, v in st.items()}, head.state, f'{name} head')
+    assert_state_equal({k: (None if v is None else v[E - S:]) for k, v in st.items()}, tail.state, f'{name} tail')
+    assert int(eng.stats()[K.STAT_AGENT_STEPS].item()) == total
+    assert (st['error'] == 0).all() and (st['cell'][(st['flags'] & K.ST_IN_GRID) != 0] < spec.rows * spec.cols).all()
+    health_agents = (np.asarray(spec.klass) & K.AG_HEALTH) != 0
+    active = (st['flags'] & K.ST_ACTIVE) != 0
+    assert np.array_equal(active[:, health_agents], st['health'][:, health_agents] > 0)      # agent.py:192-196
+
+
 @pytest.mark.parametrize('zero_copy', [True, False])
 def test_step_host_returns_exactly_the_valid_rows(mirror, zero_copy):
     """bgw_gather_valid / BatchedGridWorld.step_host: the compacted host buffers hold the rows with BGW_OUT_VALID
