@@ -369,6 +369,93 @@ def case_restricted_selective_attack_actor(kind):            # test_actor.py:150
     assert be.ammo()[3] == 98
 
 
+def _sim3_agents(strength):
+    """the 2x2 board of test_actor.py:988-1012 / 1088-1113: the attacker (ammo 100 so that len(attacked_agents) shows)
+    shares its cell with three attackable agents, a fourth sits on (0, 0)"""
+    return [dict(enc=3, pos=(1, 1), klass=LRN | OBS | ATT | AMM, att_range=1, strength=strength, accuracy=1, view=1, simatt=3, ammo=100),
+            dict(enc=1, pos=(0, 0), klass=HEA, health=1), dict(enc=2, pos=(1, 1), klass=HEA, health=1),
+            dict(enc=2, pos=(1, 1), klass=HEA, health=1), dict(enc=1, pos=(1, 1), klass=HEA, health=1)]
+
+
+_ALL3 = {1: {1, 2, 3}, 2: {1, 2, 3}, 3: {1, 2, 3}}
+
+
+def case_selective_attack_actor_simultaneous_attacks(kind):  # test_actor.py:988-1085
+    kw = dict(overlapping=_ALL3, attack_mapping={3: {1, 2}}, attack_actor=K.ATTACK_SELECTIVE)
+    be = Backend(make_spec(2, 2, _sim3_agents(0), **kw), kind)
+    be.reset()
+    used = []
+    for k in (0, 1, 2, 3):                                    # k attacks on the cells (0, 0) and (1, 1)
+        before = int(be.ammo()[0])
+        be.step([(0, 0) + tuple(np.array([[k, 0, 0], [0, k, 0], [0, 0, 0]]).ravel())])
+        used.append(before - int(be.ammo()[0]))
+        np.testing.assert_allclose(be.rewards(), [-0.1 - 0.01], atol=1e-6)          # attempted or not, nobody dies, no failure
+    assert used == [0, 2, 3, 4]                               # 1 + min(k, 3 agents on the own cell)
+    be = Backend(make_spec(2, 2, _sim3_agents(1), **kw), kind)
+    be.reset()
+    be.step([(0, 0) + tuple(np.array([[3, 0, 0], [0, 3, 0], [0, 0, 0]]).ravel())])
+    np.testing.assert_allclose(be.rewards(), [4 - 0.1 - 0.01], atol=1e-6)
+    assert not any(be.flags()[a] & K.ST_ACTIVE for a in (1, 2, 3, 4)) and be.flags()[0] & K.ST_ACTIVE
+
+
+def case_selective_attack_actor_stacked_attack(kind):        # test_actor.py:1088-1172
+    kw = dict(overlapping=_ALL3, attack_mapping={3: {1, 2}}, attack_actor=K.ATTACK_SELECTIVE)
+    be = Backend(make_spec(2, 2, _sim3_agents(1), **kw), kind)
+    be.reset()
+    be.step([(0, 0) + tuple(np.array([[0, 0, 0], [0, 2, 0], [0, 0, 0]]).ravel())])   # two different agents of the own cell
+    np.testing.assert_allclose(be.rewards(), [2 - 0.1 - 0.01], atol=1e-6)
+    assert sum(1 for a in (2, 3, 4) if not be.flags()[a] & K.ST_ACTIVE) == 2 and be.flags()[1] & K.ST_ACTIVE
+    be = Backend(make_spec(2, 2, _sim3_agents(0.5), stacked=True, **kw), kind)
+    be.reset()
+    be.step([(0, 0) + tuple(np.array([[1, 0, 0], [0, 3, 0], [0, 0, 0]]).ravel())])   # stacked: 1 + 3 draws with replacement
+    assert be.ammo()[0] == 96
+    h = np.array(be.health())
+    assert h[1] == 0.5 and sorted(2 * (1 - h[a]) for a in (2, 3, 4)) in ([0, 0, 2], [0, 1, 2], [1, 1, 1])   # three hits of 0.5 in all
+    be.step([(0, 0) + tuple(np.array([[3, 3, 3], [3, 3, 3], [3, 3, 3]]).ravel())])
+    assert be.ammo()[0] == 96 - 3 - 3 * (sum(1 for a in (2, 3, 4) if h[a] > 0) > 0)   # 3 on (0, 0); 3 on the own cell while anyone is left
+
+
+def case_encoding_based_attack_actor_simultaneous_attacks(kind):   # test_actor.py:1324-1436
+    def agents(strength):
+        return [dict(enc=1, pos=(0, 0), klass=HEA), dict(enc=2, pos=(0, 1), klass=HEA), dict(enc=2, pos=(1, 0), klass=HEA),
+                dict(enc=3, pos=(1, 1), klass=LRN | OBS | ATT | AMM, att_range=1, strength=strength, accuracy=1, view=1, simatt=2, ammo=100),
+                dict(enc=1, pos=(1, 1), klass=HEA)]
+    kw = dict(overlapping={1: {3}, 3: {1}}, attack_mapping={3: {1, 2}}, attack_actor=K.ATTACK_ENCODING)
+    be = Backend(make_spec(2, 2, agents(0), **kw), kind)
+    be.reset()
+    used = []
+    for e1, e2 in ((0, 0), (1, 0), (0, 1), (1, 1), (2, 1), (1, 2), (2, 2)):
+        before = int(be.ammo()[3])
+        be.step([(0, 0, e1, e2)])
+        used.append(before - int(be.ammo()[3]))
+    assert used == [0, 1, 1, 2, 3, 3, 4]
+    be = Backend(make_spec(2, 2, agents(1), **kw), kind)
+    be.reset()
+    be.step([(0, 0, 2, 0)])                                   # both encoding-1 agents
+    np.testing.assert_allclose(be.rewards(), [2 - 0.1 - 0.01], atol=1e-6)
+    assert [bool(f & K.ST_ACTIVE) for f in be.flags()] == [False, True, True, True, False]
+    be.step([(0, 0, 2, 2)])                                   # only the two encoding-2 agents are left
+    np.testing.assert_allclose(be.rewards(), [2 - 0.1 - 0.01], atol=1e-6)
+    be.step([(0, 0, 1, 1)])                                   # attack_status True, nobody left
+    np.testing.assert_allclose(be.rewards(), [-0.1 - 0.1 - 0.01], atol=1e-6)
+
+
+def case_restricted_selective_attack_actor_ammo(kind):       # test_actor.py:1648-1709: ammo bounds the attack
+    agents = [dict(enc=1, pos=(0, 0), klass=HEA), dict(enc=2, pos=(0, 1), klass=HEA), dict(enc=2, pos=(1, 0), klass=HEA),
+              dict(enc=3, pos=(1, 1), klass=LRN | OBS | ATT | AMM, att_range=1, strength=1, accuracy=1, view=1, simatt=2, ammo=3),
+              dict(enc=1, pos=(0, 0), klass=HEA)]
+    be = Backend(make_spec(2, 2, agents, overlapping={1: {1}}, attack_mapping={3: {1, 2}}, attack_actor=K.ATTACK_RESTRICTED), kind)
+    be.reset()
+    be.step([(0, 0, 1, 1)])                                   # both agents of the cell (0, 0)
+    assert be.ammo()[3] == 1 and not be.flags()[0] & K.ST_ACTIVE and not be.flags()[4] & K.ST_ACTIVE
+    be.step([(0, 0, 2, 4)])                                   # two more named, one round left: the ammo filter keeps one
+    np.testing.assert_allclose(be.rewards(), [1 - 0.1 - 0.01], atol=1e-6)
+    assert be.ammo()[3] == 0 and sorted(bool(be.flags()[a] & K.ST_ACTIVE) for a in (1, 2)) == [False, True]
+    be.step([(0, 0, 2, 4)])                                   # out of ammo: attempted, nobody attacked
+    np.testing.assert_allclose(be.rewards(), [-0.1 - 0.1 - 0.01], atol=1e-6)
+    assert be.ammo()[3] == 0
+
+
 # ---------------------------------------------------------------------------------------------------
 # test_observer.py
 # ---------------------------------------------------------------------------------------------------
