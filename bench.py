@@ -314,8 +314,8 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=400)
-    ap.add_argument('--warmup', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=1000, help='timed steps (default: five 200-step episodes, SURVEY 8(d))')
+    ap.add_argument('--warmup', type=int, default=50)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--envs-per-gpu', type=int, default=ENVS_PER_GPU)
     ap.add_argument('--e2e-steps', type=int, default=200, help='steps of the host-buffer loop (one full episode)')
