@@ -396,6 +396,8 @@ int bgw_create(const BgwSpec *sp, int device, bgw_handle *out)
                 if (!unia) f.uniform_att = -1;
             }
             f.identity_learners = (L == A);
+            f.epoch0 = 0xFFFFEu;
+            if (const char *t = getenv("BGW_EPOCH0")) { const long v = atol(t); if (v >= 1 && v <= 0xFFFFE) f.epoch0 = (uint32_t)v; }
             if (cbytes > 96 * 1024 || fo > 227 * 1024) fast = false;
         }
         f.enabled = fast;

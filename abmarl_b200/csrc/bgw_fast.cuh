@@ -51,6 +51,7 @@ struct FastSpec {
     int async_ok;             /* rows are 16-byte aligned: stage with cp.async */
     int simd_ok;              /* A % 4 == 0: byte-parallel compaction */
     int stage_hits_slots;     /* the observation stage overlaps the reservation slots: refill them after it */
+    uint32_t epoch0;          /* first reservation epoch of a launch (0xFFFFE; tests start lower to exercise the wrap guard) */
     int b_cell, b_next, b_flags, b_act, buf_bytes;   /* layout of one staging buffer */
     /* shared-memory carve-up of the fast kernel.  `scratch` is a union: during the actor phases it holds
      * rflag | slot | rkmask | eff | pstate | killrank, during the observation phase the per-warp stage, and in
@@ -667,7 +668,7 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
     }
     cp_async_commit();
 
-    uint32_t epoch = 0xFFFFEu;                            /* tag of the next reservation round (ordered rounds, above) */
+    uint32_t epoch = f_in.epoch0;                         /* tag of the next reservation round (ordered rounds, above) */
     int it_no = -1;
     for (; e < s.E; e += gridDim.x) {
         ++it_no;

@@ -101,6 +101,16 @@ def test_aliased_reservation_slots(mirror, monkeypatch):
     run_lockstep(eng, ora, 45, label='tb_c5_small/slots32')
 
 
+def test_reservation_epochs_run_out(mirror, monkeypatch):
+    """The ordered rounds tag reservations with a decreasing epoch; a launch that starts with almost none left refills
+    the slot tables and starts over (never reached in practice: a launch has about a million epochs)."""
+    spec = compile_sim(scenarios.build_tb_c5_small(mirror), n_envs=400, seed=5, horizon=30, auto_reset=True)
+    monkeypatch.setenv('BGW_EPOCH0', '4100')
+    monkeypatch.setenv('BGW_GRID', '3')                     # three persistent CTAs: many envs, hence many rounds, per CTA
+    eng, ora = _pair(spec)
+    run_lockstep(eng, ora, 12, label='tb_c5_small/epochs')
+
+
 def test_randomized_action_order(mirror):
     """AllStepManager(randomize_action_input=True): a per-env processing order (all_step_manager.py:62-65)."""
     spec = compile_sim(scenarios.build_tb_dense(mirror), n_envs=32, seed=3, horizon=30, auto_reset=True)
