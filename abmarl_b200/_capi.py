@@ -41,7 +41,9 @@ class BgwSpec(C.Structure):
         ('attack_actor', C.c_int32), ('observer', C.c_int32), ('observe_self', C.c_int32),
         ('done_mask', C.c_int32), ('manager', C.c_int32), ('ravel_actions', C.c_int32),
         ('no_overlap_at_reset', C.c_int32), ('stacked_attacks', C.c_int32), ('horizon', C.c_int32),
-        ('auto_reset', C.c_int32), ('ammo_observer', C.c_int32), ('seed', C.c_uint64), ('reward', C.c_double * BGW_RW_COUNT),
+        ('auto_reset', C.c_int32), ('ammo_observer', C.c_int32), ('layout_kind', C.c_int32), ('layout_target', C.c_int32),
+        ('cluster_barriers', C.c_int32), ('scatter_free_agents', C.c_int32), ('seed', C.c_uint64),
+        ('barrier_encodings', C.c_uint64), ('free_encodings', C.c_uint64), ('reward', C.c_double * BGW_RW_COUNT),
         ('encoding', _p), ('klass', _p), ('role', _p), ('init_row', _p), ('init_col', _p),
         ('init_health', _p), ('init_orient', _p), ('view_range', _p), ('move_range', _p),
         ('attack_range', _p), ('attack_strength', _p), ('attack_accuracy', _p),
@@ -57,10 +59,13 @@ class BgwState(C.Structure):
 class BgwDims(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ('n_envs', 'n_agents', 'n_learners', 'obs_h', 'obs_w', 'obs_c',
                                          'obs_stride', 'action_stride', 'threads_per_env', 'envs_per_cta',
-                                         'smem_bytes', 'ammo_offset')]
+                                         'smem_bytes', 'ammo_offset', 'device_layouts')]
 
 
-EXPORTS = ('bgw_create', 'bgw_destroy', 'bgw_dims', 'bgw_bind_state', 'bgw_reset', 'bgw_step',
+LAYOUT_POSITION_STATE, LAYOUT_MAZE = range(2)
+
+EXPORTS = ('bgw_create', 'bgw_destroy', 'bgw_dims', 'bgw_bind_state', 'bgw_reset', 'bgw_step', 'bgw_generate_layouts',
+           'bgw_maze_layout_host',
            'bgw_sample_actions', 'bgw_step_sampled', 'bgw_gather_valid', 'bgw_rng_draw', 'bgw_los_mask', 'bgw_launch_count', 'bgw_last_error',
            'bgw_abi_version')
 
@@ -96,6 +101,10 @@ def load():
     lib.bgw_gather_valid.argtypes = [h] + [_p] * 10
     lib.bgw_gather_valid.restype = C.c_int
     lib.bgw_rng_draw.argtypes = [C.c_uint64] + [C.c_uint32] * 6 + [C.POINTER(C.c_uint32 * 4)]
+    lib.bgw_generate_layouts.argtypes = [h, _p, C.c_int, _p]
+    lib.bgw_generate_layouts.restype = C.c_int
+    lib.bgw_maze_layout_host.argtypes = [C.POINTER(BgwSpec), C.c_uint32, C.c_uint32, _p]
+    lib.bgw_maze_layout_host.restype = C.c_int
     lib.bgw_los_mask.argtypes = [C.c_int, C.c_int, C.c_int, _p]
     lib.bgw_launch_count.argtypes = [h]
     lib.bgw_launch_count.restype = C.c_uint64

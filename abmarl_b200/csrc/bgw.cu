@@ -17,6 +17,7 @@
 
 #include "bgw_dev.cuh"
 #include "bgw_fast.cuh"
+#include "bgw_maze.cuh"
 
 namespace {
 
@@ -50,6 +51,8 @@ int pow2ceil(int x) { int p = 1; while (p < x) p <<= 1; return p; }
 
 struct BgwEngine {
     int device = 0;
+    MazeParams maze{};            /* device-side MazePlacementState (bgw_maze.cuh); device pointers */
+    bool maze_ok = false;
     DevSpec ds{}, dsf{};          /* general kernels / fast kernel (own slot table size) */
     FastSpec fs{};
     int threads_fast = 0;
@@ -108,6 +111,17 @@ void los_apply_host(uint8_t *mask, int R, int rd, int cd)
             }
         }
     }
+}
+
+/* one thread per env (the algorithm is a serial chain of keyed draws); scratch in local memory */
+__global__ void bgw_layout_kernel(const MazeParams p, const BgwState st, int E, int env_offset, const uint8_t *env_mask, int only_done)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    if (only_done ? !(st.env_flags[e] & BGW_ENV_ALL_DONE) : (env_mask && !env_mask[e])) return;
+    MazeScratch w;
+    const int err = maze_layout(p, (uint32_t)(env_offset + e), st.episode[e] + 1u, w, st.layout + (size_t)e * p.A);
+    if (err) st.error[e] = (uint32_t)err;
 }
 
 int first_role(const BgwSpec *sp, int role)
@@ -282,6 +296,18 @@ int bgw_create(const BgwSpec *sp, int device, bgw_handle *out)
             return bail(rc);
         d.init_ammo = nullptr;
         if (n_ammo && (rc = upload(h, sp->initial_ammo, A, &d.init_ammo))) return bail(rc);
+        /* MazePlacementState on the device (bgw_maze.cuh) */
+        h->maze_ok = false;
+        if (sp->layout_kind == BGW_LAYOUT_MAZE) {
+            if (sp->layout_target < 0 || sp->layout_target >= A) return bail(fail(1, "bgw_create: MazePlacementState needs a target agent"));
+            MazeParams &m = h->maze;
+            m.rows = H; m.cols = W; m.A = A; m.max_enc = max_enc; m.no_overlap = sp->no_overlap_at_reset; m.target = sp->layout_target;
+            m.cluster_barriers = sp->cluster_barriers; m.scatter_free = sp->scatter_free_agents;
+            m.seed = sp->seed; m.barrier_encodings = sp->barrier_encodings; m.free_encodings = sp->free_encodings;
+            m.enc = d.enc; m.overlap = d.overlap;
+            if ((rc = upload(h, sp->init_row, A, &m.init_row)) || (rc = upload(h, sp->init_col, A, &m.init_col))) return bail(rc);
+            h->maze_ok = maze_supported(H, W, max_enc, sp->barrier_encodings, sp->free_encodings);
+        } else if (sp->layout_kind != BGW_LAYOUT_POSITION_STATE) return bail(fail(1, "bgw_create: unknown layout_kind %d", sp->layout_kind));
     }
 
     /* ---- launch geometry and the shared-memory carve-up ------------------------------------------ */
@@ -436,6 +462,7 @@ int bgw_create(const BgwSpec *sp, int device, bgw_handle *out)
         if (getenv("BGW_VERBOSE")) fprintf(stderr, "[bgw] fast kernel: T=%d smem=%d B/CTA, %d CTAs/SM x %d SMs, grid=%d, slots=%d\n", h->threads_fast, h->fs.smem_bytes, per_sm, sms, h->fs.grid_ctas, h->dsf.slot_mask + 1);
         if (const char *t = getenv("BGW_GRID")) { const int v = atoi(t); if (v >= 1) h->fs.grid_ctas = std::min(d.E, v); }
     }
+    dm.device_layouts = h->maze_ok ? 1 : 0;
     dm.threads_per_env = h->fs.enabled ? h->threads_fast : T; dm.envs_per_cta = 1; dm.smem_bytes = h->fs.enabled ? h->fs.smem_bytes : off;
     *out = h;
     return 0;
@@ -558,6 +585,39 @@ int bgw_gather_valid(bgw_handle h, const int8_t *obs, const float *reward, const
     CUDA_OK(cudaGetLastError());
     h->launches += 1;
     return 0;
+}
+
+int bgw_generate_layouts(bgw_handle h, const uint8_t *env_mask, int only_done, void *stream)
+{
+    if (!h) return fail(1, "bgw_generate_layouts: null handle");
+    if (!h->maze_ok) return fail(1, "bgw_generate_layouts: this simulation has no device-side layout generator (BgwDims.device_layouts == 0)");
+    if (!h->bound || !h->st.layout) return fail(1, "bgw_generate_layouts: bind a state with a `layout` array first");
+    DeviceGuard guard(h->device);
+    CUDA_OK(cudaFuncSetAttribute(bgw_layout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 0));
+    bgw_layout_kernel<<<(h->ds.E + 31) / 32, 32, 0, (cudaStream_t)stream>>>(h->maze, h->st, h->ds.E, h->ds.env_offset, env_mask, only_done);
+    CUDA_OK(cudaGetLastError());
+    h->launches += 1;
+    return 0;
+}
+
+int bgw_maze_layout_host(const BgwSpec *sp, uint32_t global_env, uint32_t episode, uint16_t *layout)
+{
+    if (!sp || !layout) return fail(1, "bgw_maze_layout_host: null argument");
+    if (sp->layout_kind != BGW_LAYOUT_MAZE) return fail(1, "bgw_maze_layout_host: the spec has no MazePlacementState");
+    int max_enc = 0;
+    for (int a = 0; a < sp->n_agents; ++a) max_enc = std::max(max_enc, (int)sp->encoding[a]);
+    if (!maze_supported(sp->rows, sp->cols, max_enc, sp->barrier_encodings, sp->free_encodings))
+        return fail(1, "bgw_maze_layout_host: grid or encoding count above the generator's limits");
+    std::vector<unsigned long long> ov(BGW_MAX_ENCODING + 1);
+    for (int i = 0; i <= BGW_MAX_ENCODING; ++i) ov[i] = sp->overlap[i];
+    MazeParams m{};
+    m.rows = sp->rows; m.cols = sp->cols; m.A = sp->n_agents; m.max_enc = max_enc; m.no_overlap = sp->no_overlap_at_reset;
+    m.target = sp->layout_target; m.cluster_barriers = sp->cluster_barriers; m.scatter_free = sp->scatter_free_agents;
+    m.seed = sp->seed; m.barrier_encodings = sp->barrier_encodings; m.free_encodings = sp->free_encodings;
+    m.enc = sp->encoding; m.init_row = sp->init_row; m.init_col = sp->init_col; m.overlap = ov.data();
+    std::vector<MazeScratch> w(1);
+    const int err = maze_layout(m, global_env, episode, w[0], layout);
+    return err ? fail(10 + err, "bgw_maze_layout_host: no cell available for an entity (state.py:598-603)") : 0;
 }
 
 int bgw_rng_draw(uint64_t seed, uint32_t env, uint32_t episode, uint32_t step, uint32_t site, uint32_t slot, uint32_t k,

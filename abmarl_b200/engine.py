@@ -51,7 +51,10 @@ class BatchedGridWorld:
         self.state['episode'].fill_(-1)      # 0xFFFFFFFF: first reset makes it 0
         self.state['turn'].fill_(-1)
         self.state['stats'] = torch.zeros((self.E, K.BGW_STAT_COUNT), dtype=torch.int64, device=dev)
-        self.state['layout'] = None
+        # MazePlacementState: start layouts are generated on the device when the library can (bgw_generate_layouts),
+        # else host-side (abmarl_b200/layouts.py) and handed over with set_layout()
+        self.device_layouts = bool(d.device_layouts)
+        self.state['layout'] = torch.full((self.E, self.A), -1, dtype=torch.int16, device=dev) if self.device_layouts else None
         self.obs = torch.zeros((self.E, self.L, d.obs_stride), dtype=torch.int8, device=dev)
         self.reward = torch.zeros((self.E, self.L), dtype=torch.float32, device=dev)
         self.done = torch.zeros((self.E, self.L), dtype=torch.uint8, device=dev)
@@ -85,7 +88,9 @@ class BatchedGridWorld:
 
     # ---- the managers' interface ---------------------------------------------------------------
     def set_layout(self, layout):
-        """[E, A] start cells generated host-side (0xFFFF = leave unplaced); None = PositionState placement."""
+        """[E, A] start cells generated host-side (0xFFFF = leave unplaced); None = PositionState placement.  Explicit
+        layouts switch the device-side generator off."""
+        self.device_layouts = False
         if layout is None:
             self.state['layout'] = None
         else:
@@ -98,6 +103,8 @@ class BatchedGridWorld:
         m = None
         if env_mask is not None:
             m = torch.as_tensor(env_mask, dtype=torch.uint8, device=self.device).contiguous()
+        if self.device_layouts:                       # MazePlacementState.reset: the layouts of the episodes about to start
+            K.check(self.lib.bgw_generate_layouts(self._h, None if m is None else m.data_ptr(), 0, self._stream()), self.lib)
         K.check(self.lib.bgw_reset(self._h, None if m is None else m.data_ptr(), self.obs.data_ptr(), self._stream()),
                 self.lib)
         return self.obs
@@ -117,7 +124,13 @@ class BatchedGridWorld:
         K.check(self.lib.bgw_step(self._h, actions.data_ptr(), None if o is None else o.data_ptr(),
                                   self.obs.data_ptr(), self.reward.data_ptr(), self.done.data_ptr(),
                                   self.all_done.data_ptr(), self._stream()), self.lib)
+        self._layouts_for_finished_envs()
         return self.obs, self.reward, self.done, self.all_done
+
+    def _layouts_for_finished_envs(self):
+        """auto-reset: the envs that just reported __all__ are reset by the next step and need their next layout"""
+        if self.device_layouts and self.spec.auto_reset:
+            K.check(self.lib.bgw_generate_layouts(self._h, None, 1, self._stream()), self.lib)
 
     def step_sampled(self, order=None):
         """sample_actions() + step() in one call (one launch on the specialised kernel): the keyed random policy
@@ -128,6 +141,7 @@ class BatchedGridWorld:
         K.check(self.lib.bgw_step_sampled(self._h, self.actions.data_ptr(), None if o is None else o.data_ptr(),
                                           self.obs.data_ptr(), self.reward.data_ptr(), self.done.data_ptr(),
                                           self.all_done.data_ptr(), self._stream()), self.lib)
+        self._layouts_for_finished_envs()
         return self.obs, self.reward, self.done, self.all_done
 
     # ---- host-facing step: HOST buffers in, only the rows the reference's manager would return out ---------

@@ -34,7 +34,7 @@ class SimulationManager(ABC):
         self._feeder = None
         if layouts is not None:
             self.engine.set_layout(layouts)
-        elif self.spec.layout_generator is not None:        # e.g. MazePlacementState: per-episode host-side layouts
+        elif self.spec.layout_generator is not None and not self.engine.device_layouts:   # MazePlacementState above the device generator's limits: host-side layouts
             from abmarl_b200.layouts import LayoutFeeder
             self._feeder = LayoutFeeder(self.spec)
         self.learner_ids = self.spec.learner_ids

@@ -89,6 +89,12 @@ class CompiledSpec:
             setattr(s, name, int(getattr(self, name)))
         for i in range(K.BGW_RW_COUNT):
             s.reward[i] = float(self.reward[i])
+        if self.layout_generator is not None and self.layout_generator[0] == 'maze':     # MazePlacementState state.py:385-485
+            p = self.layout_generator[1]
+            s.layout_kind, s.layout_target = K.LAYOUT_MAZE, int(p['target'])
+            s.cluster_barriers, s.scatter_free_agents = int(p['cluster_barriers']), int(p['scatter_free_agents'])
+            s.barrier_encodings = sum(1 << int(e) for e in p['barrier_encodings'])
+            s.free_encodings = sum(1 << int(e) for e in p['free_encodings'])
         keep = []
         for name, dt in self.TABLES + (('overlap', np.uint64), ('attack_map', np.uint64)):
             arr = np.ascontiguousarray(getattr(self, name), dtype=dt)

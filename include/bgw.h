@@ -94,6 +94,7 @@ enum {
     BGW_DONE_TARGET_AGENT = 1 << 2,     /* TargetAgentDone       done.py:59-99   */
     BGW_DONE_TARGET_DESTROYED = 1 << 3  /* TargetDestroyedDone   done.py:102-137 */
 };
+enum { BGW_LAYOUT_POSITION_STATE = 0 /* PositionState state.py:18-166 */, BGW_LAYOUT_MAZE = 1 /* MazePlacementState :385-619 */ };
 enum { BGW_MANAGER_ALL_STEP = 0 /* all_step_manager.py */, BGW_MANAGER_TURN_BASED = 1 /* turn_based_manager.py */ };
 
 /* reward constant slots (float64; values live in the user's sim, e.g. team_battle_example.py:42-59) */
@@ -154,7 +155,11 @@ typedef struct BgwSpec {
     int32_t auto_reset;    /* 1: an env that reported __all__ is reset by the NEXT bgw_step call */
     int32_t ammo_observer; /* 1: the sim has an AmmoObserver (observer.py:376-413): learners with BGW_AG_AMMO
                               also observe their ammo (BgwDims.ammo_offset) */
+    int32_t layout_kind;   /* BGW_LAYOUT_*: which placement state builds the start layout of an episode */
+    int32_t layout_target; /* MazePlacementState.target_agent (agent index) state.py:385-460 */
+    int32_t cluster_barriers, scatter_free_agents;   /* state.py:462-485 */
     uint64_t seed;         /* Philox key */
+    uint64_t barrier_encodings, free_encodings;       /* bit e set <=> encoding e in the set, state.py:430-460 */
     double reward[BGW_RW_COUNT];
 
     /* per-agent tables, length n_agents */
@@ -222,6 +227,7 @@ typedef struct BgwDims {
     int32_t threads_per_env, envs_per_cta, smem_bytes; /* launch geometry (informational)             */
     int32_t ammo_offset;         /* AmmoObserver (observer.py:376-413): byte offset inside a learner's obs row of
                                     its int32 'ammo' observation (little endian, 4-byte aligned), or -1       */
+    int32_t device_layouts;      /* 1: bgw_generate_layouts can build this spec's start layouts on the device    */
 } BgwDims;
 
 typedef struct BgwEngine *bgw_handle;
@@ -280,6 +286,19 @@ int bgw_step_sampled(bgw_handle h, int8_t *actions_out, const int16_t *order, in
  */
 int bgw_gather_valid(bgw_handle h, const int8_t *obs, const float *reward, const uint8_t *done, const uint8_t *all_done,
                      int32_t *count, int32_t *index, int8_t *obs_c, float *reward_c, uint8_t *done_c, void *stream);
+
+/*
+ * MazePlacementState.reset (state.py:487-619, generate_maze utils.py:120-212) on the device: writes the start layout
+ * of the NEXT episode (episode[e] + 1) of the selected envs into BgwState.layout ([E][A], must be bound), where the
+ * next bgw_reset / auto-reset consumes it.  only_done != 0: the envs whose last step reported BGW_ENV_ALL_DONE;
+ * otherwise the envs selected by env_mask ([E] u8 on the device, NULL = all).  Placement failures set BgwState.error.
+ * Fails when BgwDims.device_layouts is 0 (grid above 18x18 or more than 8 placed encodings: generate the layouts
+ * host-side then, abmarl_b200/layouts.py).
+ */
+int bgw_generate_layouts(bgw_handle h, const uint8_t *env_mask, int only_done, void *stream);
+
+/* The same generator on the host for one (global env, episode): layout[A].  Test / replay hook, like bgw_rng_draw. */
+int bgw_maze_layout_host(const BgwSpec *spec, uint32_t global_env, uint32_t episode, uint16_t *layout);
 
 /* Synthetic random policy (policies/policy.py:81-92 `action_space.sample()`), keyed Philox site ACTION:
  * fills actions[E][L][action_stride] for the CURRENT step of every env.  Used by bench.py and the parity tests. */

@@ -39,7 +39,8 @@ def run_lockstep(eng, ora, steps, order_fn=None, check_every=1, label=''):
         from abmarl_b200.layouts import LayoutFeeder
         feeder = LayoutFeeder(eng.spec)
         rows = feeder.prime(ora.state['episode'])
-        eng.set_layout(rows)
+        if not eng.device_layouts:                             # else the engine generates its own (bgw_generate_layouts)
+            eng.set_layout(rows)
         ora.set_layout(rows)
     eng.reset()
     ora.reset()
@@ -54,7 +55,8 @@ def run_lockstep(eng, ora, steps, order_fn=None, check_every=1, label=''):
         eng.step(act_e, order)
         ora.step(act_o, order)
         if feeder is not None and feeder.after_step(ora.all_done, ora.state['episode']):
-            eng.set_layout(feeder.rows)
+            if not eng.device_layouts:
+                eng.set_layout(feeder.rows)
             ora.set_layout(feeder.rows)
         if t % check_every == 0 or t == steps - 1:
             assert_outputs_equal(eng, ora, f"{label} step {t}")

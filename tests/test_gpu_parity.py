@@ -155,6 +155,32 @@ def test_engine_reproduces_reference_transcript(mirror, name):
         np.testing.assert_array_equal(st['next'][0][in_grid], g['next'][t][in_grid], err_msg=f'{name} call {t} next')
 
 
+@pytest.mark.parametrize('name', ['mm_c4', 'mm_random'])
+def test_device_maze_layouts(mirror, name):
+    """bgw_generate_layouts (MazePlacementState on the device, one thread per env) against the Python restatement that
+    the golden transcripts pin to the reference; then whole episodes with auto-reset run without any host layout."""
+    from abmarl_b200.engine import BatchedGridWorld
+    from abmarl_b200.layouts import layouts_for
+    builder, manager, _ = scenarios.SCENARIOS[name]
+    E = 96
+    spec = compile_sim(builder(mirror), manager=manager, n_envs=E, env_offset=1000, seed=77, horizon=15, auto_reset=True)
+    eng = BatchedGridWorld(spec, device='cuda:0')
+    assert eng.device_layouts and eng.dims.device_layouts == 1
+    eng.reset()
+    np.testing.assert_array_equal(eng.state_numpy()['layout'].view(np.uint16), layouts_for(spec, range(E), [0] * E))
+    seen = 0
+    for t in range(40):
+        eng.step_sampled()
+        flags = eng.all_done.cpu().numpy()
+        done = np.flatnonzero(flags & K.ENV_ALL_DONE)
+        if len(done):                                          # their next layouts are already on the device
+            ep = eng.state_numpy()['episode']
+            want = layouts_for(spec, done, [int(ep[e]) + 1 for e in done])
+            np.testing.assert_array_equal(eng.state_numpy()['layout'].view(np.uint16)[done], want)
+            seen += len(done)
+    assert seen > E and (eng.state_numpy()['error'] == 0).all()
+
+
 def test_rng_draw_and_los_mask_exports():
     import ctypes as C
     from abmarl_b200 import philox
