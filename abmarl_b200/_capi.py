@@ -62,7 +62,7 @@ class BgwDims(C.Structure):
                                          'smem_bytes', 'ammo_offset', 'device_layouts')]
 
 
-LAYOUT_POSITION_STATE, LAYOUT_MAZE = range(2)
+LAYOUT_POSITION_STATE, LAYOUT_MAZE, LAYOUT_TARGET_BARRIERS_FREE = range(3)
 
 EXPORTS = ('bgw_create', 'bgw_destroy', 'bgw_dims', 'bgw_bind_state', 'bgw_reset', 'bgw_step', 'bgw_generate_layouts',
            'bgw_maze_layout_host',

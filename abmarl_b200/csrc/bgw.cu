@@ -298,9 +298,10 @@ int bgw_create(const BgwSpec *sp, int device, bgw_handle *out)
         if (n_ammo && (rc = upload(h, sp->initial_ammo, A, &d.init_ammo))) return bail(rc);
         /* MazePlacementState on the device (bgw_maze.cuh) */
         h->maze_ok = false;
-        if (sp->layout_kind == BGW_LAYOUT_MAZE) {
-            if (sp->layout_target < 0 || sp->layout_target >= A) return bail(fail(1, "bgw_create: MazePlacementState needs a target agent"));
+        if (sp->layout_kind == BGW_LAYOUT_MAZE || sp->layout_kind == BGW_LAYOUT_TARGET_BARRIERS_FREE) {
+            if (sp->layout_target < 0 || sp->layout_target >= A) return bail(fail(1, "bgw_create: the placement state needs a target agent"));
             MazeParams &m = h->maze;
+            m.kind = sp->layout_kind;
             m.rows = H; m.cols = W; m.A = A; m.max_enc = max_enc; m.no_overlap = sp->no_overlap_at_reset; m.target = sp->layout_target;
             m.cluster_barriers = sp->cluster_barriers; m.scatter_free = sp->scatter_free_agents;
             m.seed = sp->seed; m.barrier_encodings = sp->barrier_encodings; m.free_encodings = sp->free_encodings;
@@ -603,7 +604,8 @@ int bgw_generate_layouts(bgw_handle h, const uint8_t *env_mask, int only_done, v
 int bgw_maze_layout_host(const BgwSpec *sp, uint32_t global_env, uint32_t episode, uint16_t *layout)
 {
     if (!sp || !layout) return fail(1, "bgw_maze_layout_host: null argument");
-    if (sp->layout_kind != BGW_LAYOUT_MAZE) return fail(1, "bgw_maze_layout_host: the spec has no MazePlacementState");
+    if (sp->layout_kind != BGW_LAYOUT_MAZE && sp->layout_kind != BGW_LAYOUT_TARGET_BARRIERS_FREE)
+        return fail(1, "bgw_maze_layout_host: the spec has no MazePlacementState / TargetBarriersFreePlacementState");
     int max_enc = 0;
     for (int a = 0; a < sp->n_agents; ++a) max_enc = std::max(max_enc, (int)sp->encoding[a]);
     if (!maze_supported(sp->rows, sp->cols, max_enc, sp->barrier_encodings, sp->free_encodings))
@@ -611,6 +613,7 @@ int bgw_maze_layout_host(const BgwSpec *sp, uint32_t global_env, uint32_t episod
     std::vector<unsigned long long> ov(BGW_MAX_ENCODING + 1);
     for (int i = 0; i <= BGW_MAX_ENCODING; ++i) ov[i] = sp->overlap[i];
     MazeParams m{};
+    m.kind = sp->layout_kind;
     m.rows = sp->rows; m.cols = sp->cols; m.A = sp->n_agents; m.max_enc = max_enc; m.no_overlap = sp->no_overlap_at_reset;
     m.target = sp->layout_target; m.cluster_barriers = sp->cluster_barriers; m.scatter_free = sp->scatter_free_agents;
     m.seed = sp->seed; m.barrier_encodings = sp->barrier_encodings; m.free_encodings = sp->free_encodings;

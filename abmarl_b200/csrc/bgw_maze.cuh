@@ -23,6 +23,7 @@
 #define BGW_MAZE_TABLE 2048         /* largest set table: first power of two above 4 * BGW_MAZE_MAX_PADDED */
 
 struct MazeParams {                 /* what the generator needs of the spec (host or device pointers alike) */
+    int kind;                       /* BGW_LAYOUT_MAZE or BGW_LAYOUT_TARGET_BARRIERS_FREE (no maze: every cell is barrier and free) */
     int rows, cols, A, max_enc, no_overlap, target, cluster_barriers, scatter_free;
     unsigned long long seed, barrier_encodings, free_encodings;
     const int8_t *enc;
@@ -193,9 +194,12 @@ BGW_HD int maze_layout(const MazeParams &p, uint32_t genv, uint32_t episode, Maz
     int sr, sc;
     if (p.init_row[p.target] >= 0) { sr = p.init_row[p.target]; sc = p.init_col[p.target]; }          /* :531-534 */
     else { sr = maze_randint(st, 0, rows); sc = maze_randint(st, 0, cols); }
-    PySet set;
-    set.key = w.tab_a; set.tmp = w.tab_b;
-    maze_generate(w.grid, pr, pc, (sr + 1) * pc + (sc + 1), st, w.walls, set);
+    const bool maze = p.kind == BGW_LAYOUT_MAZE;
+    if (maze) {
+        PySet set;
+        set.key = w.tab_a; set.tmp = w.tab_b;
+        maze_generate(w.grid, pr, pc, (sr + 1) * pc + (sc + 1), st, w.walls, set);
+    }
     /* barrier / free cell lists in ascending cell order, then the optional sorts :546-569 */
     int nlists = 0;
     for (int e = 0; e <= BGW_MAX_ENCODING; ++e) w.list_of[e] = -1;
@@ -206,8 +210,8 @@ BGW_HD int maze_layout(const MazeParams &p, uint32_t genv, uint32_t episode, Maz
         uint16_t *lst = w.list[nlists];
         int n = 0;
         for (int cell = 0; cell < HW; ++cell) {
-            const int g = w.grid[(cell / cols + 1) * pc + (cell % cols + 1)];
-            if (is_free ? g == 0 : g != 0) lst[n++] = (uint16_t)cell;       /* a key in both sets ends up free (dict.update) */
+            const int g = maze ? w.grid[(cell / cols + 1) * pc + (cell % cols + 1)] : -1;   /* -1: state.py:311-339, all cells */
+            if (g < 0 || (is_free ? g == 0 : g != 0)) lst[n++] = (uint16_t)cell;   /* a key in both sets ends up free (dict.update) */
         }
         if (is_free ? p.scatter_free : p.cluster_barriers) maze_sort(lst, n, cols, sr, sc, !is_free);
         w.list_n[nlists] = n;

@@ -63,7 +63,8 @@ def generate_maze(rows, cols, start, stream):
 
 
 def maze_layout(spec, env, episode):
-    """MazePlacementState.reset (state.py:487-619) for global env `env`, episode `episode` -> uint16[A] cells."""
+    """MazePlacementState.reset (state.py:487-619) / TargetBarriersFreePlacementState.reset (state.py:281-383: the same
+    flow without the maze) for global env `env`, episode `episode` -> uint16[A] cells."""
     p = spec.layout_generator[1]
     rows, cols, A = spec.rows, spec.cols, spec.n_agents
     stream = _Stream(spec.seed, env, episode)
@@ -72,12 +73,15 @@ def maze_layout(spec, env, episode):
         start = (int(spec.init_row[target]), int(spec.init_col[target]))
     else:
         start = (stream.randint(0, rows), stream.randint(0, cols))
-    maze = generate_maze(rows, cols, start, stream)
+    if spec.layout_generator[0] == 'maze':
+        maze = generate_maze(rows, cols, start, stream)
+    else:                                                 # TargetBarriersFreePlacementState state.py:311-339: every cell is both
+        maze = None
 
     def dist(n):
         return float(np.linalg.norm(np.array([np.unravel_index(n, (rows, cols))]) - np.array(start)))
-    barrier = [int(n) for n in np.flatnonzero(maze.ravel() == 1)]
-    free = [int(n) for n in np.flatnonzero(maze.ravel() == 0)]
+    barrier = [int(n) for n in np.flatnonzero(maze.ravel() == 1)] if maze is not None else list(range(rows * cols))
+    free = [int(n) for n in np.flatnonzero(maze.ravel() == 0)] if maze is not None else list(range(rows * cols))
     if p['cluster_barriers']:
         barrier.sort(key=dist, reverse=True)              # closest last (:546-553)
     if p['scatter_free_agents']:
@@ -119,7 +123,7 @@ def maze_layout(spec, env, episode):
 def layouts_for(spec, envs, episodes):
     """[len(envs), A] layouts; `envs` are LOCAL env indices (the global index adds spec.env_offset)."""
     kind = spec.layout_generator[0]
-    assert kind == 'maze', kind
+    assert kind in ('maze', 'target_barriers_free'), kind
     return np.stack([maze_layout(spec, spec.env_offset + int(e), int(ep)) for e, ep in zip(envs, episodes)])
 
 

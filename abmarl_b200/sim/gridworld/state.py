@@ -2,8 +2,8 @@
 
 `reset()` of each component runs on the device (bgw_reset; kernels in csrc/bgw_kernels.cu):
 PositionState state.py:88-166, HealthState :629-641, OrientationState :666-675.
-MazePlacementState (:385-619) generates its layouts host-side (abmarl_b200.layouts) and feeds them to the
-engine through BgwState.layout.
+MazePlacementState (:385-619) and TargetBarriersFreePlacementState (:169-383) build their layouts on the device
+(bgw_generate_layouts, csrc/bgw_maze.cuh) or, above its limits, host-side (abmarl_b200.layouts).
 """
 from abc import ABC
 
@@ -24,7 +24,9 @@ class PositionState(StateBaseComponent):
         self.randomize_placement_order = randomize_placement_order
 
 
-class MazePlacementState(PositionState):
+class TargetBarriersFreePlacementState(PositionState):
+    """state.py:169-383: the target first, barrier encodings clustered near it, free encodings scattered away from it."""
+
     def __init__(self, target_agent=None, barrier_encodings=None, free_encodings=None,
                  cluster_barriers=False, scatter_free_agents=False, **kwargs):
         super().__init__(**kwargs)
@@ -43,6 +45,11 @@ class MazePlacementState(PositionState):
         assert type(cluster_barriers) is bool, "Cluster barriers must be a boolean."
         assert type(scatter_free_agents) is bool, "Scatter free agents must be a boolean."
         self.cluster_barriers, self.scatter_free_agents = cluster_barriers, scatter_free_agents
+
+
+class MazePlacementState(TargetBarriersFreePlacementState):
+    """state.py:385-619: the same placement rules over a maze grown from the target (walls = barrier cells, passages =
+    free cells).  (In the reference the two classes are siblings with identical constructors.)"""
 
 
 class HealthState(StateBaseComponent):

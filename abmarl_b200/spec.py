@@ -89,9 +89,10 @@ class CompiledSpec:
             setattr(s, name, int(getattr(self, name)))
         for i in range(K.BGW_RW_COUNT):
             s.reward[i] = float(self.reward[i])
-        if self.layout_generator is not None and self.layout_generator[0] == 'maze':     # MazePlacementState state.py:385-485
+        if self.layout_generator is not None:            # MazePlacementState state.py:385-485 / TargetBarriersFreePlacementState :169-279
             p = self.layout_generator[1]
-            s.layout_kind, s.layout_target = K.LAYOUT_MAZE, int(p['target'])
+            s.layout_kind = K.LAYOUT_MAZE if self.layout_generator[0] == 'maze' else K.LAYOUT_TARGET_BARRIERS_FREE
+            s.layout_target = int(p['target'])
             s.cluster_barriers, s.scatter_free_agents = int(p['cluster_barriers']), int(p['scatter_free_agents'])
             s.barrier_encodings = sum(1 << int(e) for e in p['barrier_encodings'])
             s.free_encodings = sum(1 << int(e) for e in p['free_encodings'])
@@ -232,13 +233,11 @@ def compile_sim(sim, manager='all_step', n_envs=1, env_offset=0, seed=0, horizon
         if 'PositionState' in sn:
             sp.no_overlap_at_reset = int(bool(state.no_overlap_at_reset))
             assert not state.randomize_placement_order, "randomize_placement_order is not on the device path yet"
-            if 'MazePlacementState' in sn:
-                sp.layout_generator = ('maze', dict(
+            if 'MazePlacementState' in sn or 'TargetBarriersFreePlacementState' in sn:
+                sp.layout_generator = ('maze' if 'MazePlacementState' in sn else 'target_barriers_free', dict(
                     target=index[state.target_agent.id],
                     barrier_encodings=set(state.barrier_encodings), free_encodings=set(state.free_encodings),
                     cluster_barriers=bool(state.cluster_barriers), scatter_free_agents=bool(state.scatter_free_agents)))
-            elif sn & {'TargetBarriersFreePlacementState'}:
-                raise NotImplementedError("TargetBarriersFreePlacementState has no device implementation yet")
 
     # ---- program-specific roles and reward constants ----------------------------------------------
     rc = getattr(sim, 'reward_constants', {})

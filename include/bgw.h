@@ -94,7 +94,8 @@ enum {
     BGW_DONE_TARGET_AGENT = 1 << 2,     /* TargetAgentDone       done.py:59-99   */
     BGW_DONE_TARGET_DESTROYED = 1 << 3  /* TargetDestroyedDone   done.py:102-137 */
 };
-enum { BGW_LAYOUT_POSITION_STATE = 0 /* PositionState state.py:18-166 */, BGW_LAYOUT_MAZE = 1 /* MazePlacementState :385-619 */ };
+enum { BGW_LAYOUT_POSITION_STATE = 0 /* PositionState state.py:18-166 */, BGW_LAYOUT_MAZE = 1 /* MazePlacementState :385-619 */,
+       BGW_LAYOUT_TARGET_BARRIERS_FREE = 2 /* TargetBarriersFreePlacementState :169-383 */ };
 enum { BGW_MANAGER_ALL_STEP = 0 /* all_step_manager.py */, BGW_MANAGER_TURN_BASED = 1 /* turn_based_manager.py */ };
 
 /* reward constant slots (float64; values live in the user's sim, e.g. team_battle_example.py:42-59) */
@@ -156,7 +157,7 @@ typedef struct BgwSpec {
     int32_t ammo_observer; /* 1: the sim has an AmmoObserver (observer.py:376-413): learners with BGW_AG_AMMO
                               also observe their ammo (BgwDims.ammo_offset) */
     int32_t layout_kind;   /* BGW_LAYOUT_*: which placement state builds the start layout of an episode */
-    int32_t layout_target; /* MazePlacementState.target_agent (agent index) state.py:385-460 */
+    int32_t layout_target; /* target_agent of the placement state (agent index) state.py:200-222, 417-439 */
     int32_t cluster_barriers, scatter_free_agents;   /* state.py:462-485 */
     uint64_t seed;         /* Philox key */
     uint64_t barrier_encodings, free_encodings;       /* bit e set <=> encoding e in the set, state.py:430-460 */
@@ -288,7 +289,8 @@ int bgw_gather_valid(bgw_handle h, const int8_t *obs, const float *reward, const
                      int32_t *count, int32_t *index, int8_t *obs_c, float *reward_c, uint8_t *done_c, void *stream);
 
 /*
- * MazePlacementState.reset (state.py:487-619, generate_maze utils.py:120-212) on the device: writes the start layout
+ * MazePlacementState.reset (state.py:487-619, generate_maze utils.py:120-212) / TargetBarriersFreePlacementState.reset
+ * (state.py:281-383) on the device: writes the start layout
  * of the NEXT episode (episode[e] + 1) of the selected envs into BgwState.layout ([E][A], must be bound), where the
  * next bgw_reset / auto-reset consumes it.  only_done != 0: the envs whose last step reported BGW_ENV_ALL_DONE;
  * otherwise the envs selected by env_mask ([E] u8 on the device, NULL = all).  Placement failures set BgwState.error.

@@ -358,6 +358,26 @@ def build_mm_tiny(api):
     return sim
 
 
+def build_mm_tbf(api, cluster=True, scatter=False, fixed_target=False):
+    """Multi maze navigation with its placement state swapped for TargetBarriersFreePlacementState (state.py:169-383):
+    the target at a random cell, barriers clustered around it, navigators placed at random."""
+    agents = {'target': api.agent.GridWorldAgent(id='target', encoding=1,
+                                                 initial_position=np.array([2, 5]) if fixed_target else None)}
+    agents.update({f'barrier{i}': api.agent.GridWorldAgent(id=f'barrier{i}', encoding=2) for i in range(9)})
+    agents.update({f'navigator{i}': api.ex.MultiMazeNavigationAgent(id=f'navigator{i}', encoding=3, view_range=3)
+                   for i in range(4)})
+    kw = dict(target_agent=agents['target'], barrier_encodings={2}, free_encodings={1, 3}, cluster_barriers=cluster,
+              scatter_free_agents=scatter)
+    sim = api.ex.MultiMazeNavigationSim.build_sim(7, 8, agents=agents, overlapping={1: {3}, 3: {3}}, **kw)
+    kw['target_agent'] = sim.agents['target']
+    sim.position_state = api.state.TargetBarriersFreePlacementState(agents=sim.agents, grid=sim.grid, **kw)
+    return sim
+
+
+def build_mm_tbf_scatter(api):
+    return build_mm_tbf(api, cluster=False, scatter=True, fixed_target=True)
+
+
 SCENARIOS = {
     # name: (builder, manager, steps recorded in the golden file)
     'tb_c2': (build_tb_c2, 'all_step', 40),
@@ -382,6 +402,8 @@ SCENARIOS = {
     'mm_c4': (build_mm_c4, 'turn_based', 120),
     'mm_random': (build_mm_random, 'turn_based', 90),
     'mm_allstep': (build_mm_c4, 'all_step', 60),
+    'mm_tbf': (build_mm_tbf, 'all_step', 80),
+    'mm_tbf_scatter': (build_mm_tbf_scatter, 'turn_based', 120),
     'mm_tiny': (build_mm_tiny, 'turn_based', 400),
     'mm_tiny_allstep': (build_mm_tiny, 'all_step', 200),
 }

@@ -47,6 +47,8 @@ CASES = [
     ('mm_c4', 12, 150, 60),
     ('mm_random', 12, 120, 50),
     ('mm_allstep', 12, 100, 40),
+    ('mm_tbf', 16, 200, 30),
+    ('mm_tbf_scatter', 16, 200, 30),
     ('mm_tiny', 16, 300, 0),
     ('mm_tiny_allstep', 16, 200, 0),
 ]
@@ -155,7 +157,7 @@ def test_engine_reproduces_reference_transcript(mirror, name):
         np.testing.assert_array_equal(st['next'][0][in_grid], g['next'][t][in_grid], err_msg=f'{name} call {t} next')
 
 
-@pytest.mark.parametrize('name', ['mm_c4', 'mm_random'])
+@pytest.mark.parametrize('name', ['mm_c4', 'mm_random', 'mm_tbf', 'mm_tbf_scatter'])
 def test_device_maze_layouts(mirror, name):
     """bgw_generate_layouts (MazePlacementState on the device, one thread per env) against the Python restatement that
     the golden transcripts pin to the reference; then whole episodes with auto-reset run without any host layout."""

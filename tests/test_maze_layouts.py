@@ -19,7 +19,7 @@ def _host_layout(lib, cs, A, env, episode):
     return out
 
 
-@pytest.mark.parametrize('name', ['mm_c4', 'mm_random', 'mm_tiny'])
+@pytest.mark.parametrize('name', ['mm_c4', 'mm_random', 'mm_tiny', 'mm_tbf', 'mm_tbf_scatter'])
 def test_native_maze_layouts_equal_the_python_restatement(mirror, name):
     from abmarl_b200.csrc.build import build
     build()
@@ -27,7 +27,7 @@ def test_native_maze_layouts_equal_the_python_restatement(mirror, name):
     builder, manager, _ = scenarios.SCENARIOS[name]
     spec = compile_sim(builder(mirror), manager=manager, n_envs=4, env_offset=11, seed=0xC0FFEE)
     cs = spec.c_struct()
-    assert cs.layout_kind == K.LAYOUT_MAZE
+    assert cs.layout_kind == (K.LAYOUT_TARGET_BARRIERS_FREE if name.startswith('mm_tbf') else K.LAYOUT_MAZE)
     for env in (0, 1, 7, 4095, 70000):
         for episode in (0, 1, 2, 17, 2**32 - 1):
             want = maze_layout(spec, env, episode)
