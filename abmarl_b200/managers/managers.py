@@ -28,9 +28,14 @@ class SimulationManager(ABC):
             "randomize_action_input is an AllStepManager option (all_step_manager.py:24-35)"
         self.sim = sim
         self.randomize_action_input = bool(randomize_action_input)
-        self.spec = compile_sim(sim, manager=self._manager, n_envs=n_envs, env_offset=env_offset, seed=seed,
+        inner = sim.unwrapped if hasattr(sim, 'super_agent_mapping') else sim      # SuperAgentWrapper(sim, mapping)
+        self.spec = compile_sim(inner, manager=self._manager, n_envs=n_envs, env_offset=env_offset, seed=seed,
                                 horizon=horizon, auto_reset=auto_reset)
         self.engine = BatchedGridWorld(self.spec, device=device)
+        self.super_view = None
+        if hasattr(sim, 'super_agent_mapping'):
+            from abmarl_b200.sim.wrappers import SuperAgentView
+            self.super_view = SuperAgentView(self.spec, sim.super_agent_mapping, n_envs, device=self.engine.device)
         self._feeder = None
         if layouts is not None:
             self.engine.set_layout(layouts)
@@ -57,6 +62,8 @@ class SimulationManager(ABC):
             mask = None if env_mask is None else np.asarray(torch.as_tensor(env_mask).cpu())
             self.engine.set_layout(self._feeder.prime(episode, mask))
         self.engine.reset(env_mask)
+        if self.super_view is not None:
+            self.super_view.reset(env_mask)
         return self.engine.obs_view()
 
     def step(self, actions, order=None):
@@ -68,11 +75,21 @@ class SimulationManager(ABC):
         if order is None and self.randomize_action_input:       # all_step_manager.py:62-65
             order = torch.stack([torch.randperm(self.engine.L, generator=self._order_gen)
                                  for _ in range(self.engine.E)]).to(torch.int16)
+        if order is None and self.super_view is not None:       # SuperAgentWrapper.step: super agents' members first
+            order = self.super_view.order
         _, reward, done, all_done = self.engine.step(actions, order)
         if self._feeder is not None and self.spec.auto_reset:
             if self._feeder.after_step(all_done.cpu().numpy(), self.engine.state['episode'].cpu().numpy().view(np.uint32)):
                 self.engine.set_layout(self._feeder.rows)
         return self.engine.obs_view(), reward, done, all_done
+
+    def super_outputs(self):
+        """SuperAgentWrapper view of the last step (super_agent_wrapper.py:112-216): (obs rows with null observations for
+        covered agents done earlier, mask [E, L], reward [E, G] f64, done [E, G], valid [E, G]); groups = `super_view.groups`.
+        Call once per step."""
+        assert self.super_view is not None, "the simulation is not wrapped in a SuperAgentWrapper"
+        e = self.engine
+        return self.super_view.update(e.obs, e.reward, e.done, e.all_done)
 
     def sample_actions(self):
         """A random action per learner from the keyed Philox stream (== action_space.sample() ranges)."""
