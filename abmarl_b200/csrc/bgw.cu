@@ -230,11 +230,12 @@ int bgw_create(const BgwSpec *sp, int device, bgw_handle *out)
     if (sp->program == BGW_PROG_MAZE && (d.a_nav < 0 || d.a_target < 0 || learner_of[d.a_nav] < 0))
         return bail(fail(1, "bgw_create: MazeNavigationSim needs a learning navigator and a target"));
     if (sp->program == BGW_PROG_MULTI_MAZE && d.a_target < 0) return bail(fail(1, "bgw_create: MultiMazeNavigationSim needs a target"));
-    if (sp->program == BGW_PROG_PACMAN && (d.a_pacman < 0 || learner_of[d.a_pacman] < 0 || H <= 9 || W <= 20))
+    for (int k = 0; k < 10; ++k) d.a_script[k] = first_role(sp, BGW_ROLE_SCRIPTED_BADDIE + k);
+    if ((sp->program == BGW_PROG_PACMAN || sp->program == BGW_PROG_PACMAN_SIMPLE) && (d.a_pacman < 0 || learner_of[d.a_pacman] < 0 || H <= 9 || W <= 20))
         return bail(fail(1, "bgw_create: PacmanSim needs a learning pacman and the (9,0)<->(9,20) tunnel (pacman.py:87-92)"));
     if (sp->program == BGW_PROG_REACH_TARGET && (d.a_target < 0 || learner_of[d.a_target] < 0))
         return bail(fail(1, "bgw_create: ReachTheTargetSim needs a learning target agent"));
-    if (sp->program < BGW_PROG_TEAM_BATTLE || sp->program > BGW_PROG_TRAFFIC) return bail(fail(1, "bgw_create: unknown program %d", sp->program));
+    if (sp->program < BGW_PROG_TEAM_BATTLE || sp->program > BGW_PROG_PACMAN_SIMPLE) return bail(fail(1, "bgw_create: unknown program %d", sp->program));
 
     /* ---- observation geometry (same rule as the oracle's bgwo_dims) ------------------------------ */
     BgwDims &dm = h->dims;

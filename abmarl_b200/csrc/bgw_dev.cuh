@@ -43,6 +43,7 @@ struct DevSpec {
     int max_enc, n_blk;            /* n_blk: entities of class BLOCKING (static list blk_agents) */
     int obs_h, obs_w, obs_c, obs_stride, nchunks;
     int a_nav, a_target, a_pacman, has_food;
+    int a_script[10];              /* PacmanSimSimple: the agent of the k-th script entry (pacman.py:235-246), -1 = absent */
     int hw_words;                  /* ceil(HW / 32) */
     int n_var;                     /* entities with random placement */
     int tpl_error;
@@ -575,6 +576,61 @@ __device__ __forceinline__ void run_attack(const DevSpec &s, Env &ev, int a)
 /* reservation helpers: slot of a cell */
 __device__ __forceinline__ uint32_t *slot_of(const DevSpec &s, const Env &ev, int cell) { return &ev.slot[cell & s.slot_mask]; }
 
+/* PacmanSimSimple.step pacman.py:235-303: the baddies' scripted DriftMoveActor actions of this step.  k indexes the
+ * script's entries (baddie_20, 36, 156, 157, 159, 161, 162, 206, 222, 328); sc = step_count, o156 = orientation of
+ * baddie_156, x159 = the keyed draw that stands in for np.random.randint(0, 5) */
+__device__ void pacman_script(int sc, int o156, uint32_t x159, int move[10])
+{
+    const int base[10] = {0, 0, 0, 1, 0, 3, 0, 0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < 10; ++k) move[k] = base[k];
+    move[4] = (int)bgw_index(x159, 5);
+    if (sc == 0) { move[2] = 4; move[6] = 4; move[9] = 3; }                              /* :247-250 */
+    switch (sc % 10) {                                                                     /* :251-262 */
+    case 0: move[0] = 3; move[1] = 1; break;
+    case 3: move[0] = 2; move[1] = 2; break;
+    case 5: move[0] = 1; move[1] = 3; break;
+    case 8: move[0] = 4; move[1] = 4; break;
+    default: break;
+    }
+    if ((((sc - 8) % 16) + 16) % 16 == 0) {                                               /* :263-271 (Python's modulo) */
+        if (o156 == 4) { move[2] = 2; move[6] = 2; move[9] = 3; }
+        else { move[2] = 4; move[6] = 4; move[9] = 1; }
+    }
+    switch (sc % 14) {                                                                     /* :272-289 */
+    case 0: move[7] = 3; move[8] = 1; break;
+    case 3: move[7] = 2; move[8] = 2; break;
+    case 7: move[7] = 1; move[8] = 3; break;
+    case 9: move[7] = 4; move[8] = 4; break;
+    case 11: move[7] = 1; move[8] = 3; break;
+    case 12: move[7] = 4; move[8] = 4; break;
+    default: break;
+    }
+}
+
+/* PacmanSimSimple's overlap checks pacman.py:228-239 (with food) and :305-311 (baddies only): true when a baddie ate
+ * pacman -- the reference returns from step() at that point */
+__device__ bool pacman_simple_overlaps(const DevSpec &s, Env &ev, int p, bool eat_food)
+{
+    unsigned nx;
+    for (unsigned o = ev.head[ev.cell[p]]; o != BGW_NONE16; o = nx) {
+        nx = ev.next[o];
+        if ((int)o == p) continue;
+        const int role = __ldg(&s.role[o]);
+        if (eat_food && role == BGW_ROLE_FOOD) {
+            ev.racc[p] += s.reward[BGW_RW_EAT_FOOD];
+            grid_unlink(ev, (int)o);
+            set_health(ev, (int)o, 0.0);
+        } else if (role == BGW_ROLE_BADDIE || role >= BGW_ROLE_SCRIPTED_BADDIE) {
+            ev.racc[p] += s.reward[BGW_RW_DIE];
+            set_health(ev, p, 0.0);
+            grid_unlink(ev, p);
+            return true;
+        }
+    }
+    return false;
+}
+
 /* ------------------------------------------------------------------------------------------------- */
 /* sim programs: the user-written step()                                                             */
 /* ------------------------------------------------------------------------------------------------- */
@@ -784,6 +840,25 @@ __device__ void serial_program_step(const DevSpec &s, Env &ev, int nrank)
             if (!process_move(s, ev, a, ACT(a))) ev.racc[a] += rw[BGW_RW_MOVE_FAIL];
             ev.racc[a] += rw[BGW_RW_ENTROPY];
         }
+    } else if (s.program == BGW_PROG_PACMAN_SIMPLE) {                /* pacman.py:214-310 */
+        const int p = s.a_pacman;
+        if (!process_move(s, ev, p, ACT(p))) ev.racc[p] += rw[BGW_RW_MOVE_FAIL];
+        else ev.racc[p] += rw[BGW_RW_ENTROPY];
+        pacman_teleport(s, ev, p);
+        if (!pacman_simple_overlaps(s, ev, p, true)) {
+            int move[10];
+            const int a156 = s.a_script[2], a159 = s.a_script[4];
+            const int o156 = a156 >= 0 ? (ev.flags[a156] >> BGW_ST_ORIENT_SHIFT) & 7 : 0;
+            const uint32_t x159 = a159 >= 0 ? dev_draw(s, ev, BGW_SITE_SCRIPT, (uint32_t)a159, 0) : 0u;
+            pacman_script((int)ev.step - 1, o156, x159, move);
+            for (int k = 0; k < 10; ++k) {
+                const int a = s.a_script[k];
+                if (a < 0) continue;
+                process_move(s, ev, a, (uint32_t)move[k]);
+                pacman_teleport(s, ev, a);
+            }
+            pacman_simple_overlaps(s, ev, p, false);
+        }
     } else if (s.program == BGW_PROG_PACMAN) {
         const int p = s.a_pacman;
         if (!process_move(s, ev, p, ACT(p))) ev.racc[p] += rw[BGW_RW_MOVE_FAIL];
@@ -811,7 +886,7 @@ __device__ void compute_all_done(const DevSpec &s, Env &ev, int tid, int T)
 {
     if (s.program == BGW_PROG_MAZE) {                                /* maze_navigation.py:41-42 */
         if (tid == 0) ev.ctr[CTR_ALLDONE] = same_position(ev, s.a_nav, s.a_target);
-    } else if (s.program == BGW_PROG_PACMAN) {                       /* pacman.py:140-151 */
+    } else if (s.program == BGW_PROG_PACMAN || s.program == BGW_PROG_PACMAN_SIMPLE) {   /* pacman.py:140-151 */
         if (tid == 0) ev.ctr[CTR_ALLDONE] = !(ev.flags[s.a_pacman] & BGW_ST_ACTIVE) ? 1 : (s.has_food ? 0 : 1);
     } else if (s.program == BGW_PROG_REACH_TARGET) {                 /* OnlyAgentLeftDone reach_the_target.py:43-57 */
         if (tid == 0) ev.ctr[CTR_AND] = 0;
@@ -864,7 +939,7 @@ __device__ void compute_all_done(const DevSpec &s, Env &ev, int tid, int T)
 __device__ __forceinline__ bool prog_done(const DevSpec &s, const Env &ev, int a)
 {
     switch (s.program) {
-    case BGW_PROG_MAZE: case BGW_PROG_PACMAN: return ev.ctr[CTR_ALLDONE] != 0;      /* maze:38-39, pacman:137-138 */
+    case BGW_PROG_MAZE: case BGW_PROG_PACMAN: case BGW_PROG_PACMAN_SIMPLE: return ev.ctr[CTR_ALLDONE] != 0;   /* maze:38-39, pacman:137-138 */
     case BGW_PROG_MULTI_MAZE: return same_position(ev, a, s.a_target);              /* multi_maze:61-64 */
     case BGW_PROG_REACH_TARGET:                                                     /* reach_the_target.py:161-168 */
         if (__ldg(&s.role[a]) == BGW_ROLE_RUNNER) return !(ev.flags[a] & BGW_ST_ACTIVE) || (a != s.a_target && same_position(ev, a, s.a_target));

@@ -3,6 +3,6 @@ from .sims import (  # noqa: F401
     BattleAgent, TeamBattleSim,
     MazeNavigationAgent, MazeNavigationSim,
     MultiMazeNavigationAgent, MultiMazeNavigationSim,
-    PacmanAgent, WallAgent, FoodAgent, BaddieAgent, PacmanSim,
+    PacmanAgent, WallAgent, FoodAgent, BaddieAgent, PacmanSim, PacmanSimSimple,
     BarrierAgent, TargetAgent, RunningAgent, ReachTheTargetSim, TargetDone, OnlyAgentLeftDone,
 )

@@ -128,6 +128,35 @@ class PacmanSim(SmartGridWorldSimulation):
         return 'pacman'
 
 
+class PacmanSimSimple(PacmanSim):
+    """pacman.py:172-326: pacman against baddies that follow a fixed script (the sim `examples/rllib_pacman.py` builds).
+    The script names the baddies of the example grid by id; reward_scheme events: 'bad_move', 'entropy', 'eat_food', 'die'."""
+    default_reward_scheme = {'bad_move': -0.1, 'entropy': 0.01, 'eat_food': 0.1, 'die': -1}
+    SCRIPTED_BADDIES = ('baddie_20', 'baddie_36', 'baddie_156', 'baddie_157', 'baddie_159', 'baddie_161', 'baddie_162',
+                        'baddie_206', 'baddie_222', 'baddie_328')                 # pacman.py:235-246, in this order
+
+    def __init__(self, reward_scheme=None, **kwargs):
+        if reward_scheme is not None:
+            assert type(reward_scheme) is dict, "Reward scheme must be a dictionary."
+            for event, reward in reward_scheme.items():
+                assert event in self.default_reward_scheme, "Supported events: 'bad_move', 'entropy', 'eat_food', and 'die'."
+                assert type(reward) in [int, float], f"Reward for {event} must be numerical."
+        super().__init__(reward_scheme=None, **kwargs)
+        self.reward_scheme = reward_scheme if reward_scheme is not None else dict(self.default_reward_scheme)
+
+    def program(self):
+        return 'pacman_simple'
+
+    class _ExampleGrid:
+        def __get__(self, obj, owner):
+            import os
+            import numpy as np
+            path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'layouts', 'pacman.txt')
+            with open(path) as f:
+                return np.array([line.split() for line in f if line.strip()])
+    example_grid = _ExampleGrid()                        # pacman.py:328-377 (the layout of examples/pacman.txt)
+
+
 class TargetDone(ActiveDone):
     """reach_the_target.py:14-40: an agent is done when it stands on the target's cell."""
 

@@ -105,13 +105,17 @@ class CompiledSpec:
         return s
 
 
-_PROGRAMS = (('ReachTheTargetSim', K.PROG_REACH_TARGET), ('TrafficCorridorSimulation', K.PROG_TRAFFIC), ('TeamBattleSim', K.PROG_TEAM_BATTLE), ('MultiMazeNavigationSim', K.PROG_MULTI_MAZE),
+_PROGRAMS = (('PacmanSimSimple', K.PROG_PACMAN_SIMPLE), ('ReachTheTargetSim', K.PROG_REACH_TARGET), ('TrafficCorridorSimulation', K.PROG_TRAFFIC), ('TeamBattleSim', K.PROG_TEAM_BATTLE), ('MultiMazeNavigationSim', K.PROG_MULTI_MAZE),
              ('MazeNavigationSim', K.PROG_MAZE), ('PacmanSim', K.PROG_PACMAN))
 _OBSERVERS = (('StackedPositionCenteredEncodingObserver', K.OBS_STACKED),
               ('PositionCenteredEncodingObserver', K.OBS_POSITION_CENTERED),
               ('AbsoluteEncodingObserver', K.OBS_ABSOLUTE))
 _DONES = (('OneTeamRemainingDone', K.DONE_ONE_TEAM), ('TargetAgentDone', K.DONE_TARGET_AGENT),
           ('TargetDestroyedDone', K.DONE_TARGET_DESTROYED), ('ActiveDone', K.DONE_ACTIVE))
+
+
+_SCRIPTED_BADDIES = ('baddie_20', 'baddie_36', 'baddie_156', 'baddie_157', 'baddie_159', 'baddie_161', 'baddie_162',
+                     'baddie_206', 'baddie_222', 'baddie_328')
 
 
 def _first(names, table, what):
@@ -125,7 +129,6 @@ def compile_sim(sim, manager='all_step', n_envs=1, env_offset=0, seed=0, horizon
     """Flatten `sim` (reference-style object) into a CompiledSpec."""
     sp = CompiledSpec()
     names = _mro_names(sim)
-    assert 'PacmanSimSimple' not in names, "PacmanSimSimple (scripted baddies) has no device program yet"
     sp.program = _first(names, _PROGRAMS, 'simulation class')
     sp.manager = {'all_step': K.MANAGER_ALL_STEP, 'turn_based': K.MANAGER_TURN_BASED}[manager]
     sp.rows, sp.cols = int(sim.grid.rows), int(sim.grid.cols)
@@ -278,7 +281,7 @@ def compile_sim(sim, manager='all_step', n_envs=1, env_offset=0, seed=0, horizon
             for i, ag in enumerate(agents):
                 if 'MultiMazeNavigationAgent' in _mro_names(ag):
                     sp.role[i] = K.ROLE_NAVIGATOR
-    elif sp.program == K.PROG_PACMAN:           # pacman.py:72-78
+    elif sp.program in (K.PROG_PACMAN, K.PROG_PACMAN_SIMPLE):   # pacman.py:72-78, 196-212
         scheme = {'bad_move': -0.1, 'entropy': 0.01, 'eat_food': 0.1, 'kill': 1, 'die': -1}
         scheme.update(sim.reward_scheme)
         sp.reward[K.RW_MOVE_FAIL] = scheme['bad_move']
@@ -290,5 +293,7 @@ def compile_sim(sim, manager='all_step', n_envs=1, env_offset=0, seed=0, horizon
             n = _mro_names(ag)
             sp.role[i] = K.ROLE_PACMAN if ag.id == 'pacman' else K.ROLE_FOOD if 'FoodAgent' in n else \
                 K.ROLE_BADDIE if 'BaddieAgent' in n else K.ROLE_WALL if 'WallAgent' in n else K.ROLE_NONE
+            if sp.program == K.PROG_PACMAN_SIMPLE and ag.id in _SCRIPTED_BADDIES:     # pacman.py:235-246
+                sp.role[i] = K.ROLE_SCRIPTED_BADDIE + _SCRIPTED_BADDIES.index(ag.id)
         assert sp.rows > 9 and sp.cols > 20, "PacmanSim hardcodes the (9,0)<->(9,20) tunnel (pacman.py:87-92)"
     return sp

@@ -64,7 +64,9 @@ enum {
     BGW_ROLE_FOOD = 4,      /* pacman.py:19                                          */
     BGW_ROLE_BADDIE = 5,    /* pacman.py:24                                          */
     BGW_ROLE_WALL = 6,
-    BGW_ROLE_RUNNER = 7     /* reach_the_target.py:80-87 RunningAgent                */
+    BGW_ROLE_RUNNER = 7,    /* reach_the_target.py:80-87 RunningAgent                */
+    BGW_ROLE_SCRIPTED_BADDIE = 16 /* + k: the baddie of the k-th entry of PacmanSimSimple's script (pacman.py:235-246),
+                                     k = 0..9 for baddie_20, 36, 156, 157, 159, 161, 162, 206, 222, 328 */
 };
 
 /* ---- sim program: the user-written step()/get_* the engine reproduces ------------------------ */
@@ -74,7 +76,8 @@ enum {
     BGW_PROG_MULTI_MAZE = 2,  /* abmarl/examples/sim/multi_maze_navigation.py:17-74 */
     BGW_PROG_PACMAN = 3,      /* abmarl/examples/sim/pacman.py:29-151             */
     BGW_PROG_REACH_TARGET = 4,/* abmarl/examples/sim/reach_the_target.py:90-176   */
-    BGW_PROG_TRAFFIC = 5      /* abmarl/examples/sim/traffic_corridor.py:24-53    */
+    BGW_PROG_TRAFFIC = 5,     /* abmarl/examples/sim/traffic_corridor.py:24-53    */
+    BGW_PROG_PACMAN_SIMPLE = 6 /* abmarl/examples/sim/pacman.py:172-326 (scripted baddies, examples/rllib_pacman.py) */
 };
 
 enum { BGW_MOVE_NONE = 0, BGW_MOVE_BOX = 1 /* MoveActor actor.py:55 */, BGW_MOVE_CROSS = 2 /* :117 */,

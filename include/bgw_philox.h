@@ -46,7 +46,8 @@ enum {
     BGW_SITE_OBS = 5,     /* observers' np.random.choice            observer.py:131,234,246 slot=observer k=absolute cell */
     BGW_SITE_ACTION = 6,  /* synthetic random policy (bench / tests)          policies/policy.py:81-92 slot=agent */
     BGW_SITE_MAZE = 7,    /* MazePlacementState                               state.py:529, utils.py:193,198 */
-    BGW_SITE_AMMO = 8     /* ammo filter of process_action                    actor.py:346-350 slot=attacker k=draw# */
+    BGW_SITE_AMMO = 8,    /* ammo filter of process_action                    actor.py:346-350 slot=attacker k=draw# */
+    BGW_SITE_SCRIPT = 9   /* PacmanSimSimple's random baddie move             examples/sim/pacman.py:240 slot=baddie k=0 */
 };
 
 BGW_HD void bgw_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,

@@ -542,6 +542,37 @@ static int same_position(const Ctx *c, int a, int b) { return c->cell[a] == c->c
 
 static int prog_all_done(const Ctx *c);
 
+/* PacmanSimSimple.step pacman.py:235-303: the baddies' scripted DriftMoveActor actions for this step.  k indexes the
+ * script's entries (baddie_20, 36, 156, 157, 159, 161, 162, 206, 222, 328); sc = step_count; o156 = orientation of
+ * baddie_156; x159 = the keyed draw that stands in for np.random.randint(0, 5) */
+static void pacman_script(int sc, int o156, uint32_t x159, int move[10])
+{
+    const int base[10] = {0, 0, 0, 1, 0, 3, 0, 0, 0, 0};
+    for (int k = 0; k < 10; ++k) move[k] = base[k];
+    move[4] = (int)bgw_index(x159, 5);
+    if (sc == 0) { move[2] = 4; move[6] = 4; move[9] = 3; }                              /* :247-250 */
+    switch (sc % 10) {                                                                     /* :251-262 */
+    case 0: move[0] = 3; move[1] = 1; break;
+    case 3: move[0] = 2; move[1] = 2; break;
+    case 5: move[0] = 1; move[1] = 3; break;
+    case 8: move[0] = 4; move[1] = 4; break;
+    default: break;
+    }
+    if ((((sc - 8) % 16) + 16) % 16 == 0) {                                               /* :263-271 (Python's modulo) */
+        if (o156 == 4) { move[2] = 2; move[6] = 2; move[9] = 3; }
+        else { move[2] = 4; move[6] = 4; move[9] = 1; }
+    }
+    switch (sc % 14) {                                                                     /* :272-289 */
+    case 0: move[7] = 3; move[8] = 1; break;
+    case 3: move[7] = 2; move[8] = 2; break;
+    case 7: move[7] = 1; move[8] = 3; break;
+    case 9: move[7] = 4; move[8] = 4; break;
+    case 11: move[7] = 1; move[8] = 3; break;
+    case 12: move[7] = 4; move[8] = 4; break;
+    default: break;
+    }
+}
+
 static int smart_done(const Ctx *c, int a)   /* SmartGridWorldSimulation.get_done smart.py:106-111 */
 {
     const BgwSpec *sp = c->sp;
@@ -591,7 +622,7 @@ static int prog_done(const Ctx *c, int a)
     }
     case BGW_PROG_MAZE: return prog_all_done(c);                                    /* maze_navigation.py:38-39 */
     case BGW_PROG_MULTI_MAZE: return same_position(c, a, find_role(c, BGW_ROLE_TARGET)); /* multi_maze_navigation.py:61-64 */
-    case BGW_PROG_PACMAN: return prog_all_done(c);                                  /* pacman.py:137-138 */
+    case BGW_PROG_PACMAN: case BGW_PROG_PACMAN_SIMPLE: return prog_all_done(c);     /* pacman.py:137-138 */
     default: return smart_done(c, a);
     }
 }
@@ -608,7 +639,7 @@ static int prog_all_done(const Ctx *c)
             if (c->sp->role[a] == BGW_ROLE_NAVIGATOR && !same_position(c, a, t)) return 0;
         return 1;
     }
-    case BGW_PROG_PACMAN: {                                                         /* pacman.py:140-151 */
+    case BGW_PROG_PACMAN: case BGW_PROG_PACMAN_SIMPLE: {                            /* pacman.py:140-151 */
         const int p = find_role(c, BGW_ROLE_PACMAN);
         if (!(c->flags[p] & BGW_ST_ACTIVE)) return 1;
         for (int a = 0; a < c->A; ++a) if (c->sp->role[a] == BGW_ROLE_FOOD) return 0;  /* any FoodAgent object */
@@ -744,6 +775,49 @@ static void prog_step(Ctx *c, const int *acting, int n_act, const int8_t *action
             const int a = acting[i];
             if (!process_move(c, a, ACT(a))) c->racc[a] += rw[BGW_RW_MOVE_FAIL];
             c->racc[a] += rw[BGW_RW_ENTROPY];
+        }
+        break;
+    }
+    case BGW_PROG_PACMAN_SIMPLE: {                             /* pacman.py:214-310 */
+        const int p = find_role(c, BGW_ROLE_PACMAN);
+        if (!process_move(c, p, ACT(p))) c->racc[p] += rw[BGW_RW_MOVE_FAIL];      /* :216-220 */
+        else c->racc[p] += rw[BGW_RW_ENTROPY];
+        pacman_teleport(c, p);                                                    /* :221-226 */
+        int eaten = 0;
+        for (int pass = 0; pass < 2 && !eaten; ++pass) {
+            /* overlaps with pacman, over a copy of the cell's dict (:228-239 with food, :305-311 baddies only) */
+            uint16_t occ[512]; int n = 0;
+            for (uint16_t o = c->head[c->cell[p]]; o != NONE && n < 512; o = c->next[o]) occ[n++] = o;
+            for (int i = 0; i < n && !eaten; ++i) {
+                const int o = occ[i];
+                if (o == p) continue;
+                if (pass == 0 && sp->role[o] == BGW_ROLE_FOOD) {
+                    c->racc[p] += rw[BGW_RW_EAT_FOOD];
+                    grid_remove(c, o);
+                    set_health(c, o, 0.0);
+                } else if (sp->role[o] == BGW_ROLE_BADDIE || sp->role[o] >= BGW_ROLE_SCRIPTED_BADDIE) {
+                    c->racc[p] += rw[BGW_RW_DIE];
+                    set_health(c, p, 0.0);
+                    grid_remove(c, p);
+                    eaten = 1;                                                    /* `return`: nothing else happens this step */
+                }
+            }
+            if (pass == 1 || eaten) break;
+            /* the scripted baddies move in the script's order (:241-303) */
+            int slot_agent[10], move[10], o156 = 0;
+            for (int k = 0; k < 10; ++k) slot_agent[k] = -1;
+            for (int a = 0; a < c->A; ++a)
+                if (sp->role[a] >= BGW_ROLE_SCRIPTED_BADDIE && sp->role[a] < BGW_ROLE_SCRIPTED_BADDIE + 10) slot_agent[sp->role[a] - BGW_ROLE_SCRIPTED_BADDIE] = a;
+            if (slot_agent[2] >= 0) o156 = (c->flags[slot_agent[2]] >> BGW_ST_ORIENT_SHIFT) & 7;
+            const uint32_t x159 = slot_agent[4] >= 0 ? draw(c, BGW_SITE_SCRIPT, (uint32_t)slot_agent[4], 0) : 0;
+            pacman_script((int)step_of(c) - 1, o156, x159, move);
+            for (int k = 0; k < 10; ++k) {
+                const int a = slot_agent[k];
+                if (a < 0) continue;
+                const int8_t act4[4] = {(int8_t)move[k], 0, 0, 0};
+                process_move(c, a, act4);
+                pacman_teleport(c, a);
+            }
         }
         break;
     }

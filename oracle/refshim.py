@@ -135,6 +135,9 @@ class PhiloxReplay:
         if name == 'reset' and 'agent' in loc:               # OrientationState.reset state.py:675
             x = self._x(K.SITE_ORIENT, self.index[loc['agent'].id])
             return low + philox.index(x, high - low)
+        if name == 'step' and 'action_dict' in loc:          # PacmanSimSimple's random baddie move, pacman.py:240
+            x = self._x(K.SITE_SCRIPT, self.index['baddie_159'])
+            return low + philox.index(x, high - low)
         if name in ('_build_available_positions', 'generate_maze'):   # state.py:534, utils.py:193,198
             if self.maze_episode != self.episode:
                 self.maze_episode, self.maze_k = self.episode, 0

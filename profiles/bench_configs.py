@@ -20,7 +20,7 @@ from tests import scenarios                             # noqa: E402
 CONFIGS = {'tb_c2': (16384, 400), 'pacman_c3': (16384, 60), 'maze_c1': (16384, 400), 'tb_blocking': (16384, 200),
            'tb_encoding': (16384, 200), 'tb_restricted': (16384, 200), 'tb_selective_stacked': (16384, 200),
            'tb_ammo_selective': (16384, 200), 'reach_target': (16384, 200), 'traffic': (16384, 200),
-           'mm_c4': (16384, 400), 'mm_allstep': (16384, 200)}
+           'mm_c4': (16384, 400), 'mm_allstep': (16384, 200), 'pacman_simple': (16384, 100)}
 
 
 def main(names):
@@ -43,7 +43,15 @@ def main(names):
         torch.cuda.synchronize()
         ms = a.elapsed_time(b)
         n = int(eng.stats()[K.STAT_AGENT_STEPS]) - n0
-        print(json.dumps({"config": name, "envs": n_envs, "learners_per_env": eng.L, "entities_per_env": eng.A, "steps": steps,
+        # algorithmic bytes per agent-step as SURVEY 8(d) counts them: action row + padded int8 obs row + reward 4 + done 1 +
+        # agent state read and written 2 x 14
+        algo = eng.action_stride + eng.dims.obs_stride + 4 + 1 + 28
+        try:
+            peak = float(json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs'])
+        except Exception:
+            peak = 6650.0
+        gbs = algo * n / (ms * 1e-3) / 1e9
+        print(json.dumps({"algorithmic_bytes_per_agent_step": algo, "achieved_gbs": gbs, "roofline_frac": gbs / peak,"config": name, "envs": n_envs, "learners_per_env": eng.L, "entities_per_env": eng.A, "steps": steps,
                           "ms_per_step": ms / steps, "agent_steps_per_s": n / (ms * 1e-3),
                           "kernel": "bgw_step_fast_kernel" if eng.dims.threads_per_env <= 128 and spec.program == K.PROG_TEAM_BATTLE and not (spec.klass & (K.AG_BLOCKING | K.AG_AMMO)).any() and spec.attack_actor <= K.ATTACK_BINARY else "bgw_step_kernel"}), flush=True)
 

@@ -308,6 +308,23 @@ def build_pacman_c3(api, view_range=20):
         reward_scheme={'bad_move': 0, 'entropy': -0.01, 'eat_food': 0.05, 'kill': 1, 'die': -1})
 
 
+def build_pacman_simple(api, blocking=False):
+    """examples/rllib_pacman.py as shipped: PacmanSimSimple (scripted baddies) on the example grid, walls that do NOT block
+    (`blocking=True` is commented out there), default view range (the whole board), the script's reward scheme."""
+    px = api.pacman
+    registry = {
+        'P': lambda n: px.PacmanAgent(id='pacman', encoding=1),
+        'W': lambda n: px.WallAgent(id=f'wall_{n}', encoding=2, blocking=blocking),
+        'F': lambda n: px.FoodAgent(id=f'food_{n}', encoding=3),
+        'B': lambda n: px.BaddieAgent(id=f'baddie_{n}', encoding=4),
+    }
+    return px.PacmanSimSimple.build_sim_from_file(
+        os.path.join(LAYOUTS, 'pacman.txt'), registry,
+        states={'PositionState', 'OrientationState', 'HealthState'}, observers={'AbsoluteEncodingObserver'},
+        overlapping={1: {3, 4}, 4: {3, 4}},
+        reward_scheme={'bad_move': 0, 'entropy': -0.01, 'eat_food': 0.05, 'die': -1})
+
+
 # ---------------------------------------------------------------------------------------------------
 # multi maze (multi_maze_navigation.py; examples/rllib_multi_maze_navigation.py:7-41)
 # ---------------------------------------------------------------------------------------------------
@@ -399,6 +416,7 @@ SCENARIOS = {
     'traffic': (build_traffic, 'all_step', 120),
     'maze_c1': (build_maze_c1, 'all_step', 60),
     'pacman_c3': (build_pacman_c3, 'all_step', 12),
+    'pacman_simple': (build_pacman_simple, 'all_step', 150),
     'mm_c4': (build_mm_c4, 'turn_based', 120),
     'mm_random': (build_mm_random, 'turn_based', 90),
     'mm_allstep': (build_mm_c4, 'all_step', 60),

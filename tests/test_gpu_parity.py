@@ -44,6 +44,7 @@ CASES = [
     ('traffic', 64, 200, 50),
     ('maze_c1', 32, 150, 60),
     ('pacman_c3', 6, 40, 25),
+    ('pacman_simple', 8, 120, 60),
     ('mm_c4', 12, 150, 60),
     ('mm_random', 12, 120, 50),
     ('mm_allstep', 12, 100, 40),
