@@ -980,6 +980,60 @@ __device__ __forceinline__ int view_range_eff(const DevSpec &s, int a)
     return R;
 }
 
+/* AbsoluteEncodingObserver whose view covers the whole grid (pacman): the 16 cells of a chunk are the 16 summary
+ * bytes themselves, with masked cells turned into -2 by a byte mask expanded from the line-of-sight bits and the
+ * observer's own cell into -1 (observer.py:125-139); the few cells that hold mixed encodings are resolved one by one. */
+__device__ __forceinline__ bool obs_chunk_absolute_whole(const DevSpec &s, const Env &ev, int a, int ch, const uint32_t *maskp, uint32_t out[4])
+{
+    const int k0 = ch * 16, R = view_range_eff(s, a), n = 2 * R + 1;
+    const uint4 v = *reinterpret_cast<const uint4 *>(ev.csum + k0);
+    uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t mixed = 0;                                                       /* bit t: cell k0 + t holds mixed encodings */
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint32_t hi = w[j] & 0x80808080u;                               /* BGW_CSUM_MIXED = 0x80 (encodings are < 64) */
+        mixed |= (((hi >> 7) * 0x00204081u) >> 21 & 0xFu) << (4 * j);
+    }
+    if (k0 + 16 > s.HW) mixed &= (1u << (s.HW - k0)) - 1u;
+    const int own = ev.cell[a];
+    if ((ev.flags[a] & BGW_ST_IN_GRID) && own >= k0 && own < k0 + 16) {      /* "myself" :130-131 (the cell is occupied: by a) */
+        const int t = own - k0;
+        w[t >> 2] |= 0xFFu << ((t & 3) * 8);
+    }
+    if (maskp) {
+        const int r0 = own / s.W, c0 = own % s.W;
+        uint32_t vis = 0;                                                     /* bit t: cell k0 + t is visible */
+        int k = k0;
+        const int kend = min(k0 + 16, s.HW);
+        while (k < kend) {                                                    /* one grid row segment at a time */
+            const int gr = k / s.W, gc = k - gr * s.W, len = min(kend - k, s.W - gc);
+            const int bit0 = (gr - r0 + R) * n + (gc - c0 + R), wi = bit0 >> 5, sh = bit0 & 31;
+            const uint32_t lo = maskp[wi], hi = (sh + len > 32) ? maskp[wi + 1] : 0u;
+            const uint32_t bits = __funnelshift_r(lo, hi, sh) & ((1u << len) - 1u);
+            vis |= bits << (k - k0);
+            k += len;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t m4 = (vis >> (4 * j)) & 0xFu;
+            const uint32_t bytes = ((m4 * 0x00204081u) & 0x01010101u) * 0xFFu;      /* bit i -> byte i all ones */
+            w[j] = (w[j] & bytes) | (0xFEFEFEFEu & ~bytes);                    /* masked: -2 :135-136 */
+        }
+    }
+    if (k0 + 16 > s.HW) {                                                     /* row padding after the last cell */
+#pragma unroll
+        for (int t = 0; t < 16; ++t) if (k0 + t >= s.HW) w[t >> 2] &= ~(0xFFu << ((t & 3) * 8));
+    }
+    for (uint32_t m = mixed; m; m &= m - 1) {                                 /* np.random.choice over the occupants :133-134 */
+        const int t = __ffs(m) - 1, sh = (t & 3) * 8;
+        if (((w[t >> 2] >> sh) & 0xFFu) != 0x80u) continue;                   /* masked (-2) or myself (-1) */
+        const uint32_t e = (uint32_t)(uint8_t)(int8_t)choose_encoding(s, ev, a, k0 + t, -1);
+        w[t >> 2] = (w[t >> 2] & ~(0xFFu << sh)) | (e << sh);
+    }
+    out[0] = w[0]; out[1] = w[1]; out[2] = w[2]; out[3] = w[3];
+    return true;
+}
+
 /* 16 consecutive bytes [ch*16, ch*16+16) of learner-agent a's observation row */
 __device__ void obs_chunk(const DevSpec &s, const Env &ev, int a, int ch, const uint32_t *maskp, uint32_t out[4])
 {
@@ -990,6 +1044,7 @@ __device__ void obs_chunk(const DevSpec &s, const Env &ev, int a, int ch, const 
     const bool in_own = ev.flags[a] & BGW_ST_IN_GRID;
     const int k0 = ch * 16;
     if (s.observer == BGW_OBS_ABSOLUTE) {                           /* observer.py:95-150 */
+        if (R >= max(s.H, s.W) - 1 && k0 < s.HW && obs_chunk_absolute_whole(s, ev, a, ch, maskp, out)) return;
         const int valid = s.HW;
         int gr = k0 / s.W, gc = k0 % s.W;
         for (int t = 0; t < 16 && k0 + t < valid; ++t) {
