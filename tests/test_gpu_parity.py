@@ -415,3 +415,84 @@ def test_masked_reset_touches_only_the_selected_envs(mirror, name):
             eng.reset(mask)
         assert np.array_equal(eng.obs.cpu().numpy(), ora.obs), f'{name} step {t}'
         assert_state_equal(eng.state_numpy(), ora.state, f'{name} step {t}')
+
+
+def _tiny_battle(api, rows, cols, n_agents, teams=2, view=1, blocking=False, overlap_all=True):
+    agents = {}
+    for i in range(n_agents):
+        ag = api.ex.BattleAgent(id=f'a{i}', encoding=i % teams + 1, initial_health=1.0, blocking=blocking and i == 0)
+        ag.view_range = view
+        agents[ag.id] = ag
+    everyone = set(range(1, teams + 1))
+    overlap = {k: set(everyone) for k in everyone} if overlap_all else {k: {k} for k in everyone}
+    attack = {k: everyone - {k} for k in everyone}
+    return api.ex.TeamBattleSim.build_sim(rows, cols, agents=agents, overlapping=overlap, attack_mapping=attack,
+                                          states={'PositionState', 'HealthState'}, observers={'PositionCenteredEncodingObserver'},
+                                          dones={'OneTeamRemainingDone'})
+
+
+@pytest.mark.parametrize('rows,cols,n_agents,blocking', [(1, 1, 3, False), (1, 1, 1, False), (1, 7, 4, False), (5, 1, 4, True),
+                                                         (2, 2, 9, False), (3, 3, 2, True)])
+def test_degenerate_grids(mirror, rows, cols, n_agents, blocking):
+    """One-cell and one-line grids, a single agent, more agents than cells (everything overlaps): both kernels against
+    the oracle -- every window cell out of bounds, every move into a border, every agent on one cell."""
+    spec = compile_sim(_tiny_battle(mirror, rows, cols, n_agents, blocking=blocking), n_envs=40, seed=rows * 100 + cols, horizon=12,
+                       auto_reset=True)
+    eng, ora = _pair(spec)
+    run_lockstep(eng, ora, 40, label=f'{rows}x{cols}/{n_agents}')
+
+
+def test_placement_failure_is_reported_not_raised(mirror):
+    """More agents than cells without overlapping: the reference raises RuntimeError at state.py:161; the batch reports
+    BGW_ENV_ERROR / BgwState.error == 2 for the env and carries on, engine and oracle alike."""
+    spec = compile_sim(_tiny_battle(mirror, 2, 2, 6, teams=6, overlap_all=False), n_envs=16, seed=4, horizon=10, auto_reset=True)
+    eng, ora = _pair(spec)
+    eng.reset()
+    ora.reset()
+    assert (ora.state['error'] == 2).all() and (ora.state['env_flags'] & K.ENV_ERROR).all()
+    assert_state_equal(eng.state_numpy(), ora.state, 'placement failure')
+    for t in range(5):
+        act = ora.sample_actions()
+        eng.step(torch.from_numpy(act).cuda())
+        ora.step(act)
+        assert_outputs_equal(eng, ora, f'placement failure step {t}')
+        assert_state_equal(eng.state_numpy(), ora.state, f'placement failure step {t}')
+
+
+def test_create_rejects_what_it_cannot_run(mirror):
+    """bgw_create fails loudly (non-zero code + message) instead of running something else."""
+    import ctypes as C
+    lib = K.load()
+
+    def create(spec):
+        h = C.c_void_p()
+        rc = lib.bgw_create(C.byref(spec.c_struct()), 0, C.byref(h))
+        if rc == 0:
+            lib.bgw_destroy(h)
+        return rc, lib.bgw_last_error().decode()
+
+    spec = compile_sim(scenarios.build_tb_c2(mirror), n_envs=4)
+    spec.simultaneous_attacks = spec.simultaneous_attacks.copy()
+    spec.simultaneous_attacks[0] = 2                                    # Binary actor: TeamBattleSim.step raises in the reference
+    rc, msg = create(spec)
+    assert rc != 0 and 'simultaneous_attacks' in msg
+    spec = compile_sim(scenarios.build_tb_selective(mirror), n_envs=4)
+    spec.simultaneous_attacks = np.full_like(spec.simultaneous_attacks, 16)
+    spec.attack_range = np.full_like(spec.attack_range, 2)             # 25 cells x 16 attacks > BGW_MAX_VICTIMS
+    rc, msg = create(spec)
+    assert rc != 0 and 'could attack' in msg
+    spec = compile_sim(scenarios.build_tb_c2(mirror), n_envs=4)
+    spec.encoding = spec.encoding.copy()
+    spec.encoding[3] = 0
+    rc, msg = create(spec)
+    assert rc != 0 and 'encoding' in msg
+    spec = compile_sim(scenarios.build_tb_ammo(mirror), n_envs=4)
+    from abmarl_b200.engine import BatchedGridWorld
+    eng = BatchedGridWorld(spec, device='cuda:0')
+    st = K.BgwState()
+    for name in ('cell', 'next', 'flags', 'health', 'reward_acc', 'episode', 'step', 'env_flags', 'turn', 'error', 'stats'):
+        setattr(st, name, eng.state[name].data_ptr())
+    assert lib.bgw_bind_state(eng._h, C.byref(st)) != 0 and b'ammo' in lib.bgw_last_error()      # AmmoAgents need `ammo`
+    spec = compile_sim(scenarios.build_tb_c2(mirror), n_envs=4)
+    eng = BatchedGridWorld(spec, device='cuda:0')
+    assert lib.bgw_generate_layouts(eng._h, None, 0, None) != 0 and b'layout' in lib.bgw_last_error()
