@@ -1164,7 +1164,7 @@ __device__ void sim_reset(const DevSpec &s, const BgwState &st, Env &ev, int tid
         for (int i = tid; i < (s.HW + 1) / 2; i += T) ((uint32_t *)ev.head)[i] = 0xFFFFFFFFu;
         __syncthreads();
         if (tid == 0)
-            for (int a = 0; a < s.A; ++a) if (lay[a] != BGW_NONE16) grid_append(ev, a, lay[a]);
+            for (int a = 0; a < s.A; ++a) { if (lay[a] != BGW_NONE16) grid_append(ev, a, lay[a]); else ev.ctr[CTR_ERR] = 2; }   /* no cell: state.py:598-603 */
         __syncthreads();
     } else {
         for (int a = tid; a < s.A; a += T) {
@@ -1284,7 +1284,14 @@ __device__ void env_reset(const DevSpec &s, const BgwState &st, Env &ev, int8_t 
         ne = s.L;
     }
     __syncthreads();
-    if (obs_env) observe_learners(s, ev, ne, obs_env, tid, T);
+    if (ev.ctr[CTR_ERR]) {
+        /* the placement failed (the reference raises, state.py:147-149,161): some entity has no cell, nothing may act on
+         * this env.  It is reported BGW_ENV_ERROR | BGW_ENV_ALL_DONE with zero observations and stays inert until it is
+         * reset again (auto-reset: by the next step, with the next episode's draws). */
+        if (obs_env)
+            for (int it = tid; it < ne * s.nchunks; it += T)
+                *reinterpret_cast<uint4 *>(obs_env + (size_t)ev.plist[it / s.nchunks] * s.obs_stride + (it % s.nchunks) * 16) = make_uint4(0, 0, 0, 0);
+    } else if (obs_env) observe_learners(s, ev, ne, obs_env, tid, T);
     store_env(s, st, ev, true, tid, T);
     if (tid == 0) st.error[ev.e] = (uint32_t)ev.ctr[CTR_ERR];
 }
@@ -1304,7 +1311,7 @@ __global__ void bgw_reset_kernel(const DevSpec s, const BgwState st, const uint8
     ev.health = st.health + (size_t)e * s.A;
     ev.ammo = st.ammo ? st.ammo + (size_t)e * s.A : nullptr;
     env_reset(s, st, ev, obs ? obs + (size_t)e * s.L * s.obs_stride : nullptr, tid, T);
-    if (tid == 0) st.env_flags[e] = (uint8_t)(ev.ctr[CTR_ERR] ? BGW_ENV_ERROR : 0);
+    if (tid == 0) st.env_flags[e] = (uint8_t)(ev.ctr[CTR_ERR] ? BGW_ENV_ERROR | BGW_ENV_ALL_DONE : 0);
 }
 
 __global__ void bgw_step_kernel(const DevSpec s, const BgwState st, const uint32_t *actions, const int16_t *order,
@@ -1326,7 +1333,7 @@ __global__ void bgw_step_kernel(const DevSpec s, const BgwState st, const uint32
         if (s.auto_reset) {
             env_reset(s, st, ev, obs_env, tid, T);
             if (tid == 0) {
-                const uint8_t f = (uint8_t)((ev.ctr[CTR_ERR] ? BGW_ENV_ERROR : 0) | BGW_ENV_RESET);
+                const uint8_t f = (uint8_t)((ev.ctr[CTR_ERR] ? BGW_ENV_ERROR | BGW_ENV_ALL_DONE : 0) | BGW_ENV_RESET);
                 st.env_flags[e] = f; all_done[e] = f;
             }
         } else if (tid == 0) all_done[e] = ef0;

@@ -735,8 +735,9 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
                 store_env(s, st, evr, true, tid, T);
                 ev.episode = evr.episode; ev.step = evr.step;
             }
+            const bool bad = ev.ctr[CTR_ERR] != 0;                   /* (sim_reset ends with a barrier) */
             if (tid == 0) {
-                const uint8_t fl = (uint8_t)((ev.ctr[CTR_ERR] ? BGW_ENV_ERROR : 0) | BGW_ENV_RESET);
+                const uint8_t fl = (uint8_t)((bad ? BGW_ENV_ERROR | BGW_ENV_ALL_DONE : 0) | BGW_ENV_RESET);
                 st.error[e] = (uint32_t)ev.ctr[CTR_ERR];
                 st.env_flags[e] = fl; all_done[e] = fl;
             }
@@ -744,6 +745,13 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
             fast_init_dense(s, f, ev, fe, tid, T);                  /* the reset arena ran over summary and slots */
             if (tid < CTR_COUNT) ev.ctr[tid] = 0;
             __syncthreads();
+            if (bad) {
+                /* the placement failed (the reference raises, state.py:147-149,161): an entity without a cell must not be
+                 * touched; zero observations, the env stays inert until the next reset */
+                if (obs_env)
+                    for (int i = tid; i < s.L * nch; i += T) reinterpret_cast<uint4 *>(obs_env)[i] = make_uint4(0, 0, 0, 0);
+                continue;
+            }
             fresh = true;
         }
         BGW_PROF_MARK(2);

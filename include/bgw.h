@@ -129,7 +129,9 @@ enum {
     BGW_ENV_RESET = 1 << 1,     /* this call reset the env instead of stepping it (auto-reset): obs rows hold
                                    the reset observations of every learner, reward/done rows are zero   */
     BGW_ENV_TRUNCATED = 1 << 2, /* horizon reached (RLlib `horizon`, rllib_team_battle.py:89)           */
-    BGW_ENV_ERROR = 1 << 3      /* placement failed (state.py:147-149,161) -- see BgwState.error         */
+    BGW_ENV_ERROR = 1 << 3      /* placement failed (state.py:147-149,161; the reference raises) -- see BgwState.error.
+                                   Reported together with BGW_ENV_ALL_DONE and zero observations: the env is inert
+                                   until it is reset again (auto-reset: by the next step, with the next episode's draws) */
 };
 
 /*

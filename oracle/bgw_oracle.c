@@ -868,7 +868,7 @@ static void sim_reset(Ctx *c)
     if (st->layout) {
         /* externally generated placement (e.g. MazePlacementState state.py:487-527 run host-side) */
         const uint16_t *lay = st->layout + (size_t)c->env * c->A;
-        for (int a = 0; a < c->A; ++a) if (lay[a] != NONE) grid_insert(c, a, lay[a]);
+        for (int a = 0; a < c->A; ++a) { if (lay[a] != NONE) grid_insert(c, a, lay[a]); else st->error[c->env] = 2; }   /* no cell: state.py:598-603 */
     } else {
         uint8_t *avail = (uint8_t *)malloc((size_t)(c->max_enc + 1) * c->HW);
         memset(avail, 1, (size_t)(c->max_enc + 1) * c->HW);     /* _build_available_positions state.py:116-124 */
@@ -951,14 +951,21 @@ static void ctx_env(Ctx *c, int e)
 static void env_reset(Ctx *c, int8_t *obs_env, int stride)
 {
     sim_reset(c);
-    c->st->env_flags[c->env] = (uint8_t)(c->st->error[c->env] ? BGW_ENV_ERROR : 0);
+    /* a failed placement (the reference raises, state.py:147-149,161): the env is reported ERROR | ALL_DONE with zero
+     * observations and stays inert until it is reset again */
+    const int bad = c->st->error[c->env] != 0;
+    c->st->env_flags[c->env] = (uint8_t)(bad ? BGW_ENV_ERROR | BGW_ENV_ALL_DONE : 0);
     if (c->sp->manager == BGW_MANAGER_TURN_BASED) {
         int t = c->st->turn[c->env];
         t = (t + 1) % c->L;                                     /* next(self.agent_order); never rewound :17-20 */
         c->st->turn[c->env] = (int16_t)t;
-        if (obs_env) observe_agent(c, c->agent_of[t], obs_env + (size_t)t * stride, stride);
+        if (obs_env && bad) memset(obs_env + (size_t)t * stride, 0, (size_t)stride);
+        else if (obs_env) observe_agent(c, c->agent_of[t], obs_env + (size_t)t * stride, stride);
     } else if (obs_env) {
-        for (int l = 0; l < c->L; ++l) observe_agent(c, c->agent_of[l], obs_env + (size_t)l * stride, stride);
+        for (int l = 0; l < c->L; ++l) {
+            if (bad) memset(obs_env + (size_t)l * stride, 0, (size_t)stride);
+            else observe_agent(c, c->agent_of[l], obs_env + (size_t)l * stride, stride);
+        }
     }
 }
 
