@@ -2,7 +2,8 @@
 
 Constructing an actor assigns the action / null-action entries on the agents it supports exactly as the
 reference does (actor.py:58-66,121-126,451-453).  `process_action` itself is the device's ordered actor
-resolution (csrc/bgw_kernels.cu: attack_phase / move_phase), not a host method.
+resolution (csrc/bgw_fast.cuh: ordered rounds; csrc/bgw_dev.cuh: exec_attack / exec_attack_ext / team_battle_step), not a host
+method.
 """
 from abc import ABC, abstractmethod
 

@@ -1,6 +1,6 @@
 """Done components (declarations) -- mirror of abmarl/sim/gridworld/done.py.
 
-Evaluated on the device in the reward/done reduction (csrc/bgw_kernels.cu: finish_phase).
+Evaluated on the device in the reward/done reduction (csrc/bgw_dev.cuh: prog_done / compute_all_done).
 """
 from abc import ABC
 

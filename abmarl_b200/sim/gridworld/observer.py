@@ -2,7 +2,7 @@
 
 Constructing an observer assigns observation / null-observation entries like the reference
 (observer.py:69-79,161-174,262-278).  `get_obs` is the device's observation gather
-(csrc/bgw_kernels.cu: observe_phase).  Reference dtype is int64; the engine emits int8 that compares
+(csrc/bgw_fast.cuh: fast_obs_rows; csrc/bgw_dev.cuh: obs_chunk / observe_learners).  Reference dtype is int64; the engine emits int8 that compares
 equal after widening (max encoding <= 63).
 """
 from abc import ABC, abstractmethod

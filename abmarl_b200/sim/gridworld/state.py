@@ -1,6 +1,6 @@
 """State components (declarations) -- mirror of abmarl/sim/gridworld/state.py.
 
-`reset()` of each component runs on the device (bgw_reset; kernels in csrc/bgw_kernels.cu):
+`reset()` of each component runs on the device (bgw_reset; csrc/bgw_dev.cuh: sim_reset):
 PositionState state.py:88-166, HealthState :629-641, OrientationState :666-675.
 MazePlacementState (:385-619) and TargetBarriersFreePlacementState (:169-383) build their layouts on the device
 (bgw_generate_layouts, csrc/bgw_maze.cuh) or, above its limits, host-side (abmarl_b200.layouts).
