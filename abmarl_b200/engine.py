@@ -263,7 +263,8 @@ class HostPipeline:
         loop: for k in range(pipe.K): out = pipe.recv(k); ...; pipe.send(k, next_actions[k])
     """
 
-    def __init__(self, spec, shards=4, device=None):
+    def __init__(self, spec, shards=4, device=None, zero_copy=True):
+        self.zero_copy = bool(zero_copy)     # True: the gather kernel writes pinned host memory; False: compact on the device, then copy
         assert spec.n_envs % shards == 0, "n_envs must divide evenly over the sub-batches"
         self.K, self.Ek = shards, spec.n_envs // shards
         self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
@@ -284,7 +285,7 @@ class HostPipeline:
         """Enqueue one manager step of sub-batch k: actions_host int8 [E/K, L, 4] in pinned host memory."""
         assert not self.in_flight[k], "recv(k) the previous step of this sub-batch first"
         with torch.cuda.stream(self.streams[k]):
-            self.engines[k].enqueue_host(actions_host, order, zero_copy=True)
+            self.engines[k].enqueue_host(actions_host, order, zero_copy=self.zero_copy)
         self.in_flight[k] = True
 
     def recv(self, k):
@@ -292,7 +293,7 @@ class HostPipeline:
         learner (global env = env_offset + k * E/K + local env)."""
         assert self.in_flight[k]
         with torch.cuda.stream(self.streams[k]):
-            out = self.engines[k].collect_host(zero_copy=True)
+            out = self.engines[k].collect_host(zero_copy=self.zero_copy)
         self.in_flight[k] = False
         return out
 

@@ -217,7 +217,7 @@ def run_ours(args):
         # sub-batch uploads its pinned host actions (H2D) and lands its compacted rows in pinned host memory (D2H)
         # inside the timed region; the timed region also contains the pipeline's fill and drain.
         from abmarl_b200.engine import HostPipeline
-        pipe = HostPipeline(build_spec(E, rank * E), shards=KS, device=dev)
+        pipe = HostPipeline(build_spec(E, rank * E), shards=KS, device=dev, zero_copy=not args.e2e_staged)
         Ek = E // KS
         pipe.reset()
 
@@ -320,6 +320,7 @@ def main():
     ap.add_argument('--envs-per-gpu', type=int, default=ENVS_PER_GPU)
     ap.add_argument('--e2e-steps', type=int, default=200, help='steps of the host-buffer loop (one full episode)')
     ap.add_argument('--e2e-shards', type=int, default=2, help='sub-batches the e2e loop keeps in flight (1 = one blocking step_host call per step)')
+    ap.add_argument('--e2e-staged', action='store_true', help='e2e pipeline: compact on the device and copy with the copy engine instead of writing pinned host memory from the gather kernel')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--e2e-zero-copy', action='store_true', help='e2e: the gather kernel writes the pinned host buffers directly instead of compacting on the device and copying')
     ap.add_argument('--dump-steps', default=None, help='write the per-step kernel times (ms) to this JSON file')
