@@ -52,7 +52,7 @@ int pow2ceil(int x) { int p = 1; while (p < x) p <<= 1; return p; }
 struct BgwEngine {
     int device = 0;
     MazeParams maze{};            /* device-side MazePlacementState (bgw_maze.cuh); device pointers */
-    bool maze_ok = false;
+    bool maze_ok = false, maze_small = false;
     DevSpec ds{}, dsf{};          /* general kernels / fast kernel (own slot table size) */
     FastSpec fs{};
     int threads_fast = 0;
@@ -113,15 +113,20 @@ void los_apply_host(uint8_t *mask, int R, int rd, int cd)
     }
 }
 
-/* one thread per env (the algorithm is a serial chain of keyed draws); scratch in local memory */
+/* CTAs of one working thread walk the envs (the algorithm is a serial chain of keyed draws, about a millisecond per
+ * maze; what matters is how many run at once).  The scratch sits in shared memory: as a local array its 15 KB would make
+ * the driver reserve 4 GB (measured) for all the threads the device can hold, and in global memory every store-then-load
+ * of the set table would go to L2 (measured 3x slower). */
+template <typename Scratch>
 __global__ void bgw_layout_kernel(const MazeParams p, const BgwState st, int E, int env_offset, const uint8_t *env_mask, int only_done)
 {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= E) return;
-    if (only_done ? !(st.env_flags[e] & BGW_ENV_ALL_DONE) : (env_mask && !env_mask[e])) return;
-    MazeScratch w;
-    const int err = maze_layout(p, (uint32_t)(env_offset + e), st.episode[e] + 1u, w, st.layout + (size_t)e * p.A);
-    if (err) st.error[e] = (uint32_t)err;
+    __shared__ Scratch w;
+    if (threadIdx.x != 0) return;
+    for (int e = blockIdx.x; e < E; e += gridDim.x) {              /* the grid is what fits the device at once */
+        if (only_done ? !(st.env_flags[e] & BGW_ENV_ALL_DONE) : (env_mask && !env_mask[e])) continue;
+        const int err = maze_layout(p, (uint32_t)(env_offset + e), st.episode[e] + 1u, w, st.layout + (size_t)e * p.A);
+        if (err) st.error[e] = (uint32_t)err;
+    }
 }
 
 int first_role(const BgwSpec *sp, int role)
@@ -309,6 +314,7 @@ int bgw_create(const BgwSpec *sp, int device, bgw_handle *out)
             m.enc = d.enc; m.overlap = d.overlap;
             if ((rc = upload(h, sp->init_row, A, &m.init_row)) || (rc = upload(h, sp->init_col, A, &m.init_col))) return bail(rc);
             h->maze_ok = maze_supported(H, W, max_enc, sp->barrier_encodings, sp->free_encodings);
+            h->maze_small = maze_fits<MazeScratchSmall>(H, W, max_enc, sp->barrier_encodings, sp->free_encodings);
         } else if (sp->layout_kind != BGW_LAYOUT_POSITION_STATE) return bail(fail(1, "bgw_create: unknown layout_kind %d", sp->layout_kind));
     }
 
@@ -595,8 +601,12 @@ int bgw_generate_layouts(bgw_handle h, const uint8_t *env_mask, int only_done, v
     if (!h->maze_ok) return fail(1, "bgw_generate_layouts: this simulation has no device-side layout generator (BgwDims.device_layouts == 0)");
     if (!h->bound || !h->st.layout) return fail(1, "bgw_generate_layouts: bind a state with a `layout` array first");
     DeviceGuard guard(h->device);
-    CUDA_OK(cudaFuncSetAttribute(bgw_layout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 0));
-    bgw_layout_kernel<<<(h->ds.E + 31) / 32, 32, 0, (cudaStream_t)stream>>>(h->maze, h->st, h->ds.E, h->ds.env_offset, env_mask, only_done);
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+    if (h->maze_small)                                             /* 5.5 KB of shared memory: the 32-CTA limit of an SM binds */
+        bgw_layout_kernel<MazeScratchSmall><<<std::min(h->ds.E, sms * 32), 32, 0, (cudaStream_t)stream>>>(h->maze, h->st, h->ds.E, h->ds.env_offset, env_mask, only_done);
+    else                                                           /* 14.7 KB: 15 CTAs per SM */
+        bgw_layout_kernel<MazeScratch><<<std::min(h->ds.E, sms * 15), 32, 0, (cudaStream_t)stream>>>(h->maze, h->st, h->ds.E, h->ds.env_offset, env_mask, only_done);
     CUDA_OK(cudaGetLastError());
     h->launches += 1;
     return 0;

@@ -160,15 +160,20 @@ BGW_HD void maze_generate(uint8_t *grid, int pr, int pc, int start, MazeStream &
     }
 }
 
-/* scratch of one layout (thread-local on the device, on the stack on the host) */
-struct MazeScratch {
-    uint8_t grid[BGW_MAZE_MAX_PADDED];
-    uint16_t walls[BGW_MAZE_MAX_PADDED];
-    uint16_t tab_a[BGW_MAZE_TABLE], tab_b[BGW_MAZE_TABLE];
-    uint16_t list[BGW_MAZE_MAX_LISTS][BGW_MAZE_MAX_CELLS];      /* ravelled_positions_available per encoding */
-    int list_n[BGW_MAZE_MAX_LISTS];
+/* scratch of one layout (shared memory of one CTA on the device, heap on the host).  Two size classes: the small one
+ * (grids up to 10x10 = BASELINE config 4, at most 4 placed encodings) lets 32 CTAs share an SM. */
+template <int PADDED, int CELLS, int TABLE, int LISTS>
+struct MazeScratchT {
+    static constexpr int kPadded = PADDED, kCells = CELLS, kTable = TABLE, kLists = LISTS;
+    uint8_t grid[PADDED];
+    uint16_t walls[PADDED];
+    uint16_t tab_a[TABLE], tab_b[TABLE];                        /* TABLE = first power of two above 4 * PADDED */
+    uint16_t list[LISTS][CELLS];                                /* ravelled_positions_available per encoding */
+    int list_n[LISTS];
     int8_t list_of[BGW_MAX_ENCODING + 1];                       /* encoding -> list index or -1 */
 };
+typedef MazeScratchT<BGW_MAZE_MAX_PADDED, BGW_MAZE_MAX_CELLS, BGW_MAZE_TABLE, BGW_MAZE_MAX_LISTS> MazeScratch;
+typedef MazeScratchT<144, 100, 1024, 4> MazeScratchSmall;
 
 /* a.sort(key=distance from the start, reverse=descending): Python's sort is stable, also with reverse=True */
 BGW_HD void maze_sort(uint16_t *a, int n, int cols, int sr, int sc, bool descending)
@@ -187,7 +192,8 @@ BGW_HD void maze_sort(uint16_t *a, int n, int cols, int sr, int sc, bool descend
 
 /* MazePlacementState.reset state.py:487-619 for (global env, episode) -> layout[A] (BGW_NONE = not placed).
  * Returns 0, or 2 when an entity finds no cell (RuntimeError state.py:598-603). */
-BGW_HD int maze_layout(const MazeParams &p, uint32_t genv, uint32_t episode, MazeScratch &w, uint16_t *layout)
+template <typename Scratch>
+BGW_HD int maze_layout(const MazeParams &p, uint32_t genv, uint32_t episode, Scratch &w, uint16_t *layout)
 {
     const int rows = p.rows, cols = p.cols, HW = rows * cols, pr = rows + 2, pc = cols + 2;
     MazeStream st{p.seed, genv, episode, 0};
@@ -206,7 +212,7 @@ BGW_HD int maze_layout(const MazeParams &p, uint32_t genv, uint32_t episode, Maz
     for (int e = 1; e <= p.max_enc && e <= BGW_MAX_ENCODING; ++e) {
         const bool is_free = (p.free_encodings >> e) & 1ull, is_barrier = (p.barrier_encodings >> e) & 1ull;
         if (!is_free && !is_barrier) continue;
-        if (nlists == BGW_MAZE_MAX_LISTS) return 3;
+        if (nlists == Scratch::kLists) return 3;
         uint16_t *lst = w.list[nlists];
         int n = 0;
         for (int cell = 0; cell < HW; ++cell) {
@@ -248,9 +254,15 @@ BGW_HD int maze_layout(const MazeParams &p, uint32_t genv, uint32_t episode, Maz
     return err;
 }
 
-BGW_HD bool maze_supported(int rows, int cols, int max_enc, unsigned long long barrier, unsigned long long freee)
+template <typename Scratch>
+BGW_HD bool maze_fits(int rows, int cols, int max_enc, unsigned long long barrier, unsigned long long freee)
 {
     int lists = 0;
     for (int e = 1; e <= max_enc; ++e) lists += (int)(((barrier | freee) >> e) & 1ull);
-    return rows * cols <= BGW_MAZE_MAX_CELLS && (rows + 2) * (cols + 2) <= BGW_MAZE_MAX_PADDED && lists <= BGW_MAZE_MAX_LISTS;
+    return rows * cols <= Scratch::kCells && (rows + 2) * (cols + 2) <= Scratch::kPadded && lists <= Scratch::kLists;
+}
+
+BGW_HD bool maze_supported(int rows, int cols, int max_enc, unsigned long long barrier, unsigned long long freee)
+{
+    return maze_fits<MazeScratch>(rows, cols, max_enc, barrier, freee);
 }
