@@ -496,3 +496,48 @@ def test_create_rejects_what_it_cannot_run(mirror):
     spec = compile_sim(scenarios.build_tb_c2(mirror), n_envs=4)
     eng = BatchedGridWorld(spec, device='cuda:0')
     assert lib.bgw_generate_layouts(eng._h, None, 0, None) != 0 and b'layout' in lib.bgw_last_error()
+
+
+@pytest.mark.parametrize('name', ['tb_encoding', 'tb_restricted', 'tb_selective', 'tb_ammo'])
+def test_manager_encodes_reference_style_action_dicts(mirror, name):
+    """AllStepManager.encode_actions packs the reference's action dicts ({'move': ..., 'attack': dict | vector | matrix |
+    count}) into the action rows the kernels read: driving the manager with dicts equals driving the oracle with bytes;
+    as_dicts() hands back reference-shaped observations (with 'ammo' where the sim has an AmmoObserver)."""
+    from abmarl_b200.managers import AllStepManager
+    from oracle.oracle import OracleEnv
+    builder, _, _ = scenarios.SCENARIOS[name]
+    sim = builder(mirror)
+    mgr = AllStepManager(sim, n_envs=3, seed=19, horizon=30, auto_reset=True, device='cuda:0')
+    spec = mgr.spec
+    ora = OracleEnv(spec)
+    mgr.reset()
+    ora.reset()
+    for t in range(25):
+        act = ora.sample_actions()
+        dicts = []
+        for e in range(3):
+            d = {}
+            for l, a in enumerate(spec.learner_agents):
+                agent = sim.agents[spec.agent_ids[a]]
+                att = act[e, l, 2:].view(np.uint8).astype(int)
+                n = 2 * agent.attack_range + 1
+                if spec.attack_actor == K.ATTACK_ENCODING:
+                    attack = {enc: int(att[enc - 1]) for enc in sorted(agent.action_space['attack'].spaces)}
+                elif spec.attack_actor == K.ATTACK_RESTRICTED:
+                    attack = att[:agent.simultaneous_attacks]
+                elif spec.attack_actor == K.ATTACK_SELECTIVE:
+                    attack = att[:n * n].reshape(n, n)
+                else:
+                    attack = int(att[0])
+                d[agent.id] = {'move': np.array([int(act[e, l, 0]), int(act[e, l, 1])]), 'attack': attack}
+            dicts.append(d)
+        packed = mgr.encode_actions(dicts)
+        np.testing.assert_array_equal(packed.cpu().numpy(), act)
+        mgr.step(packed)
+        ora.step(act)
+        assert_outputs_equal(mgr.engine, ora, f'{name} step {t}')
+        obs, rew, dn, _ = mgr.as_dicts(env=1)
+        for agent_id, o in obs.items():
+            if spec.ammo_observer:
+                assert o['ammo'] == int(ora.state['ammo'][1, spec.agent_ids.index(agent_id)])
+            assert 'position_centered_encoding' in o
