@@ -6,7 +6,7 @@ is missing or does not load, importing the engine raises.
 import ctypes as C
 import os
 
-BGW_ABI_VERSION = 2
+BGW_ABI_VERSION = 3
 BGW_MAX_ENCODING = 63
 BGW_MAX_AGENTS = 4096
 BGW_NONE = 0xFFFF
@@ -67,7 +67,7 @@ LAYOUT_POSITION_STATE, LAYOUT_MAZE, LAYOUT_TARGET_BARRIERS_FREE = range(3)
 
 EXPORTS = ('bgw_create', 'bgw_destroy', 'bgw_dims', 'bgw_bind_state', 'bgw_reset', 'bgw_step', 'bgw_generate_layouts',
            'bgw_maze_layout_host',
-           'bgw_sample_actions', 'bgw_step_sampled', 'bgw_gather_valid', 'bgw_rng_draw', 'bgw_los_mask', 'bgw_launch_count', 'bgw_last_error',
+           'bgw_sample_actions', 'bgw_step_sampled', 'bgw_rollout_sampled', 'bgw_gather_valid', 'bgw_rng_draw', 'bgw_los_mask', 'bgw_launch_count', 'bgw_last_error',
            'bgw_abi_version')
 
 _LIB = None
@@ -99,6 +99,8 @@ def load():
     lib.bgw_sample_actions.argtypes = [h, _p, _p]
     lib.bgw_step_sampled.argtypes = [h, _p, _p, _p, _p, _p, _p, _p]
     lib.bgw_step_sampled.restype = C.c_int
+    lib.bgw_rollout_sampled.argtypes = [h, C.c_int, _p, _p, _p, _p, _p, _p, _p]
+    lib.bgw_rollout_sampled.restype = C.c_int
     lib.bgw_gather_valid.argtypes = [h] + [_p] * 10
     lib.bgw_gather_valid.restype = C.c_int
     lib.bgw_rng_draw.argtypes = [C.c_uint64] + [C.c_uint32] * 6 + [C.POINTER(C.c_uint32 * 4)]

@@ -56,6 +56,12 @@ struct BgwEngine {
     DevSpec ds{}, dsf{};          /* general kernels / fast kernel (own slot table size) */
     FastSpec fs{};
     int threads_fast = 0;
+    bool pdl = true;              /* launch the fast step kernel with programmatic stream serialization */
+    bool poisoned = false;        /* a step launch was rejected: the ticket counters are out of step */
+    bool chain_ok = false;        /* consecutive launches of bgw_rollout_sampled may be chained per env (bgw_fast.cuh) */
+    uint32_t seq = 0;             /* sequence number of the last fast step launch */
+    uint32_t *ticket_ring = nullptr;                /* [BGW_TICKET_RING] device: env ticket counters, one per launch in flight */
+    std::vector<uint32_t> ticket_uses;              /* launches that have drawn from each counter (each draws exactly E) */
     bool fast_static = false;     /* compile-time shapes of the headline workload apply (FastStaticC5) */
     BgwDims dims{};
     BgwState st{};
@@ -468,7 +474,20 @@ int bgw_create(const BgwSpec *sp, int device, bgw_handle *out)
             if (cudaMalloc(&pp, (size_t)h->fs.grid_ctas * 8 * 16 * sizeof(long long)) == cudaSuccess) { h->allocs.push_back(pp); cudaMemset(pp, 0, (size_t)h->fs.grid_ctas * 8 * 16 * sizeof(long long)); h->fs.prof = (long long *)pp; }
         }
         if (getenv("BGW_VERBOSE")) fprintf(stderr, "[bgw] fast kernel: T=%d smem=%d B/CTA, %d CTAs/SM x %d SMs, grid=%d, slots=%d\n", h->threads_fast, h->fs.smem_bytes, per_sm, sms, h->fs.grid_ctas, h->dsf.slot_mask + 1);
+        if (const char *t = getenv("BGW_PDL")) h->pdl = atoi(t) != 0;
         if (const char *t = getenv("BGW_GRID")) { const int v = atoi(t); if (v >= 1) h->fs.grid_ctas = std::min(d.E, v); }
+        {   /* env tickets + per-env launch stamps (bgw_fast.cuh, "env tickets and chained launches") */
+            void *pp = nullptr;
+            const size_t nb = ((size_t)d.E + BGW_TICKET_RING) * sizeof(uint32_t);
+            if ((ce = cudaMalloc(&pp, nb)) != cudaSuccess || (ce = cudaMemset(pp, 0, nb)) != cudaSuccess)
+                return bail(fail(2, "bgw_create: env stamps: %s", cudaGetErrorString(ce)));
+            h->allocs.push_back(pp);
+            h->ticket_ring = (uint32_t *)pp;
+            h->fs.env_seq = (uint32_t *)pp + BGW_TICKET_RING;
+        }
+        /* chained launches: nothing may run between two steps (no layout kernel) */
+        h->chain_ok = h->pdl && !(h->maze_ok && sp->auto_reset);
+        if (const char *t = getenv("BGW_CHAIN")) if (!atoi(t)) h->chain_ok = false;
     }
     dm.device_layouts = h->maze_ok ? 1 : 0;
     dm.threads_per_env = h->fs.enabled ? h->threads_fast : T; dm.envs_per_cta = 1; dm.smem_bytes = h->fs.enabled ? h->fs.smem_bytes : off;
@@ -516,17 +535,38 @@ int bgw_reset(bgw_handle h, const uint8_t *env_mask, int8_t *obs, void *stream)
 }
 
 static int step_impl(bgw_handle h, const int8_t *actions, int8_t *sampled, const int16_t *order, int8_t *obs, float *reward,
-                     uint8_t *done, uint8_t *all_done, void *stream)
+                     uint8_t *done, uint8_t *all_done, void *stream, bool chained = false)
 {
     DeviceGuard guard(h->device);
     if (h->fs.enabled) {
+        if (h->poisoned) return fail(2, "bgw_step: an earlier step launch failed; the handle cannot be used any more");
+        h->fs.seq = ++h->seq;
+        h->fs.chain = (chained && h->chain_ok) ? 1 : 0;
+        if (h->ticket_uses.empty()) h->ticket_uses.assign(BGW_TICKET_RING, 0u);
+        const uint32_t slot = h->fs.seq % BGW_TICKET_RING;
+        h->fs.ticket = h->ticket_ring + slot;
+        h->fs.ticket_base = h->ticket_uses[slot]++ * (uint32_t)h->ds.E;
+        h->poisoned = true;                            /* until the launch below has been accepted */
+        /* Programmatic dependent launch: when the previous operation on the stream is another step launch, the
+         * CTAs of this one become resident as that one's CTAs retire and run their env-independent set-up (spec
+         * tables, clean dense arrays) while its last envs finish; they read and write nothing of the step state
+         * before griddepcontrol.wait, which returns once the previous grid has completed and its writes are visible.
+         * After any other stream operation the attribute changes nothing.  BGW_PDL=0 turns it off (A/B). */
+        cudaLaunchAttribute pdl_attr[1];
+        pdl_attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        pdl_attr[0].val.programmaticStreamSerializationAllowed = h->pdl ? 1 : 0;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)h->fs.grid_ctas); cfg.blockDim = dim3((unsigned)h->threads_fast);
+        cfg.dynamicSmemBytes = (size_t)h->fs.smem_bytes; cfg.stream = (cudaStream_t)stream;
+        cfg.attrs = pdl_attr; cfg.numAttrs = 1;
 #define BGW_LAUNCH_FAST(ST, HT)                                                                                       \
-    bgw_step_fast_kernel<ST, HT><<<h->fs.grid_ctas, h->threads_fast, h->fs.smem_bytes, (cudaStream_t)stream>>>(          \
-        h->dsf, h->fs, h->st, (const uint32_t *)actions, (uint32_t *)sampled, order, obs, reward, done, all_done)
+    CUDA_OK(cudaLaunchKernelEx(&cfg, bgw_step_fast_kernel<ST, HT>, h->dsf, h->fs, h->st, (const uint32_t *)actions,       \
+                               (uint32_t *)sampled, order, obs, reward, done, all_done))
         if (h->fast_static) BGW_LAUNCH_FAST(true, uint8_t);
         else if (h->fs.head_elem == 1) BGW_LAUNCH_FAST(false, uint8_t);
         else BGW_LAUNCH_FAST(false, uint16_t);
 #undef BGW_LAUNCH_FAST
+        h->poisoned = false;
     } else {
         if (sampled) {                                 /* general kernel: sample, then step (two launches) */
             const size_t n = (size_t)h->ds.E * h->ds.L;
@@ -566,6 +606,25 @@ int bgw_step_sampled(bgw_handle h, int8_t *actions_out, const int16_t *order, in
     if (!h->bound) return fail(1, "bgw_step_sampled: call bgw_bind_state first");
     if (!actions_out || !reward || !done || !all_done) return fail(1, "bgw_step_sampled: actions_out, reward, done and all_done are required");
     return step_impl(h, nullptr, actions_out, order, obs, reward, done, all_done, stream);
+}
+
+int bgw_rollout_sampled(bgw_handle h, int n_steps, int8_t *actions_out, const int16_t *order, int8_t *obs, float *reward,
+                        uint8_t *done, uint8_t *all_done, void *stream)
+{
+    if (!h) return fail(1, "bgw_rollout_sampled: null handle");
+    if (!h->bound) return fail(1, "bgw_rollout_sampled: call bgw_bind_state first");
+    if (n_steps < 0) return fail(1, "bgw_rollout_sampled: n_steps < 0");
+    if (!actions_out || !reward || !done || !all_done) return fail(1, "bgw_rollout_sampled: actions_out, reward, done and all_done are required");
+    for (int i = 0; i < n_steps; ++i) {
+        /* launches 2..n follow a step launch of this handle directly: they may be chained per env */
+        const int rc = step_impl(h, nullptr, actions_out, order, obs, reward, done, all_done, stream, i > 0);
+        if (rc) return rc;
+        if (h->maze_ok && h->st.layout && h->ds.auto_reset) {      /* next episode's layouts of the envs that just finished */
+            const int rl = bgw_generate_layouts(h, nullptr, 1, stream);
+            if (rl) return rl;
+        }
+    }
+    return 0;
 }
 
 int bgw_sample_actions(bgw_handle h, int8_t *actions, void *stream)

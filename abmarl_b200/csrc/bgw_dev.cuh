@@ -1151,7 +1151,7 @@ __device__ void observe_learners(const DevSpec &s, Env &ev, int ne, int8_t *obs_
 __device__ void sim_reset(const DevSpec &s, const BgwState &st, Env &ev, int tid, int T)
 {
     const int e = ev.e;
-    ev.episode = st.episode[e] + 1u;
+    ev.episode = __ldcg(&st.episode[e]) + 1u;
     ev.step = 0;
     __syncthreads();                       /* every thread has read episode[e] */
     if (tid == 0) { st.episode[e] = ev.episode; st.step[e] = 0; ev.ctr[CTR_ERR] = 0; }

@@ -61,6 +61,13 @@ struct FastSpec {
     int r_racc, r_avail;      /* reset arena (over cenc | head | scratch, from o_cenc): u16 heads at 0, then racc, avail */
     int head_elem;            /* bytes per list head: 1 when A <= 256, else 2 */
     long long *prof;          /* debug (BGW_PROF_FILE): clock64 at phase boundaries, [cta][8 envs][16 marks] */
+    /* env scheduling across launches (see "env tickets and chained launches" below) */
+    uint32_t *env_seq;        /* [E] sequence number of the last fast step launch that finished this env */
+    uint32_t *ticket;         /* this launch's env ticket counter: one of a ring of BGW_TICKET_RING, never reset */
+    uint32_t ticket_base;     /* value of *ticket before this launch: every launch draws exactly E tickets */
+    uint32_t seq;             /* sequence number of this launch (1, 2, ... per handle) */
+    int chain;                /* 1: the previous operation on the stream is the fast step launch seq - 1 of the same
+                                 rollout (bgw_rollout_sampled): wait per env on env_seq, not for the whole grid */
 };
 
 /* The shared-memory carve-up of the fast kernel: ONE definition used by bgw_create (run-time shapes) and by the
@@ -224,6 +231,54 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+/* ---- env tickets and chained launches -----------------------------------------------------------------------
+ * A CTA takes blockIdx.x as its first env and every further env from a ticket counter (arrival order), so CTAs
+ * that drew cheap envs take more of them and a launch has no fixed 2-or-3-envs-per-CTA tail.  Every env a launch
+ * finishes is stamped with the launch's sequence number (release).  Inside bgw_rollout_sampled, where the library
+ * itself enqueues consecutive step launches with nothing in between, launch k+1 is a programmatic dependent launch
+ * that does NOT wait for launch k as a whole: its CTAs become resident as k's CTAs retire and start an env as
+ * soon as THAT env carries the stamp k (acquire) -- envs never interact, so this is the only dependency.
+ * Launch k+1 is not scheduled before every CTA of k has started (griddepcontrol.launch_dependents), so a waiting
+ * CTA only ever waits for envs that started or finished CTAs of the launch before own: the chain cannot deadlock.
+ * Any number of launches can be in flight (a CTA of k that drew an expensive env -- one that resets -- is still
+ * running while k+1, k+2, ... pass by, each leaving one CTA waiting for that env), at most one per resident CTA:
+ * each launch has its own ticket counter in a ring of BGW_TICKET_RING > resident CTAs.  A launch draws exactly E
+ * tickets (E - grid envs and one terminal ticket per CTA), so the counters are never reset: the host passes the
+ * value a counter has before the launch. */
+#define BGW_TICKET_RING 2048
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(uint32_t *p, uint32_t v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+#ifdef BGW_CHAIN_DEBUG
+__device__ int bgw_chain_dbg_count = 0;
+#endif
+__device__ __forceinline__ void chain_wait_env(const FastSpec &f, int e)
+{
+    if (!f.chain) return;
+#ifdef BGW_CHAIN_DEBUG   /* diagnosis build: report a wait that does not end and go on without it */
+    unsigned spins = 0;
+    while ((int32_t)(ld_acquire_u32(f.env_seq + e) - (f.seq - 1u)) < 0) {
+        __nanosleep(64);
+        if (++spins == (1u << 21)) {
+            if (threadIdx.x == 0 && atomicAdd(&bgw_chain_dbg_count, 1) < 24)
+                printf("[chain] launch %u cta %d waits for env %d: stamp %u, ticket counter %u (base %u)\n", f.seq, (int)blockIdx.x, e,
+                       ld_acquire_u32(f.env_seq + e), ld_acquire_u32(f.ticket), f.ticket_base);
+            break;
+        }
+    }
+#else
+    while ((int32_t)(ld_acquire_u32(f.env_seq + e) - (f.seq - 1u)) < 0) __nanosleep(64);
+#endif
+}
+#define BGW_TSLOT 68          /* wsum[68], wsum[69]: the env after this one / the one after that */
 
 /* stream env e's rows into one staging buffer */
 __device__ __forceinline__ void fast_issue_env(const DevSpec &s, const FastSpec &f, const BgwState &st, const uint32_t *actions,
@@ -657,26 +712,49 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
             (bgw_smem + f.o_lmask)[a] = (k & BGW_AG_LEARNER) ? 0xFF : 0;
         }
     }
+    uint32_t *const tk = f_in.ticket;                      /* this launch's ticket counter */
+    const uint32_t tk_off = gridDim.x - f_in.ticket_base;  /* env = counter value - base + grid size (mod 2^32) */
+    int *const tslot = fe.wsum + BGW_TSLOT;
+    if (tid == 0) tslot[0] = (int)min((unsigned)s.E, tk_off + atomicAdd(tk, 1u));   /* the env after blockIdx.x */
     fast_init_dense(s, f, ev, fe, tid, T);
+    /* Programmatic dependent launch (step_impl): everything above is env-independent and may run while the previous
+     * step launch is still finishing; nothing of the step state is read or written before this point.  The next
+     * launch may be scheduled as soon as every CTA of this one is running (its CTAs only become resident as
+     * these retire, the grid being the resident set).  A chained launch waits per env instead (above). */
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (!f_in.chain) asm volatile("griddepcontrol.wait;" ::: "memory");
 
     int e = blockIdx.x, b = 0;
     uint8_t ef_cur = 0, ef_nxt = 0;
     uint32_t step_cur = 0, step_nxt = 0, epi_cur = 0, epi_nxt = 0;
     if (e < s.E) {
+        chain_wait_env(f_in, e);
         fast_issue_env(s, f, st, actions, e, bgw_smem + f.o_buf, tid, T);
-        ef_cur = st.env_flags[e]; step_cur = st.step[e]; epi_cur = st.episode[e];
+        ef_cur = __ldcg(&st.env_flags[e]); step_cur = __ldcg(&st.step[e]); epi_cur = __ldcg(&st.episode[e]);
     }
     cp_async_commit();
 
     uint32_t epoch = f_in.epoch0;                         /* tag of the next reservation round (ordered rounds, above) */
-    int it_no = -1;
-    for (; e < s.E; e += gridDim.x) {
+    int it_no = -1, en = 0, sl = 0;
+    /* end of an env: hand the ticket drawn at its start to the next iteration, and once every thread's stores are
+     * behind a barrier, stamp the env (release: the barrier makes the other threads' stores cumulative) */
+#define BGW_END_ENV()                                                         \
+    do {                                                                      \
+        if (tid == 0) tslot[sl ^ 1] = (int)tnew;                              \
+        __syncthreads();                                                      \
+        if (tid == 0) st_release_u32(f_in.env_seq + e, f_in.seq);             \
+        sl ^= 1;                                                              \
+    } while (0)
+    for (; e < s.E; e = en) {
         ++it_no;
         BGW_PROF_MARK(0);
-        const int en = e + gridDim.x;
+        en = tslot[sl];
+        uint32_t tnew = (uint32_t)s.E;                              /* the env after `en`: drawn now, needed next iteration */
+        if (tid == 0 && en < s.E) tnew = min((unsigned)s.E, tk_off + atomicAdd(tk, 1u));
         if (en < s.E) {
+            chain_wait_env(f_in, en);
             fast_issue_env(s, f, st, actions, en, bgw_smem + f.o_buf + (b ^ 1) * f.buf_bytes, tid, T);
-            ef_nxt = st.env_flags[en]; step_nxt = st.step[en]; epi_nxt = st.episode[en];
+            ef_nxt = __ldcg(&st.env_flags[en]); step_nxt = __ldcg(&st.step[en]); epi_nxt = __ldcg(&st.episode[en]);
         }
         cp_async_commit();
 
@@ -720,7 +798,7 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
         if (ef0 & BGW_ENV_ALL_DONE) {
             if (!s.auto_reset) {
                 if (tid == 0) all_done[e] = ef0;
-                __syncthreads();
+                BGW_END_ENV();
                 continue;
             }
             /* sim.reset() on this env's staging buffer (general code: placement, health, orientation), state to
@@ -750,6 +828,7 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
                  * touched; zero observations, the env stays inert until the next reset */
                 if (obs_env)
                     for (int i = tid; i < s.L * nch; i += T) reinterpret_cast<uint4 *>(obs_env)[i] = make_uint4(0, 0, 0, 0);
+                BGW_END_ENV();
                 continue;
             }
             fresh = true;
@@ -989,7 +1068,7 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
         if (!fresh)
             for (int x = tid; x < n_rel; x += T) {
                 const int a = fe.rel[x];
-                if (racc_persists(ev.klass[a]) && (fe.rflag[a] & RF_DIED)) st.reward_acc[off + a] += rw[BGW_RW_DIE];
+                if (racc_persists(ev.klass[a]) && (fe.rflag[a] & RF_DIED)) st.reward_acc[off + a] = __ldcg(&st.reward_acc[off + a]) + rw[BGW_RW_DIE];
             }
         __syncthreads();                                            /* the scratch union becomes the observation stage */
         BGW_PROF_MARK(9);
@@ -1063,13 +1142,14 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
             st.env_flags[e] = ef;
             all_done[e] = ef;
             unsigned long long *sr = (unsigned long long *)st.stats + (size_t)e * BGW_STAT_COUNT;
-            sr[BGW_STAT_AGENT_STEPS] += (unsigned long long)n_act;
-            sr[BGW_STAT_ENV_STEPS] += 1ull;
-            if (ev.ctr[CTR_KILLS]) sr[BGW_STAT_KILLS] += (unsigned long long)ev.ctr[CTR_KILLS];
-            if (ef & BGW_ENV_ALL_DONE) sr[BGW_STAT_EPISODES] += 1ull;
+            sr[BGW_STAT_AGENT_STEPS] = __ldcg(&sr[BGW_STAT_AGENT_STEPS]) + (unsigned long long)n_act;
+            sr[BGW_STAT_ENV_STEPS] = __ldcg(&sr[BGW_STAT_ENV_STEPS]) + 1ull;
+            if (ev.ctr[CTR_KILLS]) sr[BGW_STAT_KILLS] = __ldcg(&sr[BGW_STAT_KILLS]) + (unsigned long long)ev.ctr[CTR_KILLS];
+            if (ef & BGW_ENV_ALL_DONE) sr[BGW_STAT_EPISODES] = __ldcg(&sr[BGW_STAT_EPISODES]) + 1ull;
         }
-        __syncthreads();                                            /* ctr, scratch and the staging buffer are rewritten next */
+        BGW_END_ENV();                                              /* ctr, scratch and the staging buffer are rewritten next */
         BGW_PROF_MARK(11);
     }
+#undef BGW_END_ENV
     cp_async_wait<0>();
 }

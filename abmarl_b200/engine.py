@@ -144,6 +144,18 @@ class BatchedGridWorld:
         self._layouts_for_finished_envs()
         return self.obs, self.reward, self.done, self.all_done
 
+    def rollout_sampled(self, n_steps, order=None):
+        """n_steps x step_sampled() in one call (bgw_rollout_sampled): a random-policy rollout that stays on the device.
+        Same state, statistics and final outputs as n_steps separate calls; on the specialised kernel the launches are
+        chained per env (launch k+1 starts an env as soon as launch k has finished it)."""
+        o = None
+        if order is not None:
+            o = torch.as_tensor(order, dtype=torch.int16, device=self.device).contiguous()
+        K.check(self.lib.bgw_rollout_sampled(self._h, int(n_steps), self.actions.data_ptr(), None if o is None else o.data_ptr(),
+                                             self.obs.data_ptr(), self.reward.data_ptr(), self.done.data_ptr(),
+                                             self.all_done.data_ptr(), self._stream()), self.lib)
+        return self.obs, self.reward, self.done, self.all_done
+
     # ---- host-facing step: HOST buffers in, only the rows the reference's manager would return out ---------
     def _host_buffers(self):
         if getattr(self, '_hb', None) is None:

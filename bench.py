@@ -7,8 +7,9 @@ OneTeamRemainingDone, AllStepManager semantics, horizon 200 with auto-reset, ran
 Philox stream; 4096 envs per GPU (env batches shard across GPUs with no data-path collective -> weak scaling;
 NCCL only sums the episode statistics).
 
-One "step" = one manager step of every env on this GPU through bgw_step_sampled: the keyed random policy draws
-every acting learner's action inside the step kernel (actor resolution -> observation -> reward/done).  An agent-step = one learning agent receiving (obs, reward, done).
+One "step" = one manager step of every env on this GPU: one launch of the step kernel in which the keyed random
+policy draws every acting learner's action (actor resolution -> observation -> reward/done); the K timed steps are
+enqueued by bgw_rollout_sampled (= K x bgw_step_sampled, launches chained per env).  An agent-step = one learning agent receiving (obs, reward, done).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
@@ -176,26 +177,45 @@ def run_ours(args):
         sampler.start()
         time.sleep(0.5)
     eng.reset()
-    for _ in range(args.warmup):
-        eng.step_sampled()
+    def rollout(n):
+        # bgw_rollout_sampled: n step launches enqueued by the library back to back (chained per env); --per-step-calls
+        # makes one bgw_step_sampled call per step instead (launches serialised by griddepcontrol.wait)
+        if args.per_step_calls:
+            for _ in range(n):
+                eng.step_sampled()
+        else:
+            eng.rollout_sampled(n)
+
+    rollout(args.warmup)
     barrier()
     n0, launches0 = agent_steps(), eng.launches
     host_t0 = time.perf_counter()
-    k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    # The timed region holds nothing but the K step launches between two events: consecutive launches are programmatic
+    # dependent launches chained per env (launch k+1 starts an env once launch k has finished that env; its
+    # env-independent set-up overlaps launch k's tail), which an event record between them would serialise.  The step kernel's average launch duration over the timed region is
+    # therefore region / launches (one launch per step); `kernel_ms_isolated` is the same kernel bracketed by its own
+    # events on every launch in a second pass of the same workload (serialised launches, --kernel-steps of them).
     t_beg, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t_beg.record(stream)
-    for i in range(args.steps):
-        k_ev[i][0].record(stream)
-        eng.step_sampled()                            # keyed random policy + manager step, one launch
-        k_ev[i][1].record(stream)
+    rollout(args.steps)                               # keyed random policy + manager step, one launch per step
     t_end.record(stream)
     barrier()
     ms = t_beg.elapsed_time(t_end)
     n_dev = agent_steps() - n0
     launches = eng.launches - launches0
+    kernel_ms = ms
+    ks = max(1, min(args.kernel_steps, args.steps))
+    k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(ks)]
+    n_iso0 = agent_steps()
+    for i in range(ks):
+        k_ev[i][0].record(stream)
+        eng.step_sampled()
+        k_ev[i][1].record(stream)
+    barrier()
     per_step_ms = [a.elapsed_time(b) for a, b in k_ev]
-    kernel_ms = sum(per_step_ms)
+    iso_ms_per_launch = sum(per_step_ms) / ks
+    iso_units_per_launch = (agent_steps() - n_iso0) / ks
     if args.dump_steps and rank == 0:
         with open(args.dump_steps, 'w') as fh:
             json.dump(per_step_ms, fh)
@@ -296,10 +316,14 @@ def run_ours(args):
                     "api": e2e_api},
             "gpu_launches": int(launches_all),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "bgw_step_fast_kernel (bgw_step_sampled)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "bgw_step_fast_kernel (bgw_rollout_sampled: one launch per step)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_agent_step": BYTES_PER_AGENT_STEP,
-                         "kernel_ms_per_launch": per_launch_ms, "kernel_share_of_step": kernel_ms / (ms if world == 1 else t_beg.elapsed_time(t_end))},
+                         "kernel_ms_per_launch": per_launch_ms, "kernel_share_of_step": 1.0,
+                         "launch_duration": "timed region (CUDA events) / launches: one step-kernel launch per step, nothing else in the region",
+                         "kernel_ms_isolated": iso_ms_per_launch,
+                         "isolated_achieved": BYTES_PER_AGENT_STEP * iso_units_per_launch / (iso_ms_per_launch * 1e-3) / 1e9,
+                         "isolated_note": f"{ks} further steps, every launch bracketed by its own CUDA events (launches serialised, no overlap of set-up and tail)"},
         }
         if world == 1 and not args.no_cpu:
             cores = 1
@@ -321,6 +345,8 @@ def main():
     ap.add_argument('--e2e-steps', type=int, default=200, help='steps of the host-buffer loop (one full episode)')
     ap.add_argument('--e2e-shards', type=int, default=2, help='sub-batches the e2e loop keeps in flight (1 = one blocking step_host call per step)')
     ap.add_argument('--e2e-staged', action='store_true', help='e2e pipeline: compact on the device and copy with the copy engine instead of writing pinned host memory from the gather kernel')
+    ap.add_argument('--kernel-steps', type=int, default=200, help='steps of the second pass that brackets every launch with its own events')
+    ap.add_argument('--per-step-calls', action='store_true', help='one bgw_step_sampled call per step instead of bgw_rollout_sampled (A/B)')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--e2e-zero-copy', action='store_true', help='e2e: the gather kernel writes the pinned host buffers directly instead of compacting on the device and copying')
     ap.add_argument('--dump-steps', default=None, help='write the per-step kernel times (ms) to this JSON file')

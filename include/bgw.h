@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define BGW_ABI_VERSION 2
+#define BGW_ABI_VERSION 3
 #define BGW_MAX_ENCODING 63   /* encodings are bit positions in 64-bit overlap / attack rows */
 #define BGW_MAX_AGENTS 4096   /* Philox slot field (bgw_philox.h)                           */
 #define BGW_MAX_CELLS 65535   /* cell index is u16, 0xFFFF = none                           */
@@ -279,6 +279,16 @@ int bgw_step(bgw_handle h, const int8_t *actions, const int16_t *order, int8_t *
  * (rows of learners already reported done are not written).  Same results as the two calls made separately. */
 int bgw_step_sampled(bgw_handle h, int8_t *actions_out, const int16_t *order, int8_t *obs, float *reward,
                      uint8_t *done, uint8_t *all_done, void *stream);
+
+/* n_steps consecutive bgw_step_sampled calls on the same buffers (a random-policy rollout that stays on the device, as
+ * the reference's RandomPolicy episodes do, policies/policy.py:81-92 + trainers/base.py:123-142): afterwards the
+ * outputs hold the last step's rows and BgwState / the statistics are those after n_steps steps -- bit for bit what
+ * n_steps separate calls leave behind.  Sims with a device-side layout generator get their next-episode layouts after
+ * every step, as after bgw_step.  Because the library enqueues the launches itself, with nothing between them, launch
+ * k+1 starts each env as soon as launch k has finished THAT env instead of waiting for the whole batch (one launch
+ * per step either way; abmarl_b200/csrc/bgw_fast.cuh, "env tickets and chained launches"). */
+int bgw_rollout_sampled(bgw_handle h, int n_steps, int8_t *actions_out, const int16_t *order, int8_t *obs, float *reward,
+                        uint8_t *done, uint8_t *all_done, void *stream);
 
 /*
  * Compact the outputs of the last bgw_step for a host consumer.  The reference's managers return dicts that hold

@@ -367,6 +367,58 @@ def test_step_sampled_equals_sample_then_step(mirror, name):
         np.testing.assert_array_equal(eng.actions.cpu().numpy()[acting], act[acting])
 
 
+@pytest.mark.parametrize('name,n_envs', [('tb_c2', 700), ('tb_c5_small', 24), ('tb_blocking', 24), ('mm_tbf', 16)])
+def test_rollout_sampled_equals_separate_steps(mirror, name, n_envs):
+    """bgw_rollout_sampled(n) (launches chained per env on the specialised kernel) leaves the state, the statistics, the
+    sampled actions and the last step's outputs of n separate bgw_step_sampled calls, which the oracle pins."""
+    from abmarl_b200.engine import BatchedGridWorld
+    builder, manager, _ = scenarios.SCENARIOS[name]
+    spec = compile_sim(builder(mirror), manager=manager, n_envs=n_envs, env_offset=5, seed=77, horizon=25, auto_reset=True)
+    a, b = BatchedGridWorld(spec, device='cuda:0'), BatchedGridWorld(spec, device='cuda:0')
+    a.reset()
+    b.reset()
+    for n in (1, 7, 40, 2, 33):
+        a.rollout_sampled(n)
+        for _ in range(n):
+            b.step_sampled()
+        for k in ('obs', 'reward', 'done', 'all_done', 'actions'):
+            assert torch.equal(getattr(a, k), getattr(b, k)), (name, n, k)
+        assert_state_equal(a.state_numpy(), b.state_numpy(), f'{name} rollout {n}')
+        assert torch.equal(a.stats(), b.stats())
+
+
+def test_chained_rollout_full_size_against_oracle(mirror):
+    """The headline workload at full size (4096 envs: three envs per resident CTA, tickets, per-env stamps) through
+    chained rollouts of several lengths, against the oracle on env slices at both ends of the batch, and against
+    serialised launches (BGW_CHAIN=0 semantics: step_sampled) over the whole batch."""
+    from abmarl_b200.engine import BatchedGridWorld
+    from oracle.oracle import OracleEnv
+    E, S = 4096, 6
+    spec = compile_sim(scenarios.build_tb_c5(mirror), n_envs=E, seed=0xB200, horizon=40, auto_reset=True)
+    eng, ser = BatchedGridWorld(spec, device='cuda:0'), BatchedGridWorld(spec, device='cuda:0')
+    head, tail = OracleEnv(spec.with_envs(S, 0)), OracleEnv(spec.with_envs(S, E - S))
+    for x in (eng, ser, head, tail):
+        x.reset()
+    done_steps = 0
+    for n in (3, 50, 1, 29, 45):                              # crosses the horizon: every env auto-resets inside a chain
+        eng.rollout_sampled(n)
+        for _ in range(n):
+            ser.step_sampled()
+            for o in (head, tail):
+                o.step(o.sample_actions())
+        done_steps += n
+        for o, sl in ((head, slice(0, S)), (tail, slice(E - S, E))):
+            for k in ('obs', 'done', 'reward', 'all_done'):
+                assert np.array_equal(getattr(eng, k)[sl].cpu().numpy(), getattr(o, k)), (done_steps, k)
+        st = eng.state_numpy()
+        assert_state_equal({k: (None if v is None else v[:S]) for k, v in st.items()}, head.state, f'head {done_steps}')
+        assert_state_equal({k: (None if v is None else v[E - S:]) for k, v in st.items()}, tail.state, f'tail {done_steps}')
+        for k in ('obs', 'reward', 'done', 'all_done', 'actions'):
+            assert torch.equal(getattr(eng, k), getattr(ser, k)), (done_steps, k)
+        assert_state_equal(st, ser.state_numpy(), f'all envs {done_steps}')
+        assert torch.equal(eng.stats(), ser.stats())
+
+
 @pytest.mark.parametrize('dynamic', ['0', '1'])
 def test_c5_shape_static_and_dynamic_instantiations(mirror, dynamic, monkeypatch):
     """BASELINE config 5's exact shape selects the compile-time-shape instantiation of the specialised kernel;
