@@ -257,26 +257,10 @@ __device__ __forceinline__ void st_release_u32(uint32_t *p, uint32_t v)
 {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-#ifdef BGW_CHAIN_DEBUG
-__device__ int bgw_chain_dbg_count = 0;
-#endif
 __device__ __forceinline__ void chain_wait_env(const FastSpec &f, int e)
 {
-    if (!f.chain) return;
-#ifdef BGW_CHAIN_DEBUG   /* diagnosis build: report a wait that does not end and go on without it */
-    unsigned spins = 0;
-    while ((int32_t)(ld_acquire_u32(f.env_seq + e) - (f.seq - 1u)) < 0) {
-        __nanosleep(64);
-        if (++spins == (1u << 21)) {
-            if (threadIdx.x == 0 && atomicAdd(&bgw_chain_dbg_count, 1) < 24)
-                printf("[chain] launch %u cta %d waits for env %d: stamp %u, ticket counter %u (base %u)\n", f.seq, (int)blockIdx.x, e,
-                       ld_acquire_u32(f.env_seq + e), ld_acquire_u32(f.ticket), f.ticket_base);
-            break;
-        }
-    }
-#else
-    while ((int32_t)(ld_acquire_u32(f.env_seq + e) - (f.seq - 1u)) < 0) __nanosleep(64);
-#endif
+    if (f.chain)
+        while ((int32_t)(ld_acquire_u32(f.env_seq + e) - (f.seq - 1u)) < 0) __nanosleep(64);
 }
 #define BGW_TSLOT 68          /* wsum[68], wsum[69]: the env after this one / the one after that */
 
@@ -641,10 +625,13 @@ __device__ void fast_obs_rows(const DevSpec &s, const FastSpec &f, const Env &ev
  * view 5, MoveActor, observe_self, OneTeamRemainingDone).  bgw_create selects the <true> instantiation when the
  * compiled spec matches it exactly; every other sim runs the <false> instantiation with run-time shapes.  The
  * code is the same: the constants below only let the compiler fold divisions, strides and trip counts. */
+#ifndef BGW_STATIC_T
+#define BGW_STATIC_T 96      /* threads per env of the compile-time-shape instantiation (A/B builds: -DBGW_STATIC_T=64 with BGW_THREADS=64) */
+#endif
 struct FastStaticC5 {
     static constexpr int A = 256, L = 256, H = 64, W = 64, P = 5, PL = 5, PW = 76, PH = 74, obs_stride = 128, nchunks = 8,
                          obs_h = 11, view = 5, move_actor = BGW_MOVE_BOX, ravel = 0, observe_self = 1, done_mask = BGW_DONE_ONE_TEAM,
-                         max_enc = 4, simd_ok = 1, async_ok = 1, slots = 512, T = 96, att = 1, identity = 1;
+                         max_enc = 4, simd_ok = 1, async_ok = 1, slots = 512, T = BGW_STATIC_T, att = 1, identity = 1;
 };
 
 template <bool STATIC, typename HT>

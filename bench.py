@@ -345,7 +345,7 @@ def main():
     ap.add_argument('--e2e-steps', type=int, default=200, help='steps of the host-buffer loop (one full episode)')
     ap.add_argument('--e2e-shards', type=int, default=2, help='sub-batches the e2e loop keeps in flight (1 = one blocking step_host call per step)')
     ap.add_argument('--e2e-staged', action='store_true', help='e2e pipeline: compact on the device and copy with the copy engine instead of writing pinned host memory from the gather kernel')
-    ap.add_argument('--kernel-steps', type=int, default=200, help='steps of the second pass that brackets every launch with its own events')
+    ap.add_argument('--kernel-steps', type=int, default=1000, help='steps of the second pass that brackets every launch with its own events')
     ap.add_argument('--per-step-calls', action='store_true', help='one bgw_step_sampled call per step instead of bgw_rollout_sampled (A/B)')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--e2e-zero-copy', action='store_true', help='e2e: the gather kernel writes the pinned host buffers directly instead of compacting on the device and copying')

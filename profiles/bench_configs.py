@@ -31,14 +31,17 @@ def main(names):
         spec = compile_sim(builder(api), manager=manager, n_envs=n_envs, seed=7, horizon=200, auto_reset=True)
         eng = BatchedGridWorld(spec, device='cuda:0')
         eng.reset()
-        for _ in range(10):
-            eng.step_sampled()
+        per_step = bool(os.environ.get('BGW_PER_STEP_CALLS'))       # one bgw_step_sampled call per step instead of bgw_rollout_sampled
+        eng.rollout_sampled(10)
         torch.cuda.synchronize()
         n0 = int(eng.stats()[K.STAT_AGENT_STEPS])
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        for _ in range(steps):
-            eng.step_sampled()
+        if per_step:
+            for _ in range(steps):
+                eng.step_sampled()
+        else:
+            eng.rollout_sampled(steps)
         b.record()
         torch.cuda.synchronize()
         ms = a.elapsed_time(b)
@@ -52,7 +55,7 @@ def main(names):
             peak = 6650.0
         gbs = algo * n / (ms * 1e-3) / 1e9
         print(json.dumps({"algorithmic_bytes_per_agent_step": algo, "achieved_gbs": gbs, "roofline_frac": gbs / peak,"config": name, "envs": n_envs, "learners_per_env": eng.L, "entities_per_env": eng.A, "steps": steps,
-                          "ms_per_step": ms / steps, "agent_steps_per_s": n / (ms * 1e-3),
+                          "ms_per_step": ms / steps, "agent_steps_per_s": n / (ms * 1e-3), "calls": "bgw_step_sampled per step" if per_step else "bgw_rollout_sampled",
                           "kernel": "bgw_step_fast_kernel" if eng.dims.threads_per_env <= 128 and spec.program == K.PROG_TEAM_BATTLE and not (spec.klass & (K.AG_BLOCKING | K.AG_AMMO)).any() and spec.attack_actor <= K.ATTACK_BINARY else "bgw_step_kernel"}), flush=True)
 
 
