@@ -51,6 +51,7 @@ struct FastSpec {
     int async_ok;             /* rows are 16-byte aligned: stage with cp.async */
     int simd_ok;              /* A % 4 == 0: byte-parallel compaction */
     int stage_hits_slots;     /* the observation stage overlaps the reservation slots: refill them after it */
+    int stage_hits_rflag;     /* ... and the reward flags: a barrier between the reward loop and the row gather */
     uint32_t epoch0;          /* first reservation epoch of a launch (0xFFFFE; tests start lower to exercise the wrap guard) */
     int b_cell, b_next, b_flags, b_act, buf_bytes;   /* layout of one staging buffer */
     /* shared-memory carve-up of the fast kernel.  `scratch` is a union: during the actor phases it holds
@@ -75,7 +76,7 @@ struct FastSpec {
 struct FastLayout {
     int b_cell, b_next, b_flags, b_act, buf_bytes;
     int o_enc, o_klass, o_tmp, o_lmask, o_head, o_cenc, o_rel, o_ragent, o_plist, o_ctr, o_wsum, o_buf, o_scratch;
-    int s_rflag, s_slot, s_rkmask, s_eff, s_pstate, s_killrank, scratch_bytes, smem_bytes, stage_hits_slots;
+    int s_rflag, s_slot, s_rkmask, s_eff, s_pstate, s_killrank, scratch_bytes, smem_bytes, stage_hits_slots, stage_hits_rflag;
     int r_racc, r_avail, head_elem;
 };
 
@@ -104,12 +105,12 @@ __host__ __device__ constexpr FastLayout fast_layout(int A, int L, int HW, int P
     y.o_buf = fo; fo += 2 * bo;
     /* scratch union, actor phases: rflag | rkmask | eff | pstate | killrank | slot */
     int so = 0;
-    y.s_rflag = so; so += fl_align16(A);
     y.s_rkmask = so; so += fl_align16(L * 4);
     y.s_eff = so; so += fl_align16(L * 2);
     y.s_pstate = so; so += fl_align16(L);
     y.s_killrank = so; so += fl_align16(A * 2);
-    y.s_slot = so; so += fl_align16(slots * 4);           /* last: the observation stage may spill over the arrays before it */
+    y.s_slot = so; so += fl_align16(slots * 4);           /* the observation stage may spill over the arrays before it (and refills the slots) */
+    y.s_rflag = so; so += fl_align16(A);                  /* last: still read (rewards) while the first warps stage their rows */
     const int actor_bytes = so;
     /* cenc | head | scratch are contiguous: the observation stage spans head + scratch (the lists are dead once the
      * row gather starts), and the general reset path uses all three as one arena: u16 heads | racc | avail */
@@ -128,6 +129,7 @@ __host__ __device__ constexpr FastLayout fast_layout(int A, int L, int HW, int P
     y.o_head = fo; fo += head_bytes;
     y.o_scratch = fo; fo += sb;
     y.stage_hits_slots = (stage_bytes - head_bytes > y.s_slot) ? 1 : 0;   /* the stage reaches the slots */
+    y.stage_hits_rflag = (stage_bytes - head_bytes > y.s_rflag) ? 1 : 0;  /* ... and the reward flags */
     y.smem_bytes = fo;
     return y;
 }
@@ -141,7 +143,7 @@ __host__ __device__ inline void fast_apply_layout(FastSpec &f, const FastLayout 
     f.s_rflag = y.s_rflag; f.s_slot = y.s_slot; f.s_rkmask = y.s_rkmask; f.s_eff = y.s_eff; f.s_pstate = y.s_pstate;
     f.s_killrank = y.s_killrank; f.scratch_bytes = y.scratch_bytes; f.smem_bytes = y.smem_bytes;
     f.r_racc = y.r_racc; f.r_avail = y.r_avail; f.head_elem = y.head_elem;
-    f.stage_hits_slots = y.stage_hits_slots;
+    f.stage_hits_slots = y.stage_hits_slots; f.stage_hits_rflag = y.stage_hits_rflag;
 }
 
 /* what happened to an entity this step, in the order the reference adds the rewards (team_battle_example.py:38-59):
@@ -1057,7 +1059,9 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
                 const int a = fe.rel[x];
                 if (racc_persists(ev.klass[a]) && (fe.rflag[a] & RF_DIED)) st.reward_acc[off + a] = __ldcg(&st.reward_acc[off + a]) + rw[BGW_RW_DIE];
             }
-        __syncthreads();                                            /* the scratch union becomes the observation stage */
+        /* the scratch union becomes the observation stage: everything it covers is dead since the barrier that ended the
+         * move rounds, except the reward flags when the stage reaches that far (the per-cell path stages nothing) */
+        if (f.stage_hits_rflag) __syncthreads();
         BGW_PROF_MARK(9);
 
         /* ---- observations ------------------------------------------------------------------------------ */
@@ -1129,10 +1133,12 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
             st.env_flags[e] = ef;
             all_done[e] = ef;
             unsigned long long *sr = (unsigned long long *)st.stats + (size_t)e * BGW_STAT_COUNT;
-            sr[BGW_STAT_AGENT_STEPS] = __ldcg(&sr[BGW_STAT_AGENT_STEPS]) + (unsigned long long)n_act;
-            sr[BGW_STAT_ENV_STEPS] = __ldcg(&sr[BGW_STAT_ENV_STEPS]) + 1ull;
-            if (ev.ctr[CTR_KILLS]) sr[BGW_STAT_KILLS] = __ldcg(&sr[BGW_STAT_KILLS]) + (unsigned long long)ev.ctr[CTR_KILLS];
-            if (ef & BGW_ENV_ALL_DONE) sr[BGW_STAT_EPISODES] = __ldcg(&sr[BGW_STAT_EPISODES]) + 1ull;
+            /* reductions without a return value (the row belongs to this env: no contention): thread 0, which every
+             * other thread of the CTA is about to wait for, does not sit out an L2 round trip */
+            atomicAdd(&sr[BGW_STAT_AGENT_STEPS], (unsigned long long)n_act);
+            atomicAdd(&sr[BGW_STAT_ENV_STEPS], 1ull);
+            if (ev.ctr[CTR_KILLS]) atomicAdd(&sr[BGW_STAT_KILLS], (unsigned long long)ev.ctr[CTR_KILLS]);
+            if (ef & BGW_ENV_ALL_DONE) atomicAdd(&sr[BGW_STAT_EPISODES], 1ull);
         }
         BGW_END_ENV();                                              /* ctr, scratch and the staging buffer are rewritten next */
         BGW_PROF_MARK(11);

@@ -13,7 +13,7 @@ MARKS = [('exec_attack', r'__device__ void fast_exec_attack'), ('attack rounds',
          ('init_dense', r'__device__ void fast_init_dense'), ('obs per-cell path', r'__device__ void fast_obs_chunk_slow'),
          ('obs row gather', r'__device__ void fast_obs_rows'), ('env staging (cp.async)', r'void fast_issue_env'),
          ('kernel prologue', r'__global__ void bgw_step_fast_kernel'), ('per-CTA setup', r'once per CTA'),
-         ('env prologue', r'for \(int e = blockIdx.x'), ('relevant+acting compaction', r'relevant entities and acting'),
+         ('env prologue', r'for \(; e < s\.E; e = en\)'), ('relevant+acting compaction', r'relevant entities and acting'),
          ('order compaction', r'if \(order\) \{'), ('lists+summary', r'occupant lists and summary'),
          ('attack pre-pass', r'attack phase team'), ('settle+classify', r'settle attackers'),
          ('emit reward/done', r'entropy :58'), ('obs dispatch', r'---- observations ----'),
