@@ -400,6 +400,7 @@ int bgw_create(const BgwSpec *sp, int device, bgw_handle *out)
                     (2 * rmax_att + 1) * (2 * rmax_att + 1) <= 32;
         if (const char *t = getenv("BGW_GENERIC_KERNEL")) if (atoi(t)) fast = false;
         int TF = A <= 32 ? 32 : A <= 64 ? 64 : 96;      /* 3 warps: 10 envs per SM fit (shared memory and registers) */
+        if (A == FastStaticC5::A && H == FastStaticC5::H && W == FastStaticC5::W) TF = FastStaticC5::T;   /* 2 warps: 11 envs per SM */
         if (const char *t = getenv("BGW_THREADS")) { const int v = atoi(t); if (v >= 32 && v <= 1024 && v % 32 == 0) TF = std::min(v, 128); }   /* __launch_bounds__(128, 7) */
         if (fast) {
             f.P = P;
@@ -412,7 +413,7 @@ int bgw_create(const BgwSpec *sp, int device, bgw_handle *out)
             h->dsf = d;
             h->dsf.slot_mask = fslots - 1;
             const long long cbytes = (long long)f.PH * f.PW + 32;
-            const FastLayout ly = fast_layout(A, L, HW, f.PH, f.PW, fslots, TF, max_enc, d.hw_words);
+            const FastLayout ly = fast_layout(A, L, HW, f.PH, f.PW, fslots, TF, max_enc, d.hw_words, L == A);
             fast_apply_layout(f, ly);
             const int fo = ly.smem_bytes;
             f.async_ok = (A % 16 == 0) && (L % 4 == 0);
@@ -465,7 +466,11 @@ int bgw_create(const BgwSpec *sp, int device, bgw_handle *out)
         return bail(fail(2, "bgw_create: cudaFuncSetAttribute: %s", cudaGetErrorString(ce)));
     if (h->fs.enabled) {
         int per_sm = 0, sms = 0;
-        if ((ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bgw_step_fast_kernel<false, uint16_t>, h->threads_fast, h->fs.smem_bytes)) != cudaSuccess ||
+        /* the instantiation step_impl launches for this handle */
+        ce = h->fast_static ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bgw_step_fast_kernel<true, uint8_t>, h->threads_fast, h->fs.smem_bytes)
+           : h->fs.head_elem == 1 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bgw_step_fast_kernel<false, uint8_t>, h->threads_fast, h->fs.smem_bytes)
+                                  : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bgw_step_fast_kernel<false, uint16_t>, h->threads_fast, h->fs.smem_bytes);
+        if (ce != cudaSuccess ||
             (ce = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess)
             return bail(fail(2, "bgw_create: occupancy query: %s", cudaGetErrorString(ce)));
         h->fs.grid_ctas = std::max(1, std::min(d.E, per_sm * sms));

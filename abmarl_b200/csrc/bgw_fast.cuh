@@ -53,11 +53,11 @@ struct FastSpec {
     int stage_hits_slots;     /* the observation stage overlaps the reservation slots: refill them after it */
     int stage_hits_rflag;     /* ... and the reward flags: a barrier between the reward loop and the row gather */
     uint32_t epoch0;          /* first reservation epoch of a launch (0xFFFFE; tests start lower to exercise the wrap guard) */
-    int b_cell, b_next, b_flags, b_act, buf_bytes;   /* layout of one staging buffer */
+    int b_cell, b_next, b_flags, buf_bytes;   /* layout of one staging buffer */
     /* shared-memory carve-up of the fast kernel.  `scratch` is a union: during the actor phases it holds
      * rflag | slot | rkmask | eff | pstate | killrank, during the observation phase the per-warp stage, and in
      * the (general) reset path racc | avail. */
-    int o_enc, o_klass, o_tmp, o_lmask, o_head, o_cenc, o_rel, o_ragent, o_plist, o_ctr, o_wsum, o_buf, o_scratch;
+    int o_enc, o_klass, o_tmp, o_act, o_head, o_cenc, o_rel, o_ragent, o_plist, o_ctr, o_wsum, o_buf, o_scratch;
     int s_rflag, s_slot, s_rkmask, s_eff, s_pstate, s_killrank, scratch_bytes, smem_bytes;
     int r_racc, r_avail;      /* reset arena (over cenc | head | scratch, from o_cenc): u16 heads at 0, then racc, avail */
     int head_elem;            /* bytes per list head: 1 when A <= 256, else 2 */
@@ -74,8 +74,8 @@ struct FastSpec {
 /* The shared-memory carve-up of the fast kernel: ONE definition used by bgw_create (run-time shapes) and by the
  * compile-time-shape instantiation (where every offset folds into an immediate). */
 struct FastLayout {
-    int b_cell, b_next, b_flags, b_act, buf_bytes;
-    int o_enc, o_klass, o_tmp, o_lmask, o_head, o_cenc, o_rel, o_ragent, o_plist, o_ctr, o_wsum, o_buf, o_scratch;
+    int b_cell, b_next, b_flags, buf_bytes;
+    int o_enc, o_klass, o_tmp, o_act, o_head, o_cenc, o_rel, o_ragent, o_plist, o_ctr, o_wsum, o_buf, o_scratch;
     int s_rflag, s_slot, s_rkmask, s_eff, s_pstate, s_killrank, scratch_bytes, smem_bytes, stage_hits_slots, stage_hits_rflag;
     int r_racc, r_avail, head_elem;
 };
@@ -83,24 +83,24 @@ struct FastLayout {
 __host__ __device__ constexpr int fl_align16(int x) { return (x + 15) & ~15; }
 
 __host__ __device__ constexpr FastLayout fast_layout(int A, int L, int HW, int PH, int PW, int slots, int T, int max_enc,
-                                                     int hw_words)
+                                                     int hw_words, int identity)
 {
     FastLayout y{};
     int fo = 0;
     y.o_enc = fo; fo += fl_align16(A);
     y.o_klass = fo; fo += fl_align16(A);
     y.o_tmp = fo; fo += fl_align16(A);
-    y.o_lmask = fo; fo += fl_align16(A);
     y.o_rel = fo; fo += fl_align16(A * 2);
     y.o_ragent = fo; fo += fl_align16(L * 2);
-    y.o_plist = fo; fo += fl_align16(L * 2);
+    y.o_plist = identity ? y.o_ragent : fo;               /* learner index == entity index: one list serves as both */
+    if (!identity) fo += fl_align16(L * 2);
+    y.o_act = fo; fo += fl_align16(L * 4);                /* this env's action words (not double-buffered: read or drawn by the attack pre-pass) */
     y.o_ctr = fo; fo += fl_align16(CTR_COUNT * 4);
-    y.o_wsum = fo; fo += fl_align16(72 * 4);
+    y.o_wsum = fo; fo += fl_align16(16 * 4);             /* [0..1] totals, [2..5] / [8..11] per-warp counts (T <= 128), [12..13] env tickets */
     int bo = 0;
     y.b_cell = bo; bo += fl_align16(A * 2);
     y.b_next = bo; bo += fl_align16(A * 2);
     y.b_flags = bo; bo += fl_align16(A);
-    y.b_act = bo; bo += fl_align16(L * 4);
     y.buf_bytes = bo;
     y.o_buf = fo; fo += 2 * bo;
     /* scratch union, actor phases: rflag | rkmask | eff | pstate | killrank | slot */
@@ -136,8 +136,8 @@ __host__ __device__ constexpr FastLayout fast_layout(int A, int L, int HW, int P
 
 __host__ __device__ inline void fast_apply_layout(FastSpec &f, const FastLayout &y)
 {
-    f.b_cell = y.b_cell; f.b_next = y.b_next; f.b_flags = y.b_flags; f.b_act = y.b_act; f.buf_bytes = y.buf_bytes;
-    f.o_enc = y.o_enc; f.o_klass = y.o_klass; f.o_tmp = y.o_tmp; f.o_lmask = y.o_lmask; f.o_head = y.o_head;
+    f.b_cell = y.b_cell; f.b_next = y.b_next; f.b_flags = y.b_flags; f.buf_bytes = y.buf_bytes;
+    f.o_enc = y.o_enc; f.o_klass = y.o_klass; f.o_tmp = y.o_tmp; f.o_act = y.o_act; f.o_head = y.o_head;
     f.o_cenc = y.o_cenc; f.o_rel = y.o_rel; f.o_ragent = y.o_ragent; f.o_plist = y.o_plist; f.o_ctr = y.o_ctr;
     f.o_wsum = y.o_wsum; f.o_buf = y.o_buf; f.o_scratch = y.o_scratch;
     f.s_rflag = y.s_rflag; f.s_slot = y.s_slot; f.s_rkmask = y.s_rkmask; f.s_eff = y.s_eff; f.s_pstate = y.s_pstate;
@@ -158,7 +158,6 @@ struct FastEnv {
     int8_t *cenc;
     uint16_t *killrank, *eff, *rel;
     uint32_t *rkmask, *act;
-    const uint32_t *lmask;
     int *wsum;
 };
 
@@ -264,12 +263,16 @@ __device__ __forceinline__ void chain_wait_env(const FastSpec &f, int e)
     if (f.chain)
         while ((int32_t)(ld_acquire_u32(f.env_seq + e) - (f.seq - 1u)) < 0) __nanosleep(64);
 }
-#define BGW_TSLOT 68          /* wsum[68], wsum[69]: the env after this one / the one after that */
+#define BGW_TSLOT 12          /* wsum[12], wsum[13]: the env after this one / the one after that */
 
 /* stream env e's rows into one staging buffer */
 __device__ __forceinline__ void fast_issue_env(const DevSpec &s, const FastSpec &f, const BgwState &st, const uint32_t *actions,
                                                int e, unsigned char *buf, int tid, int T)
 {
+    /* the action row is read by the attack pre-pass straight from global memory: warm L2 a whole env ahead */
+    if (actions)
+        for (int i = tid; i < (s.L * 4 + 127) / 128; i += T)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"((const char *)(actions + (size_t)e * s.L) + (size_t)i * 128));
     const size_t off = (size_t)e * s.A;
     if (f.async_ok) {
         const unsigned char *g;
@@ -279,16 +282,10 @@ __device__ __forceinline__ void fast_issue_env(const DevSpec &s, const FastSpec 
         for (int i = tid; i < s.A / 8; i += T) cp_async16(buf + f.b_next + i * 16, g + i * 16);
         g = (const unsigned char *)(st.flags + off);
         for (int i = tid; i < s.A / 16; i += T) cp_async16(buf + f.b_flags + i * 16, g + i * 16);
-        if (actions) {
-            g = (const unsigned char *)(actions + (size_t)e * s.L);
-            for (int i = tid; i < s.L / 4; i += T) cp_async16(buf + f.b_act + i * 16, g + i * 16);
-        }
     } else {
         uint16_t *c = (uint16_t *)(buf + f.b_cell), *n = (uint16_t *)(buf + f.b_next);
         uint8_t *fl = buf + f.b_flags;
-        uint32_t *ac = (uint32_t *)(buf + f.b_act);
         for (int a = tid; a < s.A; a += T) { c[a] = st.cell[off + a]; n[a] = st.next[off + a]; fl[a] = st.flags[off + a]; }
-        if (actions) for (int l = tid; l < s.L; l += T) ac[l] = actions[(size_t)e * s.L + l];
     }
 }
 
@@ -628,7 +625,7 @@ __device__ void fast_obs_rows(const DevSpec &s, const FastSpec &f, const Env &ev
  * compiled spec matches it exactly; every other sim runs the <false> instantiation with run-time shapes.  The
  * code is the same: the constants below only let the compiler fold divisions, strides and trip counts. */
 #ifndef BGW_STATIC_T
-#define BGW_STATIC_T 96      /* threads per env of the compile-time-shape instantiation (A/B builds: -DBGW_STATIC_T=64 with BGW_THREADS=64) */
+#define BGW_STATIC_T 64      /* threads per env of the compile-time-shape instantiation (A/B builds: -DBGW_STATIC_T=64 with BGW_THREADS=64) */
 #endif
 struct FastStaticC5 {
     static constexpr int A = 256, L = 256, H = 64, W = 64, P = 5, PL = 5, PW = 76, PH = 74, obs_stride = 128, nchunks = 8,
@@ -653,7 +650,7 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
         f.uniform_att = C::att; f.identity_learners = C::identity;
         f.magic_w = (uint32_t)(((1ull << 32) + C::W - 1) / C::W);
         s.slot_mask = C::slots - 1;
-        constexpr FastLayout LY = fast_layout(C::A, C::L, C::H * C::W, C::PH, C::PW, C::slots, C::T, C::max_enc, (C::H * C::W + 31) / 32);
+        constexpr FastLayout LY = fast_layout(C::A, C::L, C::H * C::W, C::PH, C::PW, C::slots, C::T, C::max_enc, (C::H * C::W + 31) / 32, C::identity);
         fast_apply_layout(f, LY);
     }
     const int tid = threadIdx.x, T = STATIC ? FastStaticC5::T : (int)blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = T >> 5;
@@ -677,7 +674,7 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
     fe.rflag = scratch + f.s_rflag;
     fe.cenc = (int8_t *)(bgw_smem + f.o_cenc);
     fe.rel = (uint16_t *)(bgw_smem + f.o_rel);
-    fe.lmask = (const uint32_t *)(bgw_smem + f.o_lmask);
+    fe.act = (uint32_t *)(bgw_smem + f.o_act);
     fe.wsum = (int *)(bgw_smem + f.o_wsum);
     fe.rkmask = (uint32_t *)(scratch + f.s_rkmask);
     fe.eff = (uint16_t *)(scratch + f.s_eff);
@@ -692,13 +689,11 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
             const uint32_t k = __ldg(&k32[w]);
             ((uint32_t *)ev.enc)[w] = __ldg(&e32[w]);
             ((uint32_t *)ev.klass)[w] = k;
-            ((uint32_t *)(bgw_smem + f.o_lmask))[w] = __vcmpne4(k & (0x01010101u * BGW_AG_LEARNER), 0u);
         }
     } else {
         for (int a = tid; a < s.A; a += T) {
             const uint8_t k = __ldg(&s.klass[a]);
             ev.enc[a] = __ldg(&s.enc[a]); ev.klass[a] = k;
-            (bgw_smem + f.o_lmask)[a] = (k & BGW_AG_LEARNER) ? 0xFF : 0;
         }
     }
     uint32_t *const tk = f_in.ticket;                      /* this launch's ticket counter */
@@ -751,7 +746,6 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
         ev.cell = (uint16_t *)(buf + f.b_cell);
         ev.next = (uint16_t *)(buf + f.b_next);
         ev.flags = buf + f.b_flags;
-        fe.act = (uint32_t *)(buf + f.b_act);
         ev.health = st.health + (size_t)e * s.A;
         for (int i = tid; i < (s.A * 8 + 127) / 128; i += T)       /* hits read health from HBM on demand: warm L2 now */
             asm volatile("prefetch.global.L2 [%0];" ::"l"((const char *)ev.health + (size_t)i * 128));
@@ -828,7 +822,7 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
         int n_rel = 0, n_act = 0;
         if (f.simd_ok) {
             if (warp == 0) {
-                const uint32_t *fw = (const uint32_t *)ev.flags;
+                const uint32_t *fw = (const uint32_t *)ev.flags, *kw = (const uint32_t *)ev.klass;
                 const int nwords = s.A >> 2, wpl = (nwords + 31) >> 5;
                 int cnt = 0;
                 for (int j = 0; j < wpl; ++j) {
@@ -836,7 +830,7 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
                     if (w < nwords) {
                         const uint32_t x = fw[w];
                         const uint32_t rel = ~__vcmpeq4(x & 0x07070707u, 0x04040404u);      /* not (dead, removed, reported) */
-                        const uint32_t act = fe.lmask[w] & __vcmpeq4(x & 0x04040404u, 0u);   /* learner, not reported */
+                        const uint32_t act = __vcmpne4(kw[w] & (0x01010101u * BGW_AG_LEARNER), 0u) & __vcmpeq4(x & 0x04040404u, 0u);   /* learner, not reported */
                         cnt += (__popc(rel) >> 3) + ((__popc(act) >> 3) << 16);
                     }
                 }
@@ -849,7 +843,7 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
                     if (w < nwords) {
                         const uint32_t x = fw[w];
                         const uint32_t rel = ~__vcmpeq4(x & 0x07070707u, 0x04040404u);
-                        const uint32_t act = fe.lmask[w] & __vcmpeq4(x & 0x04040404u, 0u);
+                        const uint32_t act = __vcmpne4(kw[w] & (0x01010101u * BGW_AG_LEARNER), 0u) & __vcmpeq4(x & 0x04040404u, 0u);
 #pragma unroll
                         for (int bb = 0; bb < 4; ++bb) {
                             const int a = 4 * w + bb;
@@ -872,11 +866,11 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
                     acting = (ev.klass[a] & BGW_AG_LEARNER) && !(fl & BGW_ST_DONE_REPORTED);
                 }
                 const unsigned br = __ballot_sync(0xFFFFFFFFu, rel), ba = __ballot_sync(0xFFFFFFFFu, acting);
-                if (lane == 0) { fe.wsum[2 + warp] = __popc(br); fe.wsum[34 + warp] = __popc(ba); }
+                if (lane == 0) { fe.wsum[2 + warp] = __popc(br); fe.wsum[8 + warp] = __popc(ba); }
                 __syncthreads();
                 int before_r = n_rel, before_a = n_act;
                 for (int w = 0; w < nwarp; ++w) {
-                    const int cr = fe.wsum[2 + w], ca = fe.wsum[34 + w];
+                    const int cr = fe.wsum[2 + w], ca = fe.wsum[8 + w];
                     if (w < warp) { before_r += cr; before_a += ca; }
                     n_rel += cr; n_act += ca;
                 }
@@ -942,6 +936,8 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
                     const uint32_t w = sample_action_word(s, a, ev.klass[a], ev.genv, ev.episode, ev.step - 1u);
                     fe.act[l] = w;
                     sampled[(size_t)e * s.L + l] = w;
+                } else {
+                    fe.act[l] = __ldcg(&actions[(size_t)e * s.L + l]);   /* (prefetched to L2 while the env before ran) */
                 }
                 uint8_t p = 0;
                 if ((ev.flags[a] & BGW_ST_ACTIVE) && (ev.klass[a] & BGW_AG_ATTACKING) && (int8_t)((fe.act[l] >> 16) & 0xFF) != 0) {
