@@ -114,3 +114,5 @@ class SuperAgentView:
         group_valid = (n_seen < members) & ~fresh[:, None]          # the super agent was not done before this step
         self.seen_done |= now_done
         return out_obs, mask, r, group_done, group_valid
+
+from abmarl_b200.sim.flatten import FlattenWrapper, FlattenActionWrapper, FlattenView   # noqa: E402,F401  (abmarl.sim.wrappers exports them too)
