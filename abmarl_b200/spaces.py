@@ -92,7 +92,7 @@ class MultiDiscrete(Space):
         return x.shape == self.nvec.shape and bool(np.all(x >= 0) and np.all(x < self.nvec))
 
     def sample(self):
-        return np.array([self.rng().integers(0, n) for n in self.nvec], dtype=int)
+        return np.array([self.rng.integers(0, n) for n in self.nvec], dtype=int)
 
     def __len__(self):
         return len(self.nvec)

@@ -79,6 +79,14 @@ def test_flatten_functions_on_plain_spaces():
     assert flatten_space(Discrete(5)).dtype == int
 
 
+def test_every_space_samples_points_it_contains():
+    for sp in (Box(-2, 3, (4, 4), int), Box(0.0, 1.0, (3,), float), Discrete(5), MultiDiscrete([26, 26, 3]),
+               Dict({'move': Box(-1, 1, (2,), int), 'attack': MultiDiscrete([4, 4])})):
+        sp.seed(3)
+        for _ in range(5):
+            assert sp.contains(sp.sample()), sp
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize('name', ['tb_c2', 'tb_encoding', 'tb_restricted', 'tb_ammo_selective', 'mm_allstep'])
 def test_flatten_view_on_the_engine(mirror, name):
