@@ -62,7 +62,7 @@ struct BgwEngine {
     uint32_t seq = 0;             /* sequence number of the last fast step launch */
     uint32_t *ticket_ring = nullptr;                /* [BGW_TICKET_RING] device: env ticket counters, one per launch in flight */
     std::vector<uint32_t> ticket_uses;              /* launches that have drawn from each counter (each draws exactly E) */
-    bool fast_static = false;     /* compile-time shapes of the headline workload apply (FastStaticC5) */
+    int fast_shape = 0;           /* compile-time shape instantiation of the fast kernel: 0 run-time shapes, 1 FastStaticC5, 2 FastStaticC2 */
     BgwDims dims{};
     BgwState st{};
     bool bound = false;
@@ -444,32 +444,27 @@ int bgw_create(const BgwSpec *sp, int device, bgw_handle *out)
         f.enabled = fast;
         h->threads_fast = TF;
         if (fast) {
-            typedef FastStaticC5 C;
-            const DevSpec &q = h->dsf;
-            h->fast_static = q.A == C::A && q.L == C::L && q.H == C::H && q.W == C::W && q.obs_stride == C::obs_stride &&
-                             q.obs_h == C::obs_h && q.obs_c == 1 && q.move_actor == C::move_actor && q.ravel == C::ravel &&
-                             q.observe_self == C::observe_self && q.done_mask == C::done_mask && q.max_enc == C::max_enc &&
-                             f.P == C::P && f.PL == C::PL && f.PW == C::PW && f.PH == C::PH && f.uniform_view == C::view &&
-                             f.simd_ok == C::simd_ok && f.async_ok == C::async_ok && q.slot_mask == C::slots - 1 && TF == C::T &&
-                             f.uniform_att == C::att && f.identity_learners == C::identity;
-            if (const char *t = getenv("BGW_DYNAMIC_SHAPES")) if (atoi(t)) h->fast_static = false;
+            h->fast_shape = fast_shape_matches<FastStaticC5>(h->dsf, f, TF) ? 1 : fast_shape_matches<FastStaticC2>(h->dsf, f, TF) ? 2 : 0;
+            if (const char *t = getenv("BGW_DYNAMIC_SHAPES")) if (atoi(t)) h->fast_shape = 0;
         }
     }
     d.smem_bytes = off;
     if (off > 227 * 1024) return bail(fail(1, "bgw_create: one environment needs %d bytes of shared memory (limit 232448): grid or entity count too large", off));
     cudaError_t ce;
     if ((ce = cudaFuncSetAttribute(bgw_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, off)) != cudaSuccess ||
-        (h->fs.enabled && (ce = cudaFuncSetAttribute(bgw_step_fast_kernel<true, uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->fs.smem_bytes)) != cudaSuccess) ||
-        (h->fs.enabled && (ce = cudaFuncSetAttribute(bgw_step_fast_kernel<false, uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->fs.smem_bytes)) != cudaSuccess) ||
-        (h->fs.enabled && (ce = cudaFuncSetAttribute(bgw_step_fast_kernel<false, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->fs.smem_bytes)) != cudaSuccess) ||
+        (h->fs.enabled && (ce = cudaFuncSetAttribute(bgw_step_fast_kernel<FastStaticC5, uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->fs.smem_bytes)) != cudaSuccess) ||
+        (h->fs.enabled && (ce = cudaFuncSetAttribute(bgw_step_fast_kernel<FastStaticC2, uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->fs.smem_bytes)) != cudaSuccess) ||
+        (h->fs.enabled && (ce = cudaFuncSetAttribute(bgw_step_fast_kernel<FastDynamic, uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->fs.smem_bytes)) != cudaSuccess) ||
+        (h->fs.enabled && (ce = cudaFuncSetAttribute(bgw_step_fast_kernel<FastDynamic, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->fs.smem_bytes)) != cudaSuccess) ||
         (ce = cudaFuncSetAttribute(bgw_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, off)) != cudaSuccess)
         return bail(fail(2, "bgw_create: cudaFuncSetAttribute: %s", cudaGetErrorString(ce)));
     if (h->fs.enabled) {
         int per_sm = 0, sms = 0;
         /* the instantiation step_impl launches for this handle */
-        ce = h->fast_static ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bgw_step_fast_kernel<true, uint8_t>, h->threads_fast, h->fs.smem_bytes)
-           : h->fs.head_elem == 1 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bgw_step_fast_kernel<false, uint8_t>, h->threads_fast, h->fs.smem_bytes)
-                                  : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bgw_step_fast_kernel<false, uint16_t>, h->threads_fast, h->fs.smem_bytes);
+        ce = h->fast_shape == 1 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bgw_step_fast_kernel<FastStaticC5, uint8_t>, h->threads_fast, h->fs.smem_bytes)
+           : h->fast_shape == 2 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bgw_step_fast_kernel<FastStaticC2, uint8_t>, h->threads_fast, h->fs.smem_bytes)
+           : h->fs.head_elem == 1 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bgw_step_fast_kernel<FastDynamic, uint8_t>, h->threads_fast, h->fs.smem_bytes)
+                                  : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bgw_step_fast_kernel<FastDynamic, uint16_t>, h->threads_fast, h->fs.smem_bytes);
         if (ce != cudaSuccess ||
             (ce = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess)
             return bail(fail(2, "bgw_create: occupancy query: %s", cudaGetErrorString(ce)));
@@ -478,7 +473,7 @@ int bgw_create(const BgwSpec *sp, int device, bgw_handle *out)
             void *pp = nullptr;
             if (cudaMalloc(&pp, (size_t)h->fs.grid_ctas * 8 * 16 * sizeof(long long)) == cudaSuccess) { h->allocs.push_back(pp); cudaMemset(pp, 0, (size_t)h->fs.grid_ctas * 8 * 16 * sizeof(long long)); h->fs.prof = (long long *)pp; }
         }
-        if (getenv("BGW_VERBOSE")) fprintf(stderr, "[bgw] fast kernel: T=%d smem=%d B/CTA, %d CTAs/SM x %d SMs, grid=%d, slots=%d\n", h->threads_fast, h->fs.smem_bytes, per_sm, sms, h->fs.grid_ctas, h->dsf.slot_mask + 1);
+        if (getenv("BGW_VERBOSE")) fprintf(stderr, "[bgw] fast kernel: shape %s, T=%d smem=%d B/CTA, %d CTAs/SM x %d SMs, grid=%d, slots=%d\n", h->fast_shape == 1 ? "C5 (compile-time)" : h->fast_shape == 2 ? "C2 (compile-time)" : "run-time", h->threads_fast, h->fs.smem_bytes, per_sm, sms, h->fs.grid_ctas, h->dsf.slot_mask + 1);
         if (const char *t = getenv("BGW_PDL")) h->pdl = atoi(t) != 0;
         if (const char *t = getenv("BGW_GRID")) { const int v = atoi(t); if (v >= 1) h->fs.grid_ctas = std::min(d.E, v); }
         {   /* env tickets + per-env launch stamps (bgw_fast.cuh, "env tickets and chained launches") */
@@ -567,9 +562,10 @@ static int step_impl(bgw_handle h, const int8_t *actions, int8_t *sampled, const
 #define BGW_LAUNCH_FAST(ST, HT)                                                                                       \
     CUDA_OK(cudaLaunchKernelEx(&cfg, bgw_step_fast_kernel<ST, HT>, h->dsf, h->fs, h->st, (const uint32_t *)actions,       \
                                (uint32_t *)sampled, order, obs, reward, done, all_done))
-        if (h->fast_static) BGW_LAUNCH_FAST(true, uint8_t);
-        else if (h->fs.head_elem == 1) BGW_LAUNCH_FAST(false, uint8_t);
-        else BGW_LAUNCH_FAST(false, uint16_t);
+        if (h->fast_shape == 1) BGW_LAUNCH_FAST(FastStaticC5, uint8_t);
+        else if (h->fast_shape == 2) BGW_LAUNCH_FAST(FastStaticC2, uint8_t);
+        else if (h->fs.head_elem == 1) BGW_LAUNCH_FAST(FastDynamic, uint8_t);
+        else BGW_LAUNCH_FAST(FastDynamic, uint16_t);
 #undef BGW_LAUNCH_FAST
         h->poisoned = false;
     } else {

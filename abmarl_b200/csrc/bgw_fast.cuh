@@ -621,27 +621,49 @@ __device__ void fast_obs_rows(const DevSpec &s, const FastSpec &f, const Env &ev
 }
 
 /* Compile-time shape of the headline workload (BASELINE configs[4]: 64x64 grid, 256 agents that are all learners,
- * view 5, MoveActor, observe_self, OneTeamRemainingDone).  bgw_create selects the <true> instantiation when the
- * compiled spec matches it exactly; every other sim runs the <false> instantiation with run-time shapes.  The
+ * view 5, MoveActor, observe_self, OneTeamRemainingDone).  bgw_create selects the instantiation of a shape when the
+ * compiled spec matches it exactly; every other sim runs the FastDynamic instantiation with run-time shapes.  The
  * code is the same: the constants below only let the compiler fold divisions, strides and trip counts. */
 #ifndef BGW_STATIC_T
 #define BGW_STATIC_T 64      /* threads per env of the compile-time-shape instantiation (A/B builds: -DBGW_STATIC_T=64 with BGW_THREADS=64) */
 #endif
 struct FastStaticC5 {
+    static constexpr bool is_static = true;
     static constexpr int A = 256, L = 256, H = 64, W = 64, P = 5, PL = 5, PW = 76, PH = 74, obs_stride = 128, nchunks = 8,
                          obs_h = 11, view = 5, move_actor = BGW_MOVE_BOX, ravel = 0, observe_self = 1, done_mask = BGW_DONE_ONE_TEAM,
                          max_enc = 4, simd_ok = 1, async_ok = 1, slots = 512, T = BGW_STATIC_T, att = 1, identity = 1;
 };
+/* BASELINE configs[1] (examples/rllib_team_battle.py: 8x8 grid, 24 agents in 4 teams, view 3): one warp per env, 32 envs
+ * per SM, each at its own place in the code -- the run-time-shape instantiation (9.3 k instructions) spends most of its
+ * stall cycles waiting for instructions (ncu: no_instruction 5.4 per issue); this one is half the size. */
+struct FastStaticC2 {
+    static constexpr bool is_static = true;
+    static constexpr int A = 24, L = 24, H = 8, W = 8, P = 3, PL = 3, PW = 16, PH = 14, obs_stride = 64, nchunks = 4,
+                         obs_h = 7, view = 3, move_actor = BGW_MOVE_BOX, ravel = 0, observe_self = 1, done_mask = BGW_DONE_ONE_TEAM,
+                         max_enc = 4, simd_ok = 1, async_ok = 0, slots = 64, T = 32, att = 1, identity = 1;
+};
+struct FastDynamic { static constexpr bool is_static = false; };
 
-template <bool STATIC, typename HT>
+/* does the compiled spec have exactly the compile-time shape C? (bgw_create) */
+template <typename C>
+inline bool fast_shape_matches(const DevSpec &q, const FastSpec &f, int threads)
+{
+    return q.A == C::A && q.L == C::L && q.H == C::H && q.W == C::W && q.obs_stride == C::obs_stride && q.obs_h == C::obs_h &&
+           q.obs_c == 1 && q.move_actor == C::move_actor && q.ravel == C::ravel && q.observe_self == C::observe_self &&
+           q.done_mask == C::done_mask && q.max_enc == C::max_enc && f.P == C::P && f.PL == C::PL && f.PW == C::PW &&
+           f.PH == C::PH && f.uniform_view == C::view && f.simd_ok == C::simd_ok && f.async_ok == C::async_ok &&
+           q.slot_mask == C::slots - 1 && threads == C::T && f.uniform_att == C::att && f.identity_learners == C::identity;
+}
+
+template <typename SHAPE, typename HT>
 __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_in, const FastSpec f_in, const BgwState st, const uint32_t *actions,
                                      uint32_t *sampled, const int16_t *order, int8_t *obs, float *reward, uint8_t *done,
                                      uint8_t *all_done)
 {
     DevSpec s = s_in;
     FastSpec f = f_in;
-    if (STATIC) {
-        typedef FastStaticC5 C;
+    if constexpr (SHAPE::is_static) {
+        typedef SHAPE C;
         s.A = C::A; s.L = C::L; s.H = C::H; s.W = C::W; s.HW = C::H * C::W; s.obs_stride = C::obs_stride; s.nchunks = C::nchunks;
         s.obs_h = s.obs_w = C::obs_h; s.obs_c = 1; s.move_actor = C::move_actor; s.ravel = C::ravel; s.observe_self = C::observe_self;
         s.done_mask = C::done_mask; s.max_enc = C::max_enc; s.n_blk = 0; s.program = BGW_PROG_TEAM_BATTLE;
@@ -653,7 +675,9 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
         constexpr FastLayout LY = fast_layout(C::A, C::L, C::H * C::W, C::PH, C::PW, C::slots, C::T, C::max_enc, (C::H * C::W + 31) / 32, C::identity);
         fast_apply_layout(f, LY);
     }
-    const int tid = threadIdx.x, T = STATIC ? FastStaticC5::T : (int)blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = T >> 5;
+    int T_ = (int)blockDim.x;
+    if constexpr (SHAPE::is_static) T_ = SHAPE::T;
+    const int tid = threadIdx.x, T = T_, lane = tid & 31, warp = tid >> 5, nwarp = T >> 5;
     unsigned char *scratch = bgw_smem + f.o_scratch;
     Env ev;
     ev.enc = (int8_t *)(bgw_smem + f.o_enc);

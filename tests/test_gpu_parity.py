@@ -420,13 +420,15 @@ def test_chained_rollout_full_size_against_oracle(mirror):
 
 
 @pytest.mark.parametrize('dynamic', ['0', '1'])
-def test_c5_shape_static_and_dynamic_instantiations(mirror, dynamic, monkeypatch):
-    """BASELINE config 5's exact shape selects the compile-time-shape instantiation of the specialised kernel;
+@pytest.mark.parametrize('name', ['tb_c5', 'tb_c2'])
+def test_static_and_dynamic_shape_instantiations(mirror, name, dynamic, monkeypatch):
+    """The exact shapes of BASELINE configs 5 and 2 select compile-time-shape instantiations of the specialised kernel;
     BGW_DYNAMIC_SHAPES=1 forces the run-time-shape one.  Both against the oracle over a full episode + reset."""
     monkeypatch.setenv('BGW_DYNAMIC_SHAPES', dynamic)
-    spec = compile_sim(scenarios.build_tb_c5(mirror), n_envs=6, env_offset=11, seed=0xB200, horizon=40, auto_reset=True)
+    builder = scenarios.build_tb_c5 if name == 'tb_c5' else scenarios.SCENARIOS[name][0]
+    spec = compile_sim(builder(mirror), n_envs=6 if name == 'tb_c5' else 300, env_offset=11, seed=0xB200, horizon=40, auto_reset=True)
     eng, ora = _pair(spec)
-    run_lockstep(eng, ora, 90, label='tb_c5/dynamic=' + dynamic)
+    run_lockstep(eng, ora, 90, label=f'{name}/dynamic={dynamic}')
 
 
 @pytest.mark.parametrize('name', ['maze_c1', 'pacman_c3', 'tb_blocking'])
