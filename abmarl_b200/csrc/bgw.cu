@@ -49,8 +49,11 @@ int pow2ceil(int x) { int p = 1; while (p < x) p <<= 1; return p; }
 
 }  // namespace
 
+typedef void (*GeneralStepFn)(const DevSpec, const BgwState, const uint32_t *, const int16_t *, int8_t *, float *, uint8_t *, uint8_t *);
+
 struct BgwEngine {
     int device = 0;
+    GeneralStepFn step_fn = nullptr;   /* the bgw_step_kernel instantiation of this sim's program */
     MazeParams maze{};            /* device-side MazePlacementState (bgw_maze.cuh); device pointers */
     bool maze_ok = false, maze_small = false;
     DevSpec ds{}, dsf{};          /* general kernels / fast kernel (own slot table size) */
@@ -133,6 +136,34 @@ __global__ void bgw_layout_kernel(const MazeParams p, const BgwState st, int E, 
         const int err = maze_layout(p, (uint32_t)(env_offset + e), st.episode[e] + 1u, w, st.layout + (size_t)e * p.A);
         if (err) st.error[e] = (uint32_t)err;
     }
+}
+
+/* the general step kernel specialised for a sim program / attack actor (bgw_dev.cuh, bgw_step_kernel) */
+GeneralStepFn general_step_fn(int program, int attack_actor)
+{
+    switch (program) {
+    case BGW_PROG_TEAM_BATTLE:
+        switch (attack_actor) {
+        case BGW_ATTACK_BINARY: return bgw_step_kernel<BGW_PROG_TEAM_BATTLE, BGW_ATTACK_BINARY>;
+        case BGW_ATTACK_ENCODING: return bgw_step_kernel<BGW_PROG_TEAM_BATTLE, BGW_ATTACK_ENCODING>;
+        case BGW_ATTACK_RESTRICTED: return bgw_step_kernel<BGW_PROG_TEAM_BATTLE, BGW_ATTACK_RESTRICTED>;
+        case BGW_ATTACK_SELECTIVE: return bgw_step_kernel<BGW_PROG_TEAM_BATTLE, BGW_ATTACK_SELECTIVE>;
+        default: break;
+        }
+        break;
+    case BGW_PROG_REACH_TARGET:                      /* examples/rllib_reach_the_target.py: SelectiveAttackActor */
+        if (attack_actor == BGW_ATTACK_SELECTIVE) return bgw_step_kernel<BGW_PROG_REACH_TARGET, BGW_ATTACK_SELECTIVE>;
+        break;
+    case BGW_PROG_TRAFFIC:                           /* traffic_corridor.py: movers only */
+        if (attack_actor == BGW_ATTACK_NONE) return bgw_step_kernel<BGW_PROG_TRAFFIC, BGW_ATTACK_NONE>;
+        break;
+    case BGW_PROG_MAZE: return bgw_step_kernel<BGW_PROG_MAZE, -1>;
+    case BGW_PROG_MULTI_MAZE: return bgw_step_kernel<BGW_PROG_MULTI_MAZE, -1>;
+    case BGW_PROG_PACMAN: return bgw_step_kernel<BGW_PROG_PACMAN, -1>;
+    /* BGW_PROG_PACMAN_SIMPLE: measured slower in its own instantiation (4.0e8 against 4.9e8 agent-steps/s): all-in-one */
+    default: break;
+    }
+    return bgw_step_kernel<-1, -1>;                  /* every program and actor in one */
 }
 
 int first_role(const BgwSpec *sp, int role)
@@ -328,7 +359,7 @@ int bgw_create(const BgwSpec *sp, int device, bgw_handle *out)
     /* general kernel: one CTA per env; small CTAs keep more envs resident (measured: maze 2.4x, pacman 1.9x faster
      * than with 128 / 256 threads) */
     int T = A <= 128 ? 32 : A <= 1024 ? 64 : 128;
-    if (const char *t = getenv("BGW_THREADS")) { const int v = atoi(t); if (v >= 32 && v <= 1024 && v % 32 == 0) T = v; }
+    if (const char *t = getenv("BGW_THREADS")) { const int v = atoi(t); if (v >= 32 && v <= 256 && v % 32 == 0) T = v; }   /* __launch_bounds__(256, 3) */
     h->threads = T;
     d.parallel_actors = ((sp->program == BGW_PROG_TEAM_BATTLE || sp->program == BGW_PROG_REACH_TARGET || sp->program == BGW_PROG_TRAFFIC) && (sp->move_actor == BGW_MOVE_BOX || sp->move_actor == BGW_MOVE_CROSS));
     if (sp->program == BGW_PROG_TRAFFIC)         /* the +1 looks at the target's cell right after the own move: rank order if a target can move */
@@ -451,7 +482,9 @@ int bgw_create(const BgwSpec *sp, int device, bgw_handle *out)
     d.smem_bytes = off;
     if (off > 227 * 1024) return bail(fail(1, "bgw_create: one environment needs %d bytes of shared memory (limit 232448): grid or entity count too large", off));
     cudaError_t ce;
-    if ((ce = cudaFuncSetAttribute(bgw_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, off)) != cudaSuccess ||
+    h->step_fn = general_step_fn(d.program, d.attack_actor);
+    if (const char *t = getenv("BGW_ALL_IN_ONE_KERNEL")) if (atoi(t)) h->step_fn = bgw_step_kernel<-1, -1>;
+    if ((ce = cudaFuncSetAttribute(h->step_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, off)) != cudaSuccess ||
         (h->fs.enabled && (ce = cudaFuncSetAttribute(bgw_step_fast_kernel<FastStaticC5, uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->fs.smem_bytes)) != cudaSuccess) ||
         (h->fs.enabled && (ce = cudaFuncSetAttribute(bgw_step_fast_kernel<FastStaticC2, uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->fs.smem_bytes)) != cudaSuccess) ||
         (h->fs.enabled && (ce = cudaFuncSetAttribute(bgw_step_fast_kernel<FastDynamic, uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->fs.smem_bytes)) != cudaSuccess) ||
@@ -576,7 +609,7 @@ static int step_impl(bgw_handle h, const int8_t *actions, int8_t *sampled, const
             h->launches += 1;
             actions = sampled;
         }
-        bgw_step_kernel<<<h->ds.E, h->threads, h->ds.smem_bytes, (cudaStream_t)stream>>>(
+        h->step_fn<<<h->ds.E, h->threads, h->ds.smem_bytes, (cudaStream_t)stream>>>(
             h->ds, h->st, (const uint32_t *)actions, order, obs, reward, done, all_done);
     }
     CUDA_OK(cudaGetLastError());

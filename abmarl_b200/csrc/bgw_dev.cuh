@@ -1314,9 +1314,17 @@ __global__ void bgw_reset_kernel(const DevSpec s, const BgwState st, const uint8
     if (tid == 0) st.env_flags[e] = (uint8_t)(ev.ctr[CTR_ERR] ? BGW_ENV_ERROR | BGW_ENV_ALL_DONE : 0);
 }
 
-__global__ void bgw_step_kernel(const DevSpec s, const BgwState st, const uint32_t *actions, const int16_t *order,
+/* The step kernel is instantiated per sim program (and, for the team battle, per attack actor): PROG / ATT >= 0 overwrite
+ * the corresponding spec fields with compile-time constants, so the dispatch on them folds and every instantiation holds
+ * only its own program's code.  One CTA of one or two warps per env runs at its own place in the code; the all-in-one
+ * instantiation <-1, -1> is 26 k instructions (415 KB) and waits for instruction fetches most of the time. */
+template <int PROG, int ATT>
+__global__ void __launch_bounds__(256, 3) bgw_step_kernel(const DevSpec s_in,   /* <= 80 registers: what the all-in-one kernel needs */ const BgwState st, const uint32_t *actions, const int16_t *order,
                                 int8_t *obs, float *reward, uint8_t *done, uint8_t *all_done)
 {
+    DevSpec s = s_in;
+    if (PROG >= 0) s.program = PROG;
+    if (ATT >= 0) s.attack_actor = ATT;
     const int e = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
     Env ev;
     env_init(ev, s, bgw_smem);
