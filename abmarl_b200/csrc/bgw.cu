@@ -574,11 +574,22 @@ static int step_impl(bgw_handle h, const int8_t *actions, int8_t *sampled, const
     if (h->fs.enabled) {
         if (h->poisoned) return fail(2, "bgw_step: an earlier step launch failed; the handle cannot be used any more");
         h->fs.seq = ++h->seq;
-        h->fs.chain = (chained && h->chain_ok) ? 1 : 0;
-        if (h->ticket_uses.empty()) h->ticket_uses.assign(BGW_TICKET_RING, 0u);
-        const uint32_t slot = h->fs.seq % BGW_TICKET_RING;
-        h->fs.ticket = h->ticket_ring + slot;
-        h->fs.ticket_base = h->ticket_uses[slot]++ * (uint32_t)h->ds.E;
+        cudaStreamCaptureStatus capture = cudaStreamCaptureStatusNone;
+        CUDA_OK(cudaStreamIsCapturing((cudaStream_t)stream, &capture));
+        if (capture != cudaStreamCaptureStatusNone) {
+            /* the launch goes into a CUDA graph and will run any number of times with these parameters: no ticket
+             * counter (its base would be stale at the second replay) -- CTA c takes envs c, c + grid, ... -- and no
+             * per-env chaining (the stamps it leaves carry this sequence number, which only ever makes a later
+             * chained launch wait less than a whole launch, never less than it must: the first launch of every
+             * rollout stamps all envs itself) */
+            h->fs.chain = 0; h->fs.ticket = nullptr; h->fs.ticket_base = 0;
+        } else {
+            h->fs.chain = (chained && h->chain_ok) ? 1 : 0;
+            if (h->ticket_uses.empty()) h->ticket_uses.assign(BGW_TICKET_RING, 0u);
+            const uint32_t slot = h->fs.seq % BGW_TICKET_RING;
+            h->fs.ticket = h->ticket_ring + slot;
+            h->fs.ticket_base = h->ticket_uses[slot]++ * (uint32_t)h->ds.E;
+        }
         h->poisoned = true;                            /* until the launch below has been accepted */
         /* Programmatic dependent launch: when the previous operation on the stream is another step launch, the
          * CTAs of this one become resident as that one's CTAs retire and run their env-independent set-up (spec

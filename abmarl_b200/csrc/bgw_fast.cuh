@@ -64,7 +64,8 @@ struct FastSpec {
     long long *prof;          /* debug (BGW_PROF_FILE): clock64 at phase boundaries, [cta][8 envs][16 marks] */
     /* env scheduling across launches (see "env tickets and chained launches" below) */
     uint32_t *env_seq;        /* [E] sequence number of the last fast step launch that finished this env */
-    uint32_t *ticket;         /* this launch's env ticket counter: one of a ring of BGW_TICKET_RING, never reset */
+    uint32_t *ticket;         /* this launch's env ticket counter: one of a ring of BGW_TICKET_RING, never reset; NULL: CTA c takes
+                                 envs c, c + grid, ... (launches captured into a CUDA graph) */
     uint32_t ticket_base;     /* value of *ticket before this launch: every launch draws exactly E tickets */
     uint32_t seq;             /* sequence number of this launch (1, 2, ... per handle) */
     int chain;                /* 1: the previous operation on the stream is the fast step launch seq - 1 of the same
@@ -723,7 +724,9 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
     uint32_t *const tk = f_in.ticket;                      /* this launch's ticket counter */
     const uint32_t tk_off = gridDim.x - f_in.ticket_base;  /* env = counter value - base + grid size (mod 2^32) */
     int *const tslot = fe.wsum + BGW_TSLOT;
-    if (tid == 0) tslot[0] = (int)min((unsigned)s.E, tk_off + atomicAdd(tk, 1u));   /* the env after blockIdx.x */
+    /* the env after blockIdx.x: the next ticket, or blockIdx.x + grid when the launch has no ticket counter (a launch
+     * captured into a CUDA graph) */
+    if (tid == 0) tslot[0] = (int)min((unsigned)s.E, tk ? tk_off + atomicAdd(tk, 1u) : blockIdx.x + gridDim.x);
     fast_init_dense(s, f, ev, fe, tid, T);
     /* Programmatic dependent launch (step_impl): everything above is env-independent and may run while the previous
      * step launch is still finishing; nothing of the step state is read or written before this point.  The next
@@ -758,7 +761,7 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
         BGW_PROF_MARK(0);
         en = tslot[sl];
         uint32_t tnew = (uint32_t)s.E;                              /* the env after `en`: drawn now, needed next iteration */
-        if (tid == 0 && en < s.E) tnew = min((unsigned)s.E, tk_off + atomicAdd(tk, 1u));
+        if (tid == 0 && en < s.E) tnew = min((unsigned)s.E, tk ? tk_off + atomicAdd(tk, 1u) : (unsigned)en + gridDim.x);
         if (en < s.E) {
             chain_wait_env(f_in, en);
             fast_issue_env(s, f, st, actions, en, bgw_smem + f.o_buf + (b ^ 1) * f.buf_bytes, tid, T);

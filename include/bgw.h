@@ -270,6 +270,7 @@ int bgw_reset(bgw_handle h, const uint8_t *env_mask, int8_t *obs, void *stream);
  *                           all_step_manager.py:62-65); NULL = dict order
  *   obs      [E][L][obs_stride] i8, reward [E][L] f32, done [E][L] u8 (BGW_OUT_*), all_done [E] u8 (BGW_ENV_*)
  * Rows whose BGW_OUT_VALID bit is clear (and BGW_ENV_RESET is clear) are not written.
+ * The launch may be captured into a CUDA graph and replayed (the library detects the capture with cudaStreamIsCapturing).
  */
 int bgw_step(bgw_handle h, const int8_t *actions, const int16_t *order, int8_t *obs, float *reward,
              uint8_t *done, uint8_t *all_done, void *stream);

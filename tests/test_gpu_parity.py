@@ -387,6 +387,41 @@ def test_rollout_sampled_equals_separate_steps(mirror, name, n_envs):
         assert torch.equal(a.stats(), b.stats())
 
 
+def test_step_launch_replayed_from_a_cuda_graph(mirror):
+    """A step launch captured into a CUDA graph runs with the parameters of capture time at every replay: the library
+    must not bake a ticket base or a chain dependency into it.  Replays, eager steps and chained rollouts mixed on one
+    engine against separate eager steps on another (2500 envs: more than one env per resident CTA)."""
+    from abmarl_b200.engine import BatchedGridWorld
+    spec = compile_sim(scenarios.build_tb_c5(mirror), n_envs=2500, seed=5, horizon=15, auto_reset=True)
+    a, b = BatchedGridWorld(spec, device='cuda:0'), BatchedGridWorld(spec, device='cuda:0')
+    a.reset()
+    b.reset()
+    a.step_sampled()
+    b.step_sampled()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        a.step_sampled()                                   # capture only: nothing runs
+    done = 1
+    for kind, n in (('graph', 4), ('rollout', 6), ('graph', 3), ('eager', 2), ('rollout', 20), ('graph', 5)):
+        for _ in range(n):
+            b.step_sampled()
+        if kind == 'graph':
+            for _ in range(n):
+                g.replay()
+        elif kind == 'rollout':
+            a.rollout_sampled(n)
+        else:
+            for _ in range(n):
+                a.step_sampled()
+        done += n
+        torch.cuda.synchronize()
+        for k in ('obs', 'reward', 'done', 'all_done', 'actions'):
+            assert torch.equal(getattr(a, k), getattr(b, k)), (kind, done, k)
+        assert_state_equal(a.state_numpy(), b.state_numpy(), f'{kind} after {done} steps')
+        assert torch.equal(a.stats(), b.stats())
+
+
 def test_chained_rollout_full_size_against_oracle(mirror):
     """The headline workload at full size (4096 envs: three envs per resident CTA, tickets, per-env stamps) through
     chained rollouts of several lengths, against the oracle on env slices at both ends of the batch, and against
