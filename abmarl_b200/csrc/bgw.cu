@@ -447,7 +447,7 @@ int bgw_create(const BgwSpec *sp, int device, bgw_handle *out)
             const FastLayout ly = fast_layout(A, L, HW, f.PH, f.PW, fslots, TF, max_enc, d.hw_words, L == A);
             fast_apply_layout(f, ly);
             const int fo = ly.smem_bytes;
-            f.async_ok = (A % 16 == 0) && (L % 4 == 0);
+            f.async_ok = (A % 16 == 0) ? 1 : (A % 8 == 0) ? 2 : 0;   /* cp.async in 16- or 8-byte chunks (rows start at multiples of A bytes) */
             f.simd_ok = (A % 4 == 0);
             f.uniform_view = -1;
             bool first = true, uniform = true;

@@ -48,7 +48,7 @@ struct FastSpec {
     int uniform_att;          /* attack range shared by every attacking entity, or -1 */
     int identity_learners;    /* every entity is a learner: learner index == entity index */
     int grid_ctas;            /* persistent grid size */
-    int async_ok;             /* rows are 16-byte aligned: stage with cp.async */
+    int async_ok;             /* stage the rows with cp.async: 1 = 16-byte chunks (A % 16 == 0), 2 = 8-byte chunks (A % 8 == 0), 0 = plain loads */
     int simd_ok;              /* A % 4 == 0: byte-parallel compaction */
     int stage_hits_slots;     /* the observation stage overlaps the reservation slots: refill them after it */
     int stage_hits_rflag;     /* ... and the reward flags: a barrier between the reward loop and the row gather */
@@ -231,6 +231,11 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
 }
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gmem_src)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gmem_src) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
@@ -275,7 +280,15 @@ __device__ __forceinline__ void fast_issue_env(const DevSpec &s, const FastSpec 
         for (int i = tid; i < (s.L * 4 + 127) / 128; i += T)
             asm volatile("prefetch.global.L2 [%0];" ::"l"((const char *)(actions + (size_t)e * s.L) + (size_t)i * 128));
     const size_t off = (size_t)e * s.A;
-    if (f.async_ok) {
+    if (f.async_ok == 2) {                                         /* rows are only 8-byte aligned (e.g. 24 entities) */
+        const unsigned char *g;
+        g = (const unsigned char *)(st.cell + off);
+        for (int i = tid; i < s.A / 4; i += T) cp_async8(buf + f.b_cell + i * 8, g + i * 8);
+        g = (const unsigned char *)(st.next + off);
+        for (int i = tid; i < s.A / 4; i += T) cp_async8(buf + f.b_next + i * 8, g + i * 8);
+        g = (const unsigned char *)(st.flags + off);
+        for (int i = tid; i < s.A / 8; i += T) cp_async8(buf + f.b_flags + i * 8, g + i * 8);
+    } else if (f.async_ok) {
         const unsigned char *g;
         g = (const unsigned char *)(st.cell + off);
         for (int i = tid; i < s.A / 8; i += T) cp_async16(buf + f.b_cell + i * 16, g + i * 16);
@@ -641,7 +654,7 @@ struct FastStaticC2 {
     static constexpr bool is_static = true;
     static constexpr int A = 24, L = 24, H = 8, W = 8, P = 3, PL = 3, PW = 16, PH = 14, obs_stride = 64, nchunks = 4,
                          obs_h = 7, view = 3, move_actor = BGW_MOVE_BOX, ravel = 0, observe_self = 1, done_mask = BGW_DONE_ONE_TEAM,
-                         max_enc = 4, simd_ok = 1, async_ok = 0, slots = 64, T = 32, att = 1, identity = 1;
+                         max_enc = 4, simd_ok = 1, async_ok = 2, slots = 64, T = 32, att = 1, identity = 1;
 };
 struct FastDynamic { static constexpr bool is_static = false; };
 
