@@ -266,8 +266,15 @@ __device__ __forceinline__ void st_release_u32(uint32_t *p, uint32_t v)
 }
 __device__ __forceinline__ void chain_wait_env(const FastSpec &f, int e)
 {
-    if (f.chain)
-        while ((int32_t)(ld_acquire_u32(f.env_seq + e) - (f.seq - 1u)) < 0) __nanosleep(64);
+    if (f.chain) {
+        /* a legitimate wait ends within one launch (tens of microseconds, milliseconds when envs reset); after about ten
+         * seconds of polling something is broken: fail the launch instead of hanging the device */
+        unsigned spins = 0;
+        while ((int32_t)(ld_acquire_u32(f.env_seq + e) - (f.seq - 1u)) < 0) {
+            __nanosleep(64);
+            if (++spins > (1u << 24)) __trap();
+        }
+    }
 }
 #define BGW_TSLOT 12          /* wsum[12], wsum[13]: the env after this one / the one after that */
 
