@@ -23,8 +23,8 @@
  *     afterwards from the rank of whoever killed them (an attacker is charged for a failed attempt iff it
  *     was still alive at its turn, team_battle_example.py:37-42);
  *   - the observation window is gathered from `cenc` with aligned 32-bit loads + funnel shifts, one thread per
- *     learner, assembled into the packed (2R+1)^2 row in registers (compile-time view range), transposed
- *     through a per-warp shared-memory stage and written to HBM with coalesced 128-bit stores.  Envs that hold
+ *     learner, assembled into the packed (2R+1)^2 row in registers (compile-time view range) and written to HBM
+ *     straight from the registers with 256-bit stores (one full 32-byte sector per lane).  Envs that hold
  *     a mixed cell (or observers that do not observe themselves, or other view ranges) take the per-cell path
  *     with the keyed np.random.choice over the occupant list.
  */
@@ -37,7 +37,6 @@
 #else
 #define BGW_PROF_MARK(k) do { } while (0)
 #endif
-#define BGW_STAGE_ROW 80        /* bytes per lane in the observation stage: 64 payload + 16 pad (conflict-free 128-bit) */
 
 struct FastSpec {
     int enabled;
@@ -50,12 +49,10 @@ struct FastSpec {
     int grid_ctas;            /* persistent grid size */
     int async_ok;             /* stage the rows with cp.async: 1 = 16-byte chunks (A % 16 == 0), 2 = 8-byte chunks (A % 8 == 0), 0 = plain loads */
     int simd_ok;              /* A % 4 == 0: byte-parallel compaction */
-    int stage_hits_slots;     /* the observation stage overlaps the reservation slots: refill them after it */
-    int stage_hits_rflag;     /* ... and the reward flags: a barrier between the reward loop and the row gather */
     uint32_t epoch0;          /* first reservation epoch of a launch (0xFFFFE; tests start lower to exercise the wrap guard) */
     int b_cell, b_next, b_flags, buf_bytes;   /* layout of one staging buffer */
     /* shared-memory carve-up of the fast kernel.  `scratch` is a union: during the actor phases it holds
-     * rflag | slot | rkmask | eff | pstate | killrank, during the observation phase the per-warp stage, and in
+     * rflag | slot | rkmask | eff | pstate | killrank, and in
      * the (general) reset path racc | avail. */
     int o_enc, o_klass, o_tmp, o_act, o_head, o_cenc, o_rel, o_ragent, o_plist, o_ctr, o_wsum, o_buf, o_scratch;
     int s_rflag, s_slot, s_rkmask, s_eff, s_pstate, s_killrank, scratch_bytes, smem_bytes;
@@ -77,7 +74,7 @@ struct FastSpec {
 struct FastLayout {
     int b_cell, b_next, b_flags, buf_bytes;
     int o_enc, o_klass, o_tmp, o_act, o_head, o_cenc, o_rel, o_ragent, o_plist, o_ctr, o_wsum, o_buf, o_scratch;
-    int s_rflag, s_slot, s_rkmask, s_eff, s_pstate, s_killrank, scratch_bytes, smem_bytes, stage_hits_slots, stage_hits_rflag;
+    int s_rflag, s_slot, s_rkmask, s_eff, s_pstate, s_killrank, scratch_bytes, smem_bytes;
     int r_racc, r_avail, head_elem;
 };
 
@@ -110,27 +107,22 @@ __host__ __device__ constexpr FastLayout fast_layout(int A, int L, int HW, int P
     y.s_eff = so; so += fl_align16(L * 2);
     y.s_pstate = so; so += fl_align16(L);
     y.s_killrank = so; so += fl_align16(A * 2);
-    y.s_slot = so; so += fl_align16(slots * 4);           /* the observation stage may spill over the arrays before it (and refills the slots) */
-    y.s_rflag = so; so += fl_align16(A);                  /* last: still read (rewards) while the first warps stage their rows */
+    y.s_slot = so; so += fl_align16(slots * 4);
+    y.s_rflag = so; so += fl_align16(A);
     const int actor_bytes = so;
-    /* cenc | head | scratch are contiguous: the observation stage spans head + scratch (the lists are dead once the
-     * row gather starts), and the general reset path uses all three as one arena: u16 heads | racc | avail */
+    /* cenc | head | scratch are contiguous: the general reset path uses all three as one arena: u16 heads | racc | avail */
     const int cenc_bytes = fl_align16(PH * PW + 32);      /* + slack: the word gather reads past a row end */
     y.head_elem = A <= 256 ? 1 : 2;
     const int head_bytes = fl_align16(HW * y.head_elem + 2);
-    const int stage_bytes = (T / 32) * 32 * BGW_STAGE_ROW;
     y.r_racc = fl_align16(HW * 2 + 2);
     y.r_avail = y.r_racc + fl_align16(A * 8);
     const int reset_bytes = y.r_avail + fl_align16((max_enc + 1) * hw_words * 4);
     int sb = actor_bytes;
-    if (stage_bytes - head_bytes > sb) sb = stage_bytes - head_bytes;
     if (reset_bytes - cenc_bytes - head_bytes > sb) sb = reset_bytes - cenc_bytes - head_bytes;
     y.scratch_bytes = sb;
     y.o_cenc = fo; fo += cenc_bytes;
     y.o_head = fo; fo += head_bytes;
     y.o_scratch = fo; fo += sb;
-    y.stage_hits_slots = (stage_bytes - head_bytes > y.s_slot) ? 1 : 0;   /* the stage reaches the slots */
-    y.stage_hits_rflag = (stage_bytes - head_bytes > y.s_rflag) ? 1 : 0;  /* ... and the reward flags */
     y.smem_bytes = fo;
     return y;
 }
@@ -144,7 +136,6 @@ __host__ __device__ inline void fast_apply_layout(FastSpec &f, const FastLayout 
     f.s_rflag = y.s_rflag; f.s_slot = y.s_slot; f.s_rkmask = y.s_rkmask; f.s_eff = y.s_eff; f.s_pstate = y.s_pstate;
     f.s_killrank = y.s_killrank; f.scratch_bytes = y.scratch_bytes; f.smem_bytes = y.smem_bytes;
     f.r_racc = y.r_racc; f.r_avail = y.r_avail; f.head_elem = y.head_elem;
-    f.stage_hits_slots = y.stage_hits_slots; f.stage_hits_rflag = y.stage_hits_rflag;
 }
 
 /* what happened to an entity this step, in the order the reference adds the rewards (team_battle_example.py:38-59):
@@ -463,28 +454,34 @@ __device__ uint32_t fast_move_rounds(const DevSpec &s, const FastSpec &f, Env &e
 {
     const int stride = WARP ? 32 : T;
     const SlotTables st = slot_tables(s, ev);
-    int which = 0, n_cur = -1, p = 0;                              /* n_cur -1: walk the ranks themselves */
+    uint32_t *cur = st.t0, *nxt = st.t1;                           /* this round's table / the next round's */
+    int which = 0, n_cur = -1;                                     /* n_cur -1: walk the ranks themselves */
     int base0 = 0, base1 = 0;                                      /* the list counters only grow: entries before base are consumed */
     while (pending) {
         const uint32_t tag = epoch << BGW_TAG_SHIFT, next_tag = (epoch - 1u) << BGW_TAG_SHIFT;
         const int n_it = n_cur < 0 ? n_act : n_cur;
+        const uint16_t *walk = which ? fe.killrank : fe.eff;
         int lost = 0;
         for (int x = tid; x < n_it; x += stride) {
-            const int i = n_cur < 0 ? x : (which ? fe.killrank : fe.eff)[x];
+            const int i = n_cur < 0 ? x : walk[x];
             const uint32_t ft = fe.rkmask[i];
             if (ft == BGW_NO_MOVE) continue;
             const int from = (int)(ft >> 16), to = (int)(ft & 0xFFFFu);
-            const uint32_t mine = tag | (uint32_t)i;
-            if (st.tab(p)[from & st.mask] != mine || st.tab(p)[to & st.mask] != mine) {
+            const uint32_t mine = tag | (uint32_t)i, sf = (uint32_t)from & st.mask, sto = (uint32_t)to & st.mask;
+            const uint32_t hf = cur[sf], ht = cur[sto];                 /* both loads in flight, one test */
+            if ((hf != mine) | (ht != mine)) {
                 lost = 1;
-                atomicMin(&st.tab(p ^ 1)[from & st.mask], next_tag | (uint32_t)i);
-                atomicMin(&st.tab(p ^ 1)[to & st.mask], next_tag | (uint32_t)i);
+                atomicMin(&nxt[sf], next_tag | (uint32_t)i);
+                atomicMin(&nxt[sto], next_tag | (uint32_t)i);
                 if (!WARP) (which ? fe.eff : fe.killrank)[atomicAdd(&ev.ctr[CTR_PA + (which ^ 1)], 1) - (which ? base0 : base1)] = (uint16_t)i;
                 continue;
             }
             const int a = ev.ragent[i], pto = pad_index(s, f, to);
+            /* the common move -- alone in its cell, destination empty -- touches no occupant list; the four conditions
+             * are loaded and combined without short-circuit branches */
             const int8_t summary = fe.cenc[pto], me = ev.enc[a];
-            if (summary == 0 && (ev.flags[a] & BGW_ST_IN_GRID) && ((const HT *)fe.head)[from] == (HT)a && ev.next[a] == BGW_NONE16) {
+            const unsigned fl = ev.flags[a], hd = ((const HT *)fe.head)[from], nx = ev.next[a];
+            if ((summary == 0) & ((fl & BGW_ST_IN_GRID) != 0) & (hd == (unsigned)a) & (nx == BGW_NONE16)) {
                 fe.cenc[pad_index(s, f, from)] = 0;                /* Grid.remove: the cell is empty again */
                 fe.cenc[pto] = me;                                 /* Grid.place into an empty cell */
                 ((HT *)fe.head)[to] = (HT)a;
@@ -501,7 +498,8 @@ __device__ uint32_t fast_move_rounds(const DevSpec &s, const FastSpec &f, Env &e
             n_cur = ev.ctr[CTR_PA + (which ^ 1)] - (which ? base0 : base1);       /* the losers of this round */
             which ^= 1;
         }
-        p ^= 1; --epoch;
+        { uint32_t *t = cur; cur = nxt; nxt = t; }
+        --epoch;
     }
     return epoch;
 }
@@ -570,31 +568,38 @@ __device__ void fast_obs_chunk_slow(const DevSpec &s, const FastSpec &f, const E
     }
 }
 
+/* 32 contiguous bytes from one lane: STG.256 (sm_100), one full sector per lane and instruction */
+__device__ __forceinline__ void st_global_256(void *p, const uint32_t *v)
+{
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+                 "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+
 /* Observation rows of the acting learners, view range R known at compile time.  One thread gathers one
  * learner's window: per window row LW aligned words, funnel-shifted to the row's first byte, then appended at
  * byte n*i of the packed output (all shifts are compile-time after unrolling).  The packed row is produced in
- * groups of 64 bytes, staged in shared memory (one BGW_STAGE_ROW per lane) and copied out by the warp as
- * 128-bit stores, 4 lanes per learner. */
+ * groups of 64 bytes held in registers and leaves the lane as two 256-bit stores per group (rows that are 32-byte
+ * aligned; 128-bit stores otherwise): every store instruction writes 32 full sectors.  (Round 1 transposed the groups
+ * through a shared-memory stage into coalesced 128-bit stores: half of the gather's instructions and a third of its
+ * shared-memory wavefronts were that transposition.) */
 template <int R>
 __device__ void fast_obs_rows(const DevSpec &s, const FastSpec &f, const Env &ev, const FastEnv &fe, int n_act, int8_t *obs_env,
-                              unsigned char *stage_all, int tid, int T)
+                              int tid, int T)
 {
     constexpr int n = 2 * R + 1, NB = n * n;
     constexpr int RW = (n + 3) / 4;            /* words of an aligned row */
     constexpr int LW = (n + 6) / 4;            /* words to load: alignment shift (<= 3 bytes) + n bytes */
     constexpr int NG = (NB + 63) / 64;         /* 64-byte groups of the output row */
-    const int lane = tid & 31, warp = tid >> 5, nwarp = T >> 5;
-    unsigned char *stage = stage_all + (size_t)warp * 32 * BGW_STAGE_ROW;
     const int pw4 = f.PW >> 2;
-    for (int base = warp * 32; base < n_act; base += nwarp * 32) {
-        const int li = base + lane;
-        const bool have = li < n_act;
-        const int a = have ? ev.ragent[li] : 0;
-        const bool observing = have && (ev.klass[a] & BGW_AG_OBSERVING);
+    const bool wide = ((s.obs_stride & 31) == 0) && ((reinterpret_cast<uintptr_t>(obs_env) & 31) == 0);
+    for (int li = tid; li < n_act; li += T) {
+        const int a = ev.ragent[li];
+        const bool observing = ev.klass[a] & BGW_AG_OBSERVING;
         const int o = pad_index(s, f, ev.cell[a]) - R * f.PW - R;
         const uint32_t *wp = reinterpret_cast<const uint32_t *>(fe.cenc + (o & ~3));
         const int sh = (o & 3) * 8;
-        const int cnt = min(32, n_act - base);
+        int8_t *dst = obs_env + (size_t)ev.plist[li] * s.obs_stride;
 #pragma unroll
         for (int g = 0; g < NG; ++g) {
             uint32_t out[16];
@@ -622,21 +627,16 @@ __device__ void fast_obs_rows(const DevSpec &s, const FastSpec &f, const Env &ev
                     }
                 }
             }
-            uint4 *sp4 = reinterpret_cast<uint4 *>(stage + lane * BGW_STAGE_ROW);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) sp4[j] = make_uint4(out[4 * j], out[4 * j + 1], out[4 * j + 2], out[4 * j + 3]);
-            __syncwarp();
-            constexpr int gch = 4;                                       /* 16-byte chunks per group */
             const int nchg = min(4, s.nchunks - 4 * g);                  /* 16-byte chunks of this group that exist */
-            for (int qq = lane; qq < cnt * gch; qq += 32) {
-                const int ll = qq >> 2, ch = qq & 3;
-                if (ch < nchg) {
-                    const uint4 v = *reinterpret_cast<const uint4 *>(stage + ll * BGW_STAGE_ROW + ch * 16);
-                    const int l = ev.plist[base + ll];
-                    *reinterpret_cast<uint4 *>(obs_env + (size_t)l * s.obs_stride + (4 * g + ch) * 16) = v;
+            int8_t *dg = dst + 64 * g;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {                                 /* the two 32-byte halves of the group */
+                if (wide && nchg >= 2 * h + 2) st_global_256(dg + 32 * h, out + 8 * h);
+                else {
+                    if (nchg >= 2 * h + 1) *reinterpret_cast<uint4 *>(dg + 32 * h) = make_uint4(out[8 * h], out[8 * h + 1], out[8 * h + 2], out[8 * h + 3]);
+                    if (nchg >= 2 * h + 2) *reinterpret_cast<uint4 *>(dg + 32 * h + 16) = make_uint4(out[8 * h + 4], out[8 * h + 5], out[8 * h + 6], out[8 * h + 7]);
                 }
             }
-            __syncwarp();
         }
     }
 }
@@ -991,13 +991,36 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
                     /* candidate cells: the summary says an attackable encoding (or a mix) is present */
                     const int R = f.uniform_att >= 0 ? f.uniform_att : __ldg(&s.attack_r[a]), n = 2 * R + 1;
                     const unsigned long long row = __ldg(&s.attack_map[ev.enc[a]]);
-                    const int8_t *w = fe.cenc + pad_index(s, f, ev.cell[a]) - R * f.PW - R;
+                    const int wo = pad_index(s, f, ev.cell[a]) - R * f.PW - R;
+                    const int8_t *w = fe.cenc + wo;
                     uint32_t mask = 0;
                     if (R == 1) {
+                        /* the three window rows as aligned word pairs, funnel-shifted to the window's first column; each
+                         * of the nine bytes is tested from the register: v in 1..max_enc selects its bit of the attack map
+                         * row, 0 (empty) and -1 (border) select nothing (bit 0 of a row is never set; shifts clamp) */
+                        const uint32_t *wp = reinterpret_cast<const uint32_t *>(fe.cenc + (wo & ~3));
+                        const int sh = (wo & 3) * 8, pw4 = f.PW >> 2;
+                        uint32_t y[3];
     #pragma unroll
-                        for (int k = 0; k < 9; ++k) {
-                            const int v = w[(k / 3) * f.PW + (k % 3)];
-                            if (v > 0 ? (int)((row >> v) & 1ull) : (v == BGW_MIXED)) mask |= 1u << k;
+                        for (int k = 0; k < 3; ++k) y[k] = __funnelshift_r(wp[k * pw4], wp[k * pw4 + 1], sh);
+                        if (s.max_enc < 32) {
+                            const uint32_t row32 = (uint32_t)row & ~1u;
+    #pragma unroll
+                            for (int k = 0; k < 9; ++k) {
+                                const uint32_t v = (y[k / 3] >> (8 * (k % 3))) & 0xFFu;
+                                mask |= (__funnelshift_rc(row32, 0u, v) & 1u) << k;
+                            }
+                        } else {
+    #pragma unroll
+                            for (int k = 0; k < 9; ++k) {
+                                const uint32_t v = (y[k / 3] >> (8 * (k % 3))) & 0xFFu;
+                                if (v < 64u && ((row >> v) & 1ull)) mask |= 1u << k;
+                            }
+                        }
+                        if (ev.ctr[CTR_MIXED]) {                        /* a mixed cell is always a candidate (the walk decides) */
+    #pragma unroll
+                            for (int k = 0; k < 9; ++k)
+                                if (((y[k / 3] >> (8 * (k % 3))) & 0xFFu) == (uint32_t)(uint8_t)BGW_MIXED) mask |= 1u << k;
                         }
                     } else {
                         for (int wr = 0; wr < n; ++wr)
@@ -1102,22 +1125,18 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
                 const int a = fe.rel[x];
                 if (racc_persists(ev.klass[a]) && (fe.rflag[a] & RF_DIED)) st.reward_acc[off + a] = __ldcg(&st.reward_acc[off + a]) + rw[BGW_RW_DIE];
             }
-        /* the scratch union becomes the observation stage: everything it covers is dead since the barrier that ended the
-         * move rounds, except the reward flags when the stage reaches that far (the per-cell path stages nothing) */
-        if (f.stage_hits_rflag) __syncthreads();
         BGW_PROF_MARK(9);
 
         /* ---- observations ------------------------------------------------------------------------------ */
-        bool staged = false;                                        /* the row gather staged through `head` + scratch */
         if (obs_env) {
             const bool direct = s.observe_self && !ev.ctr[CTR_MIXED];
             const int R = direct ? f.uniform_view : -1;
             switch (R) {
-            case 1: fast_obs_rows<1>(s, f, ev, fe, n_act, obs_env, (unsigned char *)fe.head, tid, T); staged = true; break;
-            case 2: fast_obs_rows<2>(s, f, ev, fe, n_act, obs_env, (unsigned char *)fe.head, tid, T); staged = true; break;
-            case 3: fast_obs_rows<3>(s, f, ev, fe, n_act, obs_env, (unsigned char *)fe.head, tid, T); staged = true; break;
-            case 4: fast_obs_rows<4>(s, f, ev, fe, n_act, obs_env, (unsigned char *)fe.head, tid, T); staged = true; break;
-            case 5: fast_obs_rows<5>(s, f, ev, fe, n_act, obs_env, (unsigned char *)fe.head, tid, T); staged = true; break;
+            case 1: fast_obs_rows<1>(s, f, ev, fe, n_act, obs_env, tid, T); break;
+            case 2: fast_obs_rows<2>(s, f, ev, fe, n_act, obs_env, tid, T); break;
+            case 3: fast_obs_rows<3>(s, f, ev, fe, n_act, obs_env, tid, T); break;
+            case 4: fast_obs_rows<4>(s, f, ev, fe, n_act, obs_env, tid, T); break;
+            case 5: fast_obs_rows<5>(s, f, ev, fe, n_act, obs_env, tid, T); break;
             default: {
                 const int items = n_act * nch;
                 for (int it = tid; it < items; it += T) {
@@ -1134,11 +1153,6 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
         BGW_PROF_MARK(10);
 
         /* ---- store the relevant entities, get_all_done (done.py:49-56,147-153), clean the dense arrays ---- */
-        if (staged && f.stage_hits_slots) {                         /* the observation stage ran over the reservation slots */
-            uint4 *s4 = (uint4 *)ev.slot;
-            const uint4 ones = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
-            for (int i = tid; i < (s.slot_mask + 1) / 4; i += T) s4[i] = ones;
-        }
         {
             uint32_t lo = 0, hi = 0;
             int ok = 1;
