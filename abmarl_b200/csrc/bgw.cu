@@ -15,6 +15,7 @@
 #include <cstring>
 #include <vector>
 
+#define BGW_SMALL_KERNELS
 #include "bgw_dev.cuh"
 #include "bgw_fast.cuh"
 #include "bgw_maze.cuh"
@@ -49,11 +50,10 @@ int pow2ceil(int x) { int p = 1; while (p < x) p <<= 1; return p; }
 
 }  // namespace
 
-typedef void (*GeneralStepFn)(const DevSpec, const BgwState, const uint32_t *, const int16_t *, int8_t *, float *, uint8_t *, uint8_t *);
-
 struct BgwEngine {
     int device = 0;
     GeneralStepFn step_fn = nullptr;   /* the bgw_step_kernel instantiation of this sim's program */
+    const void *fast_fn = nullptr;     /* the bgw_step_fast_kernel instantiation of this sim's shape */
     MazeParams maze{};            /* device-side MazePlacementState (bgw_maze.cuh); device pointers */
     bool maze_ok = false, maze_small = false;
     DevSpec ds{}, dsf{};          /* general kernels / fast kernel (own slot table size) */
@@ -136,34 +136,6 @@ __global__ void bgw_layout_kernel(const MazeParams p, const BgwState st, int E, 
         const int err = maze_layout(p, (uint32_t)(env_offset + e), st.episode[e] + 1u, w, st.layout + (size_t)e * p.A);
         if (err) st.error[e] = (uint32_t)err;
     }
-}
-
-/* the general step kernel specialised for a sim program / attack actor (bgw_dev.cuh, bgw_step_kernel) */
-GeneralStepFn general_step_fn(int program, int attack_actor)
-{
-    switch (program) {
-    case BGW_PROG_TEAM_BATTLE:
-        switch (attack_actor) {
-        case BGW_ATTACK_BINARY: return bgw_step_kernel<BGW_PROG_TEAM_BATTLE, BGW_ATTACK_BINARY>;
-        case BGW_ATTACK_ENCODING: return bgw_step_kernel<BGW_PROG_TEAM_BATTLE, BGW_ATTACK_ENCODING>;
-        case BGW_ATTACK_RESTRICTED: return bgw_step_kernel<BGW_PROG_TEAM_BATTLE, BGW_ATTACK_RESTRICTED>;
-        case BGW_ATTACK_SELECTIVE: return bgw_step_kernel<BGW_PROG_TEAM_BATTLE, BGW_ATTACK_SELECTIVE>;
-        default: break;
-        }
-        break;
-    case BGW_PROG_REACH_TARGET:                      /* examples/rllib_reach_the_target.py: SelectiveAttackActor */
-        if (attack_actor == BGW_ATTACK_SELECTIVE) return bgw_step_kernel<BGW_PROG_REACH_TARGET, BGW_ATTACK_SELECTIVE>;
-        break;
-    case BGW_PROG_TRAFFIC:                           /* traffic_corridor.py: movers only */
-        if (attack_actor == BGW_ATTACK_NONE) return bgw_step_kernel<BGW_PROG_TRAFFIC, BGW_ATTACK_NONE>;
-        break;
-    case BGW_PROG_MAZE: return bgw_step_kernel<BGW_PROG_MAZE, -1>;
-    case BGW_PROG_MULTI_MAZE: return bgw_step_kernel<BGW_PROG_MULTI_MAZE, -1>;
-    case BGW_PROG_PACMAN: return bgw_step_kernel<BGW_PROG_PACMAN, -1>;
-    /* BGW_PROG_PACMAN_SIMPLE: measured slower in its own instantiation (4.0e8 against 4.9e8 agent-steps/s): all-in-one */
-    default: break;
-    }
-    return bgw_step_kernel<-1, -1>;                  /* every program and actor in one */
 }
 
 int first_role(const BgwSpec *sp, int role)
@@ -439,7 +411,7 @@ int bgw_create(const BgwSpec *sp, int device, bgw_handle *out)
             f.PW = (W + 2 * P + 3) / 4 * 4;
             f.PH = H + 2 * P;
             f.magic_w = (uint32_t)(((1ull << 32) + (uint64_t)W - 1) / (uint64_t)W);
-            int fslots = std::min(std::max(pow2ceil(HW), 32), 512);
+            int fslots = std::min(std::max(pow2ceil(HW), 32), 256);   /* two tables of half that: only contested movers and effective attackers reserve */
             if (const char *t = getenv("BGW_SLOTS")) { const int v = atoi(t); if (v >= 32 && v <= 65536 && (v & (v - 1)) == 0) fslots = v; }
             h->dsf = d;
             h->dsf.slot_mask = fslots - 1;
@@ -468,6 +440,15 @@ int bgw_create(const BgwSpec *sp, int device, bgw_handle *out)
                 if (!unia) f.uniform_att = -1;
             }
             f.identity_learners = (L == A);
+            {   /* mixed cells need two DIFFERENT encodings that may overlap; accuracy draws need an accuracy below 1 */
+                unsigned long long present = 0;
+                for (int a = 0; a < A; ++a) present |= 1ull << sp->encoding[a];
+                f.can_mix = 0; f.acc_lt1 = 0;
+                for (int e = 1; e <= max_enc; ++e)
+                    if (((present >> e) & 1ull) && (sp->overlap[e] & present & ~(1ull << e))) f.can_mix = 1;
+                for (int a = 0; a < A; ++a)
+                    if ((sp->klass[a] & BGW_AG_ATTACKING) && sp->attack_accuracy[a] < 1.0) f.acc_lt1 = 1;
+            }
             f.epoch0 = 0xFFFFEu;
             if (const char *t = getenv("BGW_EPOCH0")) { const long v = atol(t); if (v >= 1 && v <= 0xFFFFE) f.epoch0 = (uint32_t)v; }
             if (cbytes > 96 * 1024 || fo > 227 * 1024) fast = false;
@@ -477,27 +458,22 @@ int bgw_create(const BgwSpec *sp, int device, bgw_handle *out)
         if (fast) {
             h->fast_shape = fast_shape_matches<FastStaticC5>(h->dsf, f, TF) ? 1 : fast_shape_matches<FastStaticC2>(h->dsf, f, TF) ? 2 : 0;
             if (const char *t = getenv("BGW_DYNAMIC_SHAPES")) if (atoi(t)) h->fast_shape = 0;
+            h->fast_fn = bgw_fast_step_fn(h->fast_shape, f.head_elem);   /* the instantiation step_impl launches for this handle */
         }
     }
     d.smem_bytes = off;
     if (off > 227 * 1024) return bail(fail(1, "bgw_create: one environment needs %d bytes of shared memory (limit 232448): grid or entity count too large", off));
     cudaError_t ce;
-    h->step_fn = general_step_fn(d.program, d.attack_actor);
-    if (const char *t = getenv("BGW_ALL_IN_ONE_KERNEL")) if (atoi(t)) h->step_fn = bgw_step_kernel<-1, -1>;
+    h->step_fn = bgw_general_step_fn(d.program, d.attack_actor);
+    if (const char *t = getenv("BGW_ALL_IN_ONE_KERNEL")) if (atoi(t)) h->step_fn = bgw_general_step_fn(-1, -1);
     if ((ce = cudaFuncSetAttribute(h->step_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, off)) != cudaSuccess ||
-        (h->fs.enabled && (ce = cudaFuncSetAttribute(bgw_step_fast_kernel<FastStaticC5, uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->fs.smem_bytes)) != cudaSuccess) ||
-        (h->fs.enabled && (ce = cudaFuncSetAttribute(bgw_step_fast_kernel<FastStaticC2, uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->fs.smem_bytes)) != cudaSuccess) ||
-        (h->fs.enabled && (ce = cudaFuncSetAttribute(bgw_step_fast_kernel<FastDynamic, uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->fs.smem_bytes)) != cudaSuccess) ||
-        (h->fs.enabled && (ce = cudaFuncSetAttribute(bgw_step_fast_kernel<FastDynamic, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->fs.smem_bytes)) != cudaSuccess) ||
+        (h->fs.enabled && (ce = cudaFuncSetAttribute(h->fast_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, h->fs.smem_bytes)) != cudaSuccess) ||
         (ce = cudaFuncSetAttribute(bgw_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, off)) != cudaSuccess)
         return bail(fail(2, "bgw_create: cudaFuncSetAttribute: %s", cudaGetErrorString(ce)));
     if (h->fs.enabled) {
         int per_sm = 0, sms = 0;
         /* the instantiation step_impl launches for this handle */
-        ce = h->fast_shape == 1 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bgw_step_fast_kernel<FastStaticC5, uint8_t>, h->threads_fast, h->fs.smem_bytes)
-           : h->fast_shape == 2 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bgw_step_fast_kernel<FastStaticC2, uint8_t>, h->threads_fast, h->fs.smem_bytes)
-           : h->fs.head_elem == 1 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bgw_step_fast_kernel<FastDynamic, uint8_t>, h->threads_fast, h->fs.smem_bytes)
-                                  : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bgw_step_fast_kernel<FastDynamic, uint16_t>, h->threads_fast, h->fs.smem_bytes);
+        ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, h->fast_fn, h->threads_fast, (size_t)h->fs.smem_bytes);
         if (ce != cudaSuccess ||
             (ce = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess)
             return bail(fail(2, "bgw_create: occupancy query: %s", cudaGetErrorString(ce)));
@@ -567,6 +543,17 @@ int bgw_reset(bgw_handle h, const uint8_t *env_mask, int8_t *obs, void *stream)
     return 0;
 }
 
+/* debug builds (BGW_PROFILE): write the phase clocks of the last launch(es) to BGW_PROF_FILE.  With BGW_PROF_LAZY only
+ * bgw_rollout_sampled dumps, after its last launch, so the per-env chaining of the launches is not broken by a synchronisation. */
+static void dump_prof(bgw_handle h, void *stream)
+{
+    const size_t n = (size_t)h->fs.grid_ctas * 8 * 16;
+    std::vector<long long> host(n);
+    cudaStreamSynchronize((cudaStream_t)stream);
+    cudaMemcpy(host.data(), h->fs.prof, n * sizeof(long long), cudaMemcpyDeviceToHost);
+    if (FILE *fp = fopen(getenv("BGW_PROF_FILE"), "wb")) { fwrite(host.data(), sizeof(long long), n, fp); fclose(fp); }
+}
+
 static int step_impl(bgw_handle h, const int8_t *actions, int8_t *sampled, const int16_t *order, int8_t *obs, float *reward,
                      uint8_t *done, uint8_t *all_done, void *stream, bool chained = false)
 {
@@ -603,14 +590,10 @@ static int step_impl(bgw_handle h, const int8_t *actions, int8_t *sampled, const
         cfg.gridDim = dim3((unsigned)h->fs.grid_ctas); cfg.blockDim = dim3((unsigned)h->threads_fast);
         cfg.dynamicSmemBytes = (size_t)h->fs.smem_bytes; cfg.stream = (cudaStream_t)stream;
         cfg.attrs = pdl_attr; cfg.numAttrs = 1;
-#define BGW_LAUNCH_FAST(ST, HT)                                                                                       \
-    CUDA_OK(cudaLaunchKernelEx(&cfg, bgw_step_fast_kernel<ST, HT>, h->dsf, h->fs, h->st, (const uint32_t *)actions,       \
-                               (uint32_t *)sampled, order, obs, reward, done, all_done))
-        if (h->fast_shape == 1) BGW_LAUNCH_FAST(FastStaticC5, uint8_t);
-        else if (h->fast_shape == 2) BGW_LAUNCH_FAST(FastStaticC2, uint8_t);
-        else if (h->fs.head_elem == 1) BGW_LAUNCH_FAST(FastDynamic, uint8_t);
-        else BGW_LAUNCH_FAST(FastDynamic, uint16_t);
-#undef BGW_LAUNCH_FAST
+        const uint32_t *act_arg = (const uint32_t *)actions;
+        uint32_t *smp_arg = (uint32_t *)sampled;
+        void *args[] = {&h->dsf, &h->fs, &h->st, &act_arg, &smp_arg, &order, &obs, &reward, &done, &all_done};
+        CUDA_OK(cudaLaunchKernelExC(&cfg, h->fast_fn, args));
         h->poisoned = false;
     } else {
         if (sampled) {                                 /* general kernel: sample, then step (two launches) */
@@ -625,13 +608,7 @@ static int step_impl(bgw_handle h, const int8_t *actions, int8_t *sampled, const
     }
     CUDA_OK(cudaGetLastError());
     h->launches += 1;
-    if (h->fs.enabled && h->fs.prof) {                 /* debug only: dump the phase clocks of this launch */
-        const size_t n = (size_t)h->fs.grid_ctas * 8 * 16;
-        std::vector<long long> host(n);
-        cudaStreamSynchronize((cudaStream_t)stream);
-        cudaMemcpy(host.data(), h->fs.prof, n * sizeof(long long), cudaMemcpyDeviceToHost);
-        if (FILE *fp = fopen(getenv("BGW_PROF_FILE"), "wb")) { fwrite(host.data(), sizeof(long long), n, fp); fclose(fp); }
-    }
+    if (h->fs.enabled && h->fs.prof && !getenv("BGW_PROF_LAZY")) dump_prof(h, stream);   /* debug only: the phase clocks of this launch */
     return 0;
 }
 
@@ -669,6 +646,7 @@ int bgw_rollout_sampled(bgw_handle h, int n_steps, int8_t *actions_out, const in
             if (rl) return rl;
         }
     }
+    if (h->fs.enabled && h->fs.prof && getenv("BGW_PROF_LAZY")) dump_prof(h, stream);
     return 0;
 }
 

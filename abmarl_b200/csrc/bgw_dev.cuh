@@ -170,7 +170,7 @@ __device__ __forceinline__ void set_health(Env &ev, int a, double v)
 __device__ __forceinline__ bool racc_persists(uint8_t klass) { return !(klass & BGW_AG_LEARNER) && (klass & BGW_AG_HEALTH); }
 
 /* rebuild the per-cell list heads from the persisted `next` pointers (all threads; ends synchronised) */
-__device__ void build_heads(const DevSpec &s, Env &ev, int tid, int T)
+static __device__ void build_heads(const DevSpec &s, Env &ev, int tid, int T)
 {
     for (int i = tid; i < (s.HW + 1) / 2; i += T) ((uint32_t *)ev.head)[i] = 0xFFFFFFFFu;
     for (int a = tid; a < s.A; a += T) ev.tmp[a] = 0;
@@ -261,7 +261,7 @@ __device__ __forceinline__ void cross_delta(int k, int &dr, int &dc)   /* CrossM
 }
 
 /* shared tail of MoveActor / CrossMoveActor.process_action actor.py:99-114,177-194 */
-__device__ bool try_move(const DevSpec &s, Env &ev, int a, int dr, int dc)
+static __device__ bool try_move(const DevSpec &s, Env &ev, int a, int dr, int dc)
 {
     const int from = ev.cell[a];
     const int r = from / s.W + dr, c = from % s.W + dc;
@@ -290,7 +290,7 @@ __device__ __forceinline__ void decode_move(const DevSpec &s, int a, uint32_t ac
 }
 
 /* move_result as the user's step() sees it (None counts as failure): actor.py:82-114,161-194,208-234 */
-__device__ bool process_move(const DevSpec &s, Env &ev, int a, uint32_t act)
+static __device__ bool process_move(const DevSpec &s, Env &ev, int a, uint32_t act)
 {
     if (!(ev.klass[a] & BGW_AG_MOVING)) return false;
     if (s.move_actor == BGW_MOVE_BOX || s.move_actor == BGW_MOVE_CROSS) {
@@ -333,7 +333,7 @@ __device__ __forceinline__ bool basic_criteria(const DevSpec &s, const Env &ev, 
 /* BinaryAttackActor._determine_attack + AttackActorBaseComponent.process_action (actor.py:455-501,
  * 306-361) followed by the reward lines of TeamBattleSim.step (team_battle_example.py:38-47) for ONE
  * attacker whose `attack` action is 1 (simultaneous_attacks == 1 is enforced at bgw_create). */
-__device__ void exec_attack(const DevSpec &s, Env &ev, int a)
+static __device__ void exec_attack(const DevSpec &s, Env &ev, int a)
 {
     if (!(ev.flags[a] & BGW_ST_ACTIVE)) return;                   /* team_battle_example.py:37 */
     const int R = __ldg(&s.attack_r[a]), n = 2 * R + 1;
@@ -449,7 +449,7 @@ __device__ __forceinline__ void for_attackables(const DevSpec &s, const Env &ev,
  * victims[nv..] and returns the new count.  Draw keys: BGW_SITE_SUBSET, slot = attacker, k = group << 8 | draw#.  The
  * choice without replacement is a partial Fisher-Yates over the candidate list, kept as a sparse map of the
  * displaced positions (k <= BGW_MAX_SIMATT picks), the positions are resolved by walking the region again. */
-__device__ int subset_attackables_dev(const DevSpec &s, const Env &ev, const AttackView &v, int wr0, int wr1, int wc0, int wc1,
+static __device__ int subset_attackables_dev(const DevSpec &s, const Env &ev, const AttackView &v, int wr0, int wr1, int wc0, int wc1,
                                       int enc_only, uint32_t group, int k, uint16_t *victims, int nv)
 {
     int ncand = 0;
@@ -488,7 +488,7 @@ __device__ int subset_attackables_dev(const DevSpec &s, const Env &ev, const Att
 /* <attack actor>._determine_attack (actor.py:455-501 Binary, 521-582 EncodingBased, 601-658 RestrictedSelective,
  * 681-728 Selective) + AttackActorBaseComponent.process_action (:306-361, with the ammo filter :343-351) + the
  * reward lines of TeamBattleSim.step (team_battle_example.py:38-47) for ONE attacker that requested an attack. */
-__device__ void exec_attack_ext(const DevSpec &s, Env &ev, int a)
+static __device__ void exec_attack_ext(const DevSpec &s, Env &ev, int a)
 {
     if (!(ev.flags[a] & BGW_ST_ACTIVE)) return;                   /* team_battle_example.py:37 */
     AttackView v;
@@ -579,7 +579,7 @@ __device__ __forceinline__ uint32_t *slot_of(const DevSpec &s, const Env &ev, in
 /* PacmanSimSimple.step pacman.py:235-303: the baddies' scripted DriftMoveActor actions of this step.  k indexes the
  * script's entries (baddie_20, 36, 156, 157, 159, 161, 162, 206, 222, 328); sc = step_count, o156 = orientation of
  * baddie_156, x159 = the keyed draw that stands in for np.random.randint(0, 5) */
-__device__ void pacman_script(int sc, int o156, uint32_t x159, int move[10])
+static __device__ void pacman_script(int sc, int o156, uint32_t x159, int move[10])
 {
     const int base[10] = {0, 0, 0, 1, 0, 3, 0, 0, 0, 0};
 #pragma unroll
@@ -610,7 +610,7 @@ __device__ void pacman_script(int sc, int o156, uint32_t x159, int move[10])
 
 /* PacmanSimSimple's overlap checks pacman.py:228-239 (with food) and :305-311 (baddies only): true when a baddie ate
  * pacman -- the reference returns from step() at that point */
-__device__ bool pacman_simple_overlaps(const DevSpec &s, Env &ev, int p, bool eat_food)
+static __device__ bool pacman_simple_overlaps(const DevSpec &s, Env &ev, int p, bool eat_food)
 {
     unsigned nx;
     for (unsigned o = ev.head[ev.cell[p]]; o != BGW_NONE16; o = nx) {
@@ -651,7 +651,7 @@ __device__ __forceinline__ void reach_check(const DevSpec &s, Env &ev, int a)
  * phase; only MovingAgents move, a runner that reaches the target leaves the grid, only runners pay the entropy
  * penalty) and TrafficCorridorSimulation.step traffic_corridor.py:46-53 (moves only; +1 while on the own target, no
  * entropy penalty); ranks 0..nrank-1 hold the acting agents (ragent) */
-__device__ void team_battle_step(const DevSpec &s, Env &ev, int nrank, int tid, int T)
+static __device__ void team_battle_step(const DevSpec &s, Env &ev, int nrank, int tid, int T)
 {
     const double *rw = s.reward;
     const bool reach = s.program == BGW_PROG_REACH_TARGET, traffic = s.program == BGW_PROG_TRAFFIC;
@@ -792,7 +792,7 @@ __device__ void team_battle_step(const DevSpec &s, Env &ev, int nrank, int tid, 
 __device__ __forceinline__ bool same_position(const Env &ev, int a, int b) { return ev.cell[a] == ev.cell[b]; }
 
 /* pacman.py:87-92,116-121: (9,0) <-> (9,20) through raw grid.remove / grid.place */
-__device__ void pacman_teleport(const DevSpec &s, Env &ev, int a)
+static __device__ void pacman_teleport(const DevSpec &s, Env &ev, int a)
 {
     const int left = 9 * s.W, right = 9 * s.W + 20;
     const int dst = ev.cell[a] == left ? right : ev.cell[a] == right ? left : -1;
@@ -802,7 +802,7 @@ __device__ void pacman_teleport(const DevSpec &s, Env &ev, int a)
 }
 
 /* pacman.py:94-105,123-131 (iterating a copy of the cell dict == reading `next` before touching the entry) */
-__device__ void pacman_overlaps(const DevSpec &s, Env &ev, int p, bool eat_food)
+static __device__ void pacman_overlaps(const DevSpec &s, Env &ev, int p, bool eat_food)
 {
     if (!(ev.flags[p] & BGW_ST_IN_GRID)) return;
     unsigned nx;
@@ -824,7 +824,7 @@ __device__ void pacman_overlaps(const DevSpec &s, Env &ev, int p, bool eat_food)
 
 /* the rank-order programs run by one thread: maze_navigation.py:25-36, multi_maze_navigation.py:40-48,
  * pacman.py:80-135 */
-__device__ void serial_program_step(const DevSpec &s, Env &ev, int nrank)
+static __device__ void serial_program_step(const DevSpec &s, Env &ev, int nrank)
 {
     const double *rw = s.reward;
 #define ACT(a) ev.act[(size_t)__ldg(&s.learner_of[(a)]) * s.act_words]
@@ -882,7 +882,7 @@ __device__ void serial_program_step(const DevSpec &s, Env &ev, int nrank)
 /* Done components (done.py) and the programs' get_done / get_all_done                               */
 /* ------------------------------------------------------------------------------------------------- */
 /* get_all_done of the sim -> ctr[CTR_ALLDONE]; all threads, ends synchronised */
-__device__ void compute_all_done(const DevSpec &s, Env &ev, int tid, int T)
+static __device__ void compute_all_done(const DevSpec &s, Env &ev, int tid, int T)
 {
     if (s.program == BGW_PROG_MAZE) {                                /* maze_navigation.py:41-42 */
         if (tid == 0) ev.ctr[CTR_ALLDONE] = same_position(ev, s.a_nav, s.a_target);
@@ -960,7 +960,7 @@ __device__ __forceinline__ bool prog_done(const DevSpec &s, const Env &ev, int a
 /* ------------------------------------------------------------------------------------------------- */
 /* np.random.choice over the encodings of a cell's occupants in arrival order (observer.py:131-134,234-236,
  * 240-248); a one-element list needs no draw (keyed stream) */
-__device__ int choose_encoding(const DevSpec &s, const Env &ev, int observer, int cell, int skip)
+static __device__ int choose_encoding(const DevSpec &s, const Env &ev, int observer, int cell, int skip)
 {
     int n = 0;
     for (unsigned o = ev.head[cell]; o != BGW_NONE16; o = ev.next[o]) n += ((int)o != skip);
@@ -1035,7 +1035,7 @@ __device__ __forceinline__ bool obs_chunk_absolute_whole(const DevSpec &s, const
 }
 
 /* 16 consecutive bytes [ch*16, ch*16+16) of learner-agent a's observation row */
-__device__ void obs_chunk(const DevSpec &s, const Env &ev, int a, int ch, const uint32_t *maskp, uint32_t out[4])
+static __device__ void obs_chunk(const DevSpec &s, const Env &ev, int a, int ch, const uint32_t *maskp, uint32_t out[4])
 {
     out[0] = out[1] = out[2] = out[3] = 0;
     if (!(ev.klass[a] & BGW_AG_OBSERVING)) return;                 /* get_obs returns {} observer.py:103,213,301 */
@@ -1090,7 +1090,7 @@ __device__ void obs_chunk(const DevSpec &s, const Env &ev, int a, int ch, const 
 }
 
 /* Observations of the learners listed in plist[0..ne) -> obs rows of this env.  All threads. */
-__device__ void observe_learners(const DevSpec &s, Env &ev, int ne, int8_t *obs_env, int tid, int T)
+static __device__ void observe_learners(const DevSpec &s, Env &ev, int ne, int8_t *obs_env, int tid, int T)
 {
     const int nch = s.nchunks;
     const bool blk = s.n_blk > 0;
@@ -1148,7 +1148,7 @@ __device__ void observe_learners(const DevSpec &s, Env &ev, int ne, int8_t *obs_
 /* AllStepManager.reset / TurnBasedManager.reset -> sim.reset(): PositionState.reset state.py:88-166,
  * HealthState.reset :629-641, OrientationState.reset :666-675, rewards = 0 smart.py:91, done_agents =
  * non-learners all_step_manager.py:41-44.  All threads; ends synchronised with lists built. */
-__device__ void sim_reset(const DevSpec &s, const BgwState &st, Env &ev, int tid, int T)
+static __device__ void sim_reset(const DevSpec &s, const BgwState &st, Env &ev, int tid, int T)
 {
     const int e = ev.e;
     ev.episode = __ldcg(&st.episode[e]) + 1u;
@@ -1257,7 +1257,7 @@ __device__ void sim_reset(const DevSpec &s, const BgwState &st, Env &ev, int tid
 }
 
 /* store the staged agent arrays back to HBM */
-__device__ void store_env(const DevSpec &s, const BgwState &st, const Env &ev, bool with_racc, int tid, int T)
+static __device__ void store_env(const DevSpec &s, const BgwState &st, const Env &ev, bool with_racc, int tid, int T)
 {
     const size_t off = (size_t)ev.e * s.A;
     for (int a = tid; a < s.A; a += T) {
@@ -1269,7 +1269,7 @@ __device__ void store_env(const DevSpec &s, const BgwState &st, const Env &ev, b
 }
 
 /* reset one env and emit its first observations (all_step_manager.py:37-49, turn_based_manager.py:22-32) */
-__device__ void env_reset(const DevSpec &s, const BgwState &st, Env &ev, int8_t *obs_env, int tid, int T)
+static __device__ void env_reset(const DevSpec &s, const BgwState &st, Env &ev, int8_t *obs_env, int tid, int T)
 {
     sim_reset(s, st, ev, tid, T);
     int ne;
@@ -1301,6 +1301,14 @@ __device__ void env_reset(const DevSpec &s, const BgwState &st, Env &ev, int8_t 
 /* ------------------------------------------------------------------------------------------------- */
 extern __shared__ __align__(16) unsigned char bgw_smem[];
 
+/* The library is built from three translation units so that they compile in parallel and a change to one kernel family
+ * does not rebuild the others: bgw.cu (host side, small kernels), bgw_general.cu (bgw_step_kernel instantiations) and
+ * bgw_fastk.cu (bgw_step_fast_kernel instantiations).  The kernel TUs hand their entry points to the host side: */
+typedef void (*GeneralStepFn)(const DevSpec, const BgwState, const uint32_t *, const int16_t *, int8_t *, float *, uint8_t *, uint8_t *);
+GeneralStepFn bgw_general_step_fn(int program, int attack_actor);   /* bgw_general.cu; (-1, -1) = every program and actor in one */
+const void *bgw_fast_step_fn(int shape, int head_elem);              /* bgw_fastk.cu; shape 0 run-time, 1 FastStaticC5, 2 FastStaticC2 */
+
+#ifdef BGW_SMALL_KERNELS   /* non-template kernels: defined in exactly one translation unit (bgw.cu) */
 __global__ void bgw_reset_kernel(const DevSpec s, const BgwState st, const uint8_t *env_mask, int8_t *obs)
 {
     const int e = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
@@ -1313,6 +1321,8 @@ __global__ void bgw_reset_kernel(const DevSpec s, const BgwState st, const uint8
     env_reset(s, st, ev, obs ? obs + (size_t)e * s.L * s.obs_stride : nullptr, tid, T);
     if (tid == 0) st.env_flags[e] = (uint8_t)(ev.ctr[CTR_ERR] ? BGW_ENV_ERROR | BGW_ENV_ALL_DONE : 0);
 }
+
+#endif
 
 /* The step kernel is instantiated per sim program (and, for the team battle, per attack actor): PROG / ATT >= 0 overwrite
  * the corresponding spec fields with compile-time constants, so the dispatch on them folds and every instantiation holds
@@ -1488,6 +1498,7 @@ __device__ __forceinline__ uint32_t sample_action_word(const DevSpec &s, int a, 
     return o;
 }
 
+#ifdef BGW_SMALL_KERNELS
 /* one thread per (env, learner).  The wider attack actions (EncodingBased / RestrictedSelective / Selective): attack
  * byte j draws word j%4 of the Philox block k = 1 + j/4 of the same (env, step, agent) key. */
 __global__ void bgw_sample_actions_kernel(const DevSpec s, const BgwState st, uint32_t *actions)
@@ -1550,3 +1561,4 @@ __global__ void bgw_gather_kernel(int L, int obs_stride, const int8_t *obs, cons
         dst[(size_t)i * nch + ch] = src[(size_t)list[i] * nch + ch];
     }
 }
+#endif  /* BGW_SMALL_KERNELS */

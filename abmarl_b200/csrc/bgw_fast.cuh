@@ -46,6 +46,8 @@ struct FastSpec {
     int uniform_view;         /* view range shared by every observing learner, or -1 */
     int uniform_att;          /* attack range shared by every attacking entity, or -1 */
     int identity_learners;    /* every entity is a learner: learner index == entity index */
+    int can_mix;              /* some encoding may share a cell with a DIFFERENT encoding (overlapping): mixed cells can exist */
+    int acc_lt1;              /* some attacker has attack_accuracy < 1: _basic_criteria draws */
     int grid_ctas;            /* persistent grid size */
     int async_ok;             /* stage the rows with cp.async: 1 = 16-byte chunks (A % 16 == 0), 2 = 8-byte chunks (A % 8 == 0), 0 = plain loads */
     int simd_ok;              /* A % 4 == 0: byte-parallel compaction */
@@ -55,7 +57,8 @@ struct FastSpec {
      * rflag | slot | rkmask | eff | pstate | killrank, and in
      * the (general) reset path racc | avail. */
     int o_enc, o_klass, o_tmp, o_act, o_head, o_cenc, o_rel, o_ragent, o_plist, o_ctr, o_wsum, o_buf, o_scratch;
-    int s_rflag, s_slot, s_rkmask, s_eff, s_pstate, s_killrank, scratch_bytes, smem_bytes;
+    int s_rflag, s_slot, s_rkmask, s_eff, s_pstate, s_killrank, s_touch, scratch_bytes, smem_bytes;
+    int touch_words;          /* words of ONE touch bitmap (power of two; two bitmaps at s_touch) */
     int r_racc, r_avail;      /* reset arena (over cenc | head | scratch, from o_cenc): u16 heads at 0, then racc, avail */
     int head_elem;            /* bytes per list head: 1 when A <= 256, else 2 */
     long long *prof;          /* debug (BGW_PROF_FILE): clock64 at phase boundaries, [cta][8 envs][16 marks] */
@@ -74,11 +77,18 @@ struct FastSpec {
 struct FastLayout {
     int b_cell, b_next, b_flags, buf_bytes;
     int o_enc, o_klass, o_tmp, o_act, o_head, o_cenc, o_rel, o_ragent, o_plist, o_ctr, o_wsum, o_buf, o_scratch;
-    int s_rflag, s_slot, s_rkmask, s_eff, s_pstate, s_killrank, scratch_bytes, smem_bytes;
+    int s_rflag, s_slot, s_rkmask, s_eff, s_pstate, s_killrank, s_touch, touch_words, scratch_bytes, smem_bytes;
     int r_racc, r_avail, head_elem;
 };
 
 __host__ __device__ constexpr int fl_align16(int x) { return (x + 15) & ~15; }
+/* words of one touch bitmap: a bit per cell up to 4096 cells (larger grids alias: only more agents go through the rounds) */
+__host__ __device__ constexpr int fl_touch_words(int HW)
+{
+    int w = 4;
+    while (w * 32 < HW && w < 128) w <<= 1;
+    return w;
+}
 
 __host__ __device__ constexpr FastLayout fast_layout(int A, int L, int HW, int PH, int PW, int slots, int T, int max_enc,
                                                      int hw_words, int identity)
@@ -108,6 +118,8 @@ __host__ __device__ constexpr FastLayout fast_layout(int A, int L, int HW, int P
     y.s_pstate = so; so += fl_align16(L);
     y.s_killrank = so; so += fl_align16(A * 2);
     y.s_slot = so; so += fl_align16(slots * 4);
+    y.touch_words = fl_touch_words(HW);
+    y.s_touch = so; so += 2 * y.touch_words * 4;          /* move phase: cells touched once / more than once */
     y.s_rflag = so; so += fl_align16(A);
     const int actor_bytes = so;
     /* cenc | head | scratch are contiguous: the general reset path uses all three as one arena: u16 heads | racc | avail */
@@ -134,7 +146,7 @@ __host__ __device__ inline void fast_apply_layout(FastSpec &f, const FastLayout 
     f.o_cenc = y.o_cenc; f.o_rel = y.o_rel; f.o_ragent = y.o_ragent; f.o_plist = y.o_plist; f.o_ctr = y.o_ctr;
     f.o_wsum = y.o_wsum; f.o_buf = y.o_buf; f.o_scratch = y.o_scratch;
     f.s_rflag = y.s_rflag; f.s_slot = y.s_slot; f.s_rkmask = y.s_rkmask; f.s_eff = y.s_eff; f.s_pstate = y.s_pstate;
-    f.s_killrank = y.s_killrank; f.scratch_bytes = y.scratch_bytes; f.smem_bytes = y.smem_bytes;
+    f.s_killrank = y.s_killrank; f.s_touch = y.s_touch; f.touch_words = y.touch_words; f.scratch_bytes = y.scratch_bytes; f.smem_bytes = y.smem_bytes;
     f.r_racc = y.r_racc; f.r_avail = y.r_avail; f.head_elem = y.head_elem;
 }
 
@@ -150,6 +162,7 @@ struct FastEnv {
     int8_t *cenc;
     uint16_t *killrank, *eff, *rel;
     uint32_t *rkmask, *act;
+    uint32_t *touch;          /* [2][touch_words]: cells named by one pending move / by more than one (move phase) */
     int *wsum;
 };
 
@@ -175,11 +188,12 @@ __device__ __forceinline__ unsigned fl_first(const FastEnv &fe, int cell, int pi
 }
 
 /* summary of the list that starts at `first` */
-__device__ __forceinline__ int8_t fl_summary(const Env &ev, unsigned first)
+__device__ __forceinline__ int8_t fl_summary(const Env &ev, unsigned first, bool can_mix)
 {
     if (first == BGW_NONE16) return 0;
     const int8_t e = ev.enc[first];
-    for (unsigned o = ev.next[first]; o != BGW_NONE16; o = ev.next[o]) if (ev.enc[o] != e) return (int8_t)BGW_MIXED;
+    if (can_mix)
+        for (unsigned o = ev.next[first]; o != BGW_NONE16; o = ev.next[o]) if (ev.enc[o] != e) return (int8_t)BGW_MIXED;
     return e;
 }
 
@@ -309,7 +323,7 @@ __device__ void fast_exec_attack(const DevSpec &s, const FastSpec &f, Env &ev, F
     const int R = f.uniform_att >= 0 ? f.uniform_att : __ldg(&s.attack_r[a]), n = 2 * R + 1;
     const int own = ev.cell[a];
     const unsigned long long row = __ldg(&s.attack_map[ev.enc[a]]);
-    const double acc = __ldg(&s.accuracy[a]);
+    const double acc = f.acc_lt1 ? __ldg(&s.accuracy[a]) : 1.0;    /* 1.0: the accuracy draws fold away */
     int ncand = 0, v = -1, vcell = 0;                              /* v: the first candidate in scan order */
     for (uint32_t m = mask; m; m &= m - 1) {
         const int b = __ffs(m) - 1, wr = b / n, wc = b - wr * n;
@@ -333,7 +347,7 @@ __device__ void fast_exec_attack(const DevSpec &s, const FastSpec &f, Env &ev, F
     /* actor.py:353-358; HealthAgent.health setter agent.py:192-196 (health stays in HBM, touched only on a hit) */
     set_health(ev, v, __ldcg(&ev.health[v]) - __ldg(&s.strength[a]));
     if (!(ev.flags[v] & BGW_ST_ACTIVE)) {
-        fe.cenc[pad_index(s, f, vcell)] = fl_summary(ev, fl_unlink<HT>(ev, fe, v));
+        fe.cenc[pad_index(s, f, vcell)] = fl_summary(ev, fl_unlink<HT>(ev, fe, v), f.can_mix);
         fe.killrank[v] = (uint16_t)rank;
         atomicAdd(&ev.ctr[CTR_KILLS], 1);
         fe.rflag[v] |= RF_DIED;                                   /* team_battle_example.py:44-47 */
@@ -419,53 +433,77 @@ __device__ uint32_t fast_attack_rounds(const DevSpec &s, const FastSpec &f, Env 
     return epoch;
 }
 
-/* one move: Grid.query through the summary, then remove / place (actor.py:99-114) */
+/* one move: Grid.query through the summary, then remove / place (actor.py:99-114).  The common move -- alone in its
+ * cell, destination empty -- touches no occupant list; its four conditions are loaded and combined without
+ * short-circuit branches. */
 template <typename HT>
-__device__ __forceinline__ void fast_exec_move(const DevSpec &s, const FastSpec &f, Env &ev, FastEnv &fe, int a, int to)
+__device__ __forceinline__ void fast_exec_move(const DevSpec &s, const FastSpec &f, Env &ev, FastEnv &fe, int a, int from, int to)
 {
-    const int from = ev.cell[a], pto = pad_index(s, f, to);
+    const int pto = pad_index(s, f, to);
     const int8_t summary = fe.cenc[pto], me = ev.enc[a];
+    const unsigned fl = ev.flags[a], hd = ((const HT *)fe.head)[from], nx = ev.next[a];
+    if ((summary == 0) & ((fl & BGW_ST_IN_GRID) != 0) & (hd == (unsigned)a) & (nx == BGW_NONE16)) {
+        fe.cenc[pad_index(s, f, from)] = 0;                        /* Grid.remove: the cell is empty again */
+        fe.cenc[pto] = me;                                         /* Grid.place into an empty cell */
+        ((HT *)fe.head)[to] = (HT)a;
+        ev.cell[a] = (uint16_t)to;
+        return;
+    }
     bool ok = true;
     if (summary != 0) {
         const unsigned long long row = __ldg(&s.overlap[me]);
-        if (summary != (int8_t)BGW_MIXED) ok = (row >> summary) & 1ull;
+        if (!f.can_mix || summary != (int8_t)BGW_MIXED) ok = (row >> summary) & 1ull;
         else                                                        /* Grid.query grid.py:81-105 over a mixed cell */
             for (unsigned o = ((const HT *)fe.head)[to]; o != BGW_NONE16; o = ev.next[o])
                 if (!((row >> ev.enc[o]) & 1ull)) { ok = false; break; }
     }
     if (!ok) { fe.rflag[a] |= RF_MOVE_FAIL; return; }
-    if (ev.flags[a] & BGW_ST_IN_GRID) fe.cenc[pad_index(s, f, from)] = fl_summary(ev, fl_unlink<HT>(ev, fe, a));
+    if (fl & BGW_ST_IN_GRID) fe.cenc[pad_index(s, f, from)] = fl_summary(ev, fl_unlink<HT>(ev, fe, a), f.can_mix);
     fl_append<HT>(ev, fe, a, to, summary != 0);
-    const int8_t ns = summary == 0 ? me : (summary == me ? me : (int8_t)BGW_MIXED);
+    /* (without mixed cells a move into an occupied cell is only legal among the mover's own encoding) */
+    const int8_t ns = (!f.can_mix || summary == 0 || summary == me) ? me : (int8_t)BGW_MIXED;
     fe.cenc[pto] = ns;
-    if (ns == (int8_t)BGW_MIXED) ev.ctr[CTR_MIXED] = 1;
+    if (f.can_mix && ns == (int8_t)BGW_MIXED) ev.ctr[CTR_MIXED] = 1;
 }
 
 #define BGW_NO_MOVE 0xFFFFFFFFu
-/* Ordered rounds over the pending movers.  rkmask[i] = (source cell << 16 | destination cell) for a pending rank,
- * BGW_NO_MOVE otherwise (the attack masks are dead by then); each reserves its source and destination cell, the first
- * reservation (table 0, `epoch`) was made by the classification loop.  The first round walks all ranks; its losers
- * are appended to a list and later rounds walk only the list of the round before (two lists in the storage of
- * eff[] / killrank[], both dead by now).  The common move -- alone in its cell, destination empty -- touches no
- * occupant list.  Returns the next unused epoch. */
+/* ---- the move phase -------------------------------------------------------------------------------------------
+ * rkmask[i] = (source cell << 16 | destination cell) for a rank with a pending move, BGW_NO_MOVE otherwise (the attack
+ * masks are dead by then).  A move reads and writes nothing but its source and its destination cell (their occupant
+ * lists and summaries), so a move whose two cells are named by no other pending move commutes with every other move
+ * and needs no ordering at all.  The classification loop marks every named cell in two bit maps (one bit per cell:
+ * named once / named again); after one barrier a mover that finds neither of its cells named twice executes at once,
+ * whatever its rank.  Only the CONTESTED movers (about one in ten on the headline workload) go through the ordered
+ * reservation rounds; being few, they rarely alias in the hashed slot tables (round 1 had every mover reserve two of
+ * 256 slots: half of them lost a round to an alias).  Contested movers are kept in two lists (the storage of eff[] /
+ * killrank[], both dead by now): a round walks the losers of the round before. */
+__device__ __forceinline__ void touch_mark(const FastSpec &f, FastEnv &fe, int cell)
+{
+    const uint32_t bit = 1u << (cell & 31);
+    uint32_t *w = fe.touch + ((cell >> 5) & (f.touch_words - 1));
+    if (atomicOr(w, bit) & bit) atomicOr(w + f.touch_words, bit);
+}
+
+/* Ordered rounds over the n_cur contested movers listed in eff[], each with its first reservation made in table 0
+ * under `epoch` and published by a barrier.  WARP = run by one warp with __syncwarp.  Returns the next unused epoch. */
 template <bool WARP, typename HT>
-__device__ uint32_t fast_move_rounds(const DevSpec &s, const FastSpec &f, Env &ev, FastEnv &fe, int n_act, int pending, uint32_t epoch,
-                                     int tid, int T)
+__device__ uint32_t fast_move_rounds(const DevSpec &s, const FastSpec &f, Env &ev, FastEnv &fe, int n_cur, uint32_t epoch, int tid, int T)
 {
     const int stride = WARP ? 32 : T;
     const SlotTables st = slot_tables(s, ev);
     uint32_t *cur = st.t0, *nxt = st.t1;                           /* this round's table / the next round's */
-    int which = 0, n_cur = -1;                                     /* n_cur -1: walk the ranks themselves */
-    int base0 = 0, base1 = 0;                                      /* the list counters only grow: entries before base are consumed */
+    int which = 0, base0 = 0, base1 = 0;                           /* the list counters only grow: entries before base are consumed */
+    int pending = 1;
     while (pending) {
         const uint32_t tag = epoch << BGW_TAG_SHIFT, next_tag = (epoch - 1u) << BGW_TAG_SHIFT;
-        const int n_it = n_cur < 0 ? n_act : n_cur;
         const uint16_t *walk = which ? fe.killrank : fe.eff;
+        uint16_t *losers = which ? fe.eff : fe.killrank;
+        int *lctr = &ev.ctr[CTR_PA + (which ^ 1)];
+        const int lbase = which ? base0 : base1;
         int lost = 0;
-        for (int x = tid; x < n_it; x += stride) {
-            const int i = n_cur < 0 ? x : walk[x];
+        for (int x = tid; x < n_cur; x += stride) {
+            const int i = walk[x];
             const uint32_t ft = fe.rkmask[i];
-            if (ft == BGW_NO_MOVE) continue;
             const int from = (int)(ft >> 16), to = (int)(ft & 0xFFFFu);
             const uint32_t mine = tag | (uint32_t)i, sf = (uint32_t)from & st.mask, sto = (uint32_t)to & st.mask;
             const uint32_t hf = cur[sf], ht = cur[sto];                 /* both loads in flight, one test */
@@ -473,40 +511,63 @@ __device__ uint32_t fast_move_rounds(const DevSpec &s, const FastSpec &f, Env &e
                 lost = 1;
                 atomicMin(&nxt[sf], next_tag | (uint32_t)i);
                 atomicMin(&nxt[sto], next_tag | (uint32_t)i);
-                if (!WARP) (which ? fe.eff : fe.killrank)[atomicAdd(&ev.ctr[CTR_PA + (which ^ 1)], 1) - (which ? base0 : base1)] = (uint16_t)i;
+                losers[atomicAdd(lctr, 1) - lbase] = (uint16_t)i;
                 continue;
             }
-            const int a = ev.ragent[i], pto = pad_index(s, f, to);
-            /* the common move -- alone in its cell, destination empty -- touches no occupant list; the four conditions
-             * are loaded and combined without short-circuit branches */
-            const int8_t summary = fe.cenc[pto], me = ev.enc[a];
-            const unsigned fl = ev.flags[a], hd = ((const HT *)fe.head)[from], nx = ev.next[a];
-            if ((summary == 0) & ((fl & BGW_ST_IN_GRID) != 0) & (hd == (unsigned)a) & (nx == BGW_NONE16)) {
-                fe.cenc[pad_index(s, f, from)] = 0;                /* Grid.remove: the cell is empty again */
-                fe.cenc[pto] = me;                                 /* Grid.place into an empty cell */
-                ((HT *)fe.head)[to] = (HT)a;
-                ev.cell[a] = (uint16_t)to;
-            } else {
-                fast_exec_move<HT>(s, f, ev, fe, a, to);
-            }
-            fe.rkmask[i] = BGW_NO_MOVE;
+            fast_exec_move<HT>(s, f, ev, fe, ev.ragent[i], from, to);
         }
         if (WARP) { pending = __any_sync(0xFFFFFFFFu, lost); __syncwarp(); }
-        else {
-            pending = __syncthreads_or(lost);
-            if (n_cur >= 0) { if (which) base1 += n_cur; else base0 += n_cur; }   /* the list walked in this round is consumed */
-            n_cur = ev.ctr[CTR_PA + (which ^ 1)] - (which ? base0 : base1);       /* the losers of this round */
-            which ^= 1;
-        }
+        else pending = __syncthreads_or(lost);
+        if (which) base1 += n_cur; else base0 += n_cur;            /* the list walked in this round is consumed */
+        n_cur = *(volatile int *)lctr - lbase;                     /* the losers of this round */
+        which ^= 1;
         { uint32_t *t = cur; cur = nxt; nxt = t; }
         --epoch;
     }
     return epoch;
 }
 
+/* All pending moves of an env (every thread of the CTA; the touch bit maps were filled by the classification loop and
+ * published by a barrier).  Leaves the bit maps clean.  Returns the next unused epoch. */
+template <typename HT>
+__device__ uint32_t fast_move_phase(const DevSpec &s, const FastSpec &f, Env &ev, FastEnv &fe, int n_act, uint32_t epoch, int tid, int T)
+{
+    const SlotTables st = slot_tables(s, ev);
+    const uint32_t *twice = fe.touch + f.touch_words;
+    const uint32_t tw = (uint32_t)f.touch_words - 1u, tag = epoch << BGW_TAG_SHIFT;
+    for (int i = tid; i < n_act; i += T) {
+        const uint32_t ft = fe.rkmask[i];
+        if (ft == BGW_NO_MOVE) continue;
+        const int from = (int)(ft >> 16), to = (int)(ft & 0xFFFFu);
+        const uint32_t c = (twice[((uint32_t)from >> 5) & tw] >> (from & 31)) | (twice[((uint32_t)to >> 5) & tw] >> (to & 31));
+        if (c & 1u) {                                               /* contested: first reservation, into the list */
+            fe.eff[atomicAdd(&ev.ctr[CTR_PA], 1)] = (uint16_t)i;
+            atomicMin(&st.t0[(uint32_t)from & st.mask], tag | (uint32_t)i);
+            atomicMin(&st.t0[(uint32_t)to & st.mask], tag | (uint32_t)i);
+        } else {
+            fast_exec_move<HT>(s, f, ev, fe, ev.ragent[i], from, to);
+        }
+    }
+    __syncthreads();
+    {
+        uint4 *t4 = reinterpret_cast<uint4 *>(fe.touch);
+        for (int w = tid; w < f.touch_words / 2; w += T) t4[w] = make_uint4(0, 0, 0, 0);
+    }
+    const int n_con = ev.ctr[CTR_PA];
+    if (n_con > 0) {                    /* few: one warp runs the rounds (also beyond 32); every thread keeps the same epoch */
+        if (tid < 32) {
+            const uint32_t e2 = fast_move_rounds<true, HT>(s, f, ev, fe, n_con, epoch, tid, T);
+            if (tid == 0) ev.ctr[CTR_EPOCH] = (int)e2;
+        }
+        __syncthreads();
+        return (uint32_t)ev.ctr[CTR_EPOCH];
+    }
+    return epoch;
+}
+
 /* (re)initialise the dense per-cell arrays of this CTA: clean head-detection marks, free reservation slots, empty
  * summary with a -1 border (the list heads need no initialisation: the summary says which are meaningful) */
-__device__ void fast_init_dense(const DevSpec &s, const FastSpec &f, Env &ev, FastEnv &fe, int tid, int T)
+static __device__ void fast_init_dense(const DevSpec &s, const FastSpec &f, Env &ev, FastEnv &fe, int tid, int T)
 {
     const uint4 ones = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
     for (int a = tid; a < s.A; a += T) ev.tmp[a] = 0;
@@ -514,6 +575,8 @@ __device__ void fast_init_dense(const DevSpec &s, const FastSpec &f, Env &ev, Fa
          * reset, whose availability maps share the scratch union) */
         uint4 *s4 = (uint4 *)ev.slot;
         for (int i = tid; i < (s.slot_mask + 1) / 4; i += T) s4[i] = ones;
+        uint4 *t4 = (uint4 *)fe.touch;                             /* touch bit maps of the move phase: clean between envs */
+        for (int i = tid; i < f.touch_words / 2; i += T) t4[i] = make_uint4(0, 0, 0, 0);
     }
     /* summary rows: word cw of an interior row has zeros where its 4 bytes fall inside the grid columns */
     uint32_t *c32 = (uint32_t *)fe.cenc;
@@ -652,7 +715,7 @@ struct FastStaticC5 {
     static constexpr bool is_static = true;
     static constexpr int A = 256, L = 256, H = 64, W = 64, P = 5, PL = 5, PW = 76, PH = 74, obs_stride = 128, nchunks = 8,
                          obs_h = 11, view = 5, move_actor = BGW_MOVE_BOX, ravel = 0, observe_self = 1, done_mask = BGW_DONE_ONE_TEAM,
-                         max_enc = 4, simd_ok = 1, async_ok = 1, slots = 512, T = BGW_STATIC_T, att = 1, identity = 1;
+                         max_enc = 4, simd_ok = 1, async_ok = 1, slots = 256, T = BGW_STATIC_T, att = 1, identity = 1, can_mix = 0, acc_lt1 = 0;
 };
 /* BASELINE configs[1] (examples/rllib_team_battle.py: 8x8 grid, 24 agents in 4 teams, view 3): one warp per env, 32 envs
  * per SM, each at its own place in the code -- the run-time-shape instantiation (9.3 k instructions) spends most of its
@@ -661,7 +724,7 @@ struct FastStaticC2 {
     static constexpr bool is_static = true;
     static constexpr int A = 24, L = 24, H = 8, W = 8, P = 3, PL = 3, PW = 16, PH = 14, obs_stride = 64, nchunks = 4,
                          obs_h = 7, view = 3, move_actor = BGW_MOVE_BOX, ravel = 0, observe_self = 1, done_mask = BGW_DONE_ONE_TEAM,
-                         max_enc = 4, simd_ok = 1, async_ok = 2, slots = 64, T = 32, att = 1, identity = 1;
+                         max_enc = 4, simd_ok = 1, async_ok = 2, slots = 64, T = 32, att = 1, identity = 1, can_mix = 0, acc_lt1 = 0;
 };
 struct FastDynamic { static constexpr bool is_static = false; };
 
@@ -673,7 +736,8 @@ inline bool fast_shape_matches(const DevSpec &q, const FastSpec &f, int threads)
            q.obs_c == 1 && q.move_actor == C::move_actor && q.ravel == C::ravel && q.observe_self == C::observe_self &&
            q.done_mask == C::done_mask && q.max_enc == C::max_enc && f.P == C::P && f.PL == C::PL && f.PW == C::PW &&
            f.PH == C::PH && f.uniform_view == C::view && f.simd_ok == C::simd_ok && f.async_ok == C::async_ok &&
-           q.slot_mask == C::slots - 1 && threads == C::T && f.uniform_att == C::att && f.identity_learners == C::identity;
+           q.slot_mask == C::slots - 1 && threads == C::T && f.uniform_att == C::att && f.identity_learners == C::identity &&
+           f.can_mix == C::can_mix && f.acc_lt1 == C::acc_lt1;
 }
 
 template <typename SHAPE, typename HT>
@@ -690,7 +754,7 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
         s.done_mask = C::done_mask; s.max_enc = C::max_enc; s.n_blk = 0; s.program = BGW_PROG_TEAM_BATTLE;
         s.manager = BGW_MANAGER_ALL_STEP; s.attack_actor = BGW_ATTACK_BINARY; s.hw_words = (C::H * C::W + 31) / 32;
         f.P = C::P; f.PL = C::PL; f.PW = C::PW; f.PH = C::PH; f.uniform_view = C::view; f.simd_ok = C::simd_ok; f.async_ok = C::async_ok;
-        f.uniform_att = C::att; f.identity_learners = C::identity;
+        f.uniform_att = C::att; f.identity_learners = C::identity; f.can_mix = C::can_mix; f.acc_lt1 = C::acc_lt1;
         f.magic_w = (uint32_t)(((1ull << 32) + C::W - 1) / C::W);
         s.slot_mask = C::slots - 1;
         constexpr FastLayout LY = fast_layout(C::A, C::L, C::H * C::W, C::PH, C::PW, C::slots, C::T, C::max_enc, (C::H * C::W + 31) / 32, C::identity);
@@ -698,7 +762,8 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
     }
     int T_ = (int)blockDim.x;
     if constexpr (SHAPE::is_static) T_ = SHAPE::T;
-    const int tid = threadIdx.x, T = T_, lane = tid & 31, warp = tid >> 5, nwarp = T >> 5;
+    const int ptid = threadIdx.x, T = T_, lane = ptid & 31, nwarp = T >> 5;
+    int tid = ptid, warp = ptid >> 5;                      /* rotated per env inside the loop (below) */
     unsigned char *scratch = bgw_smem + f.o_scratch;
     Env ev;
     ev.enc = (int8_t *)(bgw_smem + f.o_enc);
@@ -724,6 +789,7 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
     fe.rkmask = (uint32_t *)(scratch + f.s_rkmask);
     fe.eff = (uint16_t *)(scratch + f.s_eff);
     fe.killrank = (uint16_t *)(scratch + f.s_killrank);
+    fe.touch = (uint32_t *)(scratch + f.s_touch);
     const double *rw = s.reward;
     const int nch = s.nchunks;
 
@@ -778,6 +844,15 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
     } while (0)
     for (; e < s.E; e = en) {
         ++it_no;
+#ifdef BGW_WARP_ROTATION   /* measured: 0.0631 -> 0.0679 ms per step (slower); kept for A/B */
+        /* The warps of a CTA sit on different SM sub-partitions, and an env gives its first warp more to do than the others
+         * (compaction, the ordered rounds of few agents, the first ranks of every loop): measured 3:1 between the
+         * sub-partitions' instruction counts, the busy ones issue-bound while the others idle.  Rotate the roles: the thread
+         * index every phase of this env uses starts at another warp for every env the CTA processes. */
+        tid = ptid + 32 * (it_no % nwarp);
+        if (tid >= T) tid -= T;
+        warp = tid >> 5;
+#endif
         BGW_PROF_MARK(0);
         en = tslot[sl];
         uint32_t tnew = (uint32_t)s.E;                              /* the env after `en`: drawn now, needed next iteration */
@@ -966,7 +1041,7 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
                 if (!ev.tmp[a]) ((HT *)fe.head)[ev.cell[a]] = (HT)a;
                 ev.tmp[a] = 0;
                 const int p = pad_index(s, f, ev.cell[a]);
-                if (fe.cenc[p] != ev.enc[a]) { fe.cenc[p] = (int8_t)BGW_MIXED; ev.ctr[CTR_MIXED] = 1; }
+                if (f.can_mix && fe.cenc[p] != ev.enc[a]) { fe.cenc[p] = (int8_t)BGW_MIXED; ev.ctr[CTR_MIXED] = 1; }
             }
         }
         __syncthreads();
@@ -1017,7 +1092,7 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
                                 if (v < 64u && ((row >> v) & 1ull)) mask |= 1u << k;
                             }
                         }
-                        if (ev.ctr[CTR_MIXED]) {                        /* a mixed cell is always a candidate (the walk decides) */
+                        if (f.can_mix && ev.ctr[CTR_MIXED]) {           /* a mixed cell is always a candidate (the walk decides) */
     #pragma unroll
                             for (int k = 0; k < 9; ++k)
                                 if (((y[k / 3] >> (8 * (k % 3))) & 0xFFu) == (uint32_t)(uint8_t)BGW_MIXED) mask |= 1u << k;
@@ -1043,11 +1118,12 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
             BGW_PROF_MARK(5);
             {
                 const int n_eff = ev.ctr[CTR_NEMIT];
-                if (n_eff > 32) epoch = fast_attack_rounds<false, HT>(s, f, ev, fe, n_eff, epoch, tid, T);
-                else if (n_eff > 0) {                               /* one warp runs the rounds; every thread keeps the same epoch */
-                    uint32_t e2 = epoch;
-                    if (warp == 0) e2 = fast_attack_rounds<true, HT>(s, f, ev, fe, n_eff, epoch, tid, T);
-                    if (tid == 0) ev.ctr[CTR_EPOCH] = (int)e2;
+                if (n_eff > 0) {          /* few agents (an attack action AND a possible victim next to them): one warp runs the
+                                             rounds, also beyond 32 of them; every thread keeps the same epoch */
+                    if (warp == 0) {
+                        const uint32_t e2 = fast_attack_rounds<true, HT>(s, f, ev, fe, n_eff, epoch, tid, T);
+                        if (tid == 0) ev.ctr[CTR_EPOCH] = (int)e2;
+                    }
                     __syncthreads();
                     epoch = (uint32_t)ev.ctr[CTR_EPOCH];
                 }
@@ -1081,25 +1157,15 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
                     if (ft == BGW_NO_MOVE && !ok) fe.rflag[a] |= RF_MOVE_FAIL;
                 }
                 fe.rkmask[i] = ft;
-                if (ft != BGW_NO_MOVE) {                            /* first reservation of the move rounds */
-                    const SlotTables stt = slot_tables(s, ev);
-                    const uint32_t mine = (epoch << BGW_TAG_SHIFT) | (uint32_t)i;
-                    atomicMin(&stt.t0[(ft >> 16) & stt.mask], mine);
-                    atomicMin(&stt.t0[(ft & 0xFFFFu) & stt.mask], mine);
+                if (ft != BGW_NO_MOVE) {                            /* name the two cells of the move (fast_move_phase) */
+                    touch_mark(f, fe, (int)(ft >> 16));
+                    touch_mark(f, fe, (int)(ft & 0xFFFFu));
                     pend = 1;
                 }
             }
             pend = __syncthreads_or(pend);
             BGW_PROF_MARK(7);
-            if (n_act > 32) epoch = fast_move_rounds<false, HT>(s, f, ev, fe, n_act, pend, epoch, tid, T);
-            else {
-                uint32_t e2 = epoch;
-                if (warp == 0) e2 = fast_move_rounds<true, HT>(s, f, ev, fe, n_act, pend, epoch, tid, T);
-                if (tid == 0) ev.ctr[CTR_EPOCH] = (int)e2;
-                __syncthreads();
-                epoch = (uint32_t)ev.ctr[CTR_EPOCH];
-            }
-            if (!pend) --epoch;
+            if (pend) epoch = fast_move_phase<HT>(s, f, ev, fe, n_act, epoch, tid, T);
             BGW_PROF_MARK(8);
 
             /* ---- entropy :58-59, rewards / dones of the acting learners (all_step_manager.py:68-87) -------- */
@@ -1129,7 +1195,7 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
 
         /* ---- observations ------------------------------------------------------------------------------ */
         if (obs_env) {
-            const bool direct = s.observe_self && !ev.ctr[CTR_MIXED];
+            const bool direct = s.observe_self && !(f.can_mix && ev.ctr[CTR_MIXED]);
             const int R = direct ? f.uniform_view : -1;
             switch (R) {
             case 1: fast_obs_rows<1>(s, f, ev, fe, n_act, obs_env, tid, T); break;

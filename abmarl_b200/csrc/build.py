@@ -3,39 +3,67 @@
     python -m abmarl_b200.csrc.build [--force] [--verbose]
 
 In-tree build: the .so sits next to the sources so it travels with the repository snapshot.  nvcc
-cross-compiles without a GPU.  -ffp-contract=off on the host side: the line-of-sight rays of
-bgw_los_mask are (a/b)*t in IEEE float64 (utils.py:45-115); the device side uses explicit _rn intrinsics.
+cross-compiles without a GPU.  Three translation units compiled in parallel (bgw.cu: host side and small kernels,
+bgw_general.cu: the general step kernel's instantiations, bgw_fastk.cu: the specialised kernel's); an object is
+rebuilt when its source, any header of this directory / include/, this script or the variant flags changed.
+-ffp-contract=off on the host side: the line-of-sight rays of bgw_los_mask are (a/b)*t in IEEE float64
+(utils.py:45-115); the device side uses explicit _rn intrinsics.
 """
+import glob
+import hashlib
 import os
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-SRC = os.path.join(HERE, 'bgw.cu')
 OUT = os.path.join(HERE, 'libbgw.so')
-DEPS = [SRC, os.path.join(HERE, 'bgw_dev.cuh'), os.path.join(HERE, 'bgw_fast.cuh'), os.path.join(ROOT, 'include', 'bgw.h'),
-        os.path.join(ROOT, 'include', 'bgw_philox.h'), os.path.abspath(__file__)]
+UNITS = ('bgw.cu', 'bgw_general.cu', 'bgw_fastk.cu')
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 
 
+# headers a unit includes (bgw_general.cu does not see the specialised kernel: editing bgw_fast.cuh leaves it alone)
+UNIT_HEADERS = {'bgw.cu': ('bgw_dev.cuh', 'bgw_fast.cuh', 'bgw_maze.cuh'), 'bgw_general.cu': ('bgw_dev.cuh',),
+                'bgw_fastk.cu': ('bgw_dev.cuh', 'bgw_fast.cuh')}
+
+
+def _headers(unit):
+    return [os.path.join(HERE, h) for h in UNIT_HEADERS[unit]] + sorted(glob.glob(os.path.join(ROOT, 'include', '*.h'))) + [os.path.abspath(__file__)]
+
+
 def build(force=False, verbose=False):
-    if not force and os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(d) for d in DEPS):
-        return OUT
-    cmd = [NVCC, '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
-           '-shared', '-Xcompiler', '-fPIC,-ffp-contract=off,-fno-fast-math', '--fmad=false',
-           '-I', os.path.join(ROOT, 'include'), '-o', OUT, SRC, '-lcudart']
+    out = os.environ.get('BGW_OUT') or OUT
+    flags = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
+             '-Xcompiler', '-fPIC,-ffp-contract=off,-fno-fast-math', '--fmad=false', '-I', os.path.join(ROOT, 'include')]
     if os.environ.get('BGW_PROFILE'):
-        cmd.insert(1, '-DBGW_PROFILE')
-    for d in os.environ.get('BGW_DEFINES', '').split():          # kernel variants for A/B measurements
-        cmd.insert(1, '-D' + d)
-    if os.environ.get('BGW_OUT'):
-        cmd[cmd.index('-o') + 1] = os.environ['BGW_OUT']
+        flags.append('-DBGW_PROFILE')
+    flags += ['-D' + d for d in os.environ.get('BGW_DEFINES', '').split()]          # kernel variants for A/B measurements
+    flags += os.environ.get('BGW_NVCC_FLAGS', '').split()
     if verbose:
-        cmd.insert(1, '-Xptxas=-v')
-        print(' '.join(cmd))
-    subprocess.check_call(cmd)
-    return OUT
+        flags.append('-Xptxas=-v')
+    tag = hashlib.sha1(' '.join(flags).encode()).hexdigest()[:10]                   # objects of different variants do not mix
+    objdir = os.path.join(HERE, '_obj', tag)
+    os.makedirs(objdir, exist_ok=True)
+    jobs = []
+    for u in UNITS:
+        src, obj = os.path.join(HERE, u), os.path.join(objdir, u[:-3] + '.o')
+        newest = max([os.path.getmtime(src)] + [os.path.getmtime(h) for h in _headers(u)])
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < newest:
+            jobs.append([NVCC] + flags + ['-c', src, '-o', obj])
+    objs = [os.path.join(objdir, u[:-3] + '.o') for u in UNITS]
+    if not jobs and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(o) for o in objs):
+        return out
+
+    def run(cmd):
+        if verbose:
+            print(' '.join(cmd), flush=True)
+        subprocess.check_call(cmd)
+
+    with ThreadPoolExecutor(len(UNITS)) as pool:
+        list(pool.map(run, jobs))
+    run([NVCC, '-shared', '-o', out] + objs + ['-lcudart'])
+    return out
 
 
 if __name__ == '__main__':
