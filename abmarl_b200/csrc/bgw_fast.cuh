@@ -345,7 +345,11 @@ __device__ void fast_exec_attack(const DevSpec &s, const FastSpec &f, Env &ev, F
         }
     }
     /* actor.py:353-358; HealthAgent.health setter agent.py:192-196 (health stays in HBM, touched only on a hit) */
-    set_health(ev, v, __ldcg(&ev.health[v]) - __ldg(&s.strength[a]));
+    {   /* the setter clamps health to [0, 1] (here and at reset), so a hit of strength >= 1 leaves 0 whatever the health was:
+         * the common case needs no round trip to L2 on the critical path of the ordered rounds */
+        const double hit = __ldg(&s.strength[a]);
+        set_health(ev, v, hit >= 1.0 ? 0.0 : __ldcg(&ev.health[v]) - hit);
+    }
     if (!(ev.flags[v] & BGW_ST_ACTIVE)) {
         fe.cenc[pad_index(s, f, vcell)] = fl_summary(ev, fl_unlink<HT>(ev, fe, v), f.can_mix);
         fe.killrank[v] = (uint16_t)rank;
