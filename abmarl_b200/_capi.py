@@ -6,7 +6,7 @@ is missing or does not load, importing the engine raises.
 import ctypes as C
 import os
 
-BGW_ABI_VERSION = 3
+BGW_ABI_VERSION = 4
 BGW_MAX_ENCODING = 63
 BGW_MAX_AGENTS = 4096
 BGW_NONE = 0xFFFF
@@ -66,7 +66,7 @@ class BgwDims(C.Structure):
 LAYOUT_POSITION_STATE, LAYOUT_MAZE, LAYOUT_TARGET_BARRIERS_FREE = range(3)
 
 EXPORTS = ('bgw_create', 'bgw_destroy', 'bgw_dims', 'bgw_bind_state', 'bgw_reset', 'bgw_step', 'bgw_generate_layouts',
-           'bgw_maze_layout_host',
+           'bgw_maze_layout_host', 'bgw_use_device_layouts',
            'bgw_sample_actions', 'bgw_step_sampled', 'bgw_rollout_sampled', 'bgw_gather_valid', 'bgw_rng_draw', 'bgw_los_mask', 'bgw_launch_count', 'bgw_last_error',
            'bgw_abi_version')
 
@@ -106,6 +106,8 @@ def load():
     lib.bgw_rng_draw.argtypes = [C.c_uint64] + [C.c_uint32] * 6 + [C.POINTER(C.c_uint32 * 4)]
     lib.bgw_generate_layouts.argtypes = [h, _p, C.c_int, _p]
     lib.bgw_generate_layouts.restype = C.c_int
+    lib.bgw_use_device_layouts.argtypes = [h, C.c_int]
+    lib.bgw_use_device_layouts.restype = C.c_int
     lib.bgw_maze_layout_host.argtypes = [C.POINTER(BgwSpec), C.c_uint32, C.c_uint32, _p]
     lib.bgw_maze_layout_host.restype = C.c_int
     lib.bgw_los_mask.argtypes = [C.c_int, C.c_int, C.c_int, _p]

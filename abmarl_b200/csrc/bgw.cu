@@ -62,9 +62,12 @@ struct BgwEngine {
     bool pdl = true;              /* launch the fast step kernel with programmatic stream serialization */
     bool poisoned = false;        /* a step launch was rejected: the ticket counters are out of step */
     bool chain_ok = false;        /* consecutive launches of bgw_rollout_sampled may be chained per env (bgw_fast.cuh) */
+    bool rollout_fused = true;    /* bgw_rollout_sampled runs a rollout of the specialised kernel in one launch (BGW_ROLLOUT_FUSED=0: one launch per step) */
+    bool use_device_layouts = true;   /* bgw_use_device_layouts(): the caller supplies its own layouts when false */
     uint32_t seq = 0;             /* sequence number of the last fast step launch */
     uint32_t *ticket_ring = nullptr;                /* [BGW_TICKET_RING] device: env ticket counters, one per launch in flight */
-    std::vector<uint32_t> ticket_uses;              /* launches that have drawn from each counter (each draws exactly E) */
+    std::vector<uint32_t> ticket_next;              /* value each counter will have when the launches that used it are done (a launch
+                                                       draws exactly n_tickets + grid tickets) */
     int fast_shape = 0;           /* compile-time shape instantiation of the fast kernel: 0 run-time shapes, 1 FastStaticC5, 2 FastStaticC2 */
     BgwDims dims{};
     BgwState st{};
@@ -497,6 +500,7 @@ int bgw_create(const BgwSpec *sp, int device, bgw_handle *out)
         /* chained launches: nothing may run between two steps (no layout kernel) */
         h->chain_ok = h->pdl && !(h->maze_ok && sp->auto_reset);
         if (const char *t = getenv("BGW_CHAIN")) if (!atoi(t)) h->chain_ok = false;
+        if (const char *t = getenv("BGW_ROLLOUT_FUSED")) h->rollout_fused = atoi(t) != 0;
     }
     dm.device_layouts = h->maze_ok ? 1 : 0;
     dm.threads_per_env = h->fs.enabled ? h->threads_fast : T; dm.envs_per_cta = 1; dm.smem_bytes = h->fs.enabled ? h->fs.smem_bytes : off;
@@ -555,14 +559,17 @@ static void dump_prof(bgw_handle h, void *stream)
 }
 
 static int step_impl(bgw_handle h, const int8_t *actions, int8_t *sampled, const int16_t *order, int8_t *obs, float *reward,
-                     uint8_t *done, uint8_t *all_done, void *stream, bool chained = false)
+                     uint8_t *done, uint8_t *all_done, void *stream, bool chained = false, int n_steps = 1)
 {
     DeviceGuard guard(h->device);
     if (h->fs.enabled) {
         if (h->poisoned) return fail(2, "bgw_step: an earlier step launch failed; the handle cannot be used any more");
-        h->fs.seq = ++h->seq;
         cudaStreamCaptureStatus capture = cudaStreamCaptureStatusNone;
         CUDA_OK(cudaStreamIsCapturing((cudaStream_t)stream, &capture));
+        if (capture != cudaStreamCaptureStatusNone && n_steps != 1) return fail(1, "bgw_step: a captured launch is one manager step");
+        h->fs.seq = h->seq + 1u;                       /* sequence number of this launch's first manager step */
+        h->seq += (uint32_t)n_steps;
+        h->fs.n_tickets = (uint32_t)n_steps * (uint32_t)h->ds.E;
         if (capture != cudaStreamCaptureStatusNone) {
             /* the launch goes into a CUDA graph and will run any number of times with these parameters: no ticket
              * counter (its base would be stale at the second replay) -- CTA c takes envs c, c + grid, ... -- and no
@@ -572,10 +579,11 @@ static int step_impl(bgw_handle h, const int8_t *actions, int8_t *sampled, const
             h->fs.chain = 0; h->fs.ticket = nullptr; h->fs.ticket_base = 0;
         } else {
             h->fs.chain = (chained && h->chain_ok) ? 1 : 0;
-            if (h->ticket_uses.empty()) h->ticket_uses.assign(BGW_TICKET_RING, 0u);
+            if (h->ticket_next.empty()) h->ticket_next.assign(BGW_TICKET_RING, 0u);
             const uint32_t slot = h->fs.seq % BGW_TICKET_RING;
             h->fs.ticket = h->ticket_ring + slot;
-            h->fs.ticket_base = h->ticket_uses[slot]++ * (uint32_t)h->ds.E;
+            h->fs.ticket_base = h->ticket_next[slot];
+            h->ticket_next[slot] += h->fs.n_tickets + (uint32_t)h->fs.grid_ctas;   /* every CTA draws one ticket past the end */
         }
         h->poisoned = true;                            /* until the launch below has been accepted */
         /* Programmatic dependent launch: when the previous operation on the stream is another step launch, the
@@ -637,13 +645,26 @@ int bgw_rollout_sampled(bgw_handle h, int n_steps, int8_t *actions_out, const in
     if (!h->bound) return fail(1, "bgw_rollout_sampled: call bgw_bind_state first");
     if (n_steps < 0) return fail(1, "bgw_rollout_sampled: n_steps < 0");
     if (!actions_out || !reward || !done || !all_done) return fail(1, "bgw_rollout_sampled: actions_out, reward, done and all_done are required");
-    for (int i = 0; i < n_steps; ++i) {
-        /* launches 2..n follow a step launch of this handle directly: they may be chained per env */
-        const int rc = step_impl(h, nullptr, actions_out, order, obs, reward, done, all_done, stream, i > 0);
-        if (rc) return rc;
-        if (h->maze_ok && h->st.layout && h->ds.auto_reset) {      /* next episode's layouts of the envs that just finished */
-            const int rl = bgw_generate_layouts(h, nullptr, 1, stream);
-            if (rl) return rl;
+    const bool layouts_between = h->maze_ok && h->st.layout && h->ds.auto_reset && h->use_device_layouts;
+    cudaStreamCaptureStatus capture = cudaStreamCaptureStatusNone;
+    if (h->fs.enabled) { DeviceGuard guard(h->device); CUDA_OK(cudaStreamIsCapturing((cudaStream_t)stream, &capture)); }
+    if (h->fs.enabled && h->rollout_fused && !layouts_between && capture == cudaStreamCaptureStatusNone) {
+        /* the specialised kernel runs the whole rollout in ONE launch: its CTAs draw (step, env) tickets and an env's step
+         * k + 1 starts as soon as its step k is stamped (bgw_fast.cuh); the per-CTA set-up is paid once per rollout */
+        const int kmax = std::max(1, (int)(0x7FFFFFFFu / (uint32_t)h->ds.E) - 1);
+        for (int i = 0; i < n_steps; i += kmax) {
+            const int rc = step_impl(h, nullptr, actions_out, order, obs, reward, done, all_done, stream, i > 0, std::min(kmax, n_steps - i));
+            if (rc) return rc;
+        }
+    } else {
+        for (int i = 0; i < n_steps; ++i) {
+            /* launches 2..n follow a step launch of this handle directly: they may be chained per env */
+            const int rc = step_impl(h, nullptr, actions_out, order, obs, reward, done, all_done, stream, i > 0 && !layouts_between);
+            if (rc) return rc;
+            if (layouts_between) {                                 /* next episode's layouts of the envs that just finished */
+                const int rl = bgw_generate_layouts(h, nullptr, 1, stream);
+                if (rl) return rl;
+            }
         }
     }
     if (h->fs.enabled && h->fs.prof && getenv("BGW_PROF_LAZY")) dump_prof(h, stream);
@@ -691,6 +712,14 @@ int bgw_generate_layouts(bgw_handle h, const uint8_t *env_mask, int only_done, v
         bgw_layout_kernel<MazeScratch><<<std::min(h->ds.E, sms * 15), 32, 0, (cudaStream_t)stream>>>(h->maze, h->st, h->ds.E, h->ds.env_offset, env_mask, only_done);
     CUDA_OK(cudaGetLastError());
     h->launches += 1;
+    return 0;
+}
+
+int bgw_use_device_layouts(bgw_handle h, int on)
+{
+    if (!h) return fail(1, "bgw_use_device_layouts: null handle");
+    if (on && !h->maze_ok) return fail(1, "bgw_use_device_layouts: this simulation has no device-side layout generator");
+    h->use_device_layouts = on != 0;
     return 0;
 }
 

@@ -66,8 +66,10 @@ struct FastSpec {
     uint32_t *env_seq;        /* [E] sequence number of the last fast step launch that finished this env */
     uint32_t *ticket;         /* this launch's env ticket counter: one of a ring of BGW_TICKET_RING, never reset; NULL: CTA c takes
                                  envs c, c + grid, ... (launches captured into a CUDA graph) */
-    uint32_t ticket_base;     /* value of *ticket before this launch: every launch draws exactly E tickets */
-    uint32_t seq;             /* sequence number of this launch (1, 2, ... per handle) */
+    uint32_t ticket_base;     /* value of *ticket before this launch: every launch draws exactly n_tickets + grid tickets */
+    uint32_t seq;             /* sequence number of the first manager step of this launch (1, 2, ... per handle) */
+    uint32_t n_tickets;       /* manager steps in this launch x E: ticket g is step g / E of env g % E (bgw_rollout_sampled runs a
+                                 whole rollout in ONE launch; bgw_step / bgw_step_sampled: E) */
     int chain;                /* 1: the previous operation on the stream is the fast step launch seq - 1 of the same
                                  rollout (bgw_rollout_sampled): wait per env on env_seq, not for the whole grid */
 };
@@ -104,7 +106,8 @@ __host__ __device__ constexpr FastLayout fast_layout(int A, int L, int HW, int P
     if (!identity) fo += fl_align16(L * 2);
     y.o_act = fo; fo += fl_align16(L * 4);                /* this env's action words (not double-buffered: read or drawn by the attack pre-pass) */
     y.o_ctr = fo; fo += fl_align16(CTR_COUNT * 4);
-    y.o_wsum = fo; fo += fl_align16(16 * 4);             /* [0..1] totals, [2..5] / [8..11] per-warp counts (T <= 128), [12..13] env tickets */
+    y.o_wsum = fo; fo += fl_align16(32 * 4);             /* [0..1] totals, [2..5] / [8..11] per-warp counts (T <= 128), [12..13] env tickets,
+                                                              [16..31] float: this step's reward by RF_* flag combination */
     int bo = 0;
     y.b_cell = bo; bo += fl_align16(A * 2);
     y.b_next = bo; bo += fl_align16(A * 2);
@@ -269,16 +272,19 @@ __device__ __forceinline__ void st_release_u32(uint32_t *p, uint32_t v)
 {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ void chain_wait_env(const FastSpec &f, int e)
+/* has env e been stamped with sequence number `need` (or a later one)? */
+__device__ __forceinline__ bool env_stamped(const FastSpec &f, int e, uint32_t need)
 {
-    if (f.chain) {
-        /* a legitimate wait ends within one launch (tens of microseconds, milliseconds when envs reset); after about ten
-         * seconds of polling something is broken: fail the launch instead of hanging the device */
-        unsigned spins = 0;
-        while ((int32_t)(ld_acquire_u32(f.env_seq + e) - (f.seq - 1u)) < 0) {
-            __nanosleep(64);
-            if (++spins > (1u << 24)) __trap();
-        }
+    return (int32_t)(ld_acquire_u32(f.env_seq + e) - need) >= 0;
+}
+/* wait until it has.  A legitimate wait ends within one env (tens of microseconds, milliseconds when envs reset); after
+ * about ten seconds of polling something is broken: fail the launch instead of hanging the device */
+__device__ __forceinline__ void env_wait_stamp(const FastSpec &f, int e, uint32_t need)
+{
+    unsigned spins = 0;
+    while (!env_stamped(f, e, need)) {
+        __nanosleep(64);
+        if (++spins > (1u << 24)) __trap();
     }
 }
 #define BGW_TSLOT 12          /* wsum[12], wsum[13]: the env after this one / the one after that */
@@ -679,8 +685,14 @@ __device__ void fast_obs_rows(const DevSpec &s, const FastSpec &f, const Env &ev
                     if (d + n <= 64 * g || d >= 64 * (g + 1)) continue;   /* row does not touch this group */
                     const uint32_t *rp = wp + i * pw4;
                     uint32_t x[LW + 1], y[RW];
+#if defined(BGW_EXP_OBS1)          /* timing experiment only (wrong observations): one load per window row */
 #pragma unroll
-                    for (int j = 0; j < LW; ++j) x[j] = rp[j];
+                    for (int j = 0; j < LW; ++j) x[j] = rp[0];
+#else                              /* the last aligned word only where the row reaches into it: a third of the gather's
+                                      shared-memory wavefronts are bank conflicts of 32 unrelated rows, fewer lanes, fewer conflicts */
+#pragma unroll
+                    for (int j = 0; j < LW; ++j) x[j] = (j < LW - 1 || sh + 8 * n > 32 * (LW - 1)) ? rp[j] : 0u;
+#endif
                     x[LW] = 0;
 #pragma unroll
                     for (int j = 0; j < RW; ++j) y[j] = __funnelshift_r(x[j], x[j + 1], sh);
@@ -811,12 +823,27 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
             ev.enc[a] = __ldg(&s.enc[a]); ev.klass[a] = k;
         }
     }
+    /* Tickets: ticket g = manager step g / E of env g % E, g < NT.  A CTA draws all its tickets from the launch's counter
+     * (arrival order); without a counter (a launch captured into a CUDA graph: one step) CTA c takes c, c + grid, ... */
     uint32_t *const tk = f_in.ticket;                      /* this launch's ticket counter */
-    const uint32_t tk_off = gridDim.x - f_in.ticket_base;  /* env = counter value - base + grid size (mod 2^32) */
+    const uint32_t NT = f_in.n_tickets, tbase = f_in.ticket_base;
     int *const tslot = fe.wsum + BGW_TSLOT;
-    /* the env after blockIdx.x: the next ticket, or blockIdx.x + grid when the launch has no ticket counter (a launch
-     * captured into a CUDA graph) */
-    if (tid == 0) tslot[0] = (int)min((unsigned)s.E, tk ? tk_off + atomicAdd(tk, 1u) : blockIdx.x + gridDim.x);
+    if (tid == 0) {
+        const uint32_t g0 = tk ? atomicAdd(tk, 1u) - tbase : blockIdx.x;
+        tslot[0] = (int)min(NT, g0);
+        tslot[1] = (int)((g0 < NT) ? min(NT, tk ? atomicAdd(tk, 1u) - tbase : g0 + gridDim.x) : NT);
+    }
+    if (tid < 16) {
+        /* the reference's float64 sum for every combination of what can happen to an entity in a step, term by term in the
+         * order it adds them (team_battle_example.py:42,47,46,55,59), rounded to the float32 the reward row holds */
+        double r = 0.0;
+        if (tid & RF_ATTACK_FAIL) r += rw[BGW_RW_ATTACK_FAIL];
+        if (tid & RF_KILL) r += rw[BGW_RW_KILL];
+        if (tid & RF_DIED) r += rw[BGW_RW_DIE];
+        if (tid & RF_MOVE_FAIL) r += rw[BGW_RW_MOVE_FAIL];
+        r += rw[BGW_RW_ENTROPY];
+        reinterpret_cast<float *>(fe.wsum + 16)[tid] = (float)r;
+    }
     fast_init_dense(s, f, ev, fe, tid, T);
     /* Programmatic dependent launch (step_impl): everything above is env-independent and may run while the previous
      * step launch is still finishing; nothing of the step state is read or written before this point.  The next
@@ -825,46 +852,62 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (!f_in.chain) asm volatile("griddepcontrol.wait;" ::: "memory");
 
-    int e = blockIdx.x, b = 0;
+    /* (fast_init_dense ended with a barrier: the tickets are visible) */
+    uint32_t g = (uint32_t)tslot[0], gn = 0;
+    int e = 0, kstep = 0, b = 0;
     uint8_t ef_cur = 0, ef_nxt = 0;
     uint32_t step_cur = 0, step_nxt = 0, epi_cur = 0, epi_nxt = 0;
-    if (e < s.E) {
-        chain_wait_env(f_in, e);
+    /* An env's rows may be read once the manager step before has stamped it.  A CTA only ever BLOCKS for the env of its
+     * current ticket, with all its earlier tickets finished: the awaited ticket is smaller than every ticket its holder has
+     * not finished, so the wait-for relation cannot close a cycle, whatever the number of steps in flight.  For the NEXT
+     * ticket (prefetch) a thread merely looks; if the stamp is not there yet it fetches its share of the rows when the
+     * ticket becomes current (`late`, per thread: cp.async groups are per thread). */
+    bool late = false;
+    if (g < NT) {
+        kstep = (int)(g / (uint32_t)s.E); e = (int)(g - (uint32_t)kstep * (uint32_t)s.E);
+        if (f_in.chain || kstep > 0) env_wait_stamp(f_in, e, f_in.seq + (uint32_t)kstep - 1u);
         fast_issue_env(s, f, st, actions, e, bgw_smem + f.o_buf, tid, T);
         ef_cur = __ldcg(&st.env_flags[e]); step_cur = __ldcg(&st.step[e]); epi_cur = __ldcg(&st.episode[e]);
     }
     cp_async_commit();
 
     uint32_t epoch = f_in.epoch0;                         /* tag of the next reservation round (ordered rounds, above) */
-    int it_no = -1, en = 0, sl = 0;
+    int it_no = -1, sl = 1;
     /* end of an env: hand the ticket drawn at its start to the next iteration, and once every thread's stores are
      * behind a barrier, stamp the env (release: the barrier makes the other threads' stores cumulative) */
-#define BGW_END_ENV()                                                         \
-    do {                                                                      \
-        if (tid == 0) tslot[sl ^ 1] = (int)tnew;                              \
-        __syncthreads();                                                      \
-        if (tid == 0) st_release_u32(f_in.env_seq + e, f_in.seq);             \
-        sl ^= 1;                                                              \
+#define BGW_END_ENV()                                                                \
+    do {                                                                             \
+        if (tid == 0) tslot[sl ^ 1] = (int)tnew;                                     \
+        __syncthreads();                                                             \
+        if (tid == 0) st_release_u32(f_in.env_seq + e, f_in.seq + (uint32_t)kstep);   \
+        sl ^= 1;                                                                     \
     } while (0)
-    for (; e < s.E; e = en) {
+    for (; g < NT; g = gn) {
         ++it_no;
 #ifdef BGW_WARP_ROTATION   /* measured: 0.0631 -> 0.0679 ms per step (slower); kept for A/B */
-        /* The warps of a CTA sit on different SM sub-partitions, and an env gives its first warp more to do than the others
-         * (compaction, the ordered rounds of few agents, the first ranks of every loop): measured 3:1 between the
-         * sub-partitions' instruction counts, the busy ones issue-bound while the others idle.  Rotate the roles: the thread
-         * index every phase of this env uses starts at another warp for every env the CTA processes. */
         tid = ptid + 32 * (it_no % nwarp);
         if (tid >= T) tid -= T;
         warp = tid >> 5;
 #endif
         BGW_PROF_MARK(0);
-        en = tslot[sl];
-        uint32_t tnew = (uint32_t)s.E;                              /* the env after `en`: drawn now, needed next iteration */
-        if (tid == 0 && en < s.E) tnew = min((unsigned)s.E, tk ? tk_off + atomicAdd(tk, 1u) : (unsigned)en + gridDim.x);
-        if (en < s.E) {
-            chain_wait_env(f_in, en);
-            fast_issue_env(s, f, st, actions, en, bgw_smem + f.o_buf + (b ^ 1) * f.buf_bytes, tid, T);
-            ef_nxt = __ldcg(&st.env_flags[en]); step_nxt = __ldcg(&st.step[en]); epi_nxt = __ldcg(&st.episode[en]);
+        kstep = (int)(g / (uint32_t)s.E); e = (int)(g - (uint32_t)kstep * (uint32_t)s.E);
+        if (late) {                                                 /* this ticket's rows were not ready when it was `next` */
+            env_wait_stamp(f_in, e, f_in.seq + (uint32_t)kstep - 1u);
+            fast_issue_env(s, f, st, actions, e, bgw_smem + f.o_buf + b * f.buf_bytes, tid, T);
+            ef_cur = __ldcg(&st.env_flags[e]); step_cur = __ldcg(&st.step[e]); epi_cur = __ldcg(&st.episode[e]);
+            cp_async_commit();
+            late = false;
+        }
+        gn = (uint32_t)tslot[sl];
+        uint32_t tnew = NT;                                         /* the ticket after `gn`: drawn now, needed next iteration */
+        if (tid == 0 && gn < NT) tnew = min(NT, tk ? atomicAdd(tk, 1u) - tbase : gn + gridDim.x);
+        if (gn < NT) {
+            const int kn = (int)(gn / (uint32_t)s.E), en = (int)(gn - (uint32_t)kn * (uint32_t)s.E);
+            if ((f_in.chain || kn > 0) && !env_stamped(f_in, en, f_in.seq + (uint32_t)kn - 1u)) late = true;
+            else {
+                fast_issue_env(s, f, st, actions, en, bgw_smem + f.o_buf + (b ^ 1) * f.buf_bytes, tid, T);
+                ef_nxt = __ldcg(&st.env_flags[en]); step_nxt = __ldcg(&st.step[en]); epi_nxt = __ldcg(&st.episode[en]);
+            }
         }
         cp_async_commit();
 
@@ -1175,16 +1218,9 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
             /* ---- entropy :58-59, rewards / dones of the acting learners (all_step_manager.py:68-87) -------- */
             for (int i = tid; i < n_act; i += T) {
                 const int a = ev.ragent[i], l = ev.plist[i];
-                /* the reference's float64 sum, term by term in the order it adds them (:42,:47,:46,:55,:59) */
-                const unsigned rf = fe.rflag[a];
-                double r = 0.0;
-                if (rf & RF_ATTACK_FAIL) r += rw[BGW_RW_ATTACK_FAIL];
-                if (rf & RF_KILL) r += rw[BGW_RW_KILL];
-                if (rf & RF_DIED) r += rw[BGW_RW_DIE];
-                if (rf & RF_MOVE_FAIL) r += rw[BGW_RW_MOVE_FAIL];
-                r += rw[BGW_RW_ENTROPY];
+                const unsigned rf = fe.rflag[a];                     /* (table built once per CTA, above) */
                 const bool dd = prog_done(s, ev, a);
-                rew[l] = (float)r;
+                rew[l] = reinterpret_cast<const float *>(fe.wsum + 16)[rf & 15u];
                 dn[l] = (uint8_t)(BGW_OUT_VALID | (dd ? BGW_OUT_DONE : 0));
                 if (dd) ev.flags[a] |= BGW_ST_DONE_REPORTED; else atomicAdd(&ev.ctr[CTR_REMAINING], 1);
             }

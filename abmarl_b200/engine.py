@@ -34,9 +34,11 @@ class BatchedGridWorld:
         self.lib = K.load()
         self.spec = spec
         self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.index is None:              # 'cuda' without an index: the handle and the tensors must name the same device
+            self.device = torch.device('cuda', torch.cuda.current_device())
         self._c = spec.c_struct()
         h = C.c_void_p()
-        K.check(self.lib.bgw_create(C.byref(self._c), self.device.index or 0, C.byref(h)), self.lib)
+        K.check(self.lib.bgw_create(C.byref(self._c), self.device.index, C.byref(h)), self.lib)
         self._h = h
         d = K.BgwDims()
         K.check(self.lib.bgw_dims(h, C.byref(d)), self.lib)
@@ -90,6 +92,8 @@ class BatchedGridWorld:
     def set_layout(self, layout):
         """[E, A] start cells generated host-side (0xFFFF = leave unplaced); None = PositionState placement.  Explicit
         layouts switch the device-side generator off."""
+        if self.device_layouts:                    # the handle must know too: bgw_rollout_sampled regenerates layouts between its steps otherwise
+            K.check(self.lib.bgw_use_device_layouts(self._h, 0), self.lib)
         self.device_layouts = False
         if layout is None:
             self.state['layout'] = None
@@ -280,6 +284,8 @@ class HostPipeline:
         assert spec.n_envs % shards == 0, "n_envs must divide evenly over the sub-batches"
         self.K, self.Ek = shards, spec.n_envs // shards
         self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device('cuda', torch.cuda.current_device())
         self.engines = [BatchedGridWorld(spec.with_envs(self.Ek, spec.env_offset + k * self.Ek), device=self.device)
                         for k in range(shards)]
         self.streams = [torch.cuda.Stream(self.device) for _ in range(shards)]

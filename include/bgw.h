@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define BGW_ABI_VERSION 3
+#define BGW_ABI_VERSION 4
 #define BGW_MAX_ENCODING 63   /* encodings are bit positions in 64-bit overlap / attack rows */
 #define BGW_MAX_AGENTS 4096   /* Philox slot field (bgw_philox.h)                           */
 #define BGW_MAX_CELLS 65535   /* cell index is u16, 0xFFFF = none                           */
@@ -314,6 +314,12 @@ int bgw_gather_valid(bgw_handle h, const int8_t *obs, const float *reward, const
  * host-side then, abmarl_b200/layouts.py).
  */
 int bgw_generate_layouts(bgw_handle h, const uint8_t *env_mask, int only_done, void *stream);
+
+/* on == 0: the caller supplies BgwState.layout itself (host-generated layouts, state.py:487-527 run elsewhere): the library
+ * never regenerates it, in particular bgw_rollout_sampled does not write the finished envs' next layouts between its steps.
+ * on != 0 (the default when BgwDims.device_layouts is 1): bgw_rollout_sampled does, as a caller of bgw_step would through
+ * bgw_generate_layouts(only_done = 1). */
+int bgw_use_device_layouts(bgw_handle h, int on);
 
 /* The same generator on the host for one (global env, episode): layout[A].  Test / replay hook, like bgw_rng_draw. */
 int bgw_maze_layout_host(const BgwSpec *spec, uint32_t global_env, uint32_t episode, uint16_t *layout);
