@@ -7,9 +7,10 @@ OneTeamRemainingDone, AllStepManager semantics, horizon 200 with auto-reset, ran
 Philox stream; 4096 envs per GPU (env batches shard across GPUs with no data-path collective -> weak scaling;
 NCCL only sums the episode statistics).
 
-One "step" = one manager step of every env on this GPU: one launch of the step kernel in which the keyed random
-policy draws every acting learner's action (actor resolution -> observation -> reward/done); the K timed steps are
-enqueued by bgw_rollout_sampled (= K x bgw_step_sampled, launches chained per env).  An agent-step = one learning agent receiving (obs, reward, done).
+One "step" = one manager step of every env on this GPU, in which the keyed random policy draws every acting learner's
+action (actor resolution -> observation -> reward/done); the K timed steps are enqueued by ONE bgw_rollout_sampled call
+(= K x bgw_step_sampled; on the specialised kernel one launch whose CTAs draw (step, env) tickets).  An agent-step = one
+learning agent receiving (obs, reward, done).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
@@ -36,11 +37,20 @@ WORKLOAD = "synthetic team battle 64x64, 256 agents/env, view 5, horizon 200 (BA
 
 
 def build_spec(n_envs, env_offset, seed=0xB200):
-    from tests import scenarios
-    from abmarl_b200.spec import compile_sim
-    sim = scenarios.build_tb_c5(scenarios.mirror_api())
-    return compile_sim(sim, manager='all_step', n_envs=n_envs, env_offset=env_offset, seed=seed, horizon=200,
-                       auto_reset=True)
+    from abmarl_b200.examples.workloads import headline_spec
+    return headline_spec(n_envs, env_offset, seed=seed)
+
+
+def workload_config(world, envs_per_gpu=ENVS_PER_GPU):
+    """The workload both arms run, as ONE dict (the driver compares the two arms' `config`)."""
+    return {"workload": WORKLOAD, "envs_per_gpu": envs_per_gpu, "agents_per_env": 256, "global_envs": envs_per_gpu * world,
+            "parallelism": f"env-sharded x{world}, no data-path collective",
+            "l2": "working set per step (obs 134 MB + actions/state 10 MB per GPU) exceeds the 126 MB L2"}
+
+
+# the reference itself (pure Python) cannot travel to the GPU box; its single-core figure for this workload was measured in
+# the survey container (BASELINE.md section 2) and is quoted next to the C port's, which is what runs here
+PYTHON_REFERENCE_PER_CORE = {"value": 3.8e3, "unit": "agent-steps/s", "where": "survey container, one core, unmodified reference AllStepManager loop (BASELINE.md section 2); not measured in this run"}
 
 
 class ClockSampler(threading.Thread):
@@ -97,10 +107,10 @@ def cpu_rollout(n_envs, steps, threads, warmup=0):
     from concurrent.futures import ThreadPoolExecutor
     from oracle.oracle import OracleEnv
     from abmarl_b200 import _capi as K
-    shard = max(1, n_envs // threads)
-    envs = [OracleEnv(build_spec(shard, i * shard)) for i in range(threads)]
-    for o in envs:
-        o.reset()
+    threads = max(1, min(threads, n_envs))
+    sizes = [n_envs // threads + (1 if i < n_envs % threads else 0) for i in range(threads)]
+    offs = [sum(sizes[:i]) for i in range(threads)]
+    envs = [OracleEnv(build_spec(sz, off)) for sz, off in zip(sizes, offs)]
 
     def work(o, n):
         before = int(o.state['stats'][:, K.STAT_AGENT_STEPS].sum())
@@ -109,29 +119,34 @@ def cpu_rollout(n_envs, steps, threads, warmup=0):
         return int(o.state['stats'][:, K.STAT_AGENT_STEPS].sum()) - before
 
     with ThreadPoolExecutor(threads) as pool:        # ctypes releases the GIL inside the C calls
+        list(pool.map(lambda o: o.reset(), envs))
         if warmup:
             list(pool.map(lambda o: work(o, warmup), envs))
         t0 = time.perf_counter()
         n = sum(pool.map(lambda o: work(o, steps), envs))
         dt = time.perf_counter() - t0
-    return n, dt, shard * threads
+    return n, dt, n_envs
 
 
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
+    world = int(os.environ.get('WORLD_SIZE', '1'))
     cores = len(os.sched_getaffinity(0))
-    per_step_envs = cores * 16                     # bounded sample: 16 envs per host thread per step
-    n, dt, envs = cpu_rollout(per_step_envs, args.steps, cores, warmup=args.warmup)
+    # the same workload as the GPU arm: every step advances all 4096 envs (sharded over the host threads), starting from the
+    # same reset state; a step is ~0.55 M agent-steps, a few tens of milliseconds on 16 threads
+    n, dt, envs = cpu_rollout(args.envs_per_gpu, args.steps, cores, warmup=args.warmup)
     value = n / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "agent-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i8/f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "envs_per_step": envs},
+        "config": workload_config(world, args.envs_per_gpu),
+        "agent_steps_per_step": n / max(args.steps, 1),
         "cpu_baseline": {"value": value, "unit": "agent-steps/s", "cores": cores, "kind": "port",
-                         "sample": f"oracle C port of the reference loop, {envs} envs x {args.steps} steps on {cores} host threads"},
+                         "sample": f"oracle C port of the reference loop, {envs} envs x {args.steps} steps on {cores} host threads",
+                         "python_reference_per_core": PYTHON_REFERENCE_PER_CORE},
         "e2e": {"value": value, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -216,6 +231,27 @@ def run_ours(args):
     per_step_ms = [a.elapsed_time(b) for a, b in k_ev]
     iso_ms_per_launch = sum(per_step_ms) / ks
     iso_units_per_launch = (agent_steps() - n_iso0) / ks
+    # the call an RL trainer makes: bgw_step with a caller-supplied, device-resident action tensor (one launch per step,
+    # programmatic dependent launches, no fused policy); actions from a pool of pre-drawn random tensors of the same ranges
+    gs = max(1, min(args.given_steps, args.steps))
+    gpool = []
+    for i in range(8):
+        a = torch.zeros((E, L, eng.action_stride), dtype=torch.int8, device=dev)
+        a[..., 0:2] = torch.randint(-1, 2, (E, L, 2), device=dev, dtype=torch.int8)
+        a[..., 2] = torch.randint(0, 2, (E, L), device=dev, dtype=torch.int8)
+        gpool.append(a)
+    for i in range(3):
+        eng.step(gpool[i])
+    barrier()
+    n_g0 = agent_steps()
+    g_beg, g_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g_beg.record(stream)
+    for i in range(gs):
+        eng.step(gpool[i % 8])
+    g_end.record(stream)
+    barrier()
+    given_ms_per_step = g_beg.elapsed_time(g_end) / gs
+    given_units_per_step = (agent_steps() - n_g0) / gs
     if args.dump_steps and rank == 0:
         with open(args.dump_steps, 'w') as fh:
             json.dump(per_step_ms, fh)
@@ -283,53 +319,85 @@ def run_ours(args):
     h2d = E * L * 4
     d2h = d2h_total[0] / e2e_steps
 
+    # ---------------- strong scaling: BASELINE's "4096 envs sharded across 1/2/4/8" -------------------
+    strong = None
+    if world > 1 and E % world == 0:
+        Es = E // world
+        seng = BatchedGridWorld(build_spec(Es, rank * Es), device=dev)
+        seng.reset()
+        seng.rollout_sampled(args.warmup)
+        barrier()
+        s0 = int(seng.stats()[K.STAT_AGENT_STEPS].item())
+        s_beg, s_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        s_beg.record(stream)
+        seng.rollout_sampled(args.steps)
+        s_end.record(stream)
+        barrier()
+        strong = [s_beg.elapsed_time(s_end), int(seng.stats()[K.STAT_AGENT_STEPS].item()) - s0]
+
     # ---------------- reduce over ranks: times = max, counts = sum (NCCL: episode statistics only) ----
-    t = torch.tensor([ms, e2e_ms, kernel_ms], dtype=torch.float64, device=dev)
-    c = torch.tensor([n_dev, n_e2e, launches], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, e2e_ms, kernel_ms, strong[0] if strong else 0.0], dtype=torch.float64, device=dev)
+    c = torch.tensor([n_dev, n_e2e, launches, strong[1] if strong else 0.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
-    ms, e2e_ms, kernel_ms_max = (float(x) for x in t.tolist())
-    n_dev_all, n_e2e_all, launches_all = (float(x) for x in c.tolist())
+    ms, e2e_ms, kernel_ms_max, strong_ms = (float(x) for x in t.tolist())
+    n_dev_all, n_e2e_all, launches_all, strong_n = (float(x) for x in c.tolist())
 
     if rank == 0:
         peak, peak_src = measured_peak()
-        per_launch_ms = kernel_ms / args.steps                              # this rank's step kernel
-        algo_bytes = BYTES_PER_AGENT_STEP * n_dev / args.steps             # per launch, this rank
+        launches_rank = max(1, launches)
+        per_step_ms_rank = kernel_ms / args.steps                           # this rank
+        per_launch_ms = kernel_ms / launches_rank                           # this rank's step kernel, average launch duration
+        algo_bytes = BYTES_PER_AGENT_STEP * n_dev / launches_rank          # algorithmic bytes one launch processes, this rank
         achieved = algo_bytes / (per_launch_ms * 1e-3) / 1e9
-        traffic = None
+        traffic, traffic_src = None, None
         try:
             with open(os.path.join(ROOT, 'profiles', 'step_kernel_traffic.json')) as f:
-                traffic = json.load(f).get('dram_bytes_per_launch')
+                tj = json.load(f)
+                traffic, traffic_src = tj.get('dram_bytes_per_step'), tj.get('source')
         except Exception:
             pass
         line = {
             "metric": METRIC, "value": n_dev_all / (ms * 1e-3), "unit": "agent-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "i8/f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "envs_per_gpu": E, "agents_per_env": L, "global_envs": E * world,
-                       "parallelism": f"env-sharded x{world}, no data-path collective",
-                       "l2": "working set per step (obs 134 MB + actions/state 10 MB per GPU) exceeds the 126 MB L2",
-                       "agent_steps_per_step": n_dev_all / args.steps},
+            "config": workload_config(world, E),
+            "agent_steps_per_step": n_dev_all / args.steps,
             "e2e": {"value": n_e2e_all / (e2e_ms * 1e-3), "unit": "agent-steps/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "api": e2e_api},
             "gpu_launches": int(launches_all),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "bgw_step_fast_kernel (bgw_rollout_sampled: one launch per step)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+            "roofline": {"bound": "hbm",
+                         "kernel": "bgw_step_fast_kernel (bgw_rollout_sampled: the K timed manager steps of all envs in "
+                                   f"{launches_rank} launch(es); its CTAs draw (step, env) tickets)" if not args.per_step_calls else
+                                   "bgw_step_fast_kernel (one bgw_step_sampled launch per step)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic,
+                         "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes_per_agent_step": BYTES_PER_AGENT_STEP,
-                         "kernel_ms_per_launch": per_launch_ms, "kernel_share_of_step": 1.0,
-                         "launch_duration": "timed region (CUDA events) / launches: one step-kernel launch per step, nothing else in the region",
+                         "algorithmic_bytes_per_launch": algo_bytes,
+                         "kernel_ms_per_launch": per_launch_ms, "kernel_ms_per_step": per_step_ms_rank, "kernel_share_of_step": 1.0,
+                         "launch_duration": "timed region (CUDA events on the launching stream) / launches; nothing else is in the region",
                          "kernel_ms_isolated": iso_ms_per_launch,
                          "isolated_achieved": BYTES_PER_AGENT_STEP * iso_units_per_launch / (iso_ms_per_launch * 1e-3) / 1e9,
-                         "isolated_note": f"{ks} further steps, every launch bracketed by its own CUDA events (launches serialised, no overlap of set-up and tail)"},
+                         "isolated_note": f"{ks} further steps, one bgw_step_sampled launch each, every launch bracketed by its own CUDA events (launches serialised, per-CTA set-up and tail exposed)",
+                         "kernel_ms_given_actions": given_ms_per_step,
+                         "given_actions_achieved": BYTES_PER_AGENT_STEP * given_units_per_step / (given_ms_per_step * 1e-3) / 1e9,
+                         "given_actions_note": f"{gs} bgw_step calls with caller-supplied device-resident action tensors (what a trainer calls): one launch per step, no fused policy"},
         }
+        if strong is not None:
+            line["strong"] = {"global_envs": E, "envs_per_gpu": E // world, "ms_per_step": strong_ms / args.steps,
+                              "value": strong_n / (strong_ms * 1e-3), "unit": "agent-steps/s",
+                              "note": "BASELINE configs[4] as written: 4096 envs in total sharded over the GPUs (the weak line above keeps 4096 per GPU); with E/N envs a GPU's resident CTA slots are no longer all filled, the step time is bounded below by one env's latency"}
         if world == 1 and not args.no_cpu:
-            cores = 1
-            n, dt, envs = cpu_rollout(1024, 200, cores)
+            cores = len(os.sched_getaffinity(0))
+            n, dt, envs = cpu_rollout(E, args.cpu_steps, cores, warmup=2)
             line["cpu_baseline"] = {"value": n / dt, "unit": "agent-steps/s", "cores": cores, "kind": "port",
-                                    "sample": f"oracle C port of the reference loop (scalar C, 1 thread), {envs} envs x 200 steps (one full episode) of the same workload, {dt:.1f} s of CPU work"}
+                                    "sample": f"oracle C port of the reference loop (scalar C per thread) on {cores} host threads, {envs} envs x {args.cpu_steps} steps of the same workload from reset, {dt:.1f} s",
+                                    "python_reference_per_core": PYTHON_REFERENCE_PER_CORE}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -348,6 +416,8 @@ def main():
     ap.add_argument('--kernel-steps', type=int, default=1000, help='steps of the second pass that brackets every launch with its own events')
     ap.add_argument('--per-step-calls', action='store_true', help='one bgw_step_sampled call per step instead of bgw_rollout_sampled (A/B)')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--cpu-steps', type=int, default=200, help='steps of the cpu_baseline sample (all host cores, all envs)')
+    ap.add_argument('--given-steps', type=int, default=200, help='bgw_step calls with caller-supplied device actions timed next to the fused rollout')
     ap.add_argument('--e2e-zero-copy', action='store_true', help='e2e: the gather kernel writes the pinned host buffers directly instead of compacting on the device and copying')
     ap.add_argument('--dump-steps', default=None, help='write the per-step kernel times (ms) to this JSON file')
     args = ap.parse_args()
