@@ -30,7 +30,8 @@ ST_ORIENT_SHIFT = 4
 OUT_DONE, OUT_VALID = 1, 2
 ENV_ALL_DONE, ENV_RESET, ENV_TRUNCATED, ENV_ERROR = 1, 2, 4, 8
 STAT_AGENT_STEPS, STAT_EPISODES, STAT_KILLS, STAT_ENV_STEPS = range(4)
-SITE_PLACE, SITE_HEALTH, SITE_ORIENT, SITE_ACC, SITE_SUBSET, SITE_OBS, SITE_ACTION, SITE_MAZE, SITE_AMMO, SITE_SCRIPT = range(10)
+SITE_PLACE, SITE_HEALTH, SITE_ORIENT, SITE_ACC, SITE_SUBSET, SITE_OBS, SITE_ACTION, SITE_MAZE, SITE_AMMO, SITE_SCRIPT, \
+    SITE_ORDER, SITE_PLACE_ORDER = range(12)
 
 _p = C.c_void_p
 
@@ -43,7 +44,8 @@ class BgwSpec(C.Structure):
         ('done_mask', C.c_int32), ('manager', C.c_int32), ('ravel_actions', C.c_int32),
         ('no_overlap_at_reset', C.c_int32), ('stacked_attacks', C.c_int32), ('horizon', C.c_int32),
         ('auto_reset', C.c_int32), ('ammo_observer', C.c_int32), ('layout_kind', C.c_int32), ('layout_target', C.c_int32),
-        ('cluster_barriers', C.c_int32), ('scatter_free_agents', C.c_int32), ('seed', C.c_uint64),
+        ('cluster_barriers', C.c_int32), ('scatter_free_agents', C.c_int32), ('randomize_placement_order', C.c_int32),
+        ('randomize_action_input', C.c_int32), ('reserved0', C.c_int32), ('seed', C.c_uint64),
         ('barrier_encodings', C.c_uint64), ('free_encodings', C.c_uint64), ('reward', C.c_double * BGW_RW_COUNT),
         ('encoding', _p), ('klass', _p), ('role', _p), ('init_row', _p), ('init_col', _p),
         ('init_health', _p), ('init_orient', _p), ('view_range', _p), ('move_range', _p),

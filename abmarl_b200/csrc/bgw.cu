@@ -63,6 +63,8 @@ struct BgwEngine {
     bool poisoned = false;        /* a step launch was rejected: the ticket counters are out of step */
     bool chain_ok = false;        /* consecutive launches of bgw_rollout_sampled may be chained per env (bgw_fast.cuh) */
     bool rollout_fused = true;    /* bgw_rollout_sampled runs a rollout of the specialised kernel in one launch (BGW_ROLLOUT_FUSED=0: one launch per step) */
+    bool randomize_action_input = false;   /* AllStepManager(randomize_action_input): steps without a caller-given order use the keyed one */
+    int16_t *order_buf = nullptr;     /* [E][L] device: the keyed order of the step (bgw_order_kernel) */
     bool use_device_layouts = true;   /* bgw_use_device_layouts(): the caller supplies its own layouts when false */
     uint32_t seq = 0;             /* sequence number of the last fast step launch */
     uint32_t *ticket_ring = nullptr;                /* [BGW_TICKET_RING] device: env ticket counters, one per launch in flight */
@@ -179,6 +181,7 @@ int bgw_create(const BgwSpec *sp, int device, bgw_handle *out)
     d.observer = sp->observer; d.observe_self = sp->observe_self; d.done_mask = sp->done_mask;
     d.manager = sp->manager; d.ravel = sp->ravel_actions; d.no_overlap = sp->no_overlap_at_reset;
     d.stacked = sp->stacked_attacks; d.horizon = sp->horizon; d.auto_reset = sp->auto_reset;
+    d.randomize_placement_order = sp->randomize_placement_order;
     d.seed = sp->seed;
     memcpy(d.reward, sp->reward, sizeof(d.reward));
 
@@ -502,6 +505,15 @@ int bgw_create(const BgwSpec *sp, int device, bgw_handle *out)
         if (const char *t = getenv("BGW_CHAIN")) if (!atoi(t)) h->chain_ok = false;
         if (const char *t = getenv("BGW_ROLLOUT_FUSED")) h->rollout_fused = atoi(t) != 0;
     }
+    if (sp->randomize_action_input) {
+        if (sp->manager != BGW_MANAGER_ALL_STEP) return bail(fail(1, "bgw_create: randomize_action_input is an AllStepManager option (all_step_manager.py:24-35)"));
+        void *pp = nullptr;
+        if ((ce = cudaMalloc(&pp, (size_t)d.E * std::max(L, 1) * sizeof(int16_t))) != cudaSuccess)
+            return bail(fail(2, "bgw_create: order buffer: %s", cudaGetErrorString(ce)));
+        h->allocs.push_back(pp);
+        h->order_buf = (int16_t *)pp;
+        h->randomize_action_input = true;
+    }
     dm.device_layouts = h->maze_ok ? 1 : 0;
     dm.threads_per_env = h->fs.enabled ? h->threads_fast : T; dm.envs_per_cta = 1; dm.smem_bytes = h->fs.enabled ? h->fs.smem_bytes : off;
     *out = h;
@@ -562,6 +574,17 @@ static int step_impl(bgw_handle h, const int8_t *actions, int8_t *sampled, const
                      uint8_t *done, uint8_t *all_done, void *stream, bool chained = false, int n_steps = 1)
 {
     DeviceGuard guard(h->device);
+    if (h->randomize_action_input && !order) {
+        /* all_step_manager.py:62-65: the actions are processed in shuffled order -- the keyed order of this step, written
+         * by bgw_order_kernel (the step kernels skip the learners that are done already) */
+        if (n_steps != 1) return fail(1, "bgw_step: randomize_action_input needs one launch per step");
+        const int L = h->ds.L, P = pow2ceil(std::max(L, 2));
+        bgw_order_kernel<<<h->ds.E, std::min(1024, std::max(32, P / 2)), (size_t)P * sizeof(unsigned long long), (cudaStream_t)stream>>>(h->ds, h->st, P, h->order_buf);
+        CUDA_OK(cudaGetLastError());
+        h->launches += 1;
+        order = h->order_buf;
+        chained = false;                                  /* another kernel sits between this step launch and the one before */
+    }
     if (h->fs.enabled) {
         if (h->poisoned) return fail(2, "bgw_step: an earlier step launch failed; the handle cannot be used any more");
         cudaStreamCaptureStatus capture = cudaStreamCaptureStatusNone;
@@ -648,7 +671,7 @@ int bgw_rollout_sampled(bgw_handle h, int n_steps, int8_t *actions_out, const in
     const bool layouts_between = h->maze_ok && h->st.layout && h->ds.auto_reset && h->use_device_layouts;
     cudaStreamCaptureStatus capture = cudaStreamCaptureStatusNone;
     if (h->fs.enabled) { DeviceGuard guard(h->device); CUDA_OK(cudaStreamIsCapturing((cudaStream_t)stream, &capture)); }
-    if (h->fs.enabled && h->rollout_fused && !layouts_between && capture == cudaStreamCaptureStatusNone) {
+    if (h->fs.enabled && h->rollout_fused && !layouts_between && !(h->randomize_action_input && !order) && capture == cudaStreamCaptureStatusNone) {
         /* the specialised kernel runs the whole rollout in ONE launch: its CTAs draw (step, env) tickets and an env's step
          * k + 1 starts as soon as its step k is stamped (bgw_fast.cuh); the per-CTA set-up is paid once per rollout */
         const int kmax = std::max(1, (int)(0x7FFFFFFFu / (uint32_t)h->ds.E) - 1);

@@ -46,6 +46,7 @@ struct DevSpec {
     int a_script[10];              /* PacmanSimSimple: the agent of the k-th script entry (pacman.py:235-246), -1 = absent */
     int hw_words;                  /* ceil(HW / 32) */
     int n_var;                     /* entities with random placement */
+    int randomize_placement_order; /* PositionState(randomize_placement_order): keyed placement order per episode */
     int tpl_error;
     int slot_mask;                 /* reservation slots - 1 (power of two) */
     int mask_words, mask_batch;    /* LOS scratch of the observation pass */
@@ -1172,24 +1173,53 @@ static __device__ void sim_reset(const DevSpec &s, const BgwState &st, Env &ev, 
         }
         for (int i = tid; i < (s.max_enc + 1) * s.hw_words; i += T) ev.avail[i] = __ldg(&s.tpl_avail[i]);
         if (tid == 0) ev.ctr[CTR_ERR] = s.tpl_error;
-        __syncthreads();
-        build_heads(s, ev, tid, T);
-        /* the placement draws are keyed by the entity, not by the state: all threads precompute them (into the
-         * reward accumulators' storage, zeroed again below) so the serial chain holds no Philox rounds */
+        /* scratch in the reward accumulators' storage (8 A bytes, zeroed again below): 4 A bytes of draws, then the
+         * placement order as uint16 [A] */
         uint32_t *xs = reinterpret_cast<uint32_t *>(ev.racc);
-        for (int vi = tid; vi < s.n_var; vi += T) xs[vi] = dev_draw(s, ev, BGW_SITE_PLACE, (uint32_t)__ldg(&s.var_agents[vi]), 0);
+        uint16_t *ord = reinterpret_cast<uint16_t *>(xs + s.A);
+        if (s.randomize_placement_order) {
+            /* PositionState(randomize_placement_order) state.py:97-101: random.shuffle of the agents dict = the keyed order
+             * of the episode (bgw_philox.h): entity a goes to the rank of (its key, a) among all entities.  The env-independent
+             * template stays valid for which cells the fixed-position entities occupy and which remain available (both do
+             * not depend on the order), but not for the ARRIVAL order inside a shared cell: their lists are rebuilt. */
+            for (int a = tid; a < s.A; a += T) { xs[a] = dev_draw(s, ev, BGW_SITE_PLACE_ORDER, (uint32_t)a, 0); ev.next[a] = BGW_NONE16; }
+            for (int i = tid; i < (s.HW + 1) / 2; i += T) ((uint32_t *)ev.head)[i] = 0xFFFFFFFFu;
+            __syncthreads();
+            for (int a = tid; a < s.A; a += T) {
+                const uint32_t k = xs[a];
+                int rank = 0;
+                for (int b = 0; b < s.A; ++b) { const uint32_t kb = xs[b]; rank += (kb < k) || (kb == k && b < a); }
+                ord[rank] = (uint16_t)a;
+            }
+            __syncthreads();
+            if (tid == 0)
+                for (int i = 0; i < s.A; ++i) {
+                    const int a = ord[i], cell = __ldg(&s.tpl_cell[a]);
+                    if (cell != BGW_NONE16) grid_append(ev, a, cell);
+                }
+            __syncthreads();
+        } else {
+            __syncthreads();
+            build_heads(s, ev, tid, T);
+        }
+        /* the placement draws are keyed by the entity, not by the state: all threads precompute them so the serial chain
+         * holds no Philox rounds */
+        for (int vi = tid; vi < s.n_var; vi += T) { const int a = __ldg(&s.var_agents[vi]); xs[a] = dev_draw(s, ev, BGW_SITE_PLACE, (uint32_t)a, 0); }
         __syncthreads();
         if (tid < 32 && s.n_var > 0) {
-            /* variable-position entities in dict order (state.py:112-114,152-166): uniform choice over the
-             * ascending list of cells still available to the entity's encoding == select the k-th set bit */
+            /* variable-position entities in dict order (state.py:112-114,152-166), or in the episode's shuffled order:
+             * uniform choice over the ascending list of cells still available to the entity's encoding == select the
+             * k-th set bit */
             const int lane = tid, per = (s.hw_words + 31) / 32;
             const int w0 = lane * per, w1 = min(s.hw_words, (lane + 1) * per);
+            const int n_iter = s.randomize_placement_order ? s.A : s.n_var;
             int err = ev.ctr[CTR_ERR];
-            int a_next = __ldg(&s.var_agents[0]);
-            for (int vi = 0; vi < s.n_var; ++vi) {
+            int a_next = s.randomize_placement_order ? (int)ord[0] : (int)__ldg(&s.var_agents[0]);
+            for (int vi = 0; vi < n_iter; ++vi) {
                 const int a = a_next, en = ev.enc[a];
-                if (vi + 1 < s.n_var) a_next = __ldg(&s.var_agents[vi + 1]);
-                const uint32_t x = xs[vi];
+                if (vi + 1 < n_iter) a_next = s.randomize_placement_order ? (int)ord[vi + 1] : (int)__ldg(&s.var_agents[vi + 1]);
+                if (s.randomize_placement_order && __ldg(&s.tpl_cell[a]) != BGW_NONE16) continue;   /* placed with the fixed ones */
+                const uint32_t x = xs[a];
                 uint32_t *av = ev.avail + (size_t)en * s.hw_words;
                 int cnt = 0;
                 for (int w = w0; w < w1; ++w) cnt += __popc(av[w]);
@@ -1525,6 +1555,39 @@ __global__ void bgw_sample_actions_kernel(const DevSpec s, const BgwState st, ui
         else v = bgw_index(x[j & 3], sim + 1);                                                                            /* :669-679 */
         row[(2 + j) >> 2] |= (v & 0xFFu) << (((2 + j) & 3) * 8);
     }
+}
+
+/* AllStepManager(randomize_action_input) all_step_manager.py:62-65 on the device: order[e][0..L) = the learners of env e in
+ * the keyed order of the step about to be taken (include/bgw_philox.h, BGW_SITE_ORDER): sorted by (first Philox word of the
+ * agent's key, agent index).  The step kernels drop the learners already reported done while they walk the row, and the
+ * keyed order of a sub-list is the sub-list of the keyed order, so the row serves whatever subset submits actions.
+ * One CTA per env, bitonic sort of (key << 32 | learner) in shared memory (P = L rounded up to a power of two). */
+__global__ void bgw_order_kernel(const DevSpec s, const BgwState st, int P, int16_t *order)
+{
+    extern __shared__ __align__(16) unsigned long long bgw_order_keys[];
+    const int e = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
+    const uint32_t genv = (uint32_t)(s.env_offset + e), episode = st.episode[e], step = st.step[e] + 1u;
+    for (int l = tid; l < P; l += T) {
+        unsigned long long v = ~0ull;                               /* padding sorts last */
+        if (l < s.L) {
+            const int a = __ldg(&s.agent_of[l]);
+            v = ((unsigned long long)bgw_draw(s.seed, genv, episode, step, BGW_SITE_ORDER, (uint32_t)a, 0) << 32) | (unsigned)l;
+        }
+        bgw_order_keys[l] = v;
+    }
+    __syncthreads();
+    for (int k = 2; k <= P; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < P; i += T) {
+                const int p = i ^ j;
+                if (p > i) {
+                    const unsigned long long x = bgw_order_keys[i], y = bgw_order_keys[p];
+                    if (((i & k) == 0) ? (x > y) : (x < y)) { bgw_order_keys[i] = y; bgw_order_keys[p] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    for (int i = tid; i < s.L; i += T) order[(size_t)e * s.L + i] = (int16_t)(bgw_order_keys[i] & 0xFFFFu);
 }
 
 /* bgw_gather_valid: one CTA per env; rows are claimed with one global atomicAdd per env and copied as 16-byte chunks */

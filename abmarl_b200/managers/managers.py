@@ -30,7 +30,7 @@ class SimulationManager(ABC):
         self.randomize_action_input = bool(randomize_action_input)
         inner = sim.unwrapped if hasattr(sim, 'super_agent_mapping') else sim      # SuperAgentWrapper(sim, mapping)
         self.spec = compile_sim(inner, manager=self._manager, n_envs=n_envs, env_offset=env_offset, seed=seed,
-                                horizon=horizon, auto_reset=auto_reset)
+                                horizon=horizon, auto_reset=auto_reset, randomize_action_input=randomize_action_input)
         self.engine = BatchedGridWorld(self.spec, device=device)
         self.super_view = None
         if hasattr(sim, 'super_agent_mapping'):
@@ -43,8 +43,6 @@ class SimulationManager(ABC):
             from abmarl_b200.layouts import LayoutFeeder
             self._feeder = LayoutFeeder(self.spec)
         self.learner_ids = self.spec.learner_ids
-        self._order_gen = torch.Generator(device='cpu')
-        self._order_gen.manual_seed(int(seed) & 0x7FFFFFFF)
 
     # -- tensors ---------------------------------------------------------------------------------
     @property
@@ -72,9 +70,8 @@ class SimulationManager(ABC):
         `done` carries OUT_VALID for the learners that received (obs, reward, done) this call and OUT_DONE for
         those that are done; rows of learners already reported done are ignored on input (the reference
         asserts they are absent, all_step_manager.py:59-61)."""
-        if order is None and self.randomize_action_input:       # all_step_manager.py:62-65
-            order = torch.stack([torch.randperm(self.engine.L, generator=self._order_gen)
-                                 for _ in range(self.engine.E)]).to(torch.int16)
+        # (randomize_action_input, all_step_manager.py:62-65: the library shuffles on the device -- the keyed order of the
+        # step, BgwSpec.randomize_action_input -- whenever no explicit order is given)
         if order is None and self.super_view is not None:       # SuperAgentWrapper.step: super agents' members first
             order = self.super_view.order
         _, reward, done, all_done = self.engine.step(actions, order)

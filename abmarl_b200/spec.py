@@ -34,7 +34,8 @@ class CompiledSpec:
 
     SCALARS = ('rows', 'cols', 'n_agents', 'n_envs', 'env_offset', 'program', 'move_actor', 'attack_actor',
                'observer', 'observe_self', 'done_mask', 'manager', 'ravel_actions', 'no_overlap_at_reset',
-               'stacked_attacks', 'horizon', 'auto_reset', 'ammo_observer', 'seed')
+               'stacked_attacks', 'horizon', 'auto_reset', 'ammo_observer', 'randomize_placement_order',
+               'randomize_action_input', 'seed')
     TABLES = (('encoding', np.int8), ('klass', np.uint8), ('role', np.uint8), ('init_row', np.int16),
               ('init_col', np.int16), ('init_health', np.float64), ('init_orient', np.uint8),
               ('view_range', np.int16), ('move_range', np.int16), ('attack_range', np.int16),
@@ -125,9 +126,12 @@ def _first(names, table, what):
     raise NotImplementedError(f"no device implementation for this {what}: {sorted(names)}")
 
 
-def compile_sim(sim, manager='all_step', n_envs=1, env_offset=0, seed=0, horizon=0, auto_reset=False):
+def compile_sim(sim, manager='all_step', n_envs=1, env_offset=0, seed=0, horizon=0, auto_reset=False,
+                randomize_action_input=False):
     """Flatten `sim` (reference-style object) into a CompiledSpec."""
     sp = CompiledSpec()
+    if manager == 'all_step_shuffled':                  # scenario shorthand: AllStepManager(randomize_action_input=True)
+        manager, randomize_action_input = 'all_step', True
     names = _mro_names(sim)
     sp.program = _first(names, _PROGRAMS, 'simulation class')
     sp.manager = {'all_step': K.MANAGER_ALL_STEP, 'turn_based': K.MANAGER_TURN_BASED}[manager]
@@ -135,6 +139,8 @@ def compile_sim(sim, manager='all_step', n_envs=1, env_offset=0, seed=0, horizon
     assert sp.rows * sp.cols <= 65535, "grid too large for 16-bit cell indices"
     sp.n_envs, sp.env_offset, sp.seed = int(n_envs), int(env_offset), int(seed) & (2**64 - 1)
     sp.horizon, sp.auto_reset = int(horizon), int(bool(auto_reset))
+    assert not randomize_action_input or manager == 'all_step', "randomize_action_input is an AllStepManager option"
+    sp.randomize_action_input = int(bool(randomize_action_input))    # all_step_manager.py:24-35,62-65
 
     agents = list(sim.agents.values())
     A = len(agents)
@@ -235,12 +241,15 @@ def compile_sim(sim, manager='all_step', n_envs=1, env_offset=0, seed=0, horizon
         sn = _mro_names(state)
         if 'PositionState' in sn:
             sp.no_overlap_at_reset = int(bool(state.no_overlap_at_reset))
-            assert not state.randomize_placement_order, "randomize_placement_order is not on the device path yet"
+            sp.randomize_placement_order = int(bool(state.randomize_placement_order))    # state.py:97-101
             if 'MazePlacementState' in sn or 'TargetBarriersFreePlacementState' in sn:
                 sp.layout_generator = ('maze' if 'MazePlacementState' in sn else 'target_barriers_free', dict(
                     target=index[state.target_agent.id],
                     barrier_encodings=set(state.barrier_encodings), free_encodings=set(state.free_encodings),
                     cluster_barriers=bool(state.cluster_barriers), scatter_free_agents=bool(state.scatter_free_agents)))
+
+    assert not (sp.randomize_placement_order and sp.layout_generator is not None), \
+        "randomize_placement_order with a layout-generating placement state is not supported (the generator places in agent order)"
 
     # ---- program-specific roles and reward constants ----------------------------------------------
     rc = getattr(sim, 'reward_constants', {})

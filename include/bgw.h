@@ -164,6 +164,12 @@ typedef struct BgwSpec {
     int32_t layout_kind;   /* BGW_LAYOUT_*: which placement state builds the start layout of an episode */
     int32_t layout_target; /* target_agent of the placement state (agent index) state.py:200-222, 417-439 */
     int32_t cluster_barriers, scatter_free_agents;   /* state.py:462-485 */
+    int32_t randomize_placement_order;  /* PositionState(randomize_placement_order=) state.py:97-101: the entities are
+                                           placed in the keyed order BGW_SITE_PLACE_ORDER of the episode (bgw_philox.h) */
+    int32_t randomize_action_input;     /* AllStepManager(randomize_action_input=) all_step_manager.py:62-65: without a
+                                           caller-given `order`, bgw_step processes the actions in the keyed order
+                                           BGW_SITE_ORDER of the step */
+    int32_t reserved0;
     uint64_t seed;         /* Philox key */
     uint64_t barrier_encodings, free_encodings;       /* bit e set <=> encoding e in the set, state.py:430-460 */
     double reward[BGW_RW_COUNT];

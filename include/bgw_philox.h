@@ -47,7 +47,13 @@ enum {
     BGW_SITE_ACTION = 6,  /* synthetic random policy (bench / tests)          policies/policy.py:81-92 slot=agent */
     BGW_SITE_MAZE = 7,    /* MazePlacementState                               state.py:529, utils.py:193,198 */
     BGW_SITE_AMMO = 8,    /* ammo filter of process_action                    actor.py:346-350 slot=attacker k=draw# */
-    BGW_SITE_SCRIPT = 9   /* PacmanSimSimple's random baddie move             examples/sim/pacman.py:240 slot=baddie k=0 */
+    BGW_SITE_SCRIPT = 9,  /* PacmanSimSimple's random baddie move             examples/sim/pacman.py:240 slot=baddie k=0 */
+    /* random.shuffle (Python's own generator, not numpy's): the KEYED ORDER of a list of entities sorts them by
+     * (first Philox word of the entity's key, entity index) -- a uniformly random permutation that does not depend on
+     * the order the list had, and whose restriction to a sub-list is the keyed order of the sub-list */
+    BGW_SITE_ORDER = 10,       /* AllStepManager(randomize_action_input) managers/all_step_manager.py:62-65 slot=agent k=0,
+                                  step = the manager step that is being taken */
+    BGW_SITE_PLACE_ORDER = 11  /* PositionState(randomize_placement_order)      state.py:97-101 slot=agent k=0, step 0 */
 };
 
 BGW_HD void bgw_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,

@@ -855,6 +855,23 @@ static void update_available(Ctx *c, uint8_t *avail, int placed)
         if (sp->no_overlap_at_reset || !((row >> e) & 1)) avail[(size_t)e * c->HW + c->cell[placed]] = 0;
 }
 
+/* The keyed order of a list of entities (include/bgw_philox.h): sorted by (first Philox word of the entity's key, entity
+ * index).  Stands for random.shuffle -- state.py:97-101, all_step_manager.py:62-65 -- whose result the replay shim
+ * defines the same way.  Insertion sort: the lists are short and this is the checker, not the product. */
+static void keyed_order(const Ctx *c, uint32_t site, uint32_t step, int *items, int n)
+{
+    uint32_t *key = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)(n + 1));
+    for (int i = 0; i < n; ++i)
+        key[i] = bgw_draw(c->sp->seed, c->genv, c->st->episode[c->env], step, site, (uint32_t)items[i], 0);
+    for (int i = 1; i < n; ++i) {
+        const uint32_t k = key[i]; const int it = items[i];
+        int j = i - 1;
+        while (j >= 0 && (key[j] > k || (key[j] == k && items[j] > it))) { key[j + 1] = key[j]; items[j + 1] = items[j]; --j; }
+        key[j + 1] = k; items[j + 1] = it;
+    }
+    free(key);
+}
+
 static void sim_reset(Ctx *c)
 {
     const BgwSpec *sp = c->sp;
@@ -872,24 +889,31 @@ static void sim_reset(Ctx *c)
     } else {
         uint8_t *avail = (uint8_t *)malloc((size_t)(c->max_enc + 1) * c->HW);
         memset(avail, 1, (size_t)(c->max_enc + 1) * c->HW);     /* _build_available_positions state.py:116-124 */
-        for (int a = 0; a < c->A; ++a) {                        /* state.py:107-109,143-150 */
+        /* placement order: the agents dict, shuffled per episode when asked for (state.py:97-101) */
+        int *ord = (int *)malloc(sizeof(int) * (size_t)c->A);
+        for (int a = 0; a < c->A; ++a) ord[a] = a;
+        if (sp->randomize_placement_order) keyed_order(c, BGW_SITE_PLACE_ORDER, 0, ord, c->A);
+        for (int i = 0; i < c->A; ++i) {                        /* state.py:107-109,143-150 */
+            const int a = ord[i];
             if (sp->init_row[a] < 0) continue;
             const int cell = sp->init_row[a] * c->W + sp->init_col[a];
             if (!grid_place(c, a, cell)) { st->error[c->env] = 1; grid_insert(c, a, cell); }
             update_available(c, avail, a);
         }
-        for (int a = 0; a < c->A; ++a) {                        /* state.py:112-114,152-166 */
+        for (int i = 0; i < c->A; ++i) {                        /* state.py:112-114,152-166 */
+            const int a = ord[i];
             if (sp->init_row[a] >= 0) continue;
             const uint8_t *av = avail + (size_t)sp->encoding[a] * c->HW;
             int n = 0;
-            for (int i = 0; i < c->HW; ++i) n += av[i];
+            for (int j = 0; j < c->HW; ++j) n += av[j];
             if (n == 0) { if (!st->error[c->env]) st->error[c->env] = 2; continue; }   /* RuntimeError :161 */
             int k = (int)bgw_index(draw(c, BGW_SITE_PLACE, (uint32_t)a, 0), (uint32_t)n);
             int cell = 0;
-            for (int i = 0; i < c->HW; ++i) if (av[i] && k-- == 0) { cell = i; break; }
+            for (int j = 0; j < c->HW; ++j) if (av[j] && k-- == 0) { cell = j; break; }
             grid_place(c, a, cell);
             update_available(c, avail, a);
         }
+        free(ord);
         free(avail);
     }
     for (int a = 0; a < c->A; ++a) {
@@ -1030,6 +1054,8 @@ int bgwo_step(const BgwSpec *sp, BgwState *st, const int8_t *actions, const int1
                 const int a = c.agent_of[l];
                 if (!(c.flags[a] & BGW_ST_DONE_REPORTED)) acting[n_act++] = a;
             }
+            /* all_step_manager.py:62-65: the submitted actions in shuffled order (the keyed order of this step) */
+            if (!order && sp->randomize_action_input) keyed_order(&c, BGW_SITE_ORDER, st->step[e], acting, n_act);
             prog_step(&c, acting, n_act, act);                  /* :66 */
             for (int l = 0; l < L; ++l) {                       /* :68-87 */
                 const int a = c.agent_of[l];

@@ -9,6 +9,7 @@ value the engine would draw for the key (seed, env, episode, step, site, slot, k
 include/bgw_philox.h for the mapping.  Nothing in /root/reference is modified.
 """
 import os
+import random
 import sys
 
 import numpy as np
@@ -156,13 +157,31 @@ class PhiloxReplay:
                 self.step = saved_step
         raise RuntimeError(f"unexpected np.random.randint call site: {name}")
 
+    def _shuffle(self, x):
+        """random.shuffle (Python's generator) -> the keyed order of include/bgw_philox.h: the items, which name agents,
+        sorted by (first Philox word of the agent's key, agent index).  In place, like random.shuffle."""
+        f = sys._getframe(1)
+        name, loc = f.f_code.co_name, f.f_locals
+        if name == 'reset' and 'agents' in loc:              # PositionState.reset state.py:97-101: [(id, agent), ...]
+            site, step = K.SITE_PLACE_ORDER, 0
+        elif name == 'step' and 'action_list' in loc:        # AllStepManager.step all_step_manager.py:62-65: [(id, action), ...]
+            site, step = K.SITE_ORDER, self.step
+        else:
+            raise RuntimeError(f"unexpected random.shuffle call site: {name}")
+        saved, self.step = self.step, step
+        try:
+            x.sort(key=lambda item: (self._x(site, self.index[item[0]]), self.index[item[0]]))
+        finally:
+            self.step = saved
+
     def __enter__(self):
-        self._saved = (np.random.uniform, np.random.choice, np.random.randint)
+        self._saved = (np.random.uniform, np.random.choice, np.random.randint, random.shuffle)
         np.random.uniform, np.random.choice, np.random.randint = self._uniform, self._choice, self._randint
+        random.shuffle = self._shuffle
         return self
 
     def __exit__(self, *exc):
-        np.random.uniform, np.random.choice, np.random.randint = self._saved
+        np.random.uniform, np.random.choice, np.random.randint, random.shuffle = self._saved
         return False
 
 

@@ -90,7 +90,8 @@ def check(name, what, t, got, want):
 def record(name, builder, manager, n_steps):
     api = scenarios.reference_api()
     sim = builder(api)
-    mgr = {'all_step': api.managers.AllStepManager, 'turn_based': api.managers.TurnBasedManager}[manager](sim)
+    mgr = {'all_step': api.managers.AllStepManager, 'turn_based': api.managers.TurnBasedManager,
+           'all_step_shuffled': lambda s_: api.managers.AllStepManager(s_, randomize_action_input=True)}[manager](sim)
     spec = compile_sim(sim, manager=manager, n_envs=1, seed=SEED, auto_reset=False)
     ora = OracleEnv(spec)
     L, stride, astride, ammo_off = spec.n_learners, ora.dims.obs_stride, ora.dims.action_stride, ora.dims.ammo_offset

@@ -130,6 +130,40 @@ def build_tb_stacked(api):
         dones={'OneTeamRemainingDone'})
 
 
+def build_tb_shuffled(api):
+    """Keyed shuffles (Python's random.shuffle in the reference): PositionState(randomize_placement_order=True)
+    state.py:97-101 -- with fixed-position agents that share a cell (arrival order = shuffled order), a crowded grid so
+    that the order of the random placements matters -- run under AllStepManager(randomize_action_input=True)
+    all_step_manager.py:62-65 (scenario manager 'all_step_shuffled')."""
+    agents = {}
+    for i in range(22):
+        fixed = {0: (1, 1), 3: (1, 1), 6: (1, 1), 1: (3, 3), 4: (3, 3), 9: (0, 4)}.get(i)
+        ag = api.ex.BattleAgent(id=f'a{i}', encoding=i % 3 + 1, initial_health=None if i % 2 else 1.0,
+                                initial_position=None if fixed is None else np.array(fixed))
+        ag.view_range = 2
+        ag.attack_strength = 0.6
+        agents[ag.id] = ag
+    return api.ex.TeamBattleSim.build_sim(
+        5, 6, agents=agents, overlapping={1: {1}, 2: {2, 3}, 3: {3}},
+        attack_mapping={1: {2, 3}, 2: {1, 3}, 3: {1, 2}}, randomize_placement_order=True,
+        states={'PositionState', 'HealthState'}, observers={'PositionCenteredEncodingObserver'},
+        dones={'OneTeamRemainingDone'})
+
+
+def build_tb_c5_placement_shuffled(api):
+    """The reduced headline shape (the specialised kernel) with shuffled placement order only."""
+    agents = {}
+    for i in range(96):
+        ag = api.ex.BattleAgent(id=f'agent{i}', encoding=i % 4 + 1, initial_health=None)
+        ag.view_range = 5
+        agents[ag.id] = ag
+    overlap, attack = _team_maps(4)
+    return api.ex.TeamBattleSim.build_sim(
+        24, 24, agents=agents, overlapping=overlap, attack_mapping=attack, randomize_placement_order=True,
+        states={'PositionState', 'HealthState'}, observers={'PositionCenteredEncodingObserver'},
+        dones={'OneTeamRemainingDone'})
+
+
 def build_tb_noself(api):
     """observe_self=False (observer.py:238-246) with overlapping teams."""
     agents = {}
@@ -403,6 +437,8 @@ SCENARIOS = {
     'tb_blocking': (build_tb_blocking, 'all_step', 30),
     'tb_stacked': (build_tb_stacked, 'all_step', 25),
     'tb_noself': (build_tb_noself, 'all_step', 25),
+    'tb_shuffled': (build_tb_shuffled, 'all_step_shuffled', 160),
+    'tb_c5_shuffled': (build_tb_c5_placement_shuffled, 'all_step_shuffled', 30),
     'tb_encoding': (build_tb_encoding, 'all_step', 40),
     'tb_encoding_stacked': (build_tb_encoding_stacked, 'all_step', 40),
     'tb_restricted': (build_tb_restricted, 'all_step', 40),

@@ -20,7 +20,8 @@ def test_mirror_spec_equals_reference_spec(mirror, name):
     builder, manager, _ = scenarios.SCENARIOS[name]
     spec = compile_sim(builder(mirror), manager=manager, n_envs=1, seed=int(g['seed']))
     for s in CompiledSpec.SCALARS:
-        assert int(getattr(spec, s)) == int(g['spec_' + s]), s
+        want = int(g['spec_' + s]) if 'spec_' + s in g.files else 0      # (fields newer than the fixture are 0 in it)
+        assert int(getattr(spec, s)) == want, s
     for t, _ in CompiledSpec.TABLES:
         np.testing.assert_array_equal(getattr(spec, t), g['spec_' + t], err_msg=t)
     for t in ('overlap', 'attack_map', 'reward'):

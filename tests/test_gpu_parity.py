@@ -31,6 +31,8 @@ CASES = [
     ('tb_blocking', 48, 100, 40),
     ('tb_stacked', 48, 80, 30),
     ('tb_noself', 48, 80, 30),
+    ('tb_shuffled', 48, 120, 25),            # keyed random.shuffle: placement order + action input order
+    ('tb_c5_shuffled', 24, 90, 30),          # the same on the specialised kernel's shape
     ('tb_encoding', 48, 100, 30),
     ('tb_encoding_stacked', 48, 100, 30),
     ('tb_restricted', 48, 100, 30),
