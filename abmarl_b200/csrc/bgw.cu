@@ -194,6 +194,7 @@ int bgw_create(const BgwSpec *sp, int device, bgw_handle *out)
     for (int a = 0; a < A; ++a) {
         const int e = sp->encoding[a];
         if (e < 1 || e > BGW_MAX_ENCODING) return bail(fail(1, "bgw_create: entity %d has encoding %d, must be 1..%d", a, e, BGW_MAX_ENCODING));
+        if (sp->target && (sp->target[a] < -1 || sp->target[a] >= A)) return bail(fail(1, "bgw_create: entity %d names target %d, must be -1 or an entity index below %d", a, (int)sp->target[a], A));
         if (sp->klass[a] & BGW_AG_LEARNER) { learner_of[a] = (int16_t)agent_of.size(); agent_of.push_back((int16_t)a); }
         if (sp->klass[a] & BGW_AG_BLOCKING) {
             /* static = never moves, never dies, fixed start cell (walls); dynamic blockers are listed first */
@@ -504,6 +505,8 @@ int bgw_create(const BgwSpec *sp, int device, bgw_handle *out)
         h->chain_ok = h->pdl && !(h->maze_ok && sp->auto_reset);
         if (const char *t = getenv("BGW_CHAIN")) if (!atoi(t)) h->chain_ok = false;
         if (const char *t = getenv("BGW_ROLLOUT_FUSED")) h->rollout_fused = atoi(t) != 0;
+        h->fs.wait_limit_ns = 10ull * 1000ull * 1000ull * 1000ull;
+        if (const char *t = getenv("BGW_WAIT_LIMIT_MS")) { const long long v = atoll(t); if (v > 0) h->fs.wait_limit_ns = (unsigned long long)v * 1000000ull; }
     }
     if (sp->randomize_action_input) {
         if (sp->manager != BGW_MANAGER_ALL_STEP) return bail(fail(1, "bgw_create: randomize_action_input is an AllStepManager option (all_step_manager.py:24-35)"));
@@ -587,6 +590,11 @@ static int step_impl(bgw_handle h, const int8_t *actions, int8_t *sampled, const
     }
     if (h->fs.enabled) {
         if (h->poisoned) return fail(2, "bgw_step: an earlier step launch failed; the handle cannot be used any more");
+        {   /* a launch that failed asynchronously (e.g. the bounded stamp wait trapped) leaves a sticky error: find it
+             * before enqueueing more work on top of it (free: no synchronisation) */
+            const cudaError_t pe = cudaPeekAtLastError();
+            if (pe != cudaSuccess) { h->poisoned = true; return fail(2, "bgw_step: an earlier launch failed on the device (%s); the handle cannot be used any more", cudaGetErrorString(pe)); }
+        }
         cudaStreamCaptureStatus capture = cudaStreamCaptureStatusNone;
         CUDA_OK(cudaStreamIsCapturing((cudaStream_t)stream, &capture));
         if (capture != cudaStreamCaptureStatusNone && n_steps != 1) return fail(1, "bgw_step: a captured launch is one manager step");
@@ -670,7 +678,15 @@ int bgw_rollout_sampled(bgw_handle h, int n_steps, int8_t *actions_out, const in
     if (!actions_out || !reward || !done || !all_done) return fail(1, "bgw_rollout_sampled: actions_out, reward, done and all_done are required");
     const bool layouts_between = h->maze_ok && h->st.layout && h->ds.auto_reset && h->use_device_layouts;
     cudaStreamCaptureStatus capture = cudaStreamCaptureStatusNone;
-    if (h->fs.enabled) { DeviceGuard guard(h->device); CUDA_OK(cudaStreamIsCapturing((cudaStream_t)stream, &capture)); }
+    if (h->fs.enabled) {
+        DeviceGuard guard(h->device);
+        CUDA_OK(cudaStreamIsCapturing((cudaStream_t)stream, &capture));
+        if (capture == cudaStreamCaptureStatusNone) {
+            /* the stream's status (no wait): a rollout whose bounded stamp wait trapped must not be followed by another */
+            const cudaError_t qe = cudaStreamQuery((cudaStream_t)stream);
+            if (qe != cudaSuccess && qe != cudaErrorNotReady) { h->poisoned = true; return fail(2, "bgw_rollout_sampled: the stream reports %s; the handle cannot be used any more", cudaGetErrorString(qe)); }
+        }
+    }
     if (h->fs.enabled && h->rollout_fused && !layouts_between && !(h->randomize_action_input && !order) && capture == cudaStreamCaptureStatusNone) {
         /* the specialised kernel runs the whole rollout in ONE launch: its CTAs draw (step, env) tickets and an env's step
          * k + 1 starts as soon as its step k is stamped (bgw_fast.cuh); the per-CTA set-up is paid once per rollout */

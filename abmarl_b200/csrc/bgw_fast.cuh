@@ -70,6 +70,7 @@ struct FastSpec {
     uint32_t seq;             /* sequence number of the first manager step of this launch (1, 2, ... per handle) */
     uint32_t n_tickets;       /* manager steps in this launch x E: ticket g is step g / E of env g % E (bgw_rollout_sampled runs a
                                  whole rollout in ONE launch; bgw_step / bgw_step_sampled: E) */
+    unsigned long long wait_limit_ns;   /* longest legitimate wait for an env's stamp (env_wait_stamp) */
     int chain;                /* 1: the previous operation on the stream is the fast step launch seq - 1 of the same
                                  rollout (bgw_rollout_sampled): wait per env on env_seq, not for the whole grid */
 };
@@ -277,14 +278,27 @@ __device__ __forceinline__ bool env_stamped(const FastSpec &f, int e, uint32_t n
 {
     return (int32_t)(ld_acquire_u32(f.env_seq + e) - need) >= 0;
 }
-/* wait until it has.  A legitimate wait ends within one env (tens of microseconds, milliseconds when envs reset); after
- * about ten seconds of polling something is broken: fail the launch instead of hanging the device */
+/* wait until it has.  A legitimate wait ends within one env (tens of microseconds, milliseconds when envs reset).  The bound is
+ * wall time on the device (%globaltimer, looked at every 1024 polls), not a poll count: under a debugger, compute-sanitizer or a
+ * time-sliced GPU a poll can take arbitrarily long.  When FastSpec.wait_limit_ns (default 10 s, BGW_WAIT_LIMIT_MS) has passed,
+ * something is broken: fail the launch instead of hanging the device (the host then finds the handle poisoned). */
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ void env_wait_stamp(const FastSpec &f, int e, uint32_t need)
 {
     unsigned spins = 0;
+    unsigned long long t0 = 0;
     while (!env_stamped(f, e, need)) {
         __nanosleep(64);
-        if (++spins > (1u << 24)) __trap();
+        if ((++spins & 1023u) == 0) {
+            const unsigned long long now = global_timer_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > f.wait_limit_ns) __trap();
+        }
     }
 }
 #define BGW_TSLOT 12          /* wsum[12], wsum[13]: the env after this one / the one after that */

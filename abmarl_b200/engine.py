@@ -33,6 +33,7 @@ class BatchedGridWorld:
             raise RuntimeError("abmarl_b200 needs a CUDA device: the engine has no CPU fallback")
         self.lib = K.load()
         self.spec = spec
+        self.check_order = True        # validate caller-given `order` rows on every step (a device reduction; switch off in tight loops)
         self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
         if self.device.index is None:              # 'cuda' without an index: the handle and the tensors must name the same device
             self.device = torch.device('cuda', torch.cuda.current_device())
@@ -125,6 +126,8 @@ class BatchedGridWorld:
         if order is not None:
             o = torch.as_tensor(order, dtype=torch.int16, device=self.device).contiguous()
             assert tuple(o.shape) == (self.E, self.L)
+            if __debug__ and self.check_order:       # the kernels index the learner table with these values
+                assert int(o.min()) >= 0 and int(o.max()) < self.L, "order must hold learner indices 0..L-1"
         K.check(self.lib.bgw_step(self._h, actions.data_ptr(), None if o is None else o.data_ptr(),
                                   self.obs.data_ptr(), self.reward.data_ptr(), self.done.data_ptr(),
                                   self.all_done.data_ptr(), self._stream()), self.lib)

@@ -135,8 +135,10 @@ class SimulationManager(ABC):
         reward = eng.reward[env].cpu().numpy()
         flags = int(eng.all_done[env].item())
         obs, rew, dn, info = {}, {}, {}, {}
+        # TurnBasedManager.reset returns the first agent's observation only (turn_based_manager.py:22-32)
+        first = int(eng.state['turn'][env].item()) if after_reset and self._manager == 'turn_based' else None
         for l, agent_id in enumerate(self.learner_ids):
-            if after_reset or (done[l] & K.OUT_VALID):
+            if (after_reset and (first is None or l == first)) or (not after_reset and (done[l] & K.OUT_VALID)):
                 a = self.spec.learner_agents[l]
                 n = 2 * int(self.spec.view_range[a]) + 1
                 o = obs_all[l]

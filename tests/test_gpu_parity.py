@@ -389,6 +389,29 @@ def test_rollout_sampled_equals_separate_steps(mirror, name, n_envs):
         assert torch.equal(a.stats(), b.stats())
 
 
+def test_rollout_keeps_caller_supplied_layouts(mirror):
+    """set_layout() switches the device-side layout generator off in the HANDLE too (bgw_use_device_layouts): a rollout
+    must not overwrite the caller's layout rows between its steps, i.e. rollout_sampled(n) == n x step_sampled()."""
+    from abmarl_b200.engine import BatchedGridWorld
+    from abmarl_b200.layouts import layouts_for
+    builder, manager, _ = scenarios.SCENARIOS['mm_tbf']
+    spec = compile_sim(builder(mirror), manager=manager, n_envs=16, env_offset=3, seed=21, horizon=6, auto_reset=True)
+    a, b = BatchedGridWorld(spec, device='cuda:0'), BatchedGridWorld(spec, device='cuda:0')
+    assert a.device_layouts, "the scenario must be one the device generator supports"
+    rows = layouts_for(spec, list(range(16)), [5] * 16)              # some fixed layout for every episode (episode 5's)
+    for eng in (a, b):
+        eng.set_layout(rows)
+        eng.reset()
+    for n in (3, 9, 14):                                             # horizon 6: every env resets inside the rollouts
+        a.rollout_sampled(n)
+        for _ in range(n):
+            b.step_sampled()
+        for k in ('obs', 'reward', 'done', 'all_done', 'actions'):
+            assert torch.equal(getattr(a, k), getattr(b, k)), (n, k)
+        assert_state_equal(a.state_numpy(), b.state_numpy(), f'rollout {n}')
+        np.testing.assert_array_equal(a.state['layout'].cpu().numpy().view(np.uint16), np.asarray(rows, dtype=np.uint16))
+
+
 def test_step_launch_replayed_from_a_cuda_graph(mirror):
     """A step launch captured into a CUDA graph runs with the parameters of capture time at every replay: the library
     must not bake a ticket base or a chain dependency into it.  Replays, eager steps and chained rollouts mixed on one
