@@ -23,7 +23,7 @@ ATTACK_NONE, ATTACK_BINARY, ATTACK_ENCODING, ATTACK_RESTRICTED, ATTACK_SELECTIVE
 BGW_MAX_VICTIMS, BGW_MAX_SIMATT = 256, 16
 OBS_POSITION_CENTERED, OBS_ABSOLUTE, OBS_STACKED = range(3)
 DONE_ACTIVE, DONE_ONE_TEAM, DONE_TARGET_AGENT, DONE_TARGET_DESTROYED = (1 << i for i in range(4))
-MANAGER_ALL_STEP, MANAGER_TURN_BASED = range(2)
+MANAGER_ALL_STEP, MANAGER_TURN_BASED, MANAGER_DYNAMIC_ORDER = range(3)
 RW_ATTACK_FAIL, RW_KILL, RW_DIE, RW_MOVE_FAIL, RW_ENTROPY, RW_TARGET, RW_EAT_FOOD = range(7)
 ST_ACTIVE, ST_IN_GRID, ST_DONE_REPORTED = 1, 2, 4
 ST_ORIENT_SHIFT = 4
@@ -45,7 +45,7 @@ class BgwSpec(C.Structure):
         ('no_overlap_at_reset', C.c_int32), ('stacked_attacks', C.c_int32), ('horizon', C.c_int32),
         ('auto_reset', C.c_int32), ('ammo_observer', C.c_int32), ('layout_kind', C.c_int32), ('layout_target', C.c_int32),
         ('cluster_barriers', C.c_int32), ('scatter_free_agents', C.c_int32), ('randomize_placement_order', C.c_int32),
-        ('randomize_action_input', C.c_int32), ('reserved0', C.c_int32), ('seed', C.c_uint64),
+        ('randomize_action_input', C.c_int32), ('position_observer', C.c_int32), ('seed', C.c_uint64),
         ('barrier_encodings', C.c_uint64), ('free_encodings', C.c_uint64), ('reward', C.c_double * BGW_RW_COUNT),
         ('encoding', _p), ('klass', _p), ('role', _p), ('init_row', _p), ('init_col', _p),
         ('init_health', _p), ('init_orient', _p), ('view_range', _p), ('move_range', _p),
@@ -62,7 +62,7 @@ class BgwState(C.Structure):
 class BgwDims(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ('n_envs', 'n_agents', 'n_learners', 'obs_h', 'obs_w', 'obs_c',
                                          'obs_stride', 'action_stride', 'threads_per_env', 'envs_per_cta',
-                                         'smem_bytes', 'ammo_offset', 'device_layouts')]
+                                         'smem_bytes', 'ammo_offset', 'device_layouts', 'position_offset')]
 
 
 LAYOUT_POSITION_STATE, LAYOUT_MAZE, LAYOUT_TARGET_BARRIERS_FREE = range(3)

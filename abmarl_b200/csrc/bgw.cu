@@ -270,9 +270,11 @@ int bgw_create(const BgwSpec *sp, int device, bgw_handle *out)
     dm.ammo_offset = -1;
     long long obs_bytes = ncell;
     if (sp->ammo_observer) { dm.ammo_offset = (int)((ncell + 3) / 4 * 4); obs_bytes = dm.ammo_offset + 4; }   /* observer.py:376-413 */
+    dm.position_offset = -1;
+    if (sp->position_observer) { dm.position_offset = (int)((obs_bytes + 3) / 4 * 4); obs_bytes = dm.position_offset + 4; }   /* observer.py:337-373 */
     dm.obs_stride = (int)((obs_bytes + 15) / 16 * 16);
     dm.action_stride = (2 + att_payload + 3) / 4 * 4;
-    d.act_words = dm.action_stride / 4; d.ammo_offset = dm.ammo_offset; d.n_ammo = n_ammo;
+    d.act_words = dm.action_stride / 4; d.ammo_offset = dm.ammo_offset; d.n_ammo = n_ammo; d.position_offset = dm.position_offset;
     d.obs_cells = (int)ncell;
     d.obs_h = dm.obs_h; d.obs_w = dm.obs_w; d.obs_c = dm.obs_c; d.obs_stride = dm.obs_stride; d.nchunks = dm.obs_stride / 16;
 
@@ -406,7 +408,7 @@ int bgw_create(const BgwSpec *sp, int device, bgw_handle *out)
         bool fast = sp->program == BGW_PROG_TEAM_BATTLE && sp->manager == BGW_MANAGER_ALL_STEP &&
                     (sp->move_actor == BGW_MOVE_BOX || sp->move_actor == BGW_MOVE_CROSS) && d.n_blk == 0 &&
                     sp->observer == BGW_OBS_POSITION_CENTERED && sp->attack_actor == BGW_ATTACK_BINARY && n_ammo == 0 &&
-                    !sp->ammo_observer &&
+                    !sp->ammo_observer && !sp->position_observer &&
                     (2 * rmax_att + 1) * (2 * rmax_att + 1) <= 32;
         if (const char *t = getenv("BGW_GENERIC_KERNEL")) if (atoi(t)) fast = false;
         int TF = A <= 32 ? 32 : A <= 64 ? 64 : 96;      /* 3 warps: 10 envs per SM fit (shared memory and registers) */

@@ -53,6 +53,7 @@ struct DevSpec {
     int parallel_actors;           /* 1: reservation rounds (team battle, Box/Cross moves); 0: rank-order loop */
     int act_words;                 /* 32-bit words per learner action row (BgwDims.action_stride / 4) */
     int ammo_offset, n_ammo;       /* AmmoObserver slot in the obs row (-1 none); number of AmmoAgents */
+    int position_offset;           /* AbsolutePositionObserver slot in the obs row (-1 none) */
     int obs_cells;                 /* obs_h * obs_w * obs_c: grid bytes of an obs row */
     const int32_t *init_ammo;
     unsigned long long seed;
@@ -1137,6 +1138,10 @@ static __device__ void observe_learners(const DevSpec &s, Env &ev, int ne, int8_
             obs_chunk(s, ev, a, ch, blk ? ev.mask + (size_t)li * s.mask_words : nullptr, w);
             if (s.ammo_offset >= 0 && ch == (s.ammo_offset >> 4) && (ev.klass[a] & BGW_AG_AMMO) && ev.ammo)   /* AmmoObserver observer.py:406-413 */
                 w[(s.ammo_offset & 15) >> 2] = (uint32_t)ev.ammo[a];
+            if (s.position_offset >= 0 && ch == (s.position_offset >> 4)) {      /* AbsolutePositionObserver observer.py:366-373 */
+                const unsigned cell = ev.cell[a];
+                w[(s.position_offset & 15) >> 2] = (cell / (unsigned)s.W) | ((cell % (unsigned)s.W) << 16);
+            }
             *reinterpret_cast<uint4 *>(obs_env + (size_t)l * s.obs_stride + ch * 16) = make_uint4(w[0], w[1], w[2], w[3]);
         }
         if (blk) __syncthreads();
@@ -1309,6 +1314,10 @@ static __device__ void env_reset(const DevSpec &s, const BgwState &st, Env &ev, 
         __syncthreads();
         if (tid == 0) { st.turn[ev.e] = (int16_t)t; ev.plist[0] = (uint16_t)t; }
         ne = 1;
+    } else if (s.manager == BGW_MANAGER_DYNAMIC_ORDER) {             /* dynamic_order_manager.py:19-28: sim.reset names the first agent */
+        __syncthreads();
+        if (tid == 0) { st.turn[ev.e] = 0; ev.plist[0] = 0; }
+        ne = 1;
     } else {
         for (int l = tid; l < s.L; l += T) ev.plist[l] = (uint16_t)l;
         ne = s.L;
@@ -1390,7 +1399,8 @@ __global__ void __launch_bounds__(256, 3) bgw_step_kernel(const DevSpec s_in,   
 
     /* ---- stage the env ---------------------------------------------------------------------- */
     const size_t off = (size_t)e * s.A;
-    const bool turn_based = s.manager == BGW_MANAGER_TURN_BASED;
+    const bool dynamic = s.manager == BGW_MANAGER_DYNAMIC_ORDER;
+    const bool turn_based = s.manager == BGW_MANAGER_TURN_BASED || dynamic;   /* one acting learner per step: BgwState.turn */
     ev.episode = st.episode[e];
     ev.step = st.step[e] + 1u;
     for (int a = tid; a < s.A; a += T) {
@@ -1451,9 +1461,22 @@ __global__ void __launch_bounds__(256, 3) bgw_step_kernel(const DevSpec s_in,   
         __syncthreads();
         if (tid == 0) {
             int env_done = ev.ctr[CTR_ALLDONE], ne = 0, l = turn;
-            if (env_done) {                                         /* :49-57 */
+            if (env_done) {                                         /* :49-57 (dynamic_order_manager.py:43-51 alike) */
                 for (int k = 0; k < s.L; ++k)
                     if (!(ev.flags[__ldg(&s.agent_of[k])] & BGW_ST_DONE_REPORTED)) ev.plist[ne++] = (uint16_t)k;
+            } else if (dynamic) {
+                /* dynamic_order_manager.py:52-85 over next_agent = [the agent that acted, if this step finished it] + [the next
+                 * agent in dict order that is not done] (examples: DynamicOrderMultiMazeSim.step) */
+                const int a0 = __ldg(&s.agent_of[turn]);
+                if (prog_done(s, ev, a0)) { ev.plist[ne++] = (uint16_t)turn; ev.flags[a0] |= BGW_ST_DONE_REPORTED; }   /* :60-69 (someone is not done: no __all__) */
+                for (int k = 1; k <= s.L; ++k) {
+                    l = (turn + k) % s.L;
+                    const int a = __ldg(&s.agent_of[l]);
+                    if (prog_done(s, ev, a)) continue;                /* the sim's rule skips the agents that are done */
+                    if (!(ev.flags[a] & BGW_ST_DONE_REPORTED)) ev.plist[ne++] = (uint16_t)l;      /* :80-85 */
+                    break;
+                }
+                st.turn[e] = (int16_t)l;
             } else {
                 for (;;) {                                          /* :59-92 */
                     l = (l + 1) % s.L;

@@ -235,6 +235,15 @@ class BatchedGridWorld:
             return None
         return obs[..., off:off + 4].contiguous().view(torch.int32).squeeze(-1)
 
+    def position_view(self, obs=None):
+        """[E, L, 2] int16 (row, col): the AbsolutePositionObserver's 'position' observation stored in the obs rows (None
+        without one)."""
+        obs = self.obs if obs is None else obs
+        off = self.dims.position_offset
+        if off < 0:
+            return None
+        return obs[..., off:off + 4].contiguous().view(torch.int16)
+
     def state_numpy(self):
         """Host copy of the state in the oracle's numpy layout (tests)."""
         out = {}

@@ -2,7 +2,7 @@
 from .sims import (  # noqa: F401
     BattleAgent, TeamBattleSim,
     MazeNavigationAgent, MazeNavigationSim,
-    MultiMazeNavigationAgent, MultiMazeNavigationSim,
+    MultiMazeNavigationAgent, MultiMazeNavigationSim, DynamicOrderMultiMazeSim,
     PacmanAgent, WallAgent, FoodAgent, BaddieAgent, PacmanSim, PacmanSimSimple,
     BarrierAgent, TargetAgent, RunningAgent, ReachTheTargetSim, TargetDone, OnlyAgentLeftDone,
 )

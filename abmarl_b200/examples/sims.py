@@ -10,6 +10,7 @@ step()/get_reward()/get_done()/get_all_done(), and carries that sim's reward con
   ReachTheTargetSim       abmarl/examples/sim/reach_the_target.py:90-176
 """
 from abmarl_b200.sim.gridworld.smart import SmartGridWorldSimulation
+from abmarl_b200.sim.agent_based_simulation import DynamicOrderSimulation
 from abmarl_b200.sim.gridworld.base import GridWorldSimulation
 from abmarl_b200.sim.gridworld.agent import (
     GridObservingAgent, MovingAgent, AttackingAgent, HealthAgent, OrientationAgent, GridWorldAgent,
@@ -82,6 +83,15 @@ class MultiMazeNavigationSim(GridWorldSimulation):
 
     def program(self):
         return 'multi_maze'
+
+
+class DynamicOrderMultiMazeSim(MultiMazeNavigationSim, DynamicOrderSimulation):
+    """A DynamicOrderSimulation over the grid world (the reference ships the manager, managers/dynamic_order_manager.py,
+    but no grid-world sim that uses it): the navigators of MultiMazeNavigationSim take turns, the simulation skips those
+    that have reached the target.  Rule (what the step kernel implements, include/bgw.h BGW_MANAGER_DYNAMIC_ORDER, and what
+    the reference-side twin in tests/scenarios.py spells out in Python): after a step, next_agent = the agent that just
+    acted if that step took it to the target (it expects its last observation, reward and done), followed by the next
+    navigator in dict order that is not at the target; reset names the first navigator."""
 
 
 class PacmanAgent(MovingAgent, OrientationAgent, GridObservingAgent, HealthAgent):

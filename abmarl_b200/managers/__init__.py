@@ -1,2 +1,2 @@
-"""Simulation managers over the batched engine -- mirrors abmarl/managers/{all_step,turn_based}_manager.py."""
-from .managers import SimulationManager, AllStepManager, TurnBasedManager  # noqa: F401
+"""Simulation managers over the batched engine -- mirrors abmarl/managers/{all_step,turn_based,dynamic_order}_manager.py."""
+from .managers import SimulationManager, AllStepManager, TurnBasedManager, DynamicOrderManager  # noqa: F401

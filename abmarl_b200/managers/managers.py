@@ -131,12 +131,14 @@ class SimulationManager(ABC):
         obs_all = eng.obs_view()[env].cpu().numpy().astype(np.int64)
         ammo = eng.ammo_view()
         ammo = None if ammo is None else ammo[env].cpu().numpy()
+        position = eng.position_view()
+        position = None if position is None else position[env].cpu().numpy().astype(np.int64)
         done = eng.done[env].cpu().numpy()
         reward = eng.reward[env].cpu().numpy()
         flags = int(eng.all_done[env].item())
         obs, rew, dn, info = {}, {}, {}, {}
         # TurnBasedManager.reset returns the first agent's observation only (turn_based_manager.py:22-32)
-        first = int(eng.state['turn'][env].item()) if after_reset and self._manager == 'turn_based' else None
+        first = int(eng.state['turn'][env].item()) if after_reset and self._manager in ('turn_based', 'dynamic_order') else None
         for l, agent_id in enumerate(self.learner_ids):
             if (after_reset and (first is None or l == first)) or (not after_reset and (done[l] & K.OUT_VALID)):
                 a = self.spec.learner_agents[l]
@@ -148,6 +150,8 @@ class SimulationManager(ABC):
                 obs[agent_id] = {key: o} if self.spec.klass[a] & K.AG_OBSERVING else {}
                 if ammo is not None and self.spec.klass[a] & K.AG_AMMO:      # AmmoObserver observer.py:406-413
                     obs[agent_id]['ammo'] = int(ammo[l])
+                if position is not None:                                  # AbsolutePositionObserver observer.py:366-373
+                    obs[agent_id]['position'] = position[l]
                 if not after_reset:
                     rew[agent_id] = float(reward[l])
                     dn[agent_id] = bool(done[l] & K.OUT_DONE)
@@ -171,3 +175,22 @@ class TurnBasedManager(SimulationManager):
     def turn(self):
         """int16 [E]: the learner whose action the next step() consumes."""
         return self.engine.state['turn']
+
+
+class DynamicOrderManager(SimulationManager):
+    """dynamic_order_manager.py:7-87: the simulation decides whose turn it is.  `actions[e, turn[e]]` is read; the step
+    reports the agents the simulation names next (the one that just finished, if any, and the next one that is not
+    done), or every agent not yet reported once the simulation is done."""
+    _manager = 'dynamic_order'
+
+    def __init__(self, sim, **kwargs):
+        from abmarl_b200.sim import DynamicOrderSimulation
+        assert isinstance(sim, DynamicOrderSimulation), \
+            "To use the DynamicOrderManager, the simulation must be a DynamicOrderSimulation."
+        super().__init__(sim, **kwargs)
+
+    @property
+    def turn(self):
+        """int16 [E]: the learner whose action the next step() consumes (the not-done agent the simulation named)."""
+        return self.engine.state['turn']
+

@@ -178,3 +178,25 @@ class AgentBasedSimulation(ABC):
     @abstractmethod
     def program(self):
         """Which built-in device program reproduces this sim's step()/get_* (BGW_PROG_*)."""
+
+
+class DynamicOrderSimulation(AgentBasedSimulation):
+    """agent_based_simulation.py:297-317: an AgentBasedSimulation where the simulation chooses the agents' turns
+    dynamically.  On the device the choice is part of the step kernel (BGW_MANAGER_DYNAMIC_ORDER, include/bgw.h); this
+    declaration keeps the reference's property for host-side code that inspects it."""
+
+    @property
+    def next_agent(self):
+        """The next agent(s) in the game."""
+        return self._next_agent
+
+    @next_agent.setter
+    def next_agent(self, value):
+        assert isinstance(value, (list, tuple, set, frozenset, dict, str)), \
+            "The next agent must be a single string or a Container of strings."
+        if type(value) is str:
+            value = [value]
+        for agent_id in value:
+            assert agent_id in self.agents, "Every next agent must be an agent in the simulation."
+        self._next_agent = value
+

@@ -11,6 +11,7 @@ import numpy as np
 
 from abmarl_b200.spaces import Box
 from abmarl_b200.sim.gridworld.base import GridWorldBaseComponent
+from abmarl_b200.sim.agent_based_simulation import ObservingAgent
 from abmarl_b200.sim.gridworld.agent import GridObservingAgent, AmmoObservingAgent
 
 
@@ -74,6 +75,20 @@ class StackedPositionCenteredEncodingObserver(ObserverBaseComponent):
 
     def _shape(self, agent):
         return (agent.view_range * 2 + 1, agent.view_range * 2 + 1, self.number_of_encodings)
+
+
+class AbsolutePositionObserver(ObserverBaseComponent):
+    """observer.py:337-373: agents observe their absolute position (two int16 at BgwDims.position_offset of the obs row)."""
+    key = 'position'
+    supported_agent_type = ObservingAgent
+
+    def __init__(self, **kwargs):
+        super().__init__(**kwargs)
+        for agent in self.agents.values():
+            if isinstance(agent, self.supported_agent_type):
+                agent.observation_space[self.key] = Box(np.array([0, 0], dtype=int),
+                                                        np.array([self.rows - 1, self.cols - 1], dtype=int), dtype=int)
+                agent.null_observation[self.key] = np.zeros((2,), dtype=int)
 
 
 class AmmoObserver(ObserverBaseComponent):

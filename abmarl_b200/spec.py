@@ -35,7 +35,7 @@ class CompiledSpec:
     SCALARS = ('rows', 'cols', 'n_agents', 'n_envs', 'env_offset', 'program', 'move_actor', 'attack_actor',
                'observer', 'observe_self', 'done_mask', 'manager', 'ravel_actions', 'no_overlap_at_reset',
                'stacked_attacks', 'horizon', 'auto_reset', 'ammo_observer', 'randomize_placement_order',
-               'randomize_action_input', 'seed')
+               'randomize_action_input', 'position_observer', 'seed')
     TABLES = (('encoding', np.int8), ('klass', np.uint8), ('role', np.uint8), ('init_row', np.int16),
               ('init_col', np.int16), ('init_health', np.float64), ('init_orient', np.uint8),
               ('view_range', np.int16), ('move_range', np.int16), ('attack_range', np.int16),
@@ -134,7 +134,12 @@ def compile_sim(sim, manager='all_step', n_envs=1, env_offset=0, seed=0, horizon
         manager, randomize_action_input = 'all_step', True
     names = _mro_names(sim)
     sp.program = _first(names, _PROGRAMS, 'simulation class')
-    sp.manager = {'all_step': K.MANAGER_ALL_STEP, 'turn_based': K.MANAGER_TURN_BASED}[manager]
+    sp.manager = {'all_step': K.MANAGER_ALL_STEP, 'turn_based': K.MANAGER_TURN_BASED,
+                  'dynamic_order': K.MANAGER_DYNAMIC_ORDER}[manager]
+    if sp.manager == K.MANAGER_DYNAMIC_ORDER:
+        # the sim's next_agent rule runs on the device; the one rule built is DynamicOrderMultiMazeSim's (include/bgw.h)
+        assert 'DynamicOrderSimulation' in names and 'MultiMazeNavigationSim' in names, \
+            "To use the DynamicOrderManager, the simulation must be a DynamicOrderSimulation (built: DynamicOrderMultiMazeSim)."
     sp.rows, sp.cols = int(sim.grid.rows), int(sim.grid.cols)
     assert sp.rows * sp.cols <= 65535, "grid too large for 16-bit cell indices"
     sp.n_envs, sp.env_offset, sp.seed = int(n_envs), int(env_offset), int(seed) & (2**64 - 1)
@@ -223,6 +228,9 @@ def compile_sim(sim, manager='all_step', n_envs=1, env_offset=0, seed=0, horizon
     if any('AmmoObserver' in _mro_names(o) for o in observers):            # observer.py:376-413
         sp.ammo_observer = 1
         observers = [o for o in observers if 'AmmoObserver' not in _mro_names(o)]
+    if any('AbsolutePositionObserver' in _mro_names(o) for o in observers):    # observer.py:337-373
+        sp.position_observer = 1
+        observers = [o for o in observers if 'AbsolutePositionObserver' not in _mro_names(o)]
     assert len(observers) == 1, "exactly one grid observer per compiled sim is supported"
     sp.observer = _first(_mro_names(observers[0]), _OBSERVERS, 'observer')
     sp.observe_self = int(getattr(observers[0], 'observe_self', True))

@@ -99,7 +99,12 @@ enum {
 };
 enum { BGW_LAYOUT_POSITION_STATE = 0 /* PositionState state.py:18-166 */, BGW_LAYOUT_MAZE = 1 /* MazePlacementState :385-619 */,
        BGW_LAYOUT_TARGET_BARRIERS_FREE = 2 /* TargetBarriersFreePlacementState :169-383 */ };
-enum { BGW_MANAGER_ALL_STEP = 0 /* all_step_manager.py */, BGW_MANAGER_TURN_BASED = 1 /* turn_based_manager.py */ };
+enum { BGW_MANAGER_ALL_STEP = 0 /* all_step_manager.py */, BGW_MANAGER_TURN_BASED = 1 /* turn_based_manager.py */,
+       /* managers/dynamic_order_manager.py:7-87 over a DynamicOrderSimulation (sim/agent_based_simulation.py:297-317) whose
+        * next_agent rule is: the agent that just acted if that step finished it (it expects its last observation), then
+        * the next agent in dict order that is not done -- abmarl_b200.examples.DynamicOrderMultiMazeSim.  BgwState.turn
+        * holds the learner whose action the next step consumes. */
+       BGW_MANAGER_DYNAMIC_ORDER = 2 };
 
 /* reward constant slots (float64; values live in the user's sim, e.g. team_battle_example.py:42-59) */
 enum {
@@ -169,7 +174,8 @@ typedef struct BgwSpec {
     int32_t randomize_action_input;     /* AllStepManager(randomize_action_input=) all_step_manager.py:62-65: without a
                                            caller-given `order`, bgw_step processes the actions in the keyed order
                                            BGW_SITE_ORDER of the step */
-    int32_t reserved0;
+    int32_t position_observer;          /* 1: the sim has an AbsolutePositionObserver (observer.py:337-373): learners also
+                                           observe their own (row, col) (BgwDims.position_offset) */
     uint64_t seed;         /* Philox key */
     uint64_t barrier_encodings, free_encodings;       /* bit e set <=> encoding e in the set, state.py:430-460 */
     double reward[BGW_RW_COUNT];
@@ -240,6 +246,9 @@ typedef struct BgwDims {
     int32_t ammo_offset;         /* AmmoObserver (observer.py:376-413): byte offset inside a learner's obs row of
                                     its int32 'ammo' observation (little endian, 4-byte aligned), or -1       */
     int32_t device_layouts;      /* 1: bgw_generate_layouts can build this spec's start layouts on the device    */
+    int32_t position_offset;     /* AbsolutePositionObserver (observer.py:337-373): byte offset inside a learner's obs row of
+                                    its 'position' observation, int16 row then int16 col (4-byte aligned), or -1; the
+                                    position stays where the agent died (actor.py:356-358)                       */
 } BgwDims;
 
 typedef struct BgwEngine *bgw_handle;

@@ -87,6 +87,8 @@ int bgwo_dims(const BgwSpec *sp, BgwDims *d)
     int n = d->obs_h * d->obs_w * d->obs_c;
     d->ammo_offset = -1;
     if (sp->ammo_observer) { d->ammo_offset = (n + 3) / 4 * 4; n = d->ammo_offset + 4; }   /* observer.py:376-413 */
+    d->position_offset = -1;
+    if (sp->position_observer) { d->position_offset = (n + 3) / 4 * 4; n = d->position_offset + 4; }   /* observer.py:337-373 */
     d->obs_stride = (n + 15) / 16 * 16;
     d->action_stride = action_stride_of(sp);
     return 0;
@@ -281,6 +283,11 @@ static void observe_agent(Ctx *c, int a, int8_t *out, int stride)
         BgwDims dd; bgwo_dims(sp, &dd);
         const int32_t v = c->ammo[a];
         memcpy(out + dd.ammo_offset, &v, 4);
+    }
+    if (sp->position_observer) {                             /* AbsolutePositionObserver.get_obs observer.py:366-373: agent.position */
+        BgwDims dd; bgwo_dims(sp, &dd);
+        const int16_t rc[2] = {(int16_t)(c->cell[a] / c->W), (int16_t)(c->cell[a] % c->W)};
+        memcpy(out + dd.position_offset, rc, 4);
     }
     if (!(sp->klass[a] & BGW_AG_OBSERVING)) return;          /* get_obs returns {} observer.py:103,213,301 */
     const int R = sp->view_range[a], n = 2 * R + 1;
@@ -979,7 +986,11 @@ static void env_reset(Ctx *c, int8_t *obs_env, int stride)
      * observations and stays inert until it is reset again */
     const int bad = c->st->error[c->env] != 0;
     c->st->env_flags[c->env] = (uint8_t)(bad ? BGW_ENV_ERROR | BGW_ENV_ALL_DONE : 0);
-    if (c->sp->manager == BGW_MANAGER_TURN_BASED) {
+    if (c->sp->manager == BGW_MANAGER_DYNAMIC_ORDER) {          /* dynamic_order_manager.py:19-28: the sim names the first agent */
+        c->st->turn[c->env] = 0;
+        if (obs_env && bad) memset(obs_env, 0, (size_t)stride);
+        else if (obs_env) observe_agent(c, c->agent_of[0], obs_env, stride);
+    } else if (c->sp->manager == BGW_MANAGER_TURN_BASED) {
         int t = c->st->turn[c->env];
         t = (t + 1) % c->L;                                     /* next(self.agent_order); never rewound :17-20 */
         c->st->turn[c->env] = (int16_t)t;
@@ -1074,9 +1085,25 @@ int bgwo_step(const BgwSpec *sp, BgwState *st, const int8_t *actions, const int1
             acting[0] = c.agent_of[l];
             prog_step(&c, acting, 1, act);                      /* :46 */
             env_done = prog_all_done(&c);                       /* :48 */
-            if (env_done) {                                     /* :49-57 */
+            if (env_done) {                                     /* :49-57, dynamic_order_manager.py:43-51 */
                 for (int k = 0; k < L; ++k)
                     if (!(c.flags[c.agent_of[k]] & BGW_ST_DONE_REPORTED)) emit(&c, k, obs_env, stride, rew, rew64, dn);
+            } else if (sp->manager == BGW_MANAGER_DYNAMIC_ORDER) {
+                /* dynamic_order_manager.py:52-85 over the sim's next_agent = [the agent that acted, if this step finished
+                 * it] + [the next agent in dict order that is not done] (DynamicOrderMultiMazeSim.step) */
+                const int turn = l, a0 = c.agent_of[turn];
+                if (prog_done(&c, a0)) {                        /* :60-69: just finished; someone else is not done */
+                    emit(&c, turn, obs_env, stride, rew, rew64, dn);
+                    c.flags[a0] |= BGW_ST_DONE_REPORTED;
+                }
+                for (int k = 1; k <= L; ++k) {
+                    l = (turn + k) % L;
+                    const int a = c.agent_of[l];
+                    if (prog_done(&c, a)) continue;             /* the sim skips the agents that are done */
+                    if (!(c.flags[a] & BGW_ST_DONE_REPORTED)) emit(&c, l, obs_env, stride, rew, rew64, dn);   /* :80-85 */
+                    break;
+                }
+                st->turn[e] = (int16_t)l;
             } else {
                 for (;;) {                                      /* :59-92 */
                     l = (l + 1) % L;

@@ -60,7 +60,7 @@ def action_dict(spec, sim, done_agents, act, only=None):
     return out
 
 
-def ref_obs_rows(spec, ref_obs, stride, ammo_offset=-1):
+def ref_obs_rows(spec, ref_obs, stride, ammo_offset=-1, position_offset=-1):
     """reference obs dict -> (rows [L, stride] int8 zero padded, present [L] bool); the AmmoObserver's 'ammo' entry
     (observer.py:406-413) goes to the int32 slot at ammo_offset"""
     rows = np.zeros((spec.n_learners, stride), dtype=np.int8)
@@ -72,6 +72,9 @@ def ref_obs_rows(spec, ref_obs, stride, ammo_offset=-1):
             if 'ammo' in entries:
                 assert ammo_offset >= 0
                 rows[l, ammo_offset:ammo_offset + 4] = np.array([entries.pop('ammo')], dtype=np.int32).view(np.int8)
+            if 'position' in entries:                 # AbsolutePositionObserver observer.py:366-373 -> two int16
+                assert position_offset >= 0
+                rows[l, position_offset:position_offset + 4] = np.asarray(entries.pop('position')).astype(np.int16).view(np.int8)
             (key, arr), = entries.items()
             assert arr.min() >= -128 and arr.max() <= 127
             flat = np.asarray(arr).astype(np.int8).ravel()
@@ -91,17 +94,22 @@ def record(name, builder, manager, n_steps):
     api = scenarios.reference_api()
     sim = builder(api)
     mgr = {'all_step': api.managers.AllStepManager, 'turn_based': api.managers.TurnBasedManager,
-           'all_step_shuffled': lambda s_: api.managers.AllStepManager(s_, randomize_action_input=True)}[manager](sim)
+           'all_step_shuffled': lambda s_: api.managers.AllStepManager(s_, randomize_action_input=True),
+           'dynamic_order': api.managers.DynamicOrderManager}[manager](sim)
     spec = compile_sim(sim, manager=manager, n_envs=1, seed=SEED, auto_reset=False)
     ora = OracleEnv(spec)
     L, stride, astride, ammo_off = spec.n_learners, ora.dims.obs_stride, ora.dims.action_stride, ora.dims.ammo_offset
+    pos_off = ora.dims.position_offset
     learner_ids = spec.learner_ids
 
     rec = {k: [] for k in ('kind', 'actions', 'obs', 'obs_present', 'reward', 'done', 'all_done', 'cell', 'next',
                            'flags', 'health', 'ammo')}
 
     def snapshot(kind, act, obs_rows, present, reward, done, all_done):
-        st = extract_state(sim, mgr.done_agents)
+        # BgwState marks the entities that never report (non-learners) DONE_REPORTED; AllStepManager / TurnBasedManager keep
+        # them in done_agents from reset on (all_step_manager.py:41-44), DynamicOrderManager.reset starts with an empty set
+        done_set = set(mgr.done_agents) | ({a for a in sim.agents if a not in learner_ids} if manager == 'dynamic_order' else set())
+        st = extract_state(sim, done_set)
         rec['kind'].append(kind)
         rec['actions'].append(act)
         rec['obs'].append(obs_rows)
@@ -133,7 +141,7 @@ def record(name, builder, manager, n_steps):
                     ora.set_layout(layouts_for(spec, [0], [rp.episode]))
                 ref_obs = mgr.reset()
                 ora.reset()
-                rows, present = ref_obs_rows(spec, ref_obs, stride, ammo_off)
+                rows, present = ref_obs_rows(spec, ref_obs, stride, ammo_off, pos_off)
                 st = snapshot(0, np.zeros((L, astride), np.int8), rows, present, np.zeros(L), np.zeros(L, np.uint8), 0)
                 compare_state(t, st)
                 check(name, 'reset obs', t, ora.obs[0][present], rows[present])
@@ -141,10 +149,10 @@ def record(name, builder, manager, n_steps):
                 continue
             act = ora.sample_actions()[0]
             rp.step += 1
-            only = int(ora.state['turn'][0]) if manager == 'turn_based' else None
+            only = int(ora.state['turn'][0]) if manager in ('turn_based', 'dynamic_order') else None
             ref_obs, ref_rew, ref_done, _ = mgr.step(action_dict(spec, sim, mgr.done_agents, act, only))
             ora.step(act[None])
-            rows, present = ref_obs_rows(spec, ref_obs, stride, ammo_off)
+            rows, present = ref_obs_rows(spec, ref_obs, stride, ammo_off, pos_off)
             reward = np.zeros(L)
             done = np.zeros(L, np.uint8)
             for l, agent_id in enumerate(learner_ids):

@@ -164,6 +164,20 @@ def build_tb_c5_placement_shuffled(api):
         dones={'OneTeamRemainingDone'})
 
 
+def build_tb_position(api):
+    """AbsolutePositionObserver (observer.py:337-373) next to the grid observer: every agent also observes its own
+    (row, col); an agent that died keeps observing the cell it died in."""
+    agents = {}
+    for i in range(16):
+        ag = api.ex.BattleAgent(id=f'a{i}', encoding=i % 2 + 1, initial_health=None if i % 3 else 0.7)
+        ag.view_range = 2
+        agents[ag.id] = ag
+    return api.ex.TeamBattleSim.build_sim(
+        6, 7, agents=agents, overlapping={1: {1}, 2: {2}}, attack_mapping={1: {2}, 2: {1}},
+        states={'PositionState', 'HealthState'},
+        observers={'PositionCenteredEncodingObserver', 'AbsolutePositionObserver'}, dones={'OneTeamRemainingDone'})
+
+
 def build_tb_noself(api):
     """observe_self=False (observer.py:238-246) with overlapping teams."""
     agents = {}
@@ -409,6 +423,54 @@ def build_mm_tiny(api):
     return sim
 
 
+def dynamic_order_multi_maze_class(api):
+    """DynamicOrderMultiMazeSim: the mirror's declaration, or -- for the reference -- its twin written out in Python on
+    the reference's own classes (MultiMazeNavigationSim + DynamicOrderSimulation), which is what the goldens record."""
+    if api.name == 'mirror':
+        return api.ex.DynamicOrderMultiMazeSim
+    from abmarl.sim import DynamicOrderSimulation
+
+    class DynamicOrderMultiMazeSim(api.ex.MultiMazeNavigationSim, DynamicOrderSimulation):
+        def reset(self, **kwargs):
+            super().reset(**kwargs)
+            self._navigators = [a.id for a in self.agents.values() if isinstance(a, api.ex.MultiMazeNavigationAgent)]
+            self.next_agent = self._navigators[0]
+
+        def step(self, action_dict, **kwargs):
+            super().step(action_dict, **kwargs)
+            last = list(action_dict)[-1]
+            nxt = [agent_id for agent_id in action_dict if self.get_done(agent_id)]     # just finished: last report
+            i = self._navigators.index(last)
+            for k in range(1, len(self._navigators) + 1):
+                cand = self._navigators[(i + k) % len(self._navigators)]
+                if not self.get_done(cand):
+                    nxt.append(cand)
+                    break
+            self.next_agent = nxt or [last]
+
+        def get_reward(self, agent_id, **kwargs):
+            # once the sim is done, DynamicOrderManager.step asks for EVERY agent that is not done (dynamic_order_manager.py:
+            # 43-51), walls and target included (it does not park the non-learning entities in done_agents at reset as
+            # AllStepManager does, all_step_manager.py:41-44); MultiMazeNavigationSim tracks rewards for Agents only
+            if agent_id not in self.reward:
+                return 0
+            return super().get_reward(agent_id, **kwargs)
+    return DynamicOrderMultiMazeSim
+
+
+def build_mm_dynamic(api):
+    """DynamicOrderManager (managers/dynamic_order_manager.py:7-87) over a 5x6 multi maze with four navigators."""
+    agents = {'target': api.agent.GridWorldAgent(id='target', encoding=1)}
+    agents.update({f'barrier{i}': api.agent.GridWorldAgent(id=f'barrier{i}', encoding=2) for i in range(4)})
+    agents.update({f'navigator{i}': api.ex.MultiMazeNavigationAgent(id=f'navigator{i}', encoding=3, view_range=2)
+                   for i in range(4)})
+    sim = dynamic_order_multi_maze_class(api).build_sim(
+        5, 6, agents=agents, overlapping={1: {3}, 3: {3}}, target_agent=agents['target'],
+        barrier_encodings={2}, free_encodings={1, 3}, cluster_barriers=True, scatter_free_agents=False)
+    sim.move_actor = api.wrapper.RavelActionWrapper(sim.move_actor)
+    return sim
+
+
 def build_mm_tbf(api, cluster=True, scatter=False, fixed_target=False):
     """Multi maze navigation with its placement state swapped for TargetBarriersFreePlacementState (state.py:169-383):
     the target at a random cell, barriers clustered around it, navigators placed at random."""
@@ -438,6 +500,7 @@ SCENARIOS = {
     'tb_stacked': (build_tb_stacked, 'all_step', 25),
     'tb_noself': (build_tb_noself, 'all_step', 25),
     'tb_shuffled': (build_tb_shuffled, 'all_step_shuffled', 160),
+    'tb_position': (build_tb_position, 'all_step', 60),
     'tb_c5_shuffled': (build_tb_c5_placement_shuffled, 'all_step_shuffled', 30),
     'tb_encoding': (build_tb_encoding, 'all_step', 40),
     'tb_encoding_stacked': (build_tb_encoding_stacked, 'all_step', 40),
@@ -460,4 +523,5 @@ SCENARIOS = {
     'mm_tbf_scatter': (build_mm_tbf_scatter, 'turn_based', 120),
     'mm_tiny': (build_mm_tiny, 'turn_based', 400),
     'mm_tiny_allstep': (build_mm_tiny, 'all_step', 200),
+    'mm_dynamic': (build_mm_dynamic, 'dynamic_order', 500),
 }

@@ -32,7 +32,7 @@ def test_struct_layouts_match_the_header():
     from oracle.oracle import lib
     assert C.sizeof(K.BgwSpec) == lib().bgwo_sizeof(0) == 26 * 4 + 3 * 8 + 8 * K.BGW_RW_COUNT + 17 * 8
     assert C.sizeof(K.BgwState) == lib().bgwo_sizeof(1) == 13 * 8
-    assert C.sizeof(K.BgwDims) == lib().bgwo_sizeof(2) == 13 * 4
+    assert C.sizeof(K.BgwDims) == lib().bgwo_sizeof(2) == 14 * 4
 
 
 def test_host_rng_draw_matches_python_philox():

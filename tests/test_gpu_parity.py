@@ -33,6 +33,7 @@ CASES = [
     ('tb_noself', 48, 80, 30),
     ('tb_shuffled', 48, 120, 25),            # keyed random.shuffle: placement order + action input order
     ('tb_c5_shuffled', 24, 90, 30),          # the same on the specialised kernel's shape
+    ('tb_position', 48, 90, 30),             # AbsolutePositionObserver slot of the obs row
     ('tb_encoding', 48, 100, 30),
     ('tb_encoding_stacked', 48, 100, 30),
     ('tb_restricted', 48, 100, 30),
@@ -54,6 +55,7 @@ CASES = [
     ('mm_tbf_scatter', 16, 200, 30),
     ('mm_tiny', 16, 300, 0),
     ('mm_tiny_allstep', 16, 200, 0),
+    ('mm_dynamic', 16, 300, 0),              # DynamicOrderManager: the sim names the next agent(s)
 ]
 
 

@@ -134,3 +134,28 @@ def test_team_battle_rejects_simultaneous_attacks(mirror):     # SURVEY.md 8(c):
                                      observers={'PositionCenteredEncodingObserver'}, dones={'ActiveDone'})
     with pytest.raises(AssertionError):
         compile_sim(sim)
+
+
+def test_dynamic_order_manager_wrong_sim(mirror):
+    """tests/test_dynamic_order_manager.py:42-44: the manager only takes a DynamicOrderSimulation (the assertion comes
+    before anything touches a device)."""
+    import pytest
+    from abmarl_b200.managers import DynamicOrderManager
+    from tests import scenarios
+    with pytest.raises(AssertionError):
+        DynamicOrderManager(scenarios.build_mm_tiny(mirror))
+
+
+def test_dynamic_order_simulation_next_agent_property(mirror):
+    """tests/sim/test_agent_based_simulation.py: next_agent accepts an id or a container of ids of the sim's agents."""
+    import pytest
+    from tests import scenarios
+    sim = scenarios.build_mm_dynamic(mirror)
+    sim.next_agent = 'navigator1'
+    assert sim.next_agent == ['navigator1']
+    sim.next_agent = ['navigator0', 'navigator2']
+    assert sim.next_agent == ['navigator0', 'navigator2']
+    with pytest.raises(AssertionError):
+        sim.next_agent = ['nobody']
+    with pytest.raises(AssertionError):
+        sim.next_agent = 3
