@@ -123,22 +123,27 @@ class SimulationManager(ABC):
         return torch.from_numpy(act.view(np.int8)).to(self.engine.device)
 
     # -- reference-shaped view of one env --------------------------------------------------------
-    def as_dicts(self, env=0, after_reset=False):
-        """(obs, rewards, dones, infos) of env `env` as the reference's dicts (simulation_manager.py:38-53)."""
+    def host_snapshot(self):
+        """One device->host copy of the last outputs of ALL envs (numpy): what as_dicts / the external adapters slice."""
         eng = self.engine
+        ammo, position = eng.ammo_view(), eng.position_view()
+        return dict(obs=eng.obs_view().cpu().numpy(), reward=eng.reward.cpu().numpy(), done=eng.done.cpu().numpy(),
+                    all_done=eng.all_done.cpu().numpy(), turn=eng.state['turn'].cpu().numpy(),
+                    ammo=None if ammo is None else ammo.cpu().numpy(),
+                    position=None if position is None else position.cpu().numpy())
+
+    def dicts_from(self, snap, env=0, after_reset=False):
+        """(obs, rewards, dones, infos) of env `env` as the reference's dicts (simulation_manager.py:38-53), built from a
+        host_snapshot()."""
         key = {K.OBS_POSITION_CENTERED: 'position_centered_encoding', K.OBS_ABSOLUTE: 'absolute_encoding',
                K.OBS_STACKED: 'stacked_position_centered_encoding'}[self.spec.observer]
-        obs_all = eng.obs_view()[env].cpu().numpy().astype(np.int64)
-        ammo = eng.ammo_view()
-        ammo = None if ammo is None else ammo[env].cpu().numpy()
-        position = eng.position_view()
-        position = None if position is None else position[env].cpu().numpy().astype(np.int64)
-        done = eng.done[env].cpu().numpy()
-        reward = eng.reward[env].cpu().numpy()
-        flags = int(eng.all_done[env].item())
+        obs_all = snap['obs'][env].astype(np.int64)
+        ammo = None if snap['ammo'] is None else snap['ammo'][env]
+        position = None if snap['position'] is None else snap['position'][env].astype(np.int64)
+        done, reward, flags = snap['done'][env], snap['reward'][env], int(snap['all_done'][env])
         obs, rew, dn, info = {}, {}, {}, {}
-        # TurnBasedManager.reset returns the first agent's observation only (turn_based_manager.py:22-32)
-        first = int(eng.state['turn'][env].item()) if after_reset and self._manager in ('turn_based', 'dynamic_order') else None
+        # TurnBasedManager / DynamicOrderManager.reset return the first agent's observation only (turn_based_manager.py:22-32)
+        first = int(snap['turn'][env]) if after_reset and self._manager in ('turn_based', 'dynamic_order') else None
         for l, agent_id in enumerate(self.learner_ids):
             if (after_reset and (first is None or l == first)) or (not after_reset and (done[l] & K.OUT_VALID)):
                 a = self.spec.learner_agents[l]
@@ -160,6 +165,10 @@ class SimulationManager(ABC):
             return obs
         dn['__all__'] = bool(flags & K.ENV_ALL_DONE)
         return obs, rew, dn, info
+
+    def as_dicts(self, env=0, after_reset=False):
+        """(obs, rewards, dones, infos) of env `env` as the reference's dicts (simulation_manager.py:38-53)."""
+        return self.dicts_from(self.host_snapshot(), env, after_reset)
 
 
 class AllStepManager(SimulationManager):
