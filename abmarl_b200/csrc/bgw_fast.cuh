@@ -32,6 +32,21 @@
 #include "bgw_dev.cuh"
 
 #define BGW_MIXED (-128)
+/* -DBGW_JITTER: a test build that perturbs the interleavings -- a pseudo-random sleep (0..2 us, from the clock, the thread and
+ * the site) in front of every reservation, table look-up, touch mark, ticket draw and stamp access.  The parity tests, the
+ * chained / fused rollout tests and the soak run under it (profiles/gpu_jitter_r02.sh): results must not change.  (Stands in
+ * for compute-sanitizer racecheck, which is closed on this pool.) */
+#ifdef BGW_JITTER
+__device__ __forceinline__ void bgw_jitter(unsigned site)
+{
+    unsigned x = (unsigned)clock64() * 2654435761u + threadIdx.x * 40503u + site * 2246822519u;
+    x ^= x >> 15; x *= 2246822519u; x ^= x >> 13;
+    if (x & 3u) __nanosleep(x & 0x7FFu);
+}
+#define BGW_JITTER_POINT(site) bgw_jitter(site)
+#else
+#define BGW_JITTER_POINT(site) do { } while (0)
+#endif
 #ifdef BGW_PROFILE   /* debug build (BGW_PROFILE=1 python -m abmarl_b200.csrc.build): clock64 at the phase boundaries */
 #define BGW_PROF_MARK(k) do { if (f.prof && tid == 0 && it_no < 8) f.prof[((size_t)blockIdx.x * 8 + it_no) * 16 + (k)] = clock64(); } while (0)
 #else
@@ -276,6 +291,7 @@ __device__ __forceinline__ void st_release_u32(uint32_t *p, uint32_t v)
 /* has env e been stamped with sequence number `need` (or a later one)? */
 __device__ __forceinline__ bool env_stamped(const FastSpec &f, int e, uint32_t need)
 {
+    BGW_JITTER_POINT(6);
     return (int32_t)(ld_acquire_u32(f.env_seq + e) - need) >= 0;
 }
 /* wait until it has.  A legitimate wait ends within one env (tens of microseconds, milliseconds when envs reset).  The bound is
@@ -408,6 +424,7 @@ __device__ __forceinline__ SlotTables slot_tables(const DevSpec &s, const Env &e
 __device__ __forceinline__ void attack_reserve(const DevSpec &s, uint32_t *tab, uint32_t smask, int own, int R, uint32_t mask, uint32_t v)
 {
     const int n = 2 * R + 1;
+    BGW_JITTER_POINT(1);
     atomicMin(&tab[own & smask], v);
     for (uint32_t m = mask; m; m &= m - 1) {
         const int b = __ffs(m) - 1, wr = b / n, wc = b - wr * n;
@@ -418,6 +435,7 @@ __device__ __forceinline__ void attack_reserve(const DevSpec &s, uint32_t *tab, 
 __device__ __forceinline__ bool attack_holds(const DevSpec &s, const uint32_t *tab, uint32_t smask, int own, int R, uint32_t mask, uint32_t v)
 {
     const int n = 2 * R + 1;
+    BGW_JITTER_POINT(2);
     bool win = tab[own & smask] == v;
     for (uint32_t m = mask; m; m &= m - 1) {
         const int b = __ffs(m) - 1, wr = b / n, wc = b - wr * n;
@@ -448,6 +466,7 @@ __device__ uint32_t fast_attack_rounds(const DevSpec &s, const FastSpec &f, Env 
                 attack_reserve(s, st.tab(p ^ 1), st.mask, own, R, mask, next_tag | (uint32_t)i);
                 continue;
             }
+            BGW_JITTER_POINT(9);
             fast_exec_attack<HT>(s, f, ev, fe, i, a, mask);
             ev.pstate[i] = 0;
         }
@@ -503,6 +522,7 @@ __device__ __forceinline__ void fast_exec_move(const DevSpec &s, const FastSpec 
  * killrank[], both dead by now): a round walks the losers of the round before. */
 __device__ __forceinline__ void touch_mark(const FastSpec &f, FastEnv &fe, int cell)
 {
+    BGW_JITTER_POINT(3);
     const uint32_t bit = 1u << (cell & 31);
     uint32_t *w = fe.touch + ((cell >> 5) & (f.touch_words - 1));
     if (atomicOr(w, bit) & bit) atomicOr(w + f.touch_words, bit);
@@ -530,6 +550,7 @@ __device__ uint32_t fast_move_rounds(const DevSpec &s, const FastSpec &f, Env &e
             const uint32_t ft = fe.rkmask[i];
             const int from = (int)(ft >> 16), to = (int)(ft & 0xFFFFu);
             const uint32_t mine = tag | (uint32_t)i, sf = (uint32_t)from & st.mask, sto = (uint32_t)to & st.mask;
+            BGW_JITTER_POINT(4);
             const uint32_t hf = cur[sf], ht = cur[sto];                 /* both loads in flight, one test */
             if ((hf != mine) | (ht != mine)) {
                 lost = 1;
@@ -563,6 +584,7 @@ __device__ uint32_t fast_move_phase(const DevSpec &s, const FastSpec &f, Env &ev
         const uint32_t ft = fe.rkmask[i];
         if (ft == BGW_NO_MOVE) continue;
         const int from = (int)(ft >> 16), to = (int)(ft & 0xFFFFu);
+        BGW_JITTER_POINT(5);
         const uint32_t c = (twice[((uint32_t)from >> 5) & tw] >> (from & 31)) | (twice[((uint32_t)to >> 5) & tw] >> (to & 31));
         if (c & 1u) {                                               /* contested: first reservation, into the list */
             fe.eff[atomicAdd(&ev.ctr[CTR_PA], 1)] = (uint16_t)i;
@@ -893,6 +915,7 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
     do {                                                                             \
         if (tid == 0) tslot[sl ^ 1] = (int)tnew;                                     \
         __syncthreads();                                                             \
+        BGW_JITTER_POINT(7);                                                         \
         if (tid == 0) st_release_u32(f_in.env_seq + e, f_in.seq + (uint32_t)kstep);   \
         sl ^= 1;                                                                     \
     } while (0)
@@ -914,6 +937,7 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
         }
         gn = (uint32_t)tslot[sl];
         uint32_t tnew = NT;                                         /* the ticket after `gn`: drawn now, needed next iteration */
+        BGW_JITTER_POINT(8);
         if (tid == 0 && gn < NT) tnew = min(NT, tk ? atomicAdd(tk, 1u) - tbase : gn + gridDim.x);
         if (gn < NT) {
             const int kn = (int)(gn / (uint32_t)s.E), en = (int)(gn - (uint32_t)kn * (uint32_t)s.E);

@@ -42,16 +42,20 @@ def build(force=False, verbose=False):
     flags += os.environ.get('BGW_NVCC_FLAGS', '').split()
     if verbose:
         flags.append('-Xptxas=-v')
-    tag = hashlib.sha1(' '.join(flags).encode()).hexdigest()[:10]                   # objects of different variants do not mix
-    objdir = os.path.join(HERE, '_obj', tag)
-    os.makedirs(objdir, exist_ok=True)
-    jobs = []
+    # BGW_FAST_DEFINES: defines for the specialised kernel's unit only (e.g. BGW_JITTER): the other two units are shared with
+    # the plain build instead of being recompiled
+    unit_flags = {u: list(flags) for u in UNITS}
+    unit_flags['bgw_fastk.cu'] += ['-D' + d for d in os.environ.get('BGW_FAST_DEFINES', '').split()]
+    jobs, objs = [], []
     for u in UNITS:
+        tag = hashlib.sha1(' '.join(unit_flags[u]).encode()).hexdigest()[:10]       # objects of different variants do not mix
+        objdir = os.path.join(HERE, '_obj', tag)
+        os.makedirs(objdir, exist_ok=True)
         src, obj = os.path.join(HERE, u), os.path.join(objdir, u[:-3] + '.o')
+        objs.append(obj)
         newest = max([os.path.getmtime(src)] + [os.path.getmtime(h) for h in _headers(u)])
         if force or not os.path.exists(obj) or os.path.getmtime(obj) < newest:
-            jobs.append([NVCC] + flags + ['-c', src, '-o', obj])
-    objs = [os.path.join(objdir, u[:-3] + '.o') for u in UNITS]
+            jobs.append([NVCC] + unit_flags[u] + ['-c', src, '-o', obj])
     if not jobs and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(o) for o in objs):
         return out
 
@@ -60,8 +64,9 @@ def build(force=False, verbose=False):
             print(' '.join(cmd), flush=True)
         subprocess.check_call(cmd)
 
-    with ThreadPoolExecutor(len(UNITS)) as pool:
-        list(pool.map(run, jobs))
+    if jobs:
+        with ThreadPoolExecutor(len(jobs)) as pool:
+            list(pool.map(run, jobs))
     run([NVCC, '-shared', '-o', out] + objs + ['-lcudart'])
     return out
 

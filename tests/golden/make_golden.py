@@ -130,6 +130,7 @@ def record(name, builder, manager, n_steps):
         check(name, 'health', t, o['health'][0], st['health'])
         check(name, 'ammo', t, o['ammo'][0], st['ammo'])
 
+    forced = scenarios.GOLDEN_RESET_EVERY.get(name, 0)
     with PhiloxReplay(sim, SEED) as rp:
         t = 0
         need_reset = True
@@ -167,7 +168,7 @@ def record(name, builder, manager, n_steps):
             check(name, 'obs', t, ora.obs[0][present], rows[present])
             check(name, 'reward64', t, ora.reward64[0], reward)
             check(name, '__all__', t, int(ora.all_done[0] & K.ENV_ALL_DONE), all_done)
-            need_reset = bool(all_done)
+            need_reset = bool(all_done) or (forced and t % forced == 0)
         n_draws = len(rp.log)
         n_ammo_draws = sum(1 for site, _, _ in rp.log if site == K.SITE_AMMO)
         n_repeat_acc = sum(1 for site, _, k in rp.log if site == K.SITE_ACC and k >= 4096)
