@@ -550,6 +550,18 @@ int bgw_bind_state(bgw_handle h, const BgwState *state)
     if (h->ds.n_ammo && !state->ammo) return fail(1, "bgw_bind_state: the simulation has AmmoAgents: `ammo` is required");
     h->st = *state;
     h->bound = true;
+    if (state->layout && h->fs.enabled && h->fast_shape != 0) {
+        /* the compile-time-shape instantiations of the specialised kernel have no layout path in their inlined reset (code
+         * size is what the instruction cache sees): a handle that is given layouts runs the run-time-shape instantiation */
+        DeviceGuard guard(h->device);
+        h->fast_shape = 0;
+        h->fast_fn = bgw_fast_step_fn(0, h->fs.head_elem);
+        CUDA_OK(cudaFuncSetAttribute(h->fast_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, h->fs.smem_bytes));
+        int per_sm = 0, sms = 0;
+        CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, h->fast_fn, h->threads_fast, (size_t)h->fs.smem_bytes));
+        CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+        h->fs.grid_ctas = std::max(1, std::min(h->ds.E, per_sm * sms));
+    }
     return 0;
 }
 

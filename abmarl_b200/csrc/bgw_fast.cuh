@@ -767,7 +767,7 @@ struct FastStaticC5 {
     static constexpr bool is_static = true;
     static constexpr int A = 256, L = 256, H = 64, W = 64, P = 5, PL = 5, PW = 76, PH = 74, obs_stride = 128, nchunks = 8,
                          obs_h = 11, view = 5, move_actor = BGW_MOVE_BOX, ravel = 0, observe_self = 1, done_mask = BGW_DONE_ONE_TEAM,
-                         max_enc = 4, simd_ok = 1, async_ok = 1, slots = 256, T = BGW_STATIC_T, att = 1, identity = 1, can_mix = 0, acc_lt1 = 0;
+                         max_enc = 4, simd_ok = 1, async_ok = 1, slots = 256, T = BGW_STATIC_T, att = 1, identity = 1, can_mix = 0, acc_lt1 = 0, rpo = 0;
 };
 /* BASELINE configs[1] (examples/rllib_team_battle.py: 8x8 grid, 24 agents in 4 teams, view 3): one warp per env, 32 envs
  * per SM, each at its own place in the code -- the run-time-shape instantiation (9.3 k instructions) spends most of its
@@ -776,7 +776,7 @@ struct FastStaticC2 {
     static constexpr bool is_static = true;
     static constexpr int A = 24, L = 24, H = 8, W = 8, P = 3, PL = 3, PW = 16, PH = 14, obs_stride = 64, nchunks = 4,
                          obs_h = 7, view = 3, move_actor = BGW_MOVE_BOX, ravel = 0, observe_self = 1, done_mask = BGW_DONE_ONE_TEAM,
-                         max_enc = 4, simd_ok = 1, async_ok = 2, slots = 64, T = 32, att = 1, identity = 1, can_mix = 0, acc_lt1 = 0;
+                         max_enc = 4, simd_ok = 1, async_ok = 2, slots = 64, T = 32, att = 1, identity = 1, can_mix = 0, acc_lt1 = 0, rpo = 0;
 };
 struct FastDynamic { static constexpr bool is_static = false; };
 
@@ -789,7 +789,7 @@ inline bool fast_shape_matches(const DevSpec &q, const FastSpec &f, int threads)
            q.done_mask == C::done_mask && q.max_enc == C::max_enc && f.P == C::P && f.PL == C::PL && f.PW == C::PW &&
            f.PH == C::PH && f.uniform_view == C::view && f.simd_ok == C::simd_ok && f.async_ok == C::async_ok &&
            q.slot_mask == C::slots - 1 && threads == C::T && f.uniform_att == C::att && f.identity_learners == C::identity &&
-           f.can_mix == C::can_mix && f.acc_lt1 == C::acc_lt1;
+           f.can_mix == C::can_mix && f.acc_lt1 == C::acc_lt1 && q.randomize_placement_order == C::rpo;
 }
 
 template <typename SHAPE, typename HT>
@@ -804,6 +804,7 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
         s.A = C::A; s.L = C::L; s.H = C::H; s.W = C::W; s.HW = C::H * C::W; s.obs_stride = C::obs_stride; s.nchunks = C::nchunks;
         s.obs_h = s.obs_w = C::obs_h; s.obs_c = 1; s.move_actor = C::move_actor; s.ravel = C::ravel; s.observe_self = C::observe_self;
         s.done_mask = C::done_mask; s.max_enc = C::max_enc; s.n_blk = 0; s.program = BGW_PROG_TEAM_BATTLE;
+        s.randomize_placement_order = C::rpo;               /* (folds the shuffled-placement code out of the inlined reset) */
         s.manager = BGW_MANAGER_ALL_STEP; s.attack_actor = BGW_ATTACK_BINARY; s.hw_words = (C::H * C::W + 31) / 32;
         f.P = C::P; f.PL = C::PL; f.PW = C::PW; f.PH = C::PH; f.uniform_view = C::view; f.simd_ok = C::simd_ok; f.async_ok = C::async_ok;
         f.uniform_att = C::att; f.identity_learners = C::identity; f.can_mix = C::can_mix; f.acc_lt1 = C::acc_lt1;
@@ -899,8 +900,10 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
      * ticket (prefetch) a thread merely looks; if the stamp is not there yet it fetches its share of the rows when the
      * ticket becomes current (`late`, per thread: cp.async groups are per thread). */
     bool late = false;
+    int kn_carry = 0, en_carry = 0;
     if (g < NT) {
         kstep = (int)(g / (uint32_t)s.E); e = (int)(g - (uint32_t)kstep * (uint32_t)s.E);
+        kn_carry = kstep; en_carry = e;
         if (f_in.chain || kstep > 0) env_wait_stamp(f_in, e, f_in.seq + (uint32_t)kstep - 1u);
         fast_issue_env(s, f, st, actions, e, bgw_smem + f.o_buf, tid, T);
         ef_cur = __ldcg(&st.env_flags[e]); step_cur = __ldcg(&st.step[e]); epi_cur = __ldcg(&st.episode[e]);
@@ -927,7 +930,7 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
         warp = tid >> 5;
 #endif
         BGW_PROF_MARK(0);
-        kstep = (int)(g / (uint32_t)s.E); e = (int)(g - (uint32_t)kstep * (uint32_t)s.E);
+        kstep = kn_carry; e = en_carry;                             /* (step, env) of this ticket: computed when it was `next` */
         if (late) {                                                 /* this ticket's rows were not ready when it was `next` */
             env_wait_stamp(f_in, e, f_in.seq + (uint32_t)kstep - 1u);
             fast_issue_env(s, f, st, actions, e, bgw_smem + f.o_buf + b * f.buf_bytes, tid, T);
@@ -941,6 +944,7 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
         if (tid == 0 && gn < NT) tnew = min(NT, tk ? atomicAdd(tk, 1u) - tbase : gn + gridDim.x);
         if (gn < NT) {
             const int kn = (int)(gn / (uint32_t)s.E), en = (int)(gn - (uint32_t)kn * (uint32_t)s.E);
+            kn_carry = kn; en_carry = en;
             if ((f_in.chain || kn > 0) && !env_stamped(f_in, en, f_in.seq + (uint32_t)kn - 1u)) late = true;
             else {
                 fast_issue_env(s, f, st, actions, en, bgw_smem + f.o_buf + (b ^ 1) * f.buf_bytes, tid, T);
@@ -985,7 +989,7 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
         BGW_PROF_MARK(1);
 
         bool fresh = false;                                         /* this call resets the env instead of stepping it */
-        if (ef0 & BGW_ENV_ALL_DONE) {
+        if (__builtin_expect((ef0 & BGW_ENV_ALL_DONE) != 0, 0)) {     /* cold: once per episode */
             if (!s.auto_reset) {
                 if (tid == 0) all_done[e] = ef0;
                 BGW_END_ENV();
@@ -999,7 +1003,10 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
                 evr.head = (uint16_t *)arena;
                 evr.racc = (double *)(arena + f.r_racc);
                 evr.avail = (uint32_t *)(arena + f.r_avail);
-                sim_reset(s, st, evr, tid, T);
+                BgwState st_r = st;
+                if constexpr (SHAPE::is_static) st_r.layout = nullptr;   /* (bgw_bind_state moves a handle with caller-supplied layouts to the
+                                                                            run-time-shape instantiation: the layout path folds away here) */
+                sim_reset(s, st_r, evr, tid, T);
                 store_env(s, st, evr, true, tid, T);
                 ev.episode = evr.episode; ev.step = evr.step;
             }
@@ -1045,24 +1052,45 @@ __global__ void __launch_bounds__(128, 7) bgw_step_fast_kernel(const DevSpec s_i
 #pragma unroll
                 for (int dd = 1; dd < 32; dd <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, incl, dd); if (lane >= dd) incl += t; }
                 int pr = (incl - cnt) & 0xFFFF, pa = (incl - cnt) >> 16;
-                for (int j = 0; j < wpl; ++j) {
-                    const int w = lane * wpl + j;
-                    if (w < nwords) {
-                        const uint32_t x = fw[w];
-                        const uint32_t rel = ~__vcmpeq4(x & 0x07070707u, 0x04040404u);
-                        const uint32_t act = __vcmpne4(kw[w] & (0x01010101u * BGW_AG_LEARNER), 0u) & __vcmpeq4(x & 0x04040404u, 0u);
+                /* Acting learners are relevant, so equal counts mean equal lists: when every entity is a learner that is the
+                 * rule (an entity leaves both when its death has been reported; the exception is one that was reported while
+                 * still on the grid, e.g. placed with zero health).  Then ONE list is written and serves as both -- half the
+                 * stores, and half the code of this unrolled loop on the env's critical path. */
+                const int tot = __shfl_sync(0xFFFFFFFFu, incl, 31);
+                const bool same = f.identity_learners && (tot & 0xFFFF) == (tot >> 16);
+                if (same) {
+                    for (int j = 0; j < wpl; ++j) {
+                        const int w = lane * wpl + j;
+                        if (w < nwords) {
+                            const uint32_t act = __vcmpeq4(fw[w] & 0x04040404u, 0u);      /* (every entity is a learner) not reported */
 #pragma unroll
-                        for (int bb = 0; bb < 4; ++bb) {
-                            const int a = 4 * w + bb;
-                            if ((rel >> (8 * bb)) & 1u) fe.rel[pr++] = (uint16_t)a;
-                            if ((act >> (8 * bb)) & 1u) ev.ragent[pa++] = (uint16_t)a;
+                            for (int bb = 0; bb < 4; ++bb)
+                                if ((act >> (8 * bb)) & 1u) ev.ragent[pa++] = (uint16_t)(4 * w + bb);
+                        }
+                    }
+                } else {
+#pragma unroll 1
+                    for (int j = 0; j < wpl; ++j) {
+                        const int w = lane * wpl + j;
+                        if (w < nwords) {
+                            const uint32_t x = fw[w];
+                            const uint32_t rel = ~__vcmpeq4(x & 0x07070707u, 0x04040404u);
+                            const uint32_t act = __vcmpne4(kw[w] & (0x01010101u * BGW_AG_LEARNER), 0u) & __vcmpeq4(x & 0x04040404u, 0u);
+#pragma unroll 1
+                            for (int bb = 0; bb < 4; ++bb) {
+                                const int a = 4 * w + bb;
+                                if ((rel >> (8 * bb)) & 1u) fe.rel[pr++] = (uint16_t)a;
+                                if ((act >> (8 * bb)) & 1u) ev.ragent[pa++] = (uint16_t)a;
+                            }
                         }
                     }
                 }
+                if (lane == 31) fe.wsum[3] = same;
                 if (lane == 31) { fe.wsum[0] = incl & 0xFFFF; fe.wsum[1] = incl >> 16; }
             }
             __syncthreads();
             n_rel = fe.wsum[0]; n_act = fe.wsum[1];
+            fe.rel = fe.wsum[3] ? ev.ragent : (uint16_t *)(bgw_smem + f.o_rel);   /* one list serves as both (above) */
         } else {
             for (int a0 = 0; a0 < s.A; a0 += T) {
                 const int a = a0 + tid;

@@ -191,6 +191,12 @@ def run_ours(args):
     if sampler:
         sampler.start()
         time.sleep(0.5)
+    # bring the GPU out of its idle power state before anything is measured: about 50 ms of the same kernel on the same engine,
+    # then a fresh reset -- the W warm-up steps and the K timed steps below are steps 0..W+K of the episode that starts there
+    # (a 20-step timed region is one millisecond: without this it runs while the clocks are still ramping, measured 5 % jitter)
+    eng.reset()
+    eng.rollout_sampled(args.spinup_steps)
+    torch.cuda.synchronize(dev)
     eng.reset()
     def rollout(n):
         # bgw_rollout_sampled: n step launches enqueued by the library back to back (chained per env); --per-step-calls
@@ -416,6 +422,7 @@ def main():
     ap.add_argument('--kernel-steps', type=int, default=1000, help='steps of the second pass that brackets every launch with its own events')
     ap.add_argument('--per-step-calls', action='store_true', help='one bgw_step_sampled call per step instead of bgw_rollout_sampled (A/B)')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--spinup-steps', type=int, default=1500, help='untimed steps before the reset that starts the measured episode (GPU clock ramp)')
     ap.add_argument('--cpu-steps', type=int, default=200, help='steps of the cpu_baseline sample (all host cores, all envs)')
     ap.add_argument('--given-steps', type=int, default=200, help='bgw_step calls with caller-supplied device actions timed next to the fused rollout')
     ap.add_argument('--e2e-zero-copy', action='store_true', help='e2e: the gather kernel writes the pinned host buffers directly instead of compacting on the device and copying')
