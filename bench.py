@@ -362,7 +362,8 @@ def run_ours(args):
         try:
             with open(os.path.join(ROOT, 'profiles', 'step_kernel_traffic.json')) as f:
                 tj = json.load(f)
-                traffic, traffic_src = tj.get('dram_bytes_per_step'), tj.get('source')
+                key = 'dram_bytes_per_step_early' if args.steps + args.warmup <= 60 else 'dram_bytes_per_step'
+                traffic, traffic_src = tj.get(key) * args.steps / launches_rank, tj.get('source')   # per launch, like `achieved`
         except Exception:
             pass
         line = {

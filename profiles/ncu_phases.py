@@ -9,11 +9,12 @@ import re
 import sys
 
 MARKS = [('exec_attack', r'__device__ void fast_exec_attack'), ('attack rounds', r'__device__ void fast_attack_rounds'),
-         ('exec_move', r'void fast_exec_move'), ('move rounds', r'__device__ void fast_move_rounds'),
+         ('exec_move', r'void fast_exec_move'), ('touch marks', r'void touch_mark'), ('move rounds (contested)', r'uint32_t fast_move_rounds'),
+         ('move phase (uncontested movers)', r'uint32_t fast_move_phase'), ('reset (out of the step path)', r'void fast_reset_env'),
          ('init_dense', r'__device__ void fast_init_dense'), ('obs per-cell path', r'__device__ void fast_obs_chunk_slow'),
          ('obs row gather', r'__device__ void fast_obs_rows'), ('env staging (cp.async)', r'void fast_issue_env'),
          ('kernel prologue', r'__global__ void bgw_step_fast_kernel'), ('per-CTA setup', r'once per CTA'),
-         ('env prologue', r'for \(; e < s\.E; e = en\)'), ('relevant+acting compaction', r'relevant entities and acting'),
+         ('env prologue (tickets, staging)', r'for \(; g < NT; g = gn\)'), ('relevant+acting compaction', r'relevant entities and acting'),
          ('order compaction', r'if \(order\) \{'), ('lists+summary', r'occupant lists and summary'),
          ('attack pre-pass', r'attack phase team'), ('settle+classify', r'settle attackers'),
          ('emit reward/done', r'entropy :58'), ('obs dispatch', r'---- observations ----'),

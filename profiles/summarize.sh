@@ -14,7 +14,7 @@ for r in rows[2:]:
         if any(h.startswith(w) for w in want) and not h.endswith('per_second') and '.pct_of_peak_sustained_elapsed' not in h[40:]: print(f'  {h} [{rows[1][i]}] = {r[i]}')
 "
   ncu -i $REP --page source --csv --print-source cuda,sass 2>/dev/null > /tmp/_src.csv
-  echo; echo "## warp-instructions by kernel phase"; python profiles/ncu_phases.py /tmp/_src.csv
+  echo; echo "## warp-instructions by kernel phase"; python profiles/ncu_phases.py /tmp/_src.csv ${3:-4096}
   echo; echo "## top source lines"; python profiles/ncu_lines.py /tmp/_src.csv 25
 } > $OUT
 echo wrote $OUT
