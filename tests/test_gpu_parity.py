@@ -414,6 +414,32 @@ def test_rollout_keeps_caller_supplied_layouts(mirror):
         np.testing.assert_array_equal(a.state['layout'].cpu().numpy().view(np.uint16), np.asarray(rows, dtype=np.uint16))
 
 
+@pytest.mark.parametrize('name,n_envs', [('tb_c2', 48), ('tb_c5', 6)])
+def test_compile_time_shapes_with_caller_supplied_layouts(mirror, name, n_envs):
+    """The compile-time-shape instantiations of the specialised kernel have no layout path in their inlined reset;
+    bgw_bind_state moves a handle that is given layouts to the run-time-shape instantiation.  Layout = the cells of a normal
+    reset (so every placement is legal), bound before the first reset and used by every auto-reset after it."""
+    builder = scenarios.build_tb_c5 if name == 'tb_c5' else scenarios.SCENARIOS[name][0]
+    spec = compile_sim(builder(mirror), n_envs=n_envs, env_offset=1, seed=31, horizon=7, auto_reset=True)
+    eng, ora = _pair(spec)
+    from oracle.oracle import OracleEnv
+    scout = OracleEnv(spec)
+    scout.reset()
+    layout = scout.state['cell'].copy()
+    for x in (eng, ora):
+        x.set_layout(layout)
+    eng.reset()
+    ora.reset()
+    assert np.array_equal(eng.obs.cpu().numpy(), ora.obs)
+    np.testing.assert_array_equal(eng.state_numpy()['cell'], layout)
+    for t in range(20):
+        act = ora.sample_actions()
+        eng.step(torch.from_numpy(act).cuda())
+        ora.step(act)
+        assert_outputs_equal(eng, ora, f'{name} layouts step {t}')
+        assert_state_equal(eng.state_numpy(), ora.state, f'{name} layouts step {t}')
+
+
 def test_step_launch_replayed_from_a_cuda_graph(mirror):
     """A step launch captured into a CUDA graph runs with the parameters of capture time at every replay: the library
     must not bake a ticket base or a chain dependency into it.  Replays, eager steps and chained rollouts mixed on one
