@@ -67,7 +67,7 @@ def build(force=False, verbose=False):
     if jobs:
         with ThreadPoolExecutor(len(jobs)) as pool:
             list(pool.map(run, jobs))
-    run([NVCC, '-shared', '-o', out] + objs + ['-lcudart'])
+    run([NVCC, '-gencode', 'arch=compute_100a,code=sm_100a', '-shared', '-o', out] + objs + ['-lcudart'])
     return out
 
 
