@@ -24,6 +24,7 @@ class SimulationManager(ABC):
 
     def __init__(self, sim, n_envs=1, env_offset=0, seed=0, horizon=0, auto_reset=False, device=None,
                  randomize_action_input=False, layouts=None):
+        assert type(randomize_action_input) is bool, "Randomize action input must be a boolean."   # all_step_manager.py:32-35
         assert not randomize_action_input or self._manager == 'all_step', \
             "randomize_action_input is an AllStepManager option (all_step_manager.py:24-35)"
         self.sim = sim

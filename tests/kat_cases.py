@@ -18,7 +18,8 @@ OBS, MOV, ATT, HEA, ORI, LRN, BLK, AMM = (K.AG_OBSERVING, K.AG_MOVING, K.AG_ATTA
 
 def make_spec(rows, cols, agents, overlapping=None, attack_mapping=None, program=K.PROG_TEAM_BATTLE,
               move_actor=K.MOVE_BOX, attack_actor=K.ATTACK_NONE, observer=K.OBS_POSITION_CENTERED, observe_self=True,
-              done_mask=K.DONE_ACTIVE, manager=K.MANAGER_ALL_STEP, ravel=False, stacked=False, n_envs=1, seed=24):
+              done_mask=K.DONE_ACTIVE, manager=K.MANAGER_ALL_STEP, ravel=False, stacked=False, n_envs=1, seed=24,
+              position_observer=False):
     """agents: list of dicts(enc, pos=(r, c) | None, klass, view=0, move=0, att_range=0, strength=0, accuracy=1,
     health=None | float, orient=0, simatt=1, ammo=0)."""
     sp = CompiledSpec()
@@ -26,6 +27,7 @@ def make_spec(rows, cols, agents, overlapping=None, attack_mapping=None, program
     sp.program, sp.move_actor, sp.attack_actor, sp.observer = program, move_actor, attack_actor, observer
     sp.observe_self, sp.done_mask, sp.manager, sp.ravel_actions = int(observe_self), done_mask, manager, int(ravel)
     sp.stacked_attacks = int(stacked)
+    sp.position_observer = int(position_observer)
     for name, dt in CompiledSpec.TABLES:
         setattr(sp, name, np.zeros(len(agents), dtype=dt))
     sp.init_row[:] = -1
@@ -118,6 +120,12 @@ class Backend:
         c = d.obs_c
         out = flat[:n * n * c].astype(int)
         return out.reshape(n, n) if c == 1 else out.reshape(n, n, c)
+
+    def position(self, learner):
+        """The AbsolutePositionObserver's entry of one learner's observation: (row, col)."""
+        off = self.env.dims.position_offset
+        raw = np.ascontiguousarray(self._np(self.env.obs)[0, learner, off:off + 4])
+        return tuple(int(v) for v in raw.view(np.int16))
 
     def rewards(self):
         return self._np(self.env.reward)[0].astype(np.float64)
@@ -541,6 +549,20 @@ def case_multi_grid_observer(kind):                          # test_observer.py:
 # ---------------------------------------------------------------------------------------------------
 # test_wrapper.py (RavelActionWrapper) and test_done.py
 # ---------------------------------------------------------------------------------------------------
+def case_absolute_position_observer(kind):                   # test_observer.py:905-988 (+ the combined test :991-1070)
+    """Agents observe their absolute position; with a grid observer next to it both entries are filled."""
+    pos = [(0, 0), (5, 0), (0, 6), (5, 6), (0, 0), (5, 6)]
+    agents = [dict(enc=e + 1, pos=p, klass=LRN | OBS, view=2) for e, p in enumerate(pos)]
+    b = Backend(make_spec(6, 7, agents, overlapping={1: {5}, 4: {6}, 5: {1}, 6: {4}}, position_observer=True), kind)
+    b.reset()
+    for l, p in enumerate(pos):
+        assert b.position(l) == p, (l, b.position(l), p)
+    # the grid part of the row is still the position-centred window: agent0 at (0, 0) sees agent4 (encoding 5) on its own
+    # cell or itself (encoding 1) -- one draw -- and the border
+    o = b.obs(0)
+    assert o.shape == (5, 5) and o[2, 2] in (1, 5) and (o[:2] == -1).all() and (o[:, :2] == -1).all()
+
+
 def case_ravel_action_wrapper(kind):                         # test_wrapper.py:111-144: 7 -> [1, 0], 3 -> [-2, 1], 34 -> [1, 3]
     agents = _movers([(1, (2, 2), 1), (2, (4, 4), 2), (3, (4, 1), 3)])
     be = Backend(make_spec(8, 8, agents, ravel=True), kind)

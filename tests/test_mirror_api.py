@@ -159,3 +159,28 @@ def test_dynamic_order_simulation_next_agent_property(mirror):
         sim.next_agent = ['nobody']
     with pytest.raises(AssertionError):
         sim.next_agent = 3
+
+
+def test_randomize_action_input_must_be_a_boolean(mirror):
+    """tests/test_all_step_multi_corridor.py:240-241: AllStepManager(sim, randomize_action_input=0) asserts (before any
+    device work)."""
+    import pytest
+    from abmarl_b200.managers import AllStepManager, TurnBasedManager
+    from tests import scenarios
+    with pytest.raises(AssertionError):
+        AllStepManager(scenarios.build_tb_c2(mirror), randomize_action_input=0)
+    with pytest.raises(AssertionError):
+        TurnBasedManager(scenarios.build_mm_tiny(mirror), randomize_action_input=True)
+
+
+def test_randomize_placement_order_must_be_a_boolean(mirror):
+    """tests/sim/gridworld/test_state.py:970-985."""
+    import pytest
+    from abmarl_b200.sim.gridworld.state import PositionState
+    from abmarl_b200.sim.gridworld.grid import Grid
+    from abmarl_b200.sim.gridworld.agent import GridWorldAgent
+    agents = {'a': GridWorldAgent(id='a', encoding=1)}
+    state = PositionState(grid=Grid(2, 2), agents=agents, randomize_placement_order=False)
+    assert not state.randomize_placement_order
+    with pytest.raises(AssertionError):
+        PositionState(grid=Grid(2, 2), agents=agents, randomize_placement_order=1)
