@@ -6,7 +6,7 @@ is missing or does not load, importing the engine raises.
 import ctypes as C
 import os
 
-BGW_ABI_VERSION = 4
+BGW_ABI_VERSION = 5
 BGW_MAX_ENCODING = 63
 BGW_MAX_AGENTS = 4096
 BGW_NONE = 0xFFFF
@@ -67,7 +67,7 @@ class BgwDims(C.Structure):
 
 LAYOUT_POSITION_STATE, LAYOUT_MAZE, LAYOUT_TARGET_BARRIERS_FREE = range(3)
 
-EXPORTS = ('bgw_create', 'bgw_destroy', 'bgw_dims', 'bgw_bind_state', 'bgw_reset', 'bgw_step', 'bgw_generate_layouts',
+EXPORTS = ('bgw_create', 'bgw_destroy', 'bgw_dims', 'bgw_bind_state', 'bgw_reset', 'bgw_observe', 'bgw_step', 'bgw_generate_layouts',
            'bgw_maze_layout_host', 'bgw_use_device_layouts',
            'bgw_sample_actions', 'bgw_step_sampled', 'bgw_rollout_sampled', 'bgw_gather_valid', 'bgw_rng_draw', 'bgw_los_mask', 'bgw_launch_count', 'bgw_last_error',
            'bgw_abi_version')
@@ -99,6 +99,8 @@ def load():
     lib.bgw_reset.argtypes = [h, _p, _p, _p]
     lib.bgw_step.argtypes = [h, _p, _p, _p, _p, _p, _p, _p]
     lib.bgw_sample_actions.argtypes = [h, _p, _p]
+    lib.bgw_observe.argtypes = [h, _p, _p, _p]
+    lib.bgw_observe.restype = C.c_int
     lib.bgw_step_sampled.argtypes = [h, _p, _p, _p, _p, _p, _p, _p]
     lib.bgw_step_sampled.restype = C.c_int
     lib.bgw_rollout_sampled.argtypes = [h, C.c_int, _p, _p, _p, _p, _p, _p, _p]

@@ -50,6 +50,18 @@ int pow2ceil(int x) { int p = 1; while (p < x) p <<= 1; return p; }
 
 }  // namespace
 
+static const void *observe_fast_fn(int R)
+{
+    switch (R) {
+    case 1: return (const void *)bgw_observe_fast_kernel<1>;
+    case 2: return (const void *)bgw_observe_fast_kernel<2>;
+    case 3: return (const void *)bgw_observe_fast_kernel<3>;
+    case 4: return (const void *)bgw_observe_fast_kernel<4>;
+    case 5: return (const void *)bgw_observe_fast_kernel<5>;
+    }
+    return nullptr;
+}
+
 struct BgwEngine {
     int device = 0;
     GeneralStepFn step_fn = nullptr;   /* the bgw_step_kernel instantiation of this sim's program */
@@ -71,6 +83,8 @@ struct BgwEngine {
     std::vector<uint32_t> ticket_next;              /* value each counter will have when the launches that used it are done (a launch
                                                        draws exactly n_tickets + grid tickets) */
     int fast_shape = 0;           /* compile-time shape instantiation of the fast kernel: 0 run-time shapes, 1 FastStaticC5, 2 FastStaticC2 */
+    const void *observe_fn = nullptr;   /* bgw_observe_fast_kernel<view range> when the sim qualifies, else the general observe kernel runs */
+    int observe_grid = 0, observe_smem = 0;
     BgwDims dims{};
     BgwState st{};
     bool bound = false;
@@ -477,8 +491,23 @@ int bgw_create(const BgwSpec *sp, int device, bgw_handle *out)
     if (const char *t = getenv("BGW_ALL_IN_ONE_KERNEL")) if (atoi(t)) h->step_fn = bgw_general_step_fn(-1, -1);
     if ((ce = cudaFuncSetAttribute(h->step_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, off)) != cudaSuccess ||
         (h->fs.enabled && (ce = cudaFuncSetAttribute(h->fast_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, h->fs.smem_bytes)) != cudaSuccess) ||
-        (ce = cudaFuncSetAttribute(bgw_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, off)) != cudaSuccess)
+        (ce = cudaFuncSetAttribute(bgw_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, off)) != cudaSuccess ||
+        (ce = cudaFuncSetAttribute(bgw_observe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, off)) != cudaSuccess)
         return bail(fail(2, "bgw_create: cudaFuncSetAttribute: %s", cudaGetErrorString(ce)));
+    /* bgw_observe: the observer alone.  The sims of the specialised kernel whose cells never mix encodings and whose learners
+     * share a view range get the gather-only kernel (bgw_fast.cuh); the rest run observe_learners of the general kernel. */
+    if (h->fs.enabled && !h->fs.can_mix && sp->observe_self && h->fs.uniform_view >= 1 && h->fs.uniform_view <= 5 && !getenv("BGW_GENERIC_OBSERVE")) {
+        const ObserveLayout lay = observe_layout(d.A, d.L, h->fs.PH, h->fs.PW);
+        int per_sm = 0, sms = 0;
+        h->observe_fn = observe_fast_fn(h->fs.uniform_view);
+        h->observe_smem = lay.bytes;
+        if ((ce = cudaFuncSetAttribute(h->observe_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, lay.bytes)) != cudaSuccess ||
+            (ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, h->observe_fn, 128, (size_t)lay.bytes)) != cudaSuccess ||
+            (ce = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess)
+            return bail(fail(2, "bgw_create: observe kernel set-up: %s", cudaGetErrorString(ce)));
+        h->observe_grid = std::max(1, std::min(d.E, per_sm * sms));
+        if (const char *t = getenv("BGW_OBSERVE_GRID")) { const int v = atoi(t); if (v >= 1) h->observe_grid = std::min(d.E, v); }
+    }
     if (h->fs.enabled) {
         int per_sm = 0, sms = 0;
         /* the instantiation step_impl launches for this handle */
@@ -572,6 +601,23 @@ int bgw_reset(bgw_handle h, const uint8_t *env_mask, int8_t *obs, void *stream)
     DeviceGuard guard(h->device);
     bgw_reset_kernel<<<h->ds.E, h->threads, h->ds.smem_bytes, (cudaStream_t)stream>>>(h->ds, h->st, env_mask, obs);
     CUDA_OK(cudaGetLastError());
+    h->launches += 1;
+    return 0;
+}
+
+int bgw_observe(bgw_handle h, const uint8_t *env_mask, int8_t *obs, void *stream)
+{
+    if (!h) return fail(1, "bgw_observe: null handle");
+    if (!h->bound) return fail(1, "bgw_observe: call bgw_bind_state first");
+    if (!obs) return fail(1, "bgw_observe: obs is null");
+    DeviceGuard guard(h->device);
+    if (h->observe_fn) {
+        void *args[] = {(void *)&h->dsf, (void *)&h->fs, (void *)&h->st, (void *)&env_mask, (void *)&obs};
+        CUDA_OK(cudaLaunchKernel(h->observe_fn, dim3(h->observe_grid), dim3(128), args, (size_t)h->observe_smem, (cudaStream_t)stream));
+    } else {
+        bgw_observe_kernel<<<h->ds.E, h->threads, h->ds.smem_bytes, (cudaStream_t)stream>>>(h->ds, h->st, env_mask, obs);
+        CUDA_OK(cudaGetLastError());
+    }
     h->launches += 1;
     return 0;
 }

@@ -1361,6 +1361,33 @@ __global__ void bgw_reset_kernel(const DevSpec s, const BgwState st, const uint8
     if (tid == 0) st.env_flags[e] = (uint8_t)(ev.ctr[CTR_ERR] ? BGW_ENV_ERROR | BGW_ENV_ALL_DONE : 0);
 }
 
+
+/* GridWorldSimulation.get_obs(agent_id) (sim/gridworld/base.py; the observers of sim/gridworld/observer.py) for EVERY learner of
+ * the selected envs, on the state as it stands in HBM: nothing is stepped, no state is written.  The random choice among
+ * the encodings of a shared cell (observer.py:131-134,233-236) is keyed by the env's current step, so the rows equal the
+ * ones the last reset / step wrote for the learners it reported. */
+__global__ void bgw_observe_kernel(const DevSpec s, const BgwState st, const uint8_t *env_mask, int8_t *obs)
+{
+    const int e = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
+    if (env_mask && !env_mask[e]) return;
+    Env ev;
+    env_init(ev, s, bgw_smem);
+    ev.e = e; ev.genv = (uint32_t)(s.env_offset + e);
+    ev.health = st.health + (size_t)e * s.A;
+    ev.ammo = st.ammo ? st.ammo + (size_t)e * s.A : nullptr;
+    ev.episode = st.episode[e];
+    ev.step = st.step[e];
+    const size_t off = (size_t)e * s.A;
+    for (int a = tid; a < s.A; a += T) {
+        ev.cell[a] = st.cell[off + a]; ev.next[a] = st.next[off + a]; ev.flags[a] = st.flags[off + a];
+        ev.enc[a] = __ldg(&s.enc[a]); ev.klass[a] = __ldg(&s.klass[a]);
+    }
+    for (int l = tid; l < s.L; l += T) ev.plist[l] = (uint16_t)l;
+    __syncthreads();
+    build_heads(s, ev, tid, T);
+    observe_learners(s, ev, s.L, obs + (size_t)e * s.L * s.obs_stride, tid, T);
+}
+
 #endif
 
 /* The step kernel is instantiated per sim program (and, for the team battle, per attack actor): PROG / ATT >= 0 overwrite

@@ -685,6 +685,119 @@ __device__ __forceinline__ void st_global_256(void *p, const uint32_t *v)
                  : "memory");
 }
 
+/* ---- cooperative row gather (view ranges 5 and 3: the observation row is 4 / 2 chunks of 32 bytes) -----------------
+ * LPA lanes share one learner: lane q of the group produces bytes [32q, 32q + 32) of the packed row and the group writes one
+ * contiguous piece of a 128-byte line with a single 256-bit store per lane.  (One lane per learner -- fast_obs_rows_lane
+ * below -- made every lane of a store instruction write into a line of its own: ncu counted 5.5 LSU data-pipe wavefronts per
+ * row for the stores alone, more than for the window loads.)  Chunk q needs the window rows i = a*q + b + r, r = 0..NR-1
+ * (rows outside 0..n-1 do not exist and read as nothing); they are packed at n*r into the register stream S exactly as the
+ * one-lane gather packs a whole window, and the chunk is S from byte 32q - n*(a*q + b) on: a compile-time word offset plus a
+ * lane-dependent shift of 0..4 bytes (shf.r.clamp), so every register index stays static. */
+template <int R> struct ObsCoop { static constexpr bool on = false; static constexpr int LPA = 1, a = 0, b = 0, NR = 0; };
+template <> struct ObsCoop<5> { static constexpr bool on = true; static constexpr int LPA = 4, a = 3, b = -1, NR = 4; };   /* start byte 11 - q */
+template <> struct ObsCoop<3> { static constexpr bool on = true; static constexpr int LPA = 2, a = 4, b = 0, NR = 5; };    /* start byte 4q */
+
+/* bytes [lo, hi) of window-row slot r that some lane of the group needs (compile time) */
+template <int R>
+__host__ __device__ constexpr int obs_coop_lo(int r)
+{
+    typedef ObsCoop<R> C;
+    const int n = 2 * R + 1;
+    int lo = n;
+    for (int q = 0; q < C::LPA; ++q) {
+        const int st = 32 * q - n * (C::a * q + C::b) - n * r;     /* chunk start relative to the row's first byte */
+        const int l = st < 0 ? 0 : st;
+        if (l < lo && st + 32 > 0 && st < n) lo = l;
+    }
+    return lo;
+}
+template <int R>
+__host__ __device__ constexpr int obs_coop_hi(int r)
+{
+    typedef ObsCoop<R> C;
+    const int n = 2 * R + 1;
+    int hi = 0;
+    for (int q = 0; q < C::LPA; ++q) {
+        const int st = 32 * q - n * (C::a * q + C::b) - n * r;
+        const int h = st + 32 > n ? n : st + 32;
+        if (h > hi && st + 32 > 0 && st < n) hi = h;
+    }
+    return hi;
+}
+
+template <int R>
+__device__ void fast_obs_rows_coop(const DevSpec &s, const FastSpec &f, const Env &ev, const FastEnv &fe, int n_act, int8_t *obs_env,
+                                   int tid, int T)
+{
+    typedef ObsCoop<R> C;
+    constexpr int n = 2 * R + 1, LPA = C::LPA, NR = C::NR;
+    constexpr int RW = (n + 3) / 4;            /* words of an aligned row */
+    constexpr int LW = (n + 6) / 4;            /* words to load: alignment shift (<= 3 bytes) + n bytes */
+    constexpr int ST0 = -n * C::b, SLOPE = 32 - n * C::a;               /* chunk q starts at byte ST0 + SLOPE*q of S */
+    constexpr int ST_MIN = SLOPE >= 0 ? ST0 : ST0 + SLOPE * (LPA - 1);
+    constexpr int W0 = ST_MIN / 4;
+    constexpr int SW = W0 + 9;                 /* words of S the chunk extraction reads */
+    static_assert(ST_MIN >= 0 && (SLOPE >= 0 ? ST0 + SLOPE * (LPA - 1) : ST0) - 4 * W0 <= 4, "lane-dependent shift must stay within 0..4 bytes");
+    static_assert((NR * n + 3) / 4 <= SW, "stream longer than the extraction window");
+    const int q = tid & (LPA - 1);
+    const int dyn = (ST0 + SLOPE * q - 4 * W0) * 8;
+    const int pw4 = f.PW >> 2;
+    const bool wide = ((s.obs_stride & 31) == 0) && ((reinterpret_cast<uintptr_t>(obs_env) & 31) == 0);
+    for (int li = tid / LPA; li < n_act; li += T / LPA) {
+        const int a = ev.ragent[li];
+        const bool observing = ev.klass[a] & BGW_AG_OBSERVING;
+        const int i0 = C::a * q + C::b;                                   /* first window row of this lane's chunk */
+        const int o = pad_index(s, f, ev.cell[a]) - R * f.PW - R;
+        const uint32_t *wp = reinterpret_cast<const uint32_t *>(fe.cenc + (o & ~3)) + i0 * pw4;
+        const int sh = (o & 3) * 8;
+        uint32_t S[SW + 1];
+#pragma unroll
+        for (int j = 0; j <= SW; ++j) S[j] = 0;
+        if (observing) {
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+                const int lo = obs_coop_lo<R>(r), hi = obs_coop_hi<R>(r);     /* compile-time after unrolling */
+                if (hi <= lo) continue;
+                const bool ok = (unsigned)(i0 + r) < (unsigned)n;             /* the window has this row */
+                const uint32_t *rp = wp + r * pw4;
+                uint32_t x[LW + 1], y[RW];
+                /* aligned words j, j+1 of the padded row give bytes 4j..4j+3 of the window row; only the words some lane's
+                 * chunk reaches are loaded, the last one only where the row's alignment reaches into it */
+#pragma unroll
+                for (int j = 0; j <= LW; ++j) {
+                    const bool ny = j < RW && !(4 * j + 4 <= lo || 4 * j >= hi);
+                    const bool nyp = j > 0 && j - 1 < RW && !(4 * (j - 1) + 4 <= lo || 4 * (j - 1) >= hi);
+                    if (j < LW && (ny || nyp)) x[j] = (ok && (j < LW - 1 || sh + 8 * n > 32 * (LW - 1))) ? rp[j] : 0u;
+                    else x[j] = 0;
+                }
+#pragma unroll
+                for (int j = 0; j < RW; ++j)
+                    y[j] = (4 * j + 4 <= lo || 4 * j >= hi) ? 0u : __funnelshift_r(x[j], x[j + 1], sh);
+                constexpr int vb = n - 4 * (RW - 1);
+                if (vb < 4) y[RW - 1] &= (1u << (8 * (vb & 3))) - 1u;
+                const int d = n * r, qw = d >> 2, s8 = (d & 3) * 8;
+#pragma unroll
+                for (int j = 0; j < RW; ++j) {
+                    if (4 * j + 4 <= lo || 4 * j >= hi) continue;
+                    if (qw + j <= SW) S[qw + j] |= y[j] << s8;
+                    if (s8 != 0 && qw + j + 1 <= SW) S[qw + j + 1] |= y[j] >> (32 - s8);
+                }
+            }
+        }
+        uint32_t out[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) out[j] = __funnelshift_rc(S[W0 + j], S[W0 + j + 1], dyn);
+        if (32 * q < s.obs_stride) {
+            int8_t *dg = obs_env + (size_t)ev.plist[li] * s.obs_stride + 32 * q;
+            if (wide) st_global_256(dg, out);
+            else {
+                *reinterpret_cast<uint4 *>(dg) = make_uint4(out[0], out[1], out[2], out[3]);
+                *reinterpret_cast<uint4 *>(dg + 16) = make_uint4(out[4], out[5], out[6], out[7]);
+            }
+        }
+    }
+}
+
 /* Observation rows of the acting learners, view range R known at compile time.  One thread gathers one
  * learner's window: per window row LW aligned words, funnel-shifted to the row's first byte, then appended at
  * byte n*i of the packed output (all shifts are compile-time after unrolling).  The packed row is produced in
@@ -693,8 +806,8 @@ __device__ __forceinline__ void st_global_256(void *p, const uint32_t *v)
  * through a shared-memory stage into coalesced 128-bit stores: half of the gather's instructions and a third of its
  * shared-memory wavefronts were that transposition.) */
 template <int R>
-__device__ void fast_obs_rows(const DevSpec &s, const FastSpec &f, const Env &ev, const FastEnv &fe, int n_act, int8_t *obs_env,
-                              int tid, int T)
+__device__ void fast_obs_rows_lane(const DevSpec &s, const FastSpec &f, const Env &ev, const FastEnv &fe, int n_act, int8_t *obs_env,
+                                   int tid, int T)
 {
     constexpr int n = 2 * R + 1, NB = n * n;
     constexpr int RW = (n + 3) / 4;            /* words of an aligned row */
@@ -754,6 +867,17 @@ __device__ void fast_obs_rows(const DevSpec &s, const FastSpec &f, const Env &ev
             }
         }
     }
+}
+
+template <int R>
+__device__ __forceinline__ void fast_obs_rows(const DevSpec &s, const FastSpec &f, const Env &ev, const FastEnv &fe, int n_act, int8_t *obs_env,
+                                              int tid, int T)
+{
+#ifndef BGW_OBS_ONE_LANE
+    if constexpr (ObsCoop<R>::on) fast_obs_rows_coop<R>(s, f, ev, fe, n_act, obs_env, tid, T);
+    else
+#endif
+        fast_obs_rows_lane<R>(s, f, ev, fe, n_act, obs_env, tid, T);
 }
 
 /* Compile-time shape of the headline workload (BASELINE configs[4]: 64x64 grid, 256 agents that are all learners,
@@ -1383,3 +1507,79 @@ __global__ void BGW_FAST_LB bgw_step_fast_kernel(const DevSpec s_in, const FastS
 #undef BGW_END_ENV
     cp_async_wait<0>();
 }
+
+#ifdef BGW_SMALL_KERNELS
+/* ------------------------------------------------------------------------------------------------- */
+/* The observer on its own (bgw_observe): PositionCenteredEncodingObserver.get_obs observer.py:195-248  */
+/* ------------------------------------------------------------------------------------------------- */
+/* For the sims of the specialised kernel whose cells never hold two different encodings (FastSpec.can_mix == 0) and whose
+ * learners share one view range.  Persistent CTAs; per env: the entities' cells and flags are read from HBM (3 bytes each),
+ * their encodings scattered into the padded summary grid in shared memory, every learner's window gathered by
+ * fast_obs_rows (the step kernel's gather: 256-bit stores), the scattered cells cleared again.  128 bytes written per
+ * 3 read: the HBM-bound piece of the path ("K3"). */
+struct ObserveLayout { int o_cell, o_flags, o_klass, o_enc, o_ragent, o_plist, bytes; };
+inline __host__ __device__ ObserveLayout observe_layout(int A, int L, int PH, int PW)
+{
+    ObserveLayout o;
+    int off = (PH * PW + 32 + 15) & ~15;             /* summary grid + the slack words the row gather reads */
+    o.o_cell = off;   off += ((A + 7) & ~7) * 2;
+    o.o_ragent = off; off += ((L + 7) & ~7) * 2;
+    o.o_plist = off;  off += ((L + 7) & ~7) * 2;
+    o.o_flags = off;  off += (A + 15) & ~15;
+    o.o_klass = off;  off += (A + 15) & ~15;
+    o.o_enc = off;    off += (A + 15) & ~15;
+    o.bytes = off;
+    return o;
+}
+
+template <int R>
+__global__ void __launch_bounds__(128) bgw_observe_fast_kernel(const DevSpec s, const FastSpec f, const BgwState st, const uint8_t *env_mask,
+                                                               int8_t *obs)
+{
+    const int tid = threadIdx.x, T = blockDim.x;
+    const ObserveLayout lay = observe_layout(s.A, s.L, f.PH, f.PW);
+    Env ev;
+    FastEnv fe;
+    fe.cenc = (int8_t *)bgw_smem;
+    ev.cell = (uint16_t *)(bgw_smem + lay.o_cell);
+    ev.ragent = (uint16_t *)(bgw_smem + lay.o_ragent);
+    ev.plist = (uint16_t *)(bgw_smem + lay.o_plist);
+    ev.flags = bgw_smem + lay.o_flags;
+    ev.klass = bgw_smem + lay.o_klass;
+    ev.enc = (int8_t *)(bgw_smem + lay.o_enc);
+    {   /* once per CTA: the empty summary with its -1 border (as fast_init_dense), the per-entity constants */
+        uint32_t *c32 = (uint32_t *)fe.cenc;
+        const int wpr = f.PW >> 2;
+        for (int i = tid; i < f.PH * wpr + 8; i += T) {
+            const int rr = i / wpr, cw = i - rr * wpr;
+            uint32_t v = 0xFFFFFFFFu;
+            if (rr >= f.P && rr < f.P + s.H)
+                for (int bb = 0; bb < 4; ++bb) {
+                    const int cc = cw * 4 + bb;
+                    if (cc >= f.PL && cc < f.PL + s.W) v &= ~(0xFFu << (8 * bb));
+                }
+            c32[i] = v;
+        }
+        for (int a = tid; a < s.A; a += T) { ev.klass[a] = __ldg(&s.klass[a]); ev.enc[a] = __ldg(&s.enc[a]); }
+        for (int l = tid; l < s.L; l += T) { ev.ragent[l] = (uint16_t)__ldg(&s.agent_of[l]); ev.plist[l] = (uint16_t)l; }
+    }
+    __syncthreads();
+    for (int e = blockIdx.x; e < s.E; e += gridDim.x) {
+        if (env_mask && !env_mask[e]) continue;
+        const size_t off = (size_t)e * s.A;
+        for (int a = tid; a < s.A; a += T) {
+            const uint16_t c = __ldcs(&st.cell[off + a]);
+            const uint8_t fl = __ldcs(&st.flags[off + a]);
+            ev.cell[a] = c; ev.flags[a] = fl;
+            if (fl & BGW_ST_IN_GRID) fe.cenc[pad_index(s, f, c)] = ev.enc[a];   /* same encoding from every occupant of a cell */
+        }
+        __syncthreads();
+        fast_obs_rows<R>(s, f, ev, fe, s.L, obs + (size_t)e * s.L * s.obs_stride, tid, T);
+        __syncthreads();
+        for (int a = tid; a < s.A; a += T)
+            if (ev.flags[a] & BGW_ST_IN_GRID) fe.cenc[pad_index(s, f, ev.cell[a])] = 0;
+        __syncthreads();
+    }
+}
+#endif  /* BGW_SMALL_KERNELS */
+

@@ -114,6 +114,18 @@ class BatchedGridWorld:
                 self.lib)
         return self.obs
 
+    def observe(self, env_mask=None, out=None):
+        """`sim.get_obs(agent_id)` of every learner for the state as it stands (bgw_observe; smart.py:93-99): nothing is
+        stepped.  Into `out` ([E, L, obs_stride] int8 CUDA; default: the engine's obs tensor), rows of unselected envs untouched."""
+        out = self.obs if out is None else out
+        assert out.dtype == torch.int8 and tuple(out.shape) == tuple(self.obs.shape) and out.is_cuda and out.is_contiguous()
+        m = None
+        if env_mask is not None:
+            m = torch.as_tensor(env_mask, dtype=torch.uint8, device=self.device).contiguous()
+            assert tuple(m.shape) == (self.E,)
+        K.check(self.lib.bgw_observe(self._h, None if m is None else m.data_ptr(), out.data_ptr(), self._stream()), self.lib)
+        return out
+
     def sample_actions(self, out=None):
         out = self.actions if out is None else out
         K.check(self.lib.bgw_sample_actions(self._h, out.data_ptr(), self._stream()), self.lib)

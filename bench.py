@@ -258,6 +258,23 @@ def run_ours(args):
     barrier()
     given_ms_per_step = g_beg.elapsed_time(g_end) / gs
     given_units_per_step = (agent_steps() - n_g0) / gs
+    # the observer on its own (bgw_observe = sim.get_obs of every learner on the state as it stands): the bandwidth-bound piece
+    # of the path (SURVEY 8(d) "K3"); every launch writes E*L rows of obs_stride bytes (more than the L2) and reads 3 bytes of
+    # state per entity
+    obs_launches = max(1, args.observe_launches)
+    obs_out = torch.empty_like(eng.obs)
+    for i in range(3):
+        eng.observe(out=obs_out)
+    barrier()
+    o_beg, o_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    o_beg.record(stream)
+    for i in range(obs_launches):
+        eng.observe(out=obs_out)
+    o_end.record(stream)
+    barrier()
+    observe_ms = o_beg.elapsed_time(o_end) / obs_launches
+    observe_bytes = E * L * eng.dims.obs_stride + E * eng.A * 3
+    del obs_out
     if args.dump_steps and rank == 0:
         with open(args.dump_steps, 'w') as fh:
             json.dump(per_step_ms, fh)
@@ -393,7 +410,13 @@ def run_ours(args):
                          "isolated_note": f"{ks} further steps, one bgw_step_sampled launch each, every launch bracketed by its own CUDA events (launches serialised, per-CTA set-up and tail exposed)",
                          "kernel_ms_given_actions": given_ms_per_step,
                          "given_actions_achieved": BYTES_PER_AGENT_STEP * given_units_per_step / (given_ms_per_step * 1e-3) / 1e9,
-                         "given_actions_note": f"{gs} bgw_step calls with caller-supplied device-resident action tensors (what a trainer calls): one launch per step, no fused policy"},
+                         "given_actions_note": f"{gs} bgw_step calls with caller-supplied device-resident action tensors (what a trainer calls): one launch per step, no fused policy",
+                         "observe_kernel": {"kernel": "bgw_observe_fast_kernel (bgw_observe: get_obs of every learner, no step)",
+                                            "ms_per_launch": observe_ms, "bytes_per_launch": observe_bytes,
+                                            "achieved": observe_bytes / (observe_ms * 1e-3) / 1e9, "unit": "GB/s",
+                                            "frac": observe_bytes / (observe_ms * 1e-3) / 1e9 / peak,
+                                            "rows_per_s": E * L / (observe_ms * 1e-3),
+                                            "note": f"{obs_launches} launches back to back; bytes = E*L obs rows of obs_stride written + 3 B of state per entity read"}},
         }
         if strong is not None:
             line["strong"] = {"global_envs": E, "envs_per_gpu": E // world, "ms_per_step": strong_ms / args.steps,
@@ -427,6 +450,7 @@ def main():
     ap.add_argument('--cpu-steps', type=int, default=200, help='steps of the cpu_baseline sample (all host cores, all envs)')
     ap.add_argument('--given-steps', type=int, default=200, help='bgw_step calls with caller-supplied device actions timed next to the fused rollout')
     ap.add_argument('--e2e-zero-copy', action='store_true', help='e2e: the gather kernel writes the pinned host buffers directly instead of compacting on the device and copying')
+    ap.add_argument('--observe-launches', type=int, default=50, help='bgw_observe launches timed next to the step kernel')
     ap.add_argument('--dump-steps', default=None, help='write the per-step kernel times (ms) to this JSON file')
     args = ap.parse_args()
     if args.impl == 'reference':

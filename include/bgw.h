@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define BGW_ABI_VERSION 4
+#define BGW_ABI_VERSION 5
 #define BGW_MAX_ENCODING 63   /* encodings are bit positions in 64-bit overlap / attack rows */
 #define BGW_MAX_AGENTS 4096   /* Philox slot field (bgw_philox.h)                           */
 #define BGW_MAX_CELLS 65535   /* cell index is u16, 0xFFFF = none                           */
@@ -267,6 +267,18 @@ int bgw_bind_state(bgw_handle h, const BgwState *state);
  * first observations into obs[E][L][obs_stride] (rows of unselected envs are untouched).
  */
 int bgw_reset(bgw_handle h, const uint8_t *env_mask, int8_t *obs, void *stream);
+
+/*
+ * sim.get_obs(agent_id) for EVERY learner of the envs selected by env_mask (NULL = all), on the state as it stands:
+ * SmartGridWorldSimulation.get_obs (sim/gridworld/smart.py:93-99) = the sim's observers (observer.py:95-150 absolute,
+ * :195-248 position centred, :287-335 stacked, :366-373 position, :406-413 ammo) -> obs[E][L][obs_stride] (rows of
+ * unselected envs are untouched).  Nothing is stepped and no state is written; learners that are inactive or already
+ * reported done get the row the reference computes from their last position.  The random choice among the encodings
+ * sharing a cell (observer.py:131-134,233-236) is keyed by the env's current (episode, step): the rows equal the ones
+ * the last bgw_reset / bgw_step wrote for the learners it reported.  What a manager calls between steps
+ * (all_step_manager.py:47,69), and the bandwidth-bound piece of the path on its own (128 bytes written per 3 read).
+ */
+int bgw_observe(bgw_handle h, const uint8_t *env_mask, int8_t *obs, void *stream);
 
 /*
  * One manager step for every env (all_step_manager.py:51-95 / turn_based_manager.py:34-94):

@@ -148,14 +148,12 @@ class Backend:
             self.env.load_state(st)
 
     def observe_now(self):
-        """Refresh every learner's observation for the current state without stepping (oracle hook / a no-op
-        step is not available on the engine, so the engine re-observes through a reset-free kernel path:
-        step with null actions on a sim whose agents cannot move)."""
+        """Refresh every learner's observation for the current state without stepping: sim.get_obs(agent_id) for all of
+        them (oracle: bgwo_observe; engine: bgw_observe)."""
         if self.kind == 'oracle':
             self.env.obs[0] = self.env.observe(0)
         else:
-            import torch
-            self.env.step(torch.zeros((1, self.L, self.env.dims.action_stride), dtype=torch.int8, device='cuda'))
+            self.env.observe()
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -70,6 +70,50 @@ def test_engine_matches_oracle(mirror, name, n_envs, steps, horizon):
     assert int(eng.stats()[K.STAT_AGENT_STEPS].item()) == n
 
 
+OBSERVE_CASES = ['tb_c2', 'tb_c5', 'tb_c5_small', 'tb_dense', 'tb_blocking', 'tb_stacked', 'tb_noself', 'tb_position', 'tb_ammo',
+                 'tb_encoding_stacked', 'reach_target_crowd', 'traffic', 'maze_c1', 'pacman_c3', 'mm_c4', 'mm_dynamic']
+
+
+@pytest.mark.parametrize('generic', ['0', '1'])
+@pytest.mark.parametrize('name', OBSERVE_CASES)
+def test_observe_equals_get_obs_of_every_learner(mirror, name, generic, monkeypatch):
+    """bgw_observe = sim.get_obs(agent_id) for every learner on the state as it stands (smart.py:93-99), against the oracle's
+    observer on the same state: after a reset, mid-episode (dead and already-reported learners included) and after
+    auto-resets; it writes no state, repeats the rows the last step reported, and honours the env mask.  generic=1 forces
+    the general kernel's observer where the gather-only kernel would run."""
+    if generic == '1':
+        if name not in ('tb_c2', 'tb_c5', 'tb_c5_small', 'tb_dense'):
+            pytest.skip('the general observer runs anyway')
+        monkeypatch.setenv('BGW_GENERIC_OBSERVE', '1')
+    builder, manager, _ = scenarios.SCENARIOS[name] if name != 'tb_c5' else (scenarios.build_tb_c5, 'all_step', None)
+    E = 6 if name in ('tb_c5', 'pacman_c3') else 20
+    spec = compile_sim(builder(mirror), manager=manager, n_envs=E, env_offset=3, seed=0x0B5, horizon=25, auto_reset=True)
+    eng, ora = _pair(spec)
+    for steps in (0, 9, 40):
+        run_lockstep(eng, ora, steps, label=f'{name}/observe')
+        before = eng.state_numpy()
+        reported = eng.obs.cpu().numpy().copy()
+        out = torch.full_like(eng.obs, 99)
+        assert eng.observe(out=out) is out
+        got = out.cpu().numpy()
+        want = np.stack([ora.observe(e) for e in range(E)])
+        bad = np.argwhere(got != want)
+        assert bad.size == 0, f'{name} after {steps} steps: observe differs at {bad[:5].tolist()}'
+        assert_state_equal(eng.state_numpy(), before, f'{name}: observe wrote state')
+        fresh = np.ones(E, dtype=bool) if steps == 0 else (ora.all_done & K.ENV_RESET) != 0
+        rows = np.zeros((E, eng.L), dtype=bool) if steps == 0 else (ora.done & K.OUT_VALID) != 0
+        if spec.manager == K.MANAGER_ALL_STEP:
+            rows |= fresh[:, None]                                          # a reset reports every learner
+        else:
+            rows[fresh, before['turn'][fresh]] = True                       # a turn-based reset reports the learner whose turn it is
+        assert np.array_equal(got[rows], reported[rows]), f'{name}: observe does not repeat the reported rows'
+        mask = (np.arange(E) % 3 == 0).astype(np.uint8)
+        out2 = torch.full_like(eng.obs, 99)
+        eng.observe(env_mask=mask, out=out2)
+        got2 = out2.cpu().numpy()
+        assert np.array_equal(got2[mask != 0], want[mask != 0]) and (got2[mask == 0] == 99).all()
+
+
 @pytest.mark.parametrize('name', ['tb_c2', 'tb_c5_small', 'tb_dense', 'tb_noself'])
 def test_general_kernel_on_fast_path_scenarios(mirror, name, monkeypatch):
     """Scenarios that qualify for the specialised team-battle kernel must give the same results through the
