@@ -1550,16 +1550,19 @@ __global__ void __launch_bounds__(128) bgw_observe_fast_kernel(const DevSpec s, 
     {   /* once per CTA: the empty summary with its -1 border (as fast_init_dense), the per-entity constants */
         uint32_t *c32 = (uint32_t *)fe.cenc;
         const int wpr = f.PW >> 2;
-        for (int i = tid; i < f.PH * wpr + 8; i += T) {
-            const int rr = i / wpr, cw = i - rr * wpr;
-            uint32_t v = 0xFFFFFFFFu;
-            if (rr >= f.P && rr < f.P + s.H)
-                for (int bb = 0; bb < 4; ++bb) {
-                    const int cc = cw * 4 + bb;
-                    if (cc >= f.PL && cc < f.PL + s.W) v &= ~(0xFFu << (8 * bb));
-                }
-            c32[i] = v;
+        /* a thread keeps its column word (one division per CTA); rows_per_pass rows are written side by side.  A row with
+         * more words than the CTA has threads is walked by all threads, one row at a time. */
+        const int rows_per_pass = wpr <= T ? T / wpr : 1;
+        const int r0 = wpr <= T ? tid / wpr : 0;
+        for (int cw = wpr <= T ? tid - r0 * wpr : tid; cw < wpr && r0 < rows_per_pass; cw += T) {
+            uint32_t inner = 0xFFFFFFFFu;
+            for (int bb = 0; bb < 4; ++bb) {
+                const int cc = cw * 4 + bb;
+                if (cc >= f.PL && cc < f.PL + s.W) inner &= ~(0xFFu << (8 * bb));
+            }
+            for (int rr = r0; rr < f.PH; rr += rows_per_pass) c32[rr * wpr + cw] = (rr >= f.P && rr < f.P + s.H) ? inner : 0xFFFFFFFFu;
         }
+        if (tid < 8) c32[f.PH * wpr + tid] = 0xFFFFFFFFu;           /* slack words read by the row gather */
         for (int a = tid; a < s.A; a += T) { ev.klass[a] = __ldg(&s.klass[a]); ev.enc[a] = __ldg(&s.enc[a]); }
         for (int l = tid; l < s.L; l += T) { ev.ragent[l] = (uint16_t)__ldg(&s.agent_of[l]); ev.plist[l] = (uint16_t)l; }
     }

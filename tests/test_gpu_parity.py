@@ -618,14 +618,18 @@ def _tiny_battle(api, rows, cols, n_agents, teams=2, view=1, blocking=False, ove
 
 
 @pytest.mark.parametrize('rows,cols,n_agents,blocking', [(1, 1, 3, False), (1, 1, 1, False), (1, 7, 4, False), (5, 1, 4, True),
-                                                         (2, 2, 9, False), (3, 3, 2, True)])
+                                                         (2, 2, 9, False), (3, 3, 2, True), (1, 700, 12, False)])
 def test_degenerate_grids(mirror, rows, cols, n_agents, blocking):
-    """One-cell and one-line grids, a single agent, more agents than cells (everything overlaps): both kernels against
-    the oracle -- every window cell out of bounds, every move into a border, every agent on one cell."""
-    spec = compile_sim(_tiny_battle(mirror, rows, cols, n_agents, blocking=blocking), n_envs=40, seed=rows * 100 + cols, horizon=12,
-                       auto_reset=True)
+    """One-cell and one-line grids (one with more words per row than a CTA has threads), a single agent, more agents than
+    cells (everything overlaps): both kernels against the oracle -- every window cell out of bounds, every move into a
+    border, every agent on one cell; and bgw_observe on the state they end in."""
+    E = 40 if cols < 100 else 8
+    spec = compile_sim(_tiny_battle(mirror, rows, cols, n_agents, blocking=blocking, overlap_all=cols < 100), n_envs=E,
+                       seed=rows * 100 + cols, horizon=12, auto_reset=True)     # the wide grid: no mixed cells, the gather-only observe kernel
     eng, ora = _pair(spec)
     run_lockstep(eng, ora, 40, label=f'{rows}x{cols}/{n_agents}')
+    got = eng.observe(out=torch.full_like(eng.obs, 99)).cpu().numpy()
+    assert np.array_equal(got, np.stack([ora.observe(e) for e in range(E)]))
 
 
 def test_placement_failure_is_reported_not_raised(mirror):
