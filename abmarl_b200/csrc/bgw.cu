@@ -19,6 +19,7 @@
 #include "bgw_dev.cuh"
 #include "bgw_fast.cuh"
 #include "bgw_maze.cuh"
+#include "bgw_jit.h"
 
 namespace {
 
@@ -65,6 +66,7 @@ static const void *observe_fast_fn(int R)
 struct BgwEngine {
     int device = 0;
     GeneralStepFn step_fn = nullptr;   /* the bgw_step_kernel instantiation of this sim's program */
+    bgwjit::Kernel jit;                /* bgw_specialize: the same body compiled at run time for this spec alone (launched instead of step_fn) */
     const void *fast_fn = nullptr;     /* the bgw_step_fast_kernel instantiation of this sim's shape */
     MazeParams maze{};            /* device-side MazePlacementState (bgw_maze.cuh); device pointers */
     bool maze_ok = false, maze_small = false;
@@ -558,8 +560,22 @@ int bgw_destroy(bgw_handle h)
 {
     if (!h) return 0;
     DeviceGuard guard(h->device);
+    if (h->jit.module) bgwjit::driver().ModuleUnload(h->jit.module);
     for (void *p : h->allocs) cudaFree(p);
     delete h;
+    return 0;
+}
+
+int bgw_specialize(bgw_handle h, const char *cache_dir)
+{
+    if (!h) return fail(1, "bgw_specialize: null handle");
+    if (h->fs.enabled || h->jit.function) return 0;          /* the specialised team-battle kernel has its own instantiations */
+    DeviceGuard guard(h->device);
+    CUDA_OK(cudaFree(nullptr));                              /* the runtime's primary context is current for the driver calls */
+    if (!cache_dir) cache_dir = getenv("BGW_JIT_CACHE");
+    std::string msg;
+    if (const char *e = bgwjit::build(h->ds, h->ds.init_ammo != nullptr, h->threads, cache_dir, h->jit, msg))
+        return fail(2, "bgw_specialize: %s", e);
     return 0;
 }
 
@@ -702,8 +718,15 @@ static int step_impl(bgw_handle h, const int8_t *actions, int8_t *sampled, const
             h->launches += 1;
             actions = sampled;
         }
-        h->step_fn<<<h->ds.E, h->threads, h->ds.smem_bytes, (cudaStream_t)stream>>>(
-            h->ds, h->st, (const uint32_t *)actions, order, obs, reward, done, all_done);
+        if (h->jit.function) {                         /* bgw_specialize: this spec's own compilation of the same body */
+            const uint32_t *act_arg = (const uint32_t *)actions;
+            void *args[] = {&h->ds, &h->st, &act_arg, &order, &obs, &reward, &done, &all_done};
+            const int rc = bgwjit::driver().LaunchKernel(h->jit.function, (unsigned)h->ds.E, 1, 1, (unsigned)h->threads, 1, 1,
+                                                         (unsigned)h->ds.smem_bytes, stream, args, nullptr);
+            if (rc) { const char *es = nullptr; bgwjit::driver().GetErrorString(rc, &es); return fail(2, "bgw_step: cuLaunchKernel of the specialised kernel: %s", es ? es : "?"); }
+        } else
+            h->step_fn<<<h->ds.E, h->threads, h->ds.smem_bytes, (cudaStream_t)stream>>>(
+                h->ds, h->st, (const uint32_t *)actions, order, obs, reward, done, all_done);
     }
     CUDA_OK(cudaGetLastError());
     h->launches += 1;

@@ -23,7 +23,7 @@
  */
 #pragma once
 #include <cuda_runtime.h>
-#include <stdint.h>
+#include "../../include/bgw_stdint.h"
 
 #include "../../include/bgw.h"
 #include "../../include/bgw_philox.h"
@@ -1344,8 +1344,10 @@ extern __shared__ __align__(16) unsigned char bgw_smem[];
  * does not rebuild the others: bgw.cu (host side, small kernels), bgw_general.cu (bgw_step_kernel instantiations) and
  * bgw_fastk.cu (bgw_step_fast_kernel instantiations).  The kernel TUs hand their entry points to the host side: */
 typedef void (*GeneralStepFn)(const DevSpec, const BgwState, const uint32_t *, const int16_t *, int8_t *, float *, uint8_t *, uint8_t *);
+#ifndef __CUDACC_RTC__
 GeneralStepFn bgw_general_step_fn(int program, int attack_actor);   /* bgw_general.cu; (-1, -1) = every program and actor in one */
 const void *bgw_fast_step_fn(int shape, int head_elem);              /* bgw_fastk.cu; shape 0 run-time, 1 FastStaticC5, 2 FastStaticC2 */
+#endif
 
 #ifdef BGW_SMALL_KERNELS   /* non-template kernels: defined in exactly one translation unit (bgw.cu) */
 __global__ void bgw_reset_kernel(const DevSpec s, const BgwState st, const uint8_t *env_mask, int8_t *obs)
@@ -1395,13 +1397,20 @@ __global__ void bgw_observe_kernel(const DevSpec s, const BgwState st, const uin
  * only its own program's code.  One CTA of one or two warps per env runs at its own place in the code; the all-in-one
  * instantiation <-1, -1> is 26 k instructions (415 KB) and waits for instruction fetches most of the time. */
 template <int PROG, int ATT>
-__global__ void __launch_bounds__(256, 3) bgw_step_kernel(const DevSpec s_in,   /* <= 80 registers: what the all-in-one kernel needs */ const BgwState st, const uint32_t *actions, const int16_t *order,
-                                int8_t *obs, float *reward, uint8_t *done, uint8_t *all_done)
+__device__ __forceinline__ void bgw_step_body(const DevSpec &s_in, const BgwState &st, const uint32_t *actions, const int16_t *order,
+                                              int8_t *obs, float *reward, uint8_t *done, uint8_t *all_done)
 {
     DevSpec s = s_in;
     if (PROG >= 0) s.program = PROG;
     if (ATT >= 0) s.attack_actor = ATT;
+#ifdef BGW_JIT_PIN
+    BGW_JIT_PIN        /* run-time compilation for one spec (bgw_jit.cpp): the spec's scalars as compile-time constants */
+#endif
+#ifdef BGW_JIT_T
+    const int e = blockIdx.x, tid = threadIdx.x, T = BGW_JIT_T;
+#else
     const int e = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
+#endif
     Env ev;
     env_init(ev, s, bgw_smem);
     ev.e = e; ev.genv = (uint32_t)(s.env_offset + e);
@@ -1553,6 +1562,15 @@ __global__ void __launch_bounds__(256, 3) bgw_step_kernel(const DevSpec s_in,   
         if (ev.ctr[CTR_KILLS]) sr[BGW_STAT_KILLS] += (unsigned long long)ev.ctr[CTR_KILLS];
         if (ef & BGW_ENV_ALL_DONE) sr[BGW_STAT_EPISODES] += 1ull;
     }
+}
+
+/* the stock instantiations (bgw_general.cu); a run-time compilation for one spec (bgw_specialize, bgw_jit.h) wraps the same
+ * body in a kernel of its own */
+template <int PROG, int ATT>
+__global__ void __launch_bounds__(256, 3) bgw_step_kernel(const DevSpec s_in,   /* <= 80 registers: what the all-in-one kernel needs */ const BgwState st, const uint32_t *actions, const int16_t *order,
+                                int8_t *obs, float *reward, uint8_t *done, uint8_t *all_done)
+{
+    bgw_step_body<PROG, ATT>(s_in, st, actions, order, obs, reward, done, all_done);
 }
 
 /* RandomPolicy.compute_action = action_space.sample() (policies/policy.py:81-92) on the keyed stream: one

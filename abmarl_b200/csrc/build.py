@@ -24,7 +24,7 @@ NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 
 
 # headers a unit includes (bgw_general.cu does not see the specialised kernel: editing bgw_fast.cuh leaves it alone)
-UNIT_HEADERS = {'bgw.cu': ('bgw_dev.cuh', 'bgw_fast.cuh', 'bgw_maze.cuh'), 'bgw_general.cu': ('bgw_dev.cuh',),
+UNIT_HEADERS = {'bgw.cu': ('bgw_dev.cuh', 'bgw_fast.cuh', 'bgw_maze.cuh', 'bgw_jit.h'), 'bgw_general.cu': ('bgw_dev.cuh',),
                 'bgw_fastk.cu': ('bgw_dev.cuh', 'bgw_fast.cuh')}
 
 
@@ -67,7 +67,7 @@ def build(force=False, verbose=False):
     if jobs:
         with ThreadPoolExecutor(len(jobs)) as pool:
             list(pool.map(run, jobs))
-    run([NVCC, '-gencode', 'arch=compute_100a,code=sm_100a', '-shared', '-o', out] + objs + ['-lcudart'])
+    run([NVCC, '-gencode', 'arch=compute_100a,code=sm_100a', '-shared', '-o', out] + objs + ['-lcudart', '-ldl'])
     return out
 
 

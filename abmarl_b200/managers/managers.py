@@ -81,6 +81,21 @@ class SimulationManager(ABC):
                 self.engine.set_layout(self._feeder.rows)
         return self.engine.obs_view(), reward, done, all_done
 
+    def observe(self, env_mask=None):
+        """sim.get_obs(agent_id) of EVERY learner on the state as it stands (bgw_observe; smart.py:93-99) -> obs int8
+        [E, L, h, w(, c)] in the engine's obs tensor: nothing is stepped, learners already reported done included."""
+        self.engine.observe(env_mask)
+        return self.engine.obs_view()
+
+    def get_obs(self, agent_id, env=0):
+        """The reference's `sim.get_obs(agent_id)` for one env: the observers' dict of that learner (smart.py:93-99)."""
+        self.engine.observe()
+        snap = self.host_snapshot()
+        l = list(self.learner_ids).index(agent_id)
+        snap['done'] = np.zeros_like(snap['done'])
+        snap['done'][env, l] = K.OUT_VALID
+        return self.dicts_from(snap, env)[0][agent_id]
+
     def super_outputs(self):
         """SuperAgentWrapper view of the last step (super_agent_wrapper.py:112-216): (obs rows with null observations for
         covered agents done earlier, mask [E, L], reward [E, G] f64, done [E, G], valid [E, G]); groups = `super_view.groups`.

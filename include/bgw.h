@@ -29,7 +29,7 @@
 #ifndef BGW_H_
 #define BGW_H_
 
-#include <stdint.h>
+#include "bgw_stdint.h"
 
 #ifdef __cplusplus
 extern "C" {
@@ -253,6 +253,7 @@ typedef struct BgwDims {
 
 typedef struct BgwEngine *bgw_handle;
 
+#ifndef __CUDACC_RTC__   /* (the device code includes this header for the structs and constants when it is compiled at run time) */
 /* Compile the spec onto `device`; builds the line-of-sight LUT (utils.py:45-115 in IEEE float64). */
 int bgw_create(const BgwSpec *spec, int device, bgw_handle *out);
 int bgw_destroy(bgw_handle h);
@@ -365,8 +366,20 @@ int bgw_los_mask(int range, int r_diff, int c_diff, uint8_t *out);
 /* Number of kernels this handle has launched since creation (bench.py `gpu_launches`). */
 uint64_t bgw_launch_count(bgw_handle h);
 
+/*
+ * Compile the general step kernel for THIS handle's spec at run time (NVRTC, sm_100a) and use it for every later step:
+ * the spec's scalars (grid and entity counts, program, actors, observer, manager, flags) become compile-time constants,
+ * so the kernel holds only the code this sim runs (a third to a half of the instructions of the per-program build; the
+ * general kernel spends most of its stall cycles waiting for instructions).  Sims that run the specialised team-battle
+ * kernel are left alone (returns 0).  Needs libnvrtc.so.12 and the library's own sources (abmarl_b200/csrc, include/)
+ * next to libbgw.so; takes 5-15 s per spec, cached in `cache_dir` (NULL: $BGW_JIT_CACHE, else no cache) by spec hash.
+ * Results are bit-identical to the stock kernel's: it is the same source.
+ */
+int bgw_specialize(bgw_handle h, const char *cache_dir);
+
 const char *bgw_last_error(void);
 int bgw_abi_version(void);
+#endif /* __CUDACC_RTC__ */
 
 #ifdef __cplusplus
 }

@@ -24,7 +24,7 @@
 #ifndef BGW_PHILOX_H_
 #define BGW_PHILOX_H_
 
-#include <stdint.h>
+#include "bgw_stdint.h"
 
 #if defined(__CUDACC__)
 #define BGW_HD __host__ __device__ __forceinline__

@@ -3,7 +3,11 @@
 rollouts with the keyed random policy, CUDA-event timing.
 
     python profiles/bench_configs.py [tb_c2|pacman_c3|maze_c1|mm_allstep ...]
+
+BGW_SPECIALIZE=1: compile the general step kernel for each config's spec first (bgw_specialize: NVRTC at run time, cached
+in $BGW_JIT_CACHE); the record carries "specialized": true and the compile time.
 """
+import time
 import json
 import os
 import sys
@@ -30,6 +34,11 @@ def main(names):
         builder, manager, _ = scenarios.SCENARIOS[name]
         spec = compile_sim(builder(api), manager=manager, n_envs=n_envs, seed=7, horizon=200, auto_reset=True)
         eng = BatchedGridWorld(spec, device='cuda:0')
+        jit_s = None
+        if os.environ.get('BGW_SPECIALIZE'):
+            t0 = time.time()
+            eng.specialize()
+            jit_s = time.time() - t0
         eng.reset()
         per_step = bool(os.environ.get('BGW_PER_STEP_CALLS'))       # one bgw_step_sampled call per step instead of bgw_rollout_sampled
         eng.rollout_sampled(10)
@@ -56,7 +65,8 @@ def main(names):
         gbs = algo * n / (ms * 1e-3) / 1e9
         print(json.dumps({"algorithmic_bytes_per_agent_step": algo, "achieved_gbs": gbs, "roofline_frac": gbs / peak,"config": name, "envs": n_envs, "learners_per_env": eng.L, "entities_per_env": eng.A, "steps": steps,
                           "ms_per_step": ms / steps, "agent_steps_per_s": n / (ms * 1e-3), "calls": "bgw_step_sampled per step" if per_step else "bgw_rollout_sampled",
-                          "kernel": "bgw_step_fast_kernel" if eng.dims.threads_per_env <= 128 and spec.program == K.PROG_TEAM_BATTLE and not (spec.klass & (K.AG_BLOCKING | K.AG_AMMO)).any() and spec.attack_actor <= K.ATTACK_BINARY else "bgw_step_kernel"}), flush=True)
+                          "kernel": "bgw_step_fast_kernel" if eng.dims.threads_per_env <= 128 and spec.program == K.PROG_TEAM_BATTLE and not (spec.klass & (K.AG_BLOCKING | K.AG_AMMO)).any() and spec.attack_actor <= K.ATTACK_BINARY else "bgw_step_kernel",
+                          "specialized": jit_s is not None, "specialize_seconds": jit_s}), flush=True)
 
 
 if __name__ == '__main__':

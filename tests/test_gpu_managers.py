@@ -42,6 +42,31 @@ def test_manager_replays_reference_transcript(mirror, name):
     assert n_checked > 0
 
 
+@pytest.mark.parametrize('name', ['tb_c2', 'tb_blocking', 'mm_c4'])
+def test_manager_get_obs_repeats_the_reported_observations(mirror, name):
+    """manager.get_obs(agent_id) = the reference's sim.get_obs(agent_id) (smart.py:93-99): for every learner the
+    transcript reports at a step, the same observation the reference returned there; nothing is stepped by asking."""
+    g = np.load(os.path.join(GOLDEN, name + '.npz'))
+    builder, manager, _ = scenarios.SCENARIOS[name]
+    cls = {'all_step': mirror.managers.AllStepManager, 'turn_based': mirror.managers.TurnBasedManager}[manager]
+    mgr = cls(builder(mirror), n_envs=1, seed=int(g['seed']), device='cuda:0')
+    ids = mgr.learner_ids
+    n_checked = 0
+    for t in range(min(len(g['kind']), 40)):
+        if g['kind'][t] == 0:
+            mgr.reset()
+        else:
+            mgr.step(torch.from_numpy(g['actions'][t][None].copy()).cuda())
+        steps_before = int(mgr.engine.state['step'][0].item())
+        for l in np.nonzero(g['obs_present'][t])[0][:4]:
+            got = mgr.get_obs(ids[l])
+            (key, arr), = got.items()
+            np.testing.assert_array_equal(arr.ravel(), g['obs'][t][l][:arr.size])
+            n_checked += 1
+        assert int(mgr.engine.state['step'][0].item()) == steps_before
+    assert n_checked > 20
+
+
 def test_encode_actions_matches_reference_dicts(mirror):
     mgr = mirror.managers.AllStepManager(scenarios.build_tb_c2(mirror), n_envs=2, seed=1, device='cuda:0')
     act = mgr.encode_actions([{'agent0': {'move': np.array([1, -1]), 'attack': 1}}, {'agent3': {'move': np.array([0, 1]), 'attack': 0}}])

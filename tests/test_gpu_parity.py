@@ -114,6 +114,38 @@ def test_observe_equals_get_obs_of_every_learner(mirror, name, generic, monkeypa
         assert np.array_equal(got2[mask != 0], want[mask != 0]) and (got2[mask == 0] == 99).all()
 
 
+@pytest.mark.parametrize('name', ['tb_blocking', 'tb_encoding_stacked', 'tb_ammo_selective', 'reach_target_crowd', 'traffic',
+                                  'maze_c1', 'pacman_c3', 'mm_c4', 'mm_dynamic'])
+def test_specialized_kernel_matches_oracle(mirror, name, tmp_path):
+    """bgw_specialize: the general step kernel compiled at run time for the spec alone (NVRTC; the spec's scalars as
+    compile-time constants) gives the oracle's results like the stock instantiation; a second handle takes the cubin
+    from the cache directory."""
+    builder, manager, _ = scenarios.SCENARIOS[name]
+    E = 6 if name == 'pacman_c3' else 24
+    spec = compile_sim(builder(mirror), manager=manager, n_envs=E, env_offset=2, seed=0x51EC, horizon=30, auto_reset=True)
+    eng, ora = _pair(spec)
+    launches = eng.launches
+    eng.specialize(cache_dir=str(tmp_path))
+    cached = sorted(os.listdir(tmp_path))
+    assert len(cached) == 1 and cached[0].startswith('bgw_jit_') and cached[0].endswith('.cubin')
+    n = run_lockstep(eng, ora, 70, label=name + '/specialized')
+    assert n > 0 and eng.launches > launches
+    if name in ('tb_blocking', 'mm_c4'):
+        eng2, ora2 = _pair(spec)
+        stamp = os.path.getmtime(os.path.join(tmp_path, cached[0]))
+        eng2.specialize(cache_dir=str(tmp_path))
+        assert sorted(os.listdir(tmp_path)) == cached and os.path.getmtime(os.path.join(tmp_path, cached[0])) == stamp
+        run_lockstep(eng2, ora2, 30, label=name + '/specialized from the cache')
+
+
+def test_specialize_leaves_the_team_battle_kernel_alone(mirror, tmp_path):
+    spec = compile_sim(scenarios.SCENARIOS['tb_c2'][0](mirror), n_envs=16, seed=3, horizon=30, auto_reset=True)
+    eng, ora = _pair(spec)
+    eng.specialize(cache_dir=str(tmp_path))
+    assert os.listdir(tmp_path) == []
+    run_lockstep(eng, ora, 40, label='tb_c2 after specialize')
+
+
 @pytest.mark.parametrize('name', ['tb_c2', 'tb_c5_small', 'tb_dense', 'tb_noself'])
 def test_general_kernel_on_fast_path_scenarios(mirror, name, monkeypatch):
     """Scenarios that qualify for the specialised team-battle kernel must give the same results through the
