@@ -67,6 +67,8 @@ struct BgwEngine {
     int device = 0;
     GeneralStepFn step_fn = nullptr;   /* the bgw_step_kernel instantiation of this sim's program */
     bgwjit::Kernel jit;                /* bgw_specialize: the same body compiled at run time for this spec alone (launched instead of step_fn) */
+    bgwjit::Kernel fast_jit;           /* bgw_specialize: the specialised kernel's body with this spec's shape as its compile-time shape */
+    bool fast_jit_on = false;          /* launch fast_jit instead of fast_fn (off again when the caller binds its own layouts) */
     const void *fast_fn = nullptr;     /* the bgw_step_fast_kernel instantiation of this sim's shape */
     MazeParams maze{};            /* device-side MazePlacementState (bgw_maze.cuh); device pointers */
     bool maze_ok = false, maze_small = false;
@@ -561,6 +563,7 @@ int bgw_destroy(bgw_handle h)
     if (!h) return 0;
     DeviceGuard guard(h->device);
     if (h->jit.module) bgwjit::driver().ModuleUnload(h->jit.module);
+    if (h->fast_jit.module) bgwjit::driver().ModuleUnload(h->fast_jit.module);
     for (void *p : h->allocs) cudaFree(p);
     delete h;
     return 0;
@@ -569,13 +572,33 @@ int bgw_destroy(bgw_handle h)
 int bgw_specialize(bgw_handle h, const char *cache_dir)
 {
     if (!h) return fail(1, "bgw_specialize: null handle");
-    if (h->fs.enabled || h->jit.function) return 0;          /* the specialised team-battle kernel has its own instantiations */
+    if (h->jit.function || h->fast_jit.function) return 0;
+    /* nothing to gain (or not applicable): one of the shipped compile-time shapes; caller-supplied layouts (the compile-time
+     * shapes have no layout path in their reset); the debug phase clocks (sized for the stock grid) */
+    if (h->fs.enabled && (h->fast_shape != 0 || (h->bound && h->st.layout) || h->fs.prof)) return 0;
     DeviceGuard guard(h->device);
     CUDA_OK(cudaFree(nullptr));                              /* the runtime's primary context is current for the driver calls */
     if (!cache_dir) cache_dir = getenv("BGW_JIT_CACHE");
     std::string msg;
-    if (const char *e = bgwjit::build(h->ds, h->ds.init_ammo != nullptr, h->threads, cache_dir, h->jit, msg))
+    if (!h->fs.enabled) {
+        if (const char *e = bgwjit::build(h->ds, h->ds.init_ammo != nullptr, h->threads, cache_dir, h->jit, msg))
+            return fail(2, "bgw_specialize: %s", e);
+        return 0;
+    }
+    /* launch bounds as the shipped shapes choose them: as many CTAs per SM as the shared memory allows, at no fewer than 72
+     * registers per thread */
+    const int by_smem = (228 * 1024) / (h->fs.smem_bytes + 1024), by_regs = 65536 / (h->threads_fast * 72);
+    const int lb_n = std::max(1, std::min(32, std::min(by_smem, by_regs)));
+    if (const char *e = bgwjit::build_fast(h->dsf, h->fs, h->threads_fast, lb_n, cache_dir, h->fast_jit, msg))
         return fail(2, "bgw_specialize: %s", e);
+    int per_sm = 0, sms = 0;
+    const int rc = bgwjit::driver().OccupancyMaxActiveBlocks(&per_sm, h->fast_jit.function, h->threads_fast, (size_t)h->fs.smem_bytes);
+    if (rc || per_sm < 1) { bgwjit::driver().ModuleUnload(h->fast_jit.module); h->fast_jit = bgwjit::Kernel(); return fail(2, "bgw_specialize: occupancy query of the compiled kernel failed (%d)", rc); }
+    CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+    h->fs.grid_ctas = std::max(1, std::min(h->ds.E, per_sm * sms));
+    if (const char *t = getenv("BGW_GRID")) { const int v = atoi(t); if (v >= 1) h->fs.grid_ctas = std::min(h->ds.E, v); }
+    h->fast_jit_on = true;
+    if (getenv("BGW_VERBOSE")) fprintf(stderr, "[bgw] fast kernel compiled for this spec's shape: %d CTAs/SM, grid=%d\n", per_sm, h->fs.grid_ctas);
     return 0;
 }
 
@@ -595,7 +618,8 @@ int bgw_bind_state(bgw_handle h, const BgwState *state)
     if (h->ds.n_ammo && !state->ammo) return fail(1, "bgw_bind_state: the simulation has AmmoAgents: `ammo` is required");
     h->st = *state;
     h->bound = true;
-    if (state->layout && h->fs.enabled && h->fast_shape != 0) {
+    if (state->layout && h->fs.enabled && (h->fast_shape != 0 || h->fast_jit_on)) {
+        h->fast_jit_on = false;
         /* the compile-time-shape instantiations of the specialised kernel have no layout path in their inlined reset (code
          * size is what the instruction cache sees): a handle that is given layouts runs the run-time-shape instantiation */
         DeviceGuard guard(h->device);
@@ -708,7 +732,20 @@ static int step_impl(bgw_handle h, const int8_t *actions, int8_t *sampled, const
         const uint32_t *act_arg = (const uint32_t *)actions;
         uint32_t *smp_arg = (uint32_t *)sampled;
         void *args[] = {&h->dsf, &h->fs, &h->st, &act_arg, &smp_arg, &order, &obs, &reward, &done, &all_done};
-        CUDA_OK(cudaLaunchKernelExC(&cfg, h->fast_fn, args));
+        if (h->fast_jit_on) {                          /* bgw_specialize: this spec's own compile-time shape, same launch */
+            CUlaunchAttribute ja[1];
+            memset(ja, 0, sizeof(ja));
+            ja[0].id = CU_LAUNCH_ATTRIBUTE_PROGRAMMATIC_STREAM_SERIALIZATION;
+            ja[0].value.programmaticStreamSerializationAllowed = h->pdl ? 1 : 0;
+            CUlaunchConfig jc;
+            memset(&jc, 0, sizeof(jc));
+            jc.gridDimX = (unsigned)h->fs.grid_ctas; jc.gridDimY = jc.gridDimZ = 1;
+            jc.blockDimX = (unsigned)h->threads_fast; jc.blockDimY = jc.blockDimZ = 1;
+            jc.sharedMemBytes = (unsigned)h->fs.smem_bytes; jc.hStream = (CUstream)stream; jc.attrs = ja; jc.numAttrs = 1;
+            const int rc = bgwjit::driver().LaunchKernelEx(&jc, h->fast_jit.function, args, nullptr);
+            if (rc) { const char *es = nullptr; bgwjit::driver().GetErrorString(rc, &es); return fail(2, "bgw_step: cuLaunchKernelEx of the specialised kernel: %s", es ? es : "?"); }
+        } else
+            CUDA_OK(cudaLaunchKernelExC(&cfg, h->fast_fn, args));
         h->poisoned = false;
     } else {
         if (sampled) {                                 /* general kernel: sample, then step (two launches) */

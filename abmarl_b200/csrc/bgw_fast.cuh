@@ -680,6 +680,11 @@ __device__ void fast_obs_chunk_slow(const DevSpec &s, const FastSpec &f, const E
 /* 32 contiguous bytes from one lane: STG.256 (sm_100), one full sector per lane and instruction */
 __device__ __forceinline__ void st_global_256(void *p, const uint32_t *v)
 {
+#ifdef BGW_NO_ST256            /* a run-time compilation by an NVRTC older than 12.9 (PTX 8.8): two 128-bit stores */
+    reinterpret_cast<uint4 *>(p)[0] = make_uint4(v[0], v[1], v[2], v[3]);
+    reinterpret_cast<uint4 *>(p)[1] = make_uint4(v[4], v[5], v[6], v[7]);
+    return;
+#endif
     asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
                  "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
                  : "memory");
@@ -908,6 +913,7 @@ struct FastStaticC2 {
 };
 struct FastDynamic { static constexpr bool is_static = false; static constexpr int LB_T = 128, LB_N = 7; };
 
+#ifndef __CUDACC_RTC__
 /* does the compiled spec have exactly the compile-time shape C? (bgw_create) */
 template <typename C>
 inline bool fast_shape_matches(const DevSpec &q, const FastSpec &f, int threads)
@@ -919,15 +925,16 @@ inline bool fast_shape_matches(const DevSpec &q, const FastSpec &f, int threads)
            q.slot_mask == C::slots - 1 && threads == C::T && f.uniform_att == C::att && f.identity_learners == C::identity &&
            f.can_mix == C::can_mix && f.acc_lt1 == C::acc_lt1 && q.randomize_placement_order == C::rpo;
 }
+#endif
 
 /* launch bounds per instantiation: the headline shape runs 64 threads per env and is limited to 11 envs per SM by shared memory,
  * so it may use more registers than the run-time-shape code (up to 128 threads): 71 instead of 64 makes its code 5 % smaller
  * (3568 instructions; measured +1 %) */
 #define BGW_FAST_LB __launch_bounds__(SHAPE::LB_T, SHAPE::LB_N)
 template <typename SHAPE, typename HT>
-__global__ void BGW_FAST_LB bgw_step_fast_kernel(const DevSpec s_in, const FastSpec f_in, const BgwState st, const uint32_t *actions,
-                                     uint32_t *sampled, const int16_t *order, int8_t *obs, float *reward, uint8_t *done,
-                                     uint8_t *all_done)
+__device__ __forceinline__ void bgw_step_fast_body(const DevSpec &s_in, const FastSpec &f_in, const BgwState &st, const uint32_t *actions,
+                                                   uint32_t *sampled, const int16_t *order, int8_t *obs, float *reward, uint8_t *done,
+                                                   uint8_t *all_done)
 {
     DevSpec s = s_in;
     FastSpec f = f_in;
@@ -1506,6 +1513,16 @@ __global__ void BGW_FAST_LB bgw_step_fast_kernel(const DevSpec s_in, const FastS
     }
 #undef BGW_END_ENV
     cp_async_wait<0>();
+}
+
+/* the stock instantiations (bgw_fastk.cu); a run-time compilation for one spec's shape (bgw_specialize, bgw_jit.h) wraps the
+ * same body, with a shape struct of its own, in a kernel of its own */
+template <typename SHAPE, typename HT>
+__global__ void BGW_FAST_LB bgw_step_fast_kernel(const DevSpec s_in, const FastSpec f_in, const BgwState st, const uint32_t *actions,
+                                     uint32_t *sampled, const int16_t *order, int8_t *obs, float *reward, uint8_t *done,
+                                     uint8_t *all_done)
+{
+    bgw_step_fast_body<SHAPE, HT>(s_in, f_in, st, actions, sampled, order, obs, reward, done, all_done);
 }
 
 #ifdef BGW_SMALL_KERNELS

@@ -18,6 +18,7 @@
 #ifndef BGW_JIT_H_
 #define BGW_JIT_H_
 
+#include <cuda.h>          /* types and constants only: the driver is opened with dlopen, nothing links against libcuda */
 #include <dlfcn.h>
 #include <sys/stat.h>
 
@@ -26,8 +27,6 @@
 namespace bgwjit {
 
 typedef struct _nvrtcProgram *nvrtcProgram;
-typedef struct CUmod_st *CUmodule;
-typedef struct CUfunc_st *CUfunction;
 
 struct Nvrtc {
     void *lib = nullptr;
@@ -39,6 +38,8 @@ struct Nvrtc {
     int (*GetProgramLog)(nvrtcProgram, char *) = nullptr;
     int (*DestroyProgram)(nvrtcProgram *) = nullptr;
     const char *(*GetErrorString)(int) = nullptr;
+    int (*Version)(int *, int *) = nullptr;
+    int major = 0, minor = 0;
 };
 
 struct Driver {
@@ -48,6 +49,8 @@ struct Driver {
     int (*ModuleUnload)(CUmodule) = nullptr;
     int (*FuncSetAttribute)(CUfunction, int, int) = nullptr;
     int (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, void *, void **, void **) = nullptr;
+    int (*LaunchKernelEx)(const CUlaunchConfig *, CUfunction, void **, void **) = nullptr;
+    int (*OccupancyMaxActiveBlocks)(int *, CUfunction, int, size_t) = nullptr;
     int (*GetErrorString)(int, const char **) = nullptr;
 };
 
@@ -58,19 +61,30 @@ inline bool sym(void *lib, const char *name, F &out)
     return out != nullptr;
 }
 
+/* $BGW_NVRTC if set; else the newest of the toolkit's copy and whatever "libnvrtc.so.12" resolves to (inside a PyTorch
+ * process that is PyTorch's bundled copy, which may be older than the toolkit the library was built with: the 256-bit
+ * store of the row gather needs PTX 8.8 = NVRTC 12.9; with an older one the kernels are compiled with -DBGW_NO_ST256). */
 inline const char *load_nvrtc(Nvrtc &n)
 {
     if (n.lib) return nullptr;
-    const char *names[] = {"libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so.12", "libnvrtc.so"};
-    for (const char *nm : names) if ((n.lib = dlopen(nm, RTLD_NOW | RTLD_LOCAL))) break;
-    if (!n.lib) return "libnvrtc.so.12 not found (looked in the loader path and /usr/local/cuda/lib64)";
-    if (!sym(n.lib, "nvrtcCreateProgram", n.CreateProgram) || !sym(n.lib, "nvrtcCompileProgram", n.CompileProgram) ||
-        !sym(n.lib, "nvrtcGetCUBINSize", n.GetCUBINSize) || !sym(n.lib, "nvrtcGetCUBIN", n.GetCUBIN) ||
-        !sym(n.lib, "nvrtcGetProgramLogSize", n.GetProgramLogSize) || !sym(n.lib, "nvrtcGetProgramLog", n.GetProgramLog) ||
-        !sym(n.lib, "nvrtcDestroyProgram", n.DestroyProgram) || !sym(n.lib, "nvrtcGetErrorString", n.GetErrorString)) {
-        dlclose(n.lib); n.lib = nullptr;
-        return "libnvrtc lacks an entry point (nvrtcGetCUBIN needs CUDA >= 11.1)";
+    const char *forced = getenv("BGW_NVRTC");            /* this one and no other */
+    const char *names[] = {forced, "/usr/local/cuda/lib64/libnvrtc.so.12", "libnvrtc.so.12", "libnvrtc.so"};
+    for (const char *nm : names) {
+        if (!nm || !*nm || (forced && *forced && nm != forced)) continue;
+        void *lib = dlopen(nm, RTLD_NOW | RTLD_LOCAL);
+        if (!lib) continue;
+        Nvrtc c;
+        c.lib = lib;
+        if (!sym(lib, "nvrtcCreateProgram", c.CreateProgram) || !sym(lib, "nvrtcCompileProgram", c.CompileProgram) ||
+            !sym(lib, "nvrtcGetCUBINSize", c.GetCUBINSize) || !sym(lib, "nvrtcGetCUBIN", c.GetCUBIN) ||
+            !sym(lib, "nvrtcGetProgramLogSize", c.GetProgramLogSize) || !sym(lib, "nvrtcGetProgramLog", c.GetProgramLog) ||
+            !sym(lib, "nvrtcDestroyProgram", c.DestroyProgram) || !sym(lib, "nvrtcGetErrorString", c.GetErrorString) ||
+            !sym(lib, "nvrtcVersion", c.Version) || c.Version(&c.major, &c.minor) != 0) { dlclose(lib); continue; }
+        if (!n.lib || c.major * 100 + c.minor > n.major * 100 + n.minor) { if (n.lib) dlclose(n.lib); n = c; }
+        else dlclose(lib);
     }
+    if (!n.lib) return "no usable libnvrtc.so.12 ($BGW_NVRTC, /usr/local/cuda/lib64, the loader path)";
+    if (n.major * 100 + n.minor < 1208) { dlclose(n.lib); n = Nvrtc(); return "libnvrtc is older than 12.8: it cannot compile for sm_100a"; }
     return nullptr;
 }
 
@@ -80,7 +94,8 @@ inline const char *load_driver(Driver &d)
     if (!(d.lib = dlopen("libcuda.so.1", RTLD_NOW | RTLD_LOCAL))) return "libcuda.so.1 not found";
     if (!sym(d.lib, "cuModuleLoadData", d.ModuleLoadData) || !sym(d.lib, "cuModuleGetFunction", d.ModuleGetFunction) ||
         !sym(d.lib, "cuModuleUnload", d.ModuleUnload) || !sym(d.lib, "cuFuncSetAttribute", d.FuncSetAttribute) ||
-        !sym(d.lib, "cuLaunchKernel", d.LaunchKernel) || !sym(d.lib, "cuGetErrorString", d.GetErrorString)) {
+        !sym(d.lib, "cuLaunchKernel", d.LaunchKernel) || !sym(d.lib, "cuLaunchKernelEx", d.LaunchKernelEx) ||
+        !sym(d.lib, "cuOccupancyMaxActiveBlocksPerMultiprocessor", d.OccupancyMaxActiveBlocks) || !sym(d.lib, "cuGetErrorString", d.GetErrorString)) {
         dlclose(d.lib); d.lib = nullptr;
         return "libcuda.so.1 lacks an entry point";
     }
@@ -146,27 +161,19 @@ struct Kernel {
     CUfunction function = nullptr;
 };
 
-/* Compile (or fetch from cache_dir) and load the kernel.  Returns nullptr on success, else a message (static or in `msg`). */
-inline const char *build(const DevSpec &d, bool has_init_ammo, int threads, const char *cache_dir, Kernel &out, std::string &msg)
+/* Compile `src` (or fetch its cubin from cache_dir) and load the kernel `name` with `smem` bytes of dynamic shared memory.
+ * Returns nullptr on success, else a message (static or in `msg`). */
+inline const char *compile_and_load(std::string src, const char *name, int smem, const char *cache_dir, Kernel &out, std::string &msg)
 {
     if (const char *e = load_driver(driver())) return e;
     const std::string dir = library_dir(), inc = dir + "/../../include";
-    std::string dev, hdr, phl, sti;
-    if (!read_file(dir + "/bgw_dev.cuh", dev) || !read_file(inc + "/bgw.h", hdr) || !read_file(inc + "/bgw_philox.h", phl) ||
-        !read_file(inc + "/bgw_stdint.h", sti)) {
-        msg = "the kernel sources (bgw_dev.cuh, include/bgw*.h) are not next to the library in " + dir;
+    std::string dev, fst, hdr, phl, sti;
+    if (!read_file(dir + "/bgw_dev.cuh", dev) || !read_file(dir + "/bgw_fast.cuh", fst) || !read_file(inc + "/bgw.h", hdr) ||
+        !read_file(inc + "/bgw_philox.h", phl) || !read_file(inc + "/bgw_stdint.h", sti)) {
+        msg = "the kernel sources (bgw_dev.cuh, bgw_fast.cuh, include/bgw*.h) are not next to the library in " + dir;
         return msg.c_str();
     }
-    char head[1024];
-    snprintf(head, sizeof(head), "#define BGW_JIT_T %d\n#define BGW_JIT_PIN ", threads);
-    std::string src = head + pin_statements(d, has_init_ammo) + "\n#include \"bgw_dev.cuh\"\n";
-    snprintf(head, sizeof(head),
-             "extern \"C\" __global__ void __launch_bounds__(%d) bgw_step_jit(const DevSpec s_in, const BgwState st, const uint32_t *actions, "
-             "const int16_t *order, int8_t *obs, float *reward, uint8_t *done, uint8_t *all_done)\n"
-             "{ bgw_step_body<%d, %d>(s_in, st, actions, order, obs, reward, done, all_done); }\n",
-             threads, d.program, d.attack_actor);
-    src += head;
-    const unsigned long long key = fnv1a(sti, fnv1a(phl, fnv1a(hdr, fnv1a(dev, fnv1a(src)))));
+    const unsigned long long key = fnv1a(sti, fnv1a(phl, fnv1a(hdr, fnv1a(fst, fnv1a(dev, fnv1a(src))))));
     std::string cubin, cache_path;
     if (cache_dir && *cache_dir) {
         char nm[64];
@@ -181,8 +188,10 @@ inline const char *build(const DevSpec &d, bool has_init_ammo, int threads, cons
         int rc = n.CreateProgram(&prog, src.c_str(), "bgw_jit.cu", 0, nullptr, nullptr);
         if (rc) { msg = std::string("nvrtcCreateProgram: ") + n.GetErrorString(rc); return msg.c_str(); }
         const std::string i1 = "-I" + dir, i2 = "-I" + inc;
-        const char *opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "--fmad=false", i1.c_str(), i2.c_str(), "-I/usr/local/cuda/include", "-lineinfo"};
-        rc = n.CompileProgram(prog, (int)(sizeof(opts) / sizeof(opts[0])), opts);
+        const char *opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "--fmad=false", i1.c_str(), i2.c_str(), "-I/usr/local/cuda/include", "-lineinfo",
+                              "-DBGW_NO_ST256"};   /* the last one only with an NVRTC that predates PTX 8.8 */
+        const int nopt = (int)(sizeof(opts) / sizeof(opts[0])) - (n.major * 100 + n.minor >= 1209 ? 1 : 0);
+        rc = n.CompileProgram(prog, nopt, opts);
         if (rc) {
             size_t ln = 0;
             n.GetProgramLogSize(prog, &ln);
@@ -211,16 +220,51 @@ inline const char *build(const DevSpec &d, bool has_init_ammo, int threads, cons
     const char *es = nullptr;
     int rc = c.ModuleLoadData(&out.module, cubin.data());
     if (rc) { c.GetErrorString(rc, &es); msg = std::string("cuModuleLoadData: ") + (es ? es : "?"); return msg.c_str(); }
-    rc = c.ModuleGetFunction(&out.function, out.module, "bgw_step_jit");
-    if (!rc) rc = c.FuncSetAttribute(out.function, 8 /* CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES */, d.smem_bytes);
+    rc = c.ModuleGetFunction(&out.function, out.module, name);
+    if (!rc) rc = c.FuncSetAttribute(out.function, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, smem);
     if (rc) {
         c.GetErrorString(rc, &es);
-        msg = std::string("loading bgw_step_jit: ") + (es ? es : "?");
+        msg = std::string("loading ") + name + ": " + (es ? es : "?");
         c.ModuleUnload(out.module);
         out = Kernel();
         return msg.c_str();
     }
     return nullptr;
+}
+
+/* the general step kernel for one spec */
+inline const char *build(const DevSpec &d, bool has_init_ammo, int threads, const char *cache_dir, Kernel &out, std::string &msg)
+{
+    char head[1024];
+    snprintf(head, sizeof(head), "#define BGW_JIT_T %d\n#define BGW_JIT_PIN ", threads);
+    std::string src = head + pin_statements(d, has_init_ammo) + "\n#include \"bgw_dev.cuh\"\n";
+    snprintf(head, sizeof(head),
+             "extern \"C\" __global__ void __launch_bounds__(%d) bgw_step_jit(const DevSpec s_in, const BgwState st, const uint32_t *actions, "
+             "const int16_t *order, int8_t *obs, float *reward, uint8_t *done, uint8_t *all_done)\n"
+             "{ bgw_step_body<%d, %d>(s_in, st, actions, order, obs, reward, done, all_done); }\n",
+             threads, d.program, d.attack_actor);
+    src += head;
+    return compile_and_load(src, "bgw_step_jit", d.smem_bytes, cache_dir, out, msg);
+}
+
+/* the specialised team-battle kernel with THIS spec's shape as its compile-time shape (bgw_fast.cuh: FastStaticC5 / C2 are
+ * the two shapes the library ships; every other sim runs the run-time-shape instantiation, 2.4 x the instructions) */
+inline const char *build_fast(const DevSpec &q, const FastSpec &f, int threads, int lb_n, const char *cache_dir, Kernel &out, std::string &msg)
+{
+    char b[1536];
+    snprintf(b, sizeof(b),
+             "#include \"bgw_dev.cuh\"\n#include \"bgw_fast.cuh\"\n"
+             "struct FastStaticJit {\n    static constexpr bool is_static = true;\n"
+             "    static constexpr int A = %d, L = %d, H = %d, W = %d, P = %d, PL = %d, PW = %d, PH = %d, obs_stride = %d, nchunks = %d,\n"
+             "        obs_h = %d, view = %d, move_actor = %d, ravel = %d, observe_self = %d, done_mask = %d, max_enc = %d, simd_ok = %d,\n"
+             "        async_ok = %d, slots = %d, T = %d, att = %d, identity = %d, can_mix = %d, acc_lt1 = %d, rpo = %d, LB_T = %d, LB_N = %d;\n};\n"
+             "extern \"C\" __global__ void __launch_bounds__(%d, %d) bgw_step_fast_jit(const DevSpec s_in, const FastSpec f_in, const BgwState st, "
+             "const uint32_t *actions, uint32_t *sampled, const int16_t *order, int8_t *obs, float *reward, uint8_t *done, uint8_t *all_done)\n"
+             "{ bgw_step_fast_body<FastStaticJit, %s>(s_in, f_in, st, actions, sampled, order, obs, reward, done, all_done); }\n",
+             q.A, q.L, q.H, q.W, f.P, f.PL, f.PW, f.PH, q.obs_stride, q.nchunks, q.obs_h, f.uniform_view, q.move_actor, q.ravel,
+             q.observe_self, q.done_mask, q.max_enc, f.simd_ok, f.async_ok, q.slot_mask + 1, threads, f.uniform_att, f.identity_learners,
+             f.can_mix, f.acc_lt1, q.randomize_placement_order, threads, lb_n, threads, lb_n, f.head_elem == 1 ? "uint8_t" : "uint16_t");
+    return compile_and_load(b, "bgw_step_fast_jit", f.smem_bytes, cache_dir, out, msg);
 }
 
 }   // namespace bgwjit

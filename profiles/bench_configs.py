@@ -24,7 +24,8 @@ from tests import scenarios                             # noqa: E402
 CONFIGS = {'tb_c2': (16384, 400), 'pacman_c3': (16384, 60), 'maze_c1': (16384, 400), 'tb_blocking': (16384, 200),
            'tb_encoding': (16384, 200), 'tb_restricted': (16384, 200), 'tb_selective_stacked': (16384, 200),
            'tb_ammo_selective': (16384, 200), 'reach_target': (16384, 200), 'traffic': (16384, 200),
-           'mm_c4': (16384, 400), 'mm_allstep': (16384, 200), 'pacman_simple': (16384, 100)}
+           'mm_c4': (16384, 400), 'mm_allstep': (16384, 200), 'pacman_simple': (16384, 100),
+           'tb_c5_small': (16384, 200), 'tb_dense': (16384, 200)}
 
 
 def main(names):

@@ -138,7 +138,25 @@ def test_specialized_kernel_matches_oracle(mirror, name, tmp_path):
         run_lockstep(eng2, ora2, 30, label=name + '/specialized from the cache')
 
 
-def test_specialize_leaves_the_team_battle_kernel_alone(mirror, tmp_path):
+@pytest.mark.parametrize('name', ['tb_c5_small', 'tb_dense', 'tb_noself', 'tb_shuffled', 'tb_c5_shuffled'])
+def test_specialized_team_battle_shape_matches_oracle(mirror, name, tmp_path):
+    """bgw_specialize on a sim of the specialised team-battle kernel whose shape is not one of the two the library ships: the
+    kernel body compiled at run time with THIS spec's shape as its compile-time shape (mixed cells, accuracy < 1,
+    non-uniform ranges, keyed placement order included), against the oracle through resets, rollouts and chained launches."""
+    builder, manager, _ = scenarios.SCENARIOS[name]
+    spec = compile_sim(builder(mirror), manager=manager, n_envs=40, env_offset=5, seed=0x51ED, horizon=25, auto_reset=True)
+    eng, ora = _pair(spec)
+    eng.specialize(cache_dir=str(tmp_path))
+    assert len(os.listdir(tmp_path)) == 1
+    run_lockstep(eng, ora, 80, label=name + '/specialized shape')
+    eng.rollout_sampled(37)
+    for _ in range(37):
+        ora.step(ora.sample_actions())
+    assert_outputs_equal(eng, ora, name + '/specialized shape, rollout')
+    assert_state_equal(eng.state_numpy(), ora.state, name + '/specialized shape, rollout')
+
+
+def test_specialize_leaves_the_shipped_shapes_alone(mirror, tmp_path):
     spec = compile_sim(scenarios.SCENARIOS['tb_c2'][0](mirror), n_envs=16, seed=3, horizon=30, auto_reset=True)
     eng, ora = _pair(spec)
     eng.specialize(cache_dir=str(tmp_path))
@@ -490,7 +508,7 @@ def test_rollout_keeps_caller_supplied_layouts(mirror):
         np.testing.assert_array_equal(a.state['layout'].cpu().numpy().view(np.uint16), np.asarray(rows, dtype=np.uint16))
 
 
-@pytest.mark.parametrize('name,n_envs', [('tb_c2', 48), ('tb_c5', 6)])
+@pytest.mark.parametrize('name,n_envs', [('tb_c2', 48), ('tb_c5', 6), ('tb_c5_small', 24)])
 def test_compile_time_shapes_with_caller_supplied_layouts(mirror, name, n_envs):
     """The compile-time-shape instantiations of the specialised kernel have no layout path in their inlined reset;
     bgw_bind_state moves a handle that is given layouts to the run-time-shape instantiation.  Layout = the cells of a normal
@@ -498,6 +516,8 @@ def test_compile_time_shapes_with_caller_supplied_layouts(mirror, name, n_envs):
     builder = scenarios.build_tb_c5 if name == 'tb_c5' else scenarios.SCENARIOS[name][0]
     spec = compile_sim(builder(mirror), n_envs=n_envs, env_offset=1, seed=31, horizon=7, auto_reset=True)
     eng, ora = _pair(spec)
+    if name == 'tb_c5_small':                 # a shape compiled at run time (bgw_specialize) behaves like the shipped ones
+        eng.specialize()
     from oracle.oracle import OracleEnv
     scout = OracleEnv(spec)
     scout.reset()
