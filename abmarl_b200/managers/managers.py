@@ -10,6 +10,8 @@ env's last outputs into the reference's dict-of-dicts form.
 """
 from abc import ABC
 
+import os
+
 import numpy as np
 import torch
 
@@ -23,7 +25,7 @@ class SimulationManager(ABC):
     _manager = None
 
     def __init__(self, sim, n_envs=1, env_offset=0, seed=0, horizon=0, auto_reset=False, device=None,
-                 randomize_action_input=False, layouts=None):
+                 randomize_action_input=False, layouts=None, specialize=False):
         assert type(randomize_action_input) is bool, "Randomize action input must be a boolean."   # all_step_manager.py:32-35
         assert not randomize_action_input or self._manager == 'all_step', \
             "randomize_action_input is an AllStepManager option (all_step_manager.py:24-35)"
@@ -33,6 +35,8 @@ class SimulationManager(ABC):
         self.spec = compile_sim(inner, manager=self._manager, n_envs=n_envs, env_offset=env_offset, seed=seed,
                                 horizon=horizon, auto_reset=auto_reset, randomize_action_input=randomize_action_input)
         self.engine = BatchedGridWorld(self.spec, device=device)
+        if specialize:                 # compile the step kernel for this sim alone (bgw_specialize; `specialize` may name a cache directory)
+            self.engine.specialize(specialize if isinstance(specialize, (str, bytes, os.PathLike)) else None)
         self.super_view = None
         if hasattr(sim, 'super_agent_mapping'):
             from abmarl_b200.sim.wrappers import SuperAgentView

@@ -13,12 +13,13 @@ pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 
 
-@pytest.mark.parametrize('name', ['tb_c2', 'tb_blocking', 'maze_c1', 'mm_tiny', 'mm_c4', 'mm_tiny_allstep'])
+@pytest.mark.parametrize('name', ['tb_c2', 'tb_blocking', 'maze_c1', 'mm_tiny', 'mm_c4', 'mm_tiny_allstep', 'tb_blocking+specialize', 'mm_c4+specialize'])
 def test_manager_replays_reference_transcript(mirror, name):
+    name, _, specialize = name.partition('+')          # specialize=True: the step kernel compiled for this sim alone (bgw_specialize)
     g = np.load(os.path.join(GOLDEN, name + '.npz'))
     builder, manager, _ = scenarios.SCENARIOS[name]
     cls = {'all_step': mirror.managers.AllStepManager, 'turn_based': mirror.managers.TurnBasedManager}[manager]
-    mgr = cls(builder(mirror), n_envs=1, seed=int(g['seed']), device='cuda:0')
+    mgr = cls(builder(mirror), n_envs=1, seed=int(g['seed']), device='cuda:0', specialize=bool(specialize))
     ids = mgr.learner_ids
     n_checked = 0
     for t in range(len(g['kind'])):
