@@ -1,0 +1,2 @@
+BGW_LIB=$PWD/abmarl_b200/csrc/libbgw_rl.so python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "tb_c5 or tb_c2 or tb_dense or rollout or chained or full_size" 2>&1 | tail -2
+bash profiles/gpu_ab_libs.sh base=abmarl_b200/csrc/libbgw.so roundslast=abmarl_b200/csrc/libbgw_rl.so
