@@ -1074,12 +1074,28 @@ __device__ __forceinline__ void bgw_step_fast_body(const DevSpec &s_in, const Fa
                              a thread of the LAST warp, not of the warp that leads the env (measured: five episodes 0.0295 -> 0.0276 ms per step) */
 #define BGW_STAMP_TID (T - 1)
 #endif
+    /* -DBGW_STAMP_DEFERRED (A/B; measured SLOWER: five episodes 0.0272 -> 0.0288 ms per step, configs[1] 0.0299 -> 0.0317): write the
+     * stamp late -- at the emit phase of the CTA's next env, when the finished env's stores are long performed and the release's
+     * fence is free.  Deadlock-freedom then needs the pending stamp written before every blocking wait, at the end of the next
+     * env at the latest, and after the loop (all in place below).  What it costs: the env's next step finds the stamp missing
+     * more often when it looks ahead, and fetches late. */
+    int pend_e = -1;                                      /* (only ever set in the stamping thread) */
+    uint32_t pend_v = 0;
+#define BGW_FLUSH_STAMP()                                                            \
+    do {                                                                             \
+        if (pend_e >= 0) { st_release_u32(f_in.env_seq + pend_e, pend_v); pend_e = -1; } \
+    } while (0)
+#ifndef BGW_STAMP_DEFERRED
+#define BGW_STAMP_ENV() st_release_u32(f_in.env_seq + e, f_in.seq + (uint32_t)kstep)
+#else
+#define BGW_STAMP_ENV() do { pend_e = e; pend_v = f_in.seq + (uint32_t)kstep; } while (0)
+#endif
 #define BGW_END_ENV()                                                                \
     do {                                                                             \
         if (tid == 0) tslot[sl ^ 1] = (int)tnew;                                     \
         __syncthreads();                                                             \
         BGW_JITTER_POINT(7);                                                         \
-        if (tid == BGW_STAMP_TID) st_release_u32(f_in.env_seq + e, f_in.seq + (uint32_t)kstep);   \
+        if (tid == BGW_STAMP_TID) { BGW_FLUSH_STAMP(); BGW_STAMP_ENV(); }            \
         sl ^= 1;                                                                     \
     } while (0)
     for (; g < NT; g = gn) {
@@ -1092,6 +1108,7 @@ __device__ __forceinline__ void bgw_step_fast_body(const DevSpec &s_in, const Fa
         BGW_PROF_MARK(0);
         kstep = kn_carry; e = en_carry;                             /* (step, env) of this ticket: computed when it was `next` */
         if (late) {                                                 /* this ticket's rows were not ready when it was `next` */
+            BGW_FLUSH_STAMP();                                      /* (never block with a finished env unstamped) */
             env_wait_stamp(f_in, e, f_in.seq + (uint32_t)kstep - 1u);
             fast_issue_env(s, f, st, actions, e, bgw_smem + f.o_buf + b * f.buf_bytes, tid, T);
             ef_cur = __ldcg(&st.env_flags[e]); step_cur = __ldcg(&st.step[e]); epi_cur = __ldcg(&st.episode[e]);
@@ -1441,6 +1458,7 @@ __device__ __forceinline__ void bgw_step_fast_body(const DevSpec &s_in, const Fa
             if (pend) epoch = fast_move_phase<HT>(s, f, ev, fe, n_act, epoch, tid, T);
             BGW_PROF_MARK(8);
 
+            BGW_FLUSH_STAMP();                                      /* (BGW_STAMP_DEFERRED: the previous env's stores are long performed) */
             /* ---- entropy :58-59, rewards / dones of the acting learners (all_step_manager.py:68-87) -------- */
             for (int i = tid; i < n_act; i += T) {
                 const int a = ev.ragent[i], l = ev.plist[i];
@@ -1532,7 +1550,10 @@ __device__ __forceinline__ void bgw_step_fast_body(const DevSpec &s_in, const Fa
         BGW_END_ENV();                                              /* ctr, scratch and the staging buffer are rewritten next */
         BGW_PROF_MARK(11);
     }
+    BGW_FLUSH_STAMP();
 #undef BGW_END_ENV
+#undef BGW_STAMP_ENV
+#undef BGW_FLUSH_STAMP
     cp_async_wait<0>();
 }
 

@@ -1,0 +1,5 @@
+#!/bin/bash
+# per-phase clocks of the final kernel inside a fused rollout (BGW_PROFILE build): early-episode steps and late ones
+export BGW_PROF_FILE=$PWD/gpurun_out/prof_clocks.bin
+echo "== steps 5-25"; BGW_LIB=$PWD/abmarl_b200/csrc/libbgw_prof.so BGW_PROF_LAZY=1 python profiles/phase_clocks_chain.py 5 20
+echo "== steps 150-170"; BGW_LIB=$PWD/abmarl_b200/csrc/libbgw_prof.so BGW_PROF_LAZY=1 python profiles/phase_clocks_chain.py 150 20
