@@ -1,5 +1,6 @@
 #!/bin/bash
 # A/B: cooperative row gather (default build) against one lane per learner (libbgw_onelane.so, -DBGW_OBS_ONE_LANE)
+# build the variant first:  BGW_DEFINES=BGW_OBS_ONE_LANE BGW_OUT=$PWD/abmarl_b200/csrc/libbgw_onelane.so python -m abmarl_b200.csrc.build
 mkdir -p gpurun_out
 python -m pytest tests/test_gpu_parity.py -x -q -m gpu 2>&1 | tail -3
 for rep in 1 2; do

@@ -1,5 +1,7 @@
 #!/bin/bash
-# deferred env stamps: chaining / rollout / jitter tests, soak + chain probes, then A/B against immediate stamps
+# deferred env stamps: chaining / rollout / jitter tests, soak + chain probes, then A/B against immediate stamps.  The script ran with
+# deferred stamps as the default build and -DBGW_STAMP_IMMEDIATE as libbgw_si.so; today the default is immediate and the variant is
+#   BGW_FAST_DEFINES=BGW_STAMP_DEFERRED BGW_OUT=$PWD/abmarl_b200/csrc/libbgw_sd.so python -m abmarl_b200.csrc.build
 python -m pytest tests/test_gpu_parity.py tests/test_gpu_jitter.py -x -q -m gpu -k "rollout or chained or full_size or cuda_graph or step_sampled or jitter or specialized_team or tb_c2 or tb_c5" 2>&1 | tail -3
 timeout -k 5 400 python tests/soak_c5.py 700 rollout 2>&1 | tail -2
 timeout -k 5 200 python tests/chain_probe.py 50 400 1000 3000 2>&1 | grep "rollout(" | grep -c identical
