@@ -50,13 +50,15 @@ def main(path, n_envs=4096, src='abmarl_b200/csrc/bgw_fast.cuh'):
                     name = n
         else:
             name = fname
-        a = agg.setdefault(name, [0, 0])
+        tinst = int(r[hdr.index('Predicated-On Thread Instructions Executed')]) if 'Predicated-On Thread Instructions Executed' in hdr else 0
+        a = agg.setdefault(name, [0, 0, 0])
         a[0] += inst
         a[1] += samp
-    ti, ts = sum(v[0] for v in agg.values()), sum(v[1] for v in agg.values())
-    print(f"total warp-instructions {ti} ({ti / n_envs:.0f}/env), samples {ts}")
-    for name, (i, s) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
-        print(f"{name:42s} inst {100 * i / ti:5.1f}% ({i / n_envs:7.0f}/env)   samples {100 * s / ts:5.1f}%")
+        a[2] += tinst
+    ti, ts, tt = (sum(v[k] for v in agg.values()) for k in range(3))
+    print(f"total warp-instructions {ti} ({ti / n_envs:.0f}/env), samples {ts}, active lanes per instruction {tt / max(ti, 1):.1f}")
+    for name, (i, s, t) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
+        print(f"{name:42s} inst {100 * i / ti:5.1f}% ({i / n_envs:7.0f}/env)   samples {100 * s / ts:5.1f}%   lanes {t / max(i, 1):4.1f}")
 
 
 if __name__ == '__main__':
