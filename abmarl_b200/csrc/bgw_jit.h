@@ -181,52 +181,61 @@ inline const char *compile_and_load(std::string src, const char *name, int smem,
         cache_path = std::string(cache_dir) + nm;
         read_file(cache_path, cubin);
     }
-    if (cubin.empty()) {
-        if (const char *e = load_nvrtc(nvrtc())) return e;
-        Nvrtc &n = nvrtc();
-        nvrtcProgram prog = nullptr;
-        int rc = n.CreateProgram(&prog, src.c_str(), "bgw_jit.cu", 0, nullptr, nullptr);
-        if (rc) { msg = std::string("nvrtcCreateProgram: ") + n.GetErrorString(rc); return msg.c_str(); }
-        const std::string i1 = "-I" + dir, i2 = "-I" + inc;
-        const char *opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "--fmad=false", i1.c_str(), i2.c_str(), "-I/usr/local/cuda/include", "-lineinfo",
-                              "-DBGW_NO_ST256"};   /* the last one only with an NVRTC that predates PTX 8.8 */
-        const int nopt = (int)(sizeof(opts) / sizeof(opts[0])) - (n.major * 100 + n.minor >= 1209 ? 1 : 0);
-        rc = n.CompileProgram(prog, nopt, opts);
-        if (rc) {
-            size_t ln = 0;
-            n.GetProgramLogSize(prog, &ln);
-            std::string log(ln, '\0');
-            if (ln) n.GetProgramLog(prog, &log[0]);
-            msg = std::string("nvrtcCompileProgram: ") + n.GetErrorString(rc) + "\n" + log.substr(0, 1500);
+    bool from_cache = !cubin.empty();
+    for (int attempt = 0;; ++attempt) {
+        if (cubin.empty()) {
+            if (const char *e = load_nvrtc(nvrtc())) return e;
+            Nvrtc &n = nvrtc();
+            nvrtcProgram prog = nullptr;
+            int rc = n.CreateProgram(&prog, src.c_str(), "bgw_jit.cu", 0, nullptr, nullptr);
+            if (rc) { msg = std::string("nvrtcCreateProgram: ") + n.GetErrorString(rc); return msg.c_str(); }
+            const std::string i1 = "-I" + dir, i2 = "-I" + inc;
+            const char *opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "--fmad=false", i1.c_str(), i2.c_str(), "-I/usr/local/cuda/include", "-lineinfo",
+                                  "-DBGW_NO_ST256"};   /* the last one only with an NVRTC that predates PTX 8.8 */
+            const int nopt = (int)(sizeof(opts) / sizeof(opts[0])) - (n.major * 100 + n.minor >= 1209 ? 1 : 0);
+            rc = n.CompileProgram(prog, nopt, opts);
+            if (rc) {
+                size_t ln = 0;
+                n.GetProgramLogSize(prog, &ln);
+                std::string log(ln, '\0');
+                if (ln) n.GetProgramLog(prog, &log[0]);
+                msg = std::string("nvrtcCompileProgram: ") + n.GetErrorString(rc) + "\n" + log.substr(0, 1500);
+                n.DestroyProgram(&prog);
+                return msg.c_str();
+            }
+            size_t cn = 0;
+            n.GetCUBINSize(prog, &cn);
+            cubin.resize(cn);
+            n.GetCUBIN(prog, &cubin[0]);
             n.DestroyProgram(&prog);
-            return msg.c_str();
-        }
-        size_t cn = 0;
-        n.GetCUBINSize(prog, &cn);
-        cubin.resize(cn);
-        n.GetCUBIN(prog, &cubin[0]);
-        n.DestroyProgram(&prog);
-        if (!cache_path.empty()) {                    /* best effort: written under a temporary name, then renamed */
-            mkdir(cache_dir, 0755);
-            const std::string tmp = cache_path + ".tmp";
-            if (FILE *fp = fopen(tmp.c_str(), "wb")) {
-                const bool ok = fwrite(cubin.data(), 1, cubin.size(), fp) == cubin.size();
-                fclose(fp);
-                if (ok) rename(tmp.c_str(), cache_path.c_str()); else remove(tmp.c_str());
+            if (!cache_path.empty()) {                    /* best effort: written under a temporary name, then renamed */
+                mkdir(cache_dir, 0755);
+                const std::string tmp = cache_path + ".tmp";
+                if (FILE *fp = fopen(tmp.c_str(), "wb")) {
+                    const bool ok = fwrite(cubin.data(), 1, cubin.size(), fp) == cubin.size();
+                    fclose(fp);
+                    if (ok) rename(tmp.c_str(), cache_path.c_str()); else remove(tmp.c_str());
+                }
             }
         }
-    }
-    Driver &c = driver();
-    const char *es = nullptr;
-    int rc = c.ModuleLoadData(&out.module, cubin.data());
-    if (rc) { c.GetErrorString(rc, &es); msg = std::string("cuModuleLoadData: ") + (es ? es : "?"); return msg.c_str(); }
-    rc = c.ModuleGetFunction(&out.function, out.module, name);
-    if (!rc) rc = c.FuncSetAttribute(out.function, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, smem);
-    if (rc) {
+        Driver &c = driver();
+        const char *es = nullptr;
+        int rc = c.ModuleLoadData(&out.module, cubin.data());
+        if (!rc) {
+            rc = c.ModuleGetFunction(&out.function, out.module, name);
+            if (!rc) rc = c.FuncSetAttribute(out.function, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, smem);
+            if (!rc) break;
+            c.ModuleUnload(out.module);
+        }
+        out = Kernel();
+        if (from_cache && attempt == 0) {                 /* a damaged or stale cache entry: compile afresh, once */
+            from_cache = false;
+            cubin.clear();
+            remove(cache_path.c_str());
+            continue;
+        }
         c.GetErrorString(rc, &es);
         msg = std::string("loading ") + name + ": " + (es ? es : "?");
-        c.ModuleUnload(out.module);
-        out = Kernel();
         return msg.c_str();
     }
     return nullptr;

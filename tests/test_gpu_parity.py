@@ -156,6 +156,22 @@ def test_specialized_team_battle_shape_matches_oracle(mirror, name, tmp_path):
     assert_state_equal(eng.state_numpy(), ora.state, name + '/specialized shape, rollout')
 
 
+def test_specialize_recompiles_over_a_damaged_cache_entry(mirror, tmp_path):
+    """A cache file that does not load (truncated, or from another build) is replaced by a fresh compilation."""
+    builder, manager, _ = scenarios.SCENARIOS['traffic']
+    spec = compile_sim(builder(mirror), manager=manager, n_envs=8, seed=5, horizon=20, auto_reset=True)
+    eng, ora = _pair(spec)
+    eng.specialize(cache_dir=str(tmp_path))
+    (name,) = os.listdir(tmp_path)
+    good = os.path.getsize(os.path.join(tmp_path, name))
+    with open(os.path.join(tmp_path, name), 'wb') as fh:
+        fh.write(b'not a cubin')
+    eng2, ora2 = _pair(spec)
+    eng2.specialize(cache_dir=str(tmp_path))
+    assert os.path.getsize(os.path.join(tmp_path, name)) == good
+    run_lockstep(eng2, ora2, 30, label='traffic/specialized after a damaged cache entry')
+
+
 def test_specialize_leaves_the_shipped_shapes_alone(mirror, tmp_path):
     spec = compile_sim(scenarios.SCENARIOS['tb_c2'][0](mirror), n_envs=16, seed=3, horizon=30, auto_reset=True)
     eng, ora = _pair(spec)
