@@ -52,6 +52,9 @@ def test_oracle_reproduces_reference_transcript(mirror, name):
             assert int(ora.all_done[0] & K.ENV_ALL_DONE) == int(g['all_done'][t])
             n_valid += int(present.sum())
         np.testing.assert_array_equal(ora.obs[0][present], g['obs'][t][present], err_msg=f'call {t} obs')
+        # bgwo_observe (the checker of bgw_observe) = the reference's sim.get_obs(agent_id) on the standing state (smart.py:93-99):
+        # for every learner the transcript reports at this call it is the observation the reference returned
+        np.testing.assert_array_equal(ora.observe(0)[present], g['obs'][t][present], err_msg=f'call {t} observe')
         st = ora.state
         np.testing.assert_array_equal(st['flags'][0], g['flags'][t], err_msg=f'call {t} flags')
         np.testing.assert_array_equal(st['cell'][0], g['cell'][t], err_msg=f'call {t} cell')
